@@ -1,0 +1,49 @@
+"""Build recipe for libbnn_b200.so (hand-written sm_100a CUDA + the C ABI).
+
+    python -m bnn_b200.build          # or __graft_entry__.build()
+
+nvcc cross-compiles without a GPU.  The library is built IN-TREE
+(bnn_b200/libbnn_b200.so) so that it travels with the repo snapshot; it links
+the CUDA runtime statically and has no torch / Python dependency.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libbnn_b200.so")
+SOURCES = ["abi.cu", "forward_simt.cu", "moments.cu", "sampling.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "bnn_b200.h"))
+    objs = []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + headers):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            subprocess.run(cmd, check=True)
+    if force or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,182 @@
+// C-ABI glue: error state, layout queries, forward dispatch and the host-buffer
+// (end-to-end) convenience entry point.  No torch types anywhere.
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace bnn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;  // B200
+  }
+  return n;
+}
+
+int forward_simt(const BnnForwardArgs* a, cudaStream_t st);
+long long forward_simt_workspace_bytes(const BnnForwardArgs* a);
+
+static int check_forward_args(const BnnForwardArgs* a, bool host) {
+  if (!a) BNN_FAIL("bnn_forward: null args");
+  if (a->N < 1 || a->S < 1) BNN_FAIL("bnn_forward: need N >= 1 and S >= 1 (N=%lld, S=%lld)", (long long)a->N, (long long)a->S);
+  if (a->S > 0x7fffffffLL) BNN_FAIL("bnn_forward: S too large");
+  if (!a->X || !a->W) BNN_FAIL("bnn_forward: X and W must not be null");
+  Layout L;
+  if (make_layout(&a->desc, &L)) return -1;
+  if (a->w_stride != 0 && a->w_stride < L.off[L.n_lin])
+    BNN_FAIL("bnn_forward: w_stride=%lld smaller than the packed network (%lld floats)", (long long)a->w_stride, L.off[L.n_lin]);
+  if (a->w_stride & 3) BNN_FAIL("bnn_forward: w_stride must be a multiple of 4 floats");
+  if (!host && (((uintptr_t)a->W) & 15)) BNN_FAIL("bnn_forward: W must be 16-byte aligned");
+  if (a->mask.mode < BNN_MASK_NONE || a->mask.mode > BNN_MASK_CONCRETE) BNN_FAIL("bnn_forward: bad mask mode %d", a->mask.mode);
+  if (a->mask.mode == BNN_MASK_EXTERNAL && !a->mask.mask) BNN_FAIL("bnn_forward: BNN_MASK_EXTERNAL without a mask tensor");
+  if (a->precision != BNN_PREC_FP32) BNN_FAIL("bnn_forward: precision %d not available in this build", a->precision);
+  if (!a->pred && !a->mean && !a->var && !a->part_mean && !a->part_m2) BNN_FAIL("bnn_forward: no output requested");
+  return 0;
+}
+
+}  // namespace bnn
+
+using namespace bnn;
+
+extern "C" int32_t bnn_abi_version(void) { return BNN_ABI_VERSION; }
+extern "C" const char* bnn_last_error(void) { return g_err; }
+extern "C" int32_t bnn_sm_count(void) { return sm_count(); }
+extern "C" int32_t bnn_set_device(int32_t device) {
+  BNN_CUDA(cudaSetDevice(device));
+  return 0;
+}
+
+extern "C" int64_t bnn_param_stride(const BnnMlpDesc* d) {
+  Layout L;
+  if (make_layout(d, &L)) return -1;
+  return L.off[L.n_lin];
+}
+extern "C" int64_t bnn_layer_offset(const BnnMlpDesc* d, int32_t l) {
+  Layout L;
+  if (make_layout(d, &L)) return -1;
+  if (l < 0 || l > L.n_lin) { set_error("layer %d out of range", l); return -1; }
+  return L.off[l];
+}
+extern "C" int32_t bnn_layer_ld(const BnnMlpDesc* d, int32_t l) {
+  Layout L;
+  if (make_layout(d, &L)) return -1;
+  if (l < 0 || l >= L.n_lin) { set_error("layer %d out of range", l); return -1; }
+  return L.ld[l];
+}
+extern "C" int64_t bnn_mask_len(const BnnMlpDesc* d, const int32_t* layer_masked) {
+  Layout L;
+  if (make_layout(d, &L)) return -1;
+  int mo[BNN_MAX_LINEAR];
+  return make_mask_offsets(L, layer_masked, mo);
+}
+
+extern "C" int64_t bnn_forward_workspace_bytes(const BnnForwardArgs* a) {
+  if (!a) { set_error("null args"); return -1; }
+  return forward_simt_workspace_bytes(a);
+}
+
+extern "C" int32_t bnn_forward(const BnnForwardArgs* a, void* stream) {
+  if (check_forward_args(a, false)) return -1;
+  return forward_simt(a, (cudaStream_t)stream);
+}
+
+// ---- host-buffer path ---------------------------------------------------------
+namespace {
+struct HostWs {
+  void* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaStream_t st = nullptr;
+  int ensure(int i, size_t bytes) {
+    if (bytes <= cap[i]) return 0;
+    if (buf[i]) cudaFree(buf[i]);
+    buf[i] = nullptr;
+    cap[i] = 0;
+    BNN_CUDA(cudaMalloc(&buf[i], bytes));
+    cap[i] = bytes;
+    return 0;
+  }
+  void release() {
+    for (int i = 0; i < 8; ++i) {
+      if (buf[i]) cudaFree(buf[i]);
+      buf[i] = nullptr;
+      cap[i] = 0;
+    }
+    if (st) cudaStreamDestroy(st);
+    st = nullptr;
+  }
+};
+HostWs g_ws;
+std::mutex g_ws_mu;
+}  // namespace
+
+extern "C" void bnn_release_workspace(void) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  g_ws.release();
+}
+
+extern "C" int32_t bnn_forward_host(const BnnForwardArgs* ah) {
+  if (check_forward_args(ah, true)) return -1;
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  Layout L;
+  if (make_layout(&ah->desc, &L)) return -1;
+  if (!g_ws.st) BNN_CUDA(cudaStreamCreateWithFlags(&g_ws.st, cudaStreamNonBlocking));
+  cudaStream_t st = g_ws.st;
+  BnnForwardArgs a = *ah;
+  const int nout = L.out[L.n_lin - 1];
+  const long long M = a.N * nout;
+  const size_t x_bytes = (size_t)a.N * L.in[0] * 4;
+  const long long nets = a.w_stride == 0 ? 1 : a.S;
+  const long long wst = a.w_stride == 0 ? L.off[L.n_lin] : a.w_stride;
+  const size_t w_bytes = (size_t)nets * wst * 4;
+  enum { BX = 0, BW, BMASK, BPRED, BMEAN, BVAR, BPART, BWS };
+  if (g_ws.ensure(BX, x_bytes) || g_ws.ensure(BW, w_bytes)) return -2;
+  BNN_CUDA(cudaMemcpyAsync(g_ws.buf[BX], ah->X, x_bytes, cudaMemcpyHostToDevice, st));
+  BNN_CUDA(cudaMemcpyAsync(g_ws.buf[BW], ah->W, w_bytes, cudaMemcpyHostToDevice, st));
+  a.X = (const float*)g_ws.buf[BX];
+  a.W = (const float*)g_ws.buf[BW];
+  if (a.mask.mode == BNN_MASK_EXTERNAL) {
+    const size_t mb = (size_t)a.S * a.mask.mask_stride * 4;
+    if (g_ws.ensure(BMASK, mb)) return -2;
+    BNN_CUDA(cudaMemcpyAsync(g_ws.buf[BMASK], ah->mask.mask, mb, cudaMemcpyHostToDevice, st));
+    a.mask.mask = (const float*)g_ws.buf[BMASK];
+  }
+  if (ah->pred) {
+    if (g_ws.ensure(BPRED, (size_t)a.S * M * 4)) return -2;
+    a.pred = (float*)g_ws.buf[BPRED];
+  }
+  if (ah->mean) { if (g_ws.ensure(BMEAN, (size_t)M * 4)) return -2; a.mean = (float*)g_ws.buf[BMEAN]; }
+  if (ah->var) { if (g_ws.ensure(BVAR, (size_t)M * 4)) return -2; a.var = (float*)g_ws.buf[BVAR]; }
+  if (ah->part_mean || ah->part_m2) {
+    if (g_ws.ensure(BPART, (size_t)M * 16)) return -2;
+    a.part_mean = ah->part_mean ? (double*)g_ws.buf[BPART] : nullptr;
+    a.part_m2 = ah->part_m2 ? (double*)g_ws.buf[BPART] + M : nullptr;
+  }
+  const long long wsb = forward_simt_workspace_bytes(&a);
+  if (wsb < 0) return -1;
+  if (g_ws.ensure(BWS, (size_t)(wsb > 16 ? wsb : 16))) return -2;
+  a.workspace = g_ws.buf[BWS];
+  a.workspace_bytes = wsb;
+  const int rc = forward_simt(&a, st);
+  if (rc) return rc;
+  if (ah->pred) BNN_CUDA(cudaMemcpyAsync(ah->pred, a.pred, (size_t)a.S * M * 4, cudaMemcpyDeviceToHost, st));
+  if (ah->mean) BNN_CUDA(cudaMemcpyAsync(ah->mean, a.mean, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+  if (ah->var) BNN_CUDA(cudaMemcpyAsync(ah->var, a.var, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+  if (ah->part_mean) BNN_CUDA(cudaMemcpyAsync(ah->part_mean, a.part_mean, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+  if (ah->part_m2) BNN_CUDA(cudaMemcpyAsync(ah->part_m2, a.part_m2, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+  BNN_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}

@@ -1,0 +1,287 @@
+"""Tensor-level wrappers over the C ABI.  torch is plumbing here: it owns device
+memory and the current stream; every op below is one call into libbnn_b200.so.
+No op has a CPU implementation -- CPU tensors are rejected."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .layout import Arch
+
+_PREC = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3, "tf32": _lib.PREC_TF32}
+
+
+def _dev(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: bnn_b200 has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _stream(t):
+    _lib.check(_lib.lib().bnn_set_device(t.device.index), "bnn_set_device")
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class MaskConfig:
+    """Per-sample input-unit scaling (dropout family).
+
+    kind: "external" (tensor [S, mask_len]), "bernoulli" or "concrete" (Philox in-kernel).
+    layer_masked: one bool per Linear; p_drop: drop probability per Linear.
+    """
+
+    def __init__(self, kind, layer_masked, mask=None, p_drop=None, temperature=0.1, seed=0, sample_offset=0):
+        self.kind, self.layer_masked, self.mask = kind, [bool(b) for b in layer_masked], mask
+        self.p_drop = list(p_drop) if p_drop is not None else [0.0] * len(layer_masked)
+        self.temperature, self.seed, self.sample_offset = float(temperature), int(seed), int(sample_offset)
+
+    def spec(self, arch):
+        s = _lib.MaskSpec()
+        s.mode = {"external": _lib.MASK_EXTERNAL, "bernoulli": _lib.MASK_BERNOULLI, "concrete": _lib.MASK_CONCRETE}[self.kind]
+        for l in range(arch.n_linear):
+            s.layer_masked[l] = 1 if self.layer_masked[l] else 0
+            s.p_drop[l] = float(self.p_drop[l])
+        _, mlen = arch.mask_layout(self.layer_masked)
+        if self.kind == "external":
+            m = _dev(self.mask, "mask")
+            if m.dim() != 2 or m.shape[1] < mlen:
+                raise ValueError(f"mask must be [S, >= {mlen}], got {tuple(m.shape)}")
+            s.mask = m.data_ptr()
+            s.mask_stride = m.shape[1]
+        s.temperature = self.temperature
+        s.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+        s.sample_offset = self.sample_offset
+        return s
+
+
+def forward(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=False, want_moments=True,
+            want_partials=False, precision="fp32"):
+    """Fused S x N batched MLP forward (+ predictive moments).
+
+    X: [N, dim]; W: bank [S, stride] or one shared network [stride] (then pass S).
+    Returns dict with any of pred [S,N,nout], mean/var [N,nout], part_mean/part_m2 (float64 [N,nout]).
+    """
+    X = _dev(X, "X")
+    W = _dev(W, "W")
+    if X.dim() != 2 or X.shape[1] != arch.dims[0]:
+        raise ValueError(f"X must be [N, {arch.dims[0]}], got {tuple(X.shape)}")
+    a = _lib.ForwardArgs()
+    a.desc = arch.desc()
+    a.X, a.N = X.data_ptr(), X.shape[0]
+    if W.dim() == 1:
+        if S is None:
+            raise ValueError("S is required with a single shared network")
+        if W.shape[0] < arch.stride:
+            raise ValueError("W shorter than the packed network")
+        a.w_stride, a.S = 0, int(S)
+    else:
+        if W.shape[1] < arch.stride:
+            raise ValueError(f"W must be [S, >= {arch.stride}], got {tuple(W.shape)}")
+        a.w_stride, a.S = W.shape[1], W.shape[0]
+        if S is not None and int(S) != W.shape[0]:
+            raise ValueError("S does not match the bank")
+    a.W = W.data_ptr()
+    if mask is not None:
+        a.mask = mask.spec(arch)
+        if mask.kind == "external" and mask.mask.shape[0] != a.S:
+            raise ValueError("mask rows != S")
+    a.precision = _PREC[precision]
+    N, O, Sn = X.shape[0], arch.nout, int(a.S)
+    if N < 1 or Sn < 1:
+        raise ValueError("need at least one point and one sample")
+    out = {}
+    dev = X.device
+    if want_pred:
+        out["pred"] = torch.empty(Sn, N, O, dtype=torch.float32, device=dev)
+        a.pred = out["pred"].data_ptr()
+    if want_moments:
+        out["mean"] = torch.empty(N, O, dtype=torch.float32, device=dev)
+        out["var"] = torch.empty(N, O, dtype=torch.float32, device=dev)
+        a.mean, a.var = out["mean"].data_ptr(), out["var"].data_ptr()
+    if want_partials:
+        out["part_mean"] = torch.empty(N, O, dtype=torch.float64, device=dev)
+        out["part_m2"] = torch.empty(N, O, dtype=torch.float64, device=dev)
+        a.part_mean, a.part_m2 = out["part_mean"].data_ptr(), out["part_m2"].data_ptr()
+    L = _lib.lib()
+    if want_moments or want_partials:
+        nbytes = L.bnn_forward_workspace_bytes(C.byref(a))
+        if nbytes < 0:
+            _lib.check(-1, "bnn_forward_workspace_bytes")
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        out["_ws"] = ws   # keep alive until the caller drops the dict (stream-ordered use)
+    _lib.check(L.bnn_forward(C.byref(a), _stream(X)), "bnn_forward")
+    return out
+
+
+def forward_host(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=False, want_moments=True, precision="fp32"):
+    """End-to-end variant: X / W / mask / outputs are HOST tensors (pin them); the library does the
+    H2D copies, the launch, the D2H copies and synchronises."""
+    for name, t in (("X", X), ("W", W)):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous float32 host tensor")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: bnn_b200 has no CPU fallback")
+    a = _lib.ForwardArgs()
+    a.desc = arch.desc()
+    a.X, a.N = X.data_ptr(), X.shape[0]
+    if W.dim() == 1:
+        a.w_stride, a.S = 0, int(S)
+    else:
+        a.w_stride, a.S = W.shape[1], W.shape[0]
+    a.W = W.data_ptr()
+    if mask is not None:
+        if mask.kind == "external":
+            spec = MaskConfig("bernoulli", mask.layer_masked).spec(arch)   # fill the common fields
+            spec.mode = _lib.MASK_EXTERNAL
+            spec.mask = mask.mask.data_ptr()
+            spec.mask_stride = mask.mask.shape[1]
+            a.mask = spec
+        else:
+            a.mask = mask.spec(arch)
+    a.precision = _PREC[precision]
+    N, O, Sn = X.shape[0], arch.nout, int(a.S)
+    out = {}
+    if want_pred:
+        out["pred"] = torch.empty(Sn, N, O, dtype=torch.float32).pin_memory()
+        a.pred = out["pred"].data_ptr()
+    if want_moments:
+        out["mean"] = torch.empty(N, O, dtype=torch.float32).pin_memory()
+        out["var"] = torch.empty(N, O, dtype=torch.float32).pin_memory()
+        a.mean, a.var = out["mean"].data_ptr(), out["var"].data_ptr()
+    L = _lib.lib()
+    _lib.check(L.bnn_set_device(torch.cuda.current_device()), "bnn_set_device")
+    _lib.check(L.bnn_forward_host(C.byref(a)), "bnn_forward_host")
+    return out
+
+
+def moments(pred, want_partials=False):
+    """mean and unbiased var over dim 0 of pred [S, ...] (BNN.py:37)."""
+    pred = _dev(pred, "pred")
+    S = pred.shape[0]
+    tail = pred.shape[1:]
+    M = pred[0].numel()
+    L = _lib.lib()
+    mean = torch.empty(tail, dtype=torch.float32, device=pred.device)
+    var = torch.empty(tail, dtype=torch.float32, device=pred.device)
+    pm = pm2 = None
+    if want_partials:
+        pm = torch.empty(tail, dtype=torch.float64, device=pred.device)
+        pm2 = torch.empty(tail, dtype=torch.float64, device=pred.device)
+    ws = torch.empty(max(int(L.bnn_moments_workspace_bytes(S, M)), 16), dtype=torch.uint8, device=pred.device)
+    _lib.check(L.bnn_moments(_ptr(pred), S, M, _ptr(mean), _ptr(var), _ptr(pm), _ptr(pm2), _ptr(ws), ws.numel(),
+                             _stream(pred)), "bnn_moments")
+    return (mean, var, pm, pm2) if want_partials else (mean, var)
+
+
+def moments_merge(part_mean, part_m2, counts):
+    """Chan merge of R shards: part_mean/part_m2 float64 [R, ...]; counts: R ints."""
+    if part_mean.dtype != torch.float64 or part_m2.dtype != torch.float64 or not part_mean.is_cuda:
+        raise TypeError("shard moments must be float64 CUDA tensors")
+    R = part_mean.shape[0]
+    tail = part_mean.shape[1:]
+    M = part_mean[0].numel()
+    mean = torch.empty(tail, dtype=torch.float32, device=part_mean.device)
+    var = torch.empty(tail, dtype=torch.float32, device=part_mean.device)
+    cnt = (C.c_int64 * R)(*[int(c) for c in counts])
+    _lib.check(_lib.lib().bnn_moments_merge(_ptr(part_mean.contiguous()), _ptr(part_m2.contiguous()), cnt, R, M,
+                                            _ptr(mean), _ptr(var), _stream(mean)), "bnn_moments_merge")
+    return mean, var
+
+
+def metrics(mean, var, y, noise_var=None):
+    """rmse[nout], nll[nout] of BNN.validate (BNN.py:30-31); noise_var (per output) gives the
+    experiments/SGDMC.py:83-93 variant.  Raises ValueError where the reference's Normal() would."""
+    mean, var = _dev(mean, "mean"), _dev(var, "var")
+    N = mean.shape[0]
+    nout = mean[0].numel()
+    y = _dev(y.reshape(N, -1).contiguous(), "y")
+    if y.shape[1] != nout:
+        raise ValueError(f"y has {y.shape[1]} outputs, predictions have {nout}")
+    nv = None
+    if noise_var is not None:
+        nv = _dev(torch.as_tensor(noise_var, dtype=torch.float32, device=mean.device).reshape(-1).contiguous(), "noise_var")
+        if nv.numel() != nout:
+            raise ValueError("noise_var needs one value per output")
+    out = torch.empty(2 * nout + 1, dtype=torch.float32, device=mean.device)
+    _lib.check(_lib.lib().bnn_metrics(_ptr(mean), _ptr(var), _ptr(y), _ptr(nv), N, nout, _ptr(out), _stream(mean)),
+               "bnn_metrics")
+    host = out.cpu()
+    if host[2 * nout] > 0:
+        raise ValueError("predictive variance is not positive (the reference's Normal(scale) raises here too)")
+    return host[:nout].clone(), host[nout: 2 * nout].clone()
+
+
+def reparam_kl(arch: Arch, mu, rho, S, mode="bbb", eps=None, seed=0, sample_offset=0, weight_std=None):
+    """W[s] = mu + sigma(rho) * eps_s for s < S (BNN_BBB.py:24-27 / BNN_SVI.py:42-46) and, when
+    weight_std is given, KL(q || N(0, weight_std)) (BNN_BBB.py:107-110) as a float64 device scalar."""
+    mu, rho = _dev(mu, "mu"), _dev(rho, "rho")
+    if mu.numel() != arch.stride or rho.numel() != arch.stride:
+        raise ValueError("mu/rho must be packed vectors")
+    W = torch.empty(S, arch.stride, dtype=torch.float32, device=mu.device) if S > 0 else None
+    if eps is not None:
+        eps = _dev(eps, "eps")
+        if tuple(eps.shape) != (S, arch.stride):
+            raise ValueError("eps must be [S, stride]")
+    kl = torch.zeros((), dtype=torch.float64, device=mu.device) if weight_std is not None else None
+    d = arch.desc()
+    _lib.check(_lib.lib().bnn_reparam_kl(C.byref(d), _lib.SCALE_BBB if mode == "bbb" else _lib.SCALE_SVI, _ptr(mu), _ptr(rho),
+                                         _ptr(eps), seed & 0xFFFFFFFFFFFFFFFF, sample_offset, S, _ptr(W),
+                                         float(weight_std) if weight_std is not None else 0.0, _ptr(kl), _stream(mu)),
+               "bnn_reparam_kl")
+    return W, kl
+
+
+def dropout_masks(arch: Arch, cfg: MaskConfig, S, device, uniforms=None):
+    """[S, mask_len] keep masks (BNN_Dropout.py:70-75 / BNN_CDropout.py:59-65)."""
+    _, mlen = arch.mask_layout(cfg.layer_masked)
+    out = torch.empty(S, mlen, dtype=torch.float32, device=device)
+    if uniforms is not None:
+        uniforms = _dev(uniforms, "uniforms")
+    d = arch.desc()
+    spec = cfg.spec(arch)
+    _lib.check(_lib.lib().bnn_dropout_masks(C.byref(d), C.byref(spec), _ptr(uniforms), S, _ptr(out), _stream(out)),
+               "bnn_dropout_masks")
+    return out
+
+
+def apply_masks(arch: Arch, layer_masked, base, masks):
+    """Bank [S, stride] with W[s][:, j] = base[:, j] * mask[s][j] on masked layers (the reference's order)."""
+    base, masks = _dev(base, "base"), _dev(masks, "masks")
+    S = masks.shape[0]
+    W = torch.empty(S, arch.stride, dtype=torch.float32, device=base.device)
+    lm = (C.c_int32 * _lib.MAX_LINEAR)(*([1 if b else 0 for b in layer_masked] + [0] * (_lib.MAX_LINEAR - len(layer_masked))))
+    d = arch.desc()
+    _lib.check(_lib.lib().bnn_apply_masks(C.byref(d), lm, _ptr(base), _ptr(masks), masks.shape[1], S, _ptr(W), _stream(W)),
+               "bnn_apply_masks")
+    return W
+
+
+def psgld_step(theta, grad, V, lr_head, lr_tail=None, n_head=None, alpha=0.99, lam=1e-5, noise=None, seed=0, step=0):
+    """In-place preconditioned SGLD update of theta and V (see include/bnn_b200.h)."""
+    theta, grad, V = _dev(theta, "theta"), _dev(grad, "grad"), _dev(V, "V")
+    n = theta.numel()
+    if noise is not None:
+        noise = _dev(noise, "noise")
+    _lib.check(_lib.lib().bnn_psgld_step(_ptr(theta), _ptr(grad), _ptr(V), n, n if n_head is None else n_head, lr_head,
+                                         lr_head if lr_tail is None else lr_tail, alpha, lam, _ptr(noise),
+                                         seed & 0xFFFFFFFFFFFFFFFF, step, _stream(theta)), "bnn_psgld_step")
+
+
+def philox_words(seed, subsequence, tag, n, device):
+    out = torch.empty(n, dtype=torch.int32, device=device)
+    _lib.check(_lib.lib().bnn_philox_words(seed, subsequence, tag, n, _ptr(out), _stream(out)), "bnn_philox_words")
+    return out
+
+
+def philox_normals(seed, subsequence, tag, n, device):
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    _lib.check(_lib.lib().bnn_philox_normals(seed, subsequence, tag, n, _ptr(out), _stream(out)), "bnn_philox_normals")
+    return out

@@ -1,0 +1,192 @@
+/*
+ * bnn_b200.h -- C ABI of the B200-native hot path of Alaya-in-Matrix/BNN.
+ *
+ * The reference has no FFI: its "operator API" is the Python class BNN
+ * (BNN.py:6-37) and the bodies of sample / sample_predict / predict_mv /
+ * validate in its five subclasses.  Each entry point below replaces one of
+ * those bodies; the citation after "replaces:" is the reference code a
+ * maintainer would swap for a ctypes call.
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer unless the name ends in _host;
+ *     the caller owns all memory; nothing is allocated behind the caller's
+ *     back except inside the *_host convenience calls (workspace cached per
+ *     thread and freed by bnn_release_workspace());
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     device entry points are asynchronous and never synchronise;
+ *   - return value: 0 = ok, <0 = error; bnn_last_error() gives the message;
+ *     the library never aborts the process and has NO CPU fallback;
+ *   - all floating-point data are IEEE binary32 unless typed double.
+ *
+ * Packed parameter layout ("bank"): one network = one flat vector of
+ * bnn_param_stride() floats.  Linear layer l (in_l -> out_l) occupies
+ * out_l rows of ld_l = roundup4(in_l + 1) floats, row-major, starting at
+ * bnn_layer_offset(l): columns [0, in_l) are the weight row, column in_l is
+ * the bias (bias-last, as BNN_BBB.py:19,30-31,46-47 stores mu/rho), the
+ * remaining <=3 columns are zero padding that keeps every row 16-byte aligned
+ * for the bulk-copy (TMA) engine.  A bank of S networks is [S, stride].
+ */
+#ifndef BNN_B200_H_
+#define BNN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNN_ABI_VERSION 1
+#define BNN_MAX_LINEAR 8       /* Linear layers per network (hidden + output) */
+#define BNN_MAX_WIDTH 1024     /* widest layer / input the forward kernels take */
+#define BNN_MAX_FUSED_NOUT 64  /* nout limit of the fused forward+moments kernel */
+
+enum { BNN_ACT_RELU = 0, BNN_ACT_TANH = 1, BNN_ACT_SIGMOID = 2, BNN_ACT_IDENTITY = 3 };
+
+/* util.py:8-33 `NN(dim, act, num_hiddens, nout)`: dims = {dim, h1, .., hL, nout} */
+typedef struct BnnMlpDesc {
+  int32_t n_linear;                  /* L + 1 */
+  int32_t dims[BNN_MAX_LINEAR + 1];
+  int32_t act;                       /* BNN_ACT_* applied after every Linear but the last */
+} BnnMlpDesc;
+
+/* How the per-sample, per-input-unit scaling of BNN_Dropout.py:70-75 /
+ * BNN_CDropout.py:59-65 reaches the forward kernel.  The reference scales
+ * weight COLUMNS of a deep copy; scaling the layer's INPUT units is the same
+ * product and lets all S samples share one set of base weights.            */
+enum {
+  BNN_MASK_NONE = 0,
+  BNN_MASK_EXTERNAL = 1,   /* mask tensor [S, mask_len] supplied (reference-parity mode) */
+  BNN_MASK_BERNOULLI = 2,  /* generated in-kernel: Philox, keep iff u < 1-p          */
+  BNN_MASK_CONCRETE = 3    /* generated in-kernel: relaxed Bernoulli, T = temperature */
+};
+
+typedef struct BnnMaskSpec {
+  int32_t mode;                         /* BNN_MASK_* */
+  int32_t layer_masked[BNN_MAX_LINEAR]; /* 1 if Linear l's inputs are scaled */
+  const float* mask;                    /* EXTERNAL: [S, mask_len], layers concatenated in order */
+  int64_t mask_stride;                  /* floats between samples (>= mask_len) */
+  float p_drop[BNN_MAX_LINEAR];         /* BERNOULLI/CONCRETE: drop probability per layer */
+  float temperature;                    /* CONCRETE (reference: 0.1, BNN_CDropout.py:64) */
+  uint64_t seed;                        /* Philox key */
+  int64_t sample_offset;                /* global index of sample 0 (multi-GPU shards) */
+} BnnMaskSpec;
+
+/* Precision of the dense layers of the forward kernels. */
+enum {
+  BNN_PREC_FP32 = 0,    /* FP32 FFMA on the SIMT pipe: parity grade (1e-5) */
+  BNN_PREC_TF32X3 = 1,  /* tcgen05 kind::tf32, 3-pass error-compensated (~FP32) */
+  BNN_PREC_TF32 = 2     /* tcgen05 kind::tf32 single pass (looser bound) */
+};
+
+typedef struct BnnForwardArgs {
+  BnnMlpDesc desc;
+  const float* X;        /* [N, dims[0]] row-major */
+  int64_t N;
+  const float* W;        /* bank [S, w_stride] (w_stride = 0: one shared network) */
+  int64_t w_stride;
+  int64_t S;
+  BnnMaskSpec mask;
+  int32_t precision;     /* BNN_PREC_* */
+  /* outputs -- any may be NULL */
+  float* pred;           /* [S, N, nout]  (sample_predict) */
+  float* mean;           /* [N, nout]     (predict_mv)     */
+  float* var;            /* [N, nout]  unbiased, S-1       */
+  double* part_mean;     /* [N, nout]  this shard's mean   (multi-GPU merge input) */
+  double* part_m2;       /* [N, nout]  this shard's sum of squared deviations      */
+  void* workspace;       /* >= bnn_forward_workspace_bytes() bytes, 16-byte aligned */
+  int64_t workspace_bytes;
+} BnnForwardArgs;
+
+/* ---- library ------------------------------------------------------------ */
+int32_t bnn_abi_version(void);
+const char* bnn_last_error(void);
+/* number of SMs of the current device (grid sizing is a multiple of this) */
+int32_t bnn_sm_count(void);
+/* bind the calling thread to a device (the library carries its own static CUDA
+ * runtime; call this with the device your buffers live on before other calls) */
+int32_t bnn_set_device(int32_t device);
+
+/* ---- layout (host arithmetic, no GPU) ----------------------------------- */
+int64_t bnn_param_stride(const BnnMlpDesc* d);                 /* floats per network */
+int64_t bnn_layer_offset(const BnnMlpDesc* d, int32_t l);      /* first float of Linear l */
+int32_t bnn_layer_ld(const BnnMlpDesc* d, int32_t l);          /* row pitch of Linear l   */
+int64_t bnn_mask_len(const BnnMlpDesc* d, const int32_t* layer_masked);
+int64_t bnn_forward_workspace_bytes(const BnnForwardArgs* a);
+
+/* ---- (a)+(e) forward and predictive moments ----------------------------- */
+/* replaces: the `for i in range(S): pred[i] = nns[i](X)` loops
+ * (BNN_SGDMC.py:131-137, BNN_BBB.py:143-149, BNN_Dropout.py:78-84,
+ * BNN_CDropout.py:158-164, BNN_SVI.py:70-76) and, when mean/var are given,
+ * `preds.mean(0), preds.var(0)` of BNN.predict_mv (BNN.py:34-37), in one
+ * launch; pred[S,N,nout] is only written when asked for.                   */
+int32_t bnn_forward(const BnnForwardArgs* a, void* stream);
+
+/* ---- (e) standalone reduction and metrics ------------------------------- */
+/* replaces: BNN.predict_mv's `preds.mean(dim=0), preds.var(dim=0)` (BNN.py:37)
+ * on an already materialised pred[S, M] (M = N*nout).                       */
+int32_t bnn_moments(const float* pred, int64_t S, int64_t M, float* mean, float* var,
+                    double* part_mean, double* part_m2, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+int64_t bnn_moments_workspace_bytes(int64_t S, int64_t M);
+
+/* Chan merge of R shards' (count, mean, M2) -> mean/var (unbiased).  Used after
+ * the NCCL all-gather/all-reduce of the per-point moments.
+ * counts_host is a HOST array of R sample counts.                           */
+int32_t bnn_moments_merge(const double* part_mean, const double* part_m2, const int64_t* counts_host,
+                          int32_t R, int64_t M, float* mean, float* var, void* stream);
+
+/* replaces: BNN.validate's rmse / nll lines (BNN.py:30-31) and, with
+ * noise_var != NULL (per output, device), experiments/SGDMC.py:83-93.
+ * out = {rmse[nout], nll[nout]} floats followed by one float holding the count
+ * of non-positive variances (the reference raises there: Normal(scale<=0)).  */
+int32_t bnn_metrics(const float* mean, const float* var, const float* y, const float* noise_var,
+                    int64_t N, int32_t nout, float* out /* [2*nout+1] */, void* stream);
+
+/* ---- (b) reparameterised weight draws + KL ------------------------------ */
+enum { BNN_SCALE_BBB = 0 /* sqrt(softplus(max(rho,-35))) BNN_BBB.py:24-27 */,
+       BNN_SCALE_SVI = 1 /* softplus(rho)               BNN_SVI.py:42-46 */ };
+/* replaces: GaussianLinear.rsample/sample_linear (BNN_BBB.py:24-27,44-51) for all
+ * layers and all S draws at once, the guide draw of BNN_SVI.py:40-48, and the
+ * KL sum of BNN_BBB.loss (BNN_BBB.py:107-110; kl_out may be NULL).
+ * mu, rho: packed [stride]; eps: [S, stride] or NULL (= Philox in-kernel,
+ * stream (seed, sample_offset + s)); W_out: bank [S, stride].                */
+int32_t bnn_reparam_kl(const BnnMlpDesc* d, int32_t scale_mode, const float* mu, const float* rho,
+                       const float* eps, uint64_t seed, int64_t sample_offset, int64_t S,
+                       float* W_out, float weight_std, double* kl_out, void* stream);
+
+/* ---- (d) dropout masks --------------------------------------------------- */
+/* replaces: the mask draws of BNN_Dropout.py:70-75 (kind BNN_MASK_BERNOULLI) and
+ * CDropoutLinear.sample BNN_CDropout.py:59-65 (BNN_MASK_CONCRETE); same Philox
+ * streams as the in-kernel path of bnn_forward, so the two agree bit for bit.
+ * uniforms (optional, [S, mask_len]) replaces Philox by caller-supplied u.     */
+int32_t bnn_dropout_masks(const BnnMlpDesc* d, const BnnMaskSpec* spec, const float* uniforms,
+                          int64_t S, float* masks_out /* [S, mask_len] */, void* stream);
+/* materialise W[s] = base * diag(mask[s]) per masked layer (the reference's own
+ * arithmetic order, BNN_Dropout.py:74 / BNN_CDropout.py:64)                    */
+int32_t bnn_apply_masks(const BnnMlpDesc* d, const int32_t* layer_masked, const float* base,
+                        const float* masks, int64_t mask_stride, int64_t S, float* W_out, void* stream);
+
+/* ---- (c) pSGLD update ---------------------------------------------------- */
+/* replaces: pSGLD.step() + the LambdaLR factor (BNN_SGDMC.py:86-87,100-101).
+ * theta/grad/V: [n]; elements [0, n_head) use lr_head, the rest lr_tail (the two
+ * param groups of BNN_SGDMC.py:96-98).  noise: [n] or NULL (= Philox, stream
+ * (seed, step)).  V <- a V + (1-a) g^2; G = 1/(lam + sqrt(V));
+ * theta <- theta - (0.5 lr G g + sqrt(lr G) xi).  UNPINNED: pybnn absent.      */
+int32_t bnn_psgld_step(float* theta, const float* grad, float* V, int64_t n, int64_t n_head,
+                       float lr_head, float lr_tail, float alpha, float lam, const float* noise,
+                       uint64_t seed, int64_t step, void* stream);
+
+/* raw Philox stream dump for tests: out[n] 32-bit words / normals */
+int32_t bnn_philox_words(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, uint32_t* out, void* stream);
+int32_t bnn_philox_normals(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, float* out, void* stream);
+
+/* ---- host-buffer convenience (end-to-end path) --------------------------- */
+/* Same as bnn_forward but X / W / mask and all outputs are HOST pointers
+ * (pinned for full PCIe speed); copies in, runs, copies out, synchronises.   */
+int32_t bnn_forward_host(const BnnForwardArgs* a_host);
+void bnn_release_workspace(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNN_B200_H_ */

@@ -1,0 +1,234 @@
+"""CPU restatement of the reference's predictive hot path (TEST INFRASTRUCTURE).
+
+Every function cites the reference file:line (under /root/reference) whose
+arithmetic it restates.  All tensors are torch CPU float32 unless said
+otherwise, because that is what the reference computes in; the per-sample loop
+is kept as a loop on purpose -- it is also the timed CPU baseline.
+
+A "net" here is a plain list of ``(W, b)`` pairs (``W`` is ``[out, in]``,
+``b`` is ``[out]``), one pair per ``nn.Linear`` of the reference's
+``nn.Sequential`` (util.py:21-29); the activation sits between pairs and not
+after the last one.
+
+Parity status: pinned by tests/golden/*.npz (generated from the unmodified
+reference by tests/golden/make_golden.py) for everything except
+``psgld_step`` and ``svi_draw`` -- see oracle/__init__.py.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+F32_EPS = float(torch.finfo(torch.float32).eps)    # 2**-23
+F32_TINY = float(torch.finfo(torch.float32).tiny)  # 2**-126
+
+
+# --------------------------------------------------------------------------- #
+# a1-a3: the MLP and the per-sample loop
+# --------------------------------------------------------------------------- #
+def act_fn(name):
+    """Activation module shared by all layers (util.py:12, :25)."""
+    return {"relu": torch.relu, "tanh": torch.tanh,
+            "sigmoid": torch.sigmoid, "identity": (lambda t: t)}[name]
+
+
+def mlp_forward(net, x, act):
+    """util.py:31-33 -> nn.Sequential of Linear/act pairs built at util.py:21-29.
+
+    Linear is ``addmm(b, x, W^T)``; the activation follows every Linear but the
+    last.
+    """
+    f = act_fn(act)
+    h = x
+    last = len(net) - 1
+    for i, (W, b) in enumerate(net):
+        h = torch.addmm(b, h, W.t())
+        if i != last:
+            h = f(h)
+    return h
+
+
+def sample_predict(nets, X, act, nout=None):
+    """The hot loop.
+
+    nout given  -> BNN_SGDMC.sample_predict (BNN_SGDMC.py:131-137): pred [S,N,nout]
+    nout None   -> BNN_BBB.py:143-149 / BNN_Dropout.py:78-84 /
+                   BNN_CDropout.py:158-164 / BNN_SVI.py:70-76: pred [S,N] (squeeze)
+    """
+    S, N = len(nets), X.shape[0]
+    if nout is not None:
+        pred = torch.empty(S, N, nout)
+        for i in range(S):
+            pred[i] = mlp_forward(nets[i], X, act)
+    else:
+        pred = torch.zeros(S, N)
+        for i in range(S):
+            pred[i] = mlp_forward(nets[i], X, act).squeeze()
+    return pred
+
+
+def predict_mv(pred, num_test):
+    """BNN.py:34-37: view [S,N,-1]; mean over S and *unbiased* var over S."""
+    preds = pred.view(pred.shape[0], num_test, -1)
+    return preds.mean(dim=0), preds.var(dim=0)
+
+
+def normal_log_prob(value, loc, scale):
+    """torch.distributions.Normal.log_prob as called at BNN.py:31."""
+    var = scale ** 2
+    return -((value - loc) ** 2) / (2 * var) - scale.log() - math.log(math.sqrt(2 * math.pi))
+
+
+def validate_metrics(py, pv, y, noise_var=None):
+    """BNN.py:25-32 (epistemic variance only) and, with ``noise_var`` (per
+    output, already in target units), the SGDMC experiment's variant
+    experiments/SGDMC.py:83-93 (pv + ys**2/exp(log_prec))."""
+    y = y.view(py.shape[0], -1)
+    v = pv if noise_var is None else pv + noise_var
+    if bool((v <= 0).any()):
+        # torch.distributions.Normal validates scale > 0 (BNN.py:31 raises)
+        raise ValueError("predictive variance is not positive")
+    rmse = torch.mean((py - y) ** 2, dim=0).sqrt()
+    nll = -1 * normal_log_prob(y, py, v.sqrt()).mean(dim=0)
+    return rmse, nll
+
+
+# --------------------------------------------------------------------------- #
+# a5-a6: Bayes-by-Backprop draw and KL
+# --------------------------------------------------------------------------- #
+def stable_noise_var(rho):
+    """util.py:52-53: softplus(clamp(rho, min=-35)); softplus threshold 20."""
+    return F.softplus(torch.clamp(rho, min=-35.))
+
+
+def bbb_rsample(mu, rho, eps):
+    """BNN_BBB.py:24-27: wb = mu + sqrt(softplus(clamp(rho,-35))) * eps,
+    mu/rho/eps all ``[out, in+1]`` with the bias in the last column."""
+    return mu + stable_noise_var(rho).sqrt() * eps
+
+
+def bbb_split(wb):
+    """BNN_BBB.py:44-51: weight = wb[:, :-1], bias = wb[:, -1]."""
+    return wb[:, :-1].clone(), wb[:, -1].clone()
+
+
+def bbb_kl(mus, rhos, weight_std):
+    """BNN_BBB.py:107-110: sum over layers of KL(N(mu, sigma) || N(0, weight_std))
+    with the closed form torch's _kl_normal_normal uses:
+    0.5 * (var_ratio + t1 - 1 - log(var_ratio))."""
+    kld = torch.zeros(())
+    for mu, rho in zip(mus, rhos):
+        sigma = stable_noise_var(rho).sqrt()
+        var_ratio = (sigma / weight_std) ** 2
+        t1 = ((mu - 0.) / weight_std) ** 2
+        kld = kld + (0.5 * (var_ratio + t1 - 1 - var_ratio.log())).sum()
+    return kld
+
+
+def svi_draw(mu, sigma_raw, eps):
+    """BNN_SVI.py:42-46: theta = mu + softplus(sigma_raw) * eps for every
+    parameter tensor (weights and biases).  UNPINNED (pyro absent)."""
+    return mu + F.softplus(sigma_raw) * eps
+
+
+# --------------------------------------------------------------------------- #
+# a7-a8: dropout draws, applied as column scaling of the weights
+# --------------------------------------------------------------------------- #
+def scale_columns(net, masks, skip_unit_inputs):
+    """W[:, j] *= m_j per Linear.
+
+    skip_unit_inputs=True  -> BNN_Dropout.py:70-75 (only layers with in > 1)
+    skip_unit_inputs=False -> BNN_CDropout.py:59-65 (every layer)
+    ``masks`` has one 1-D tensor per *masked* layer, in layer order.
+    """
+    out, it = [], iter(masks)
+    for (W, b) in net:
+        if skip_unit_inputs and W.shape[1] <= 1:
+            out.append((W.clone(), b.clone()))
+            continue
+        m = next(it)
+        out.append((W * m, b.clone()))   # broadcasts over rows: column j scaled by m[j]
+    return out
+
+
+def bernoulli_keep_mask(u, p):
+    """BNN_Dropout.py:74: F.dropout(ones(in), p) * (1 - p) is a pure 0/1 keep
+    mask with P(keep) = 1 - p; ``u`` are the uniforms in [0, 1)."""
+    return (u < (1.0 - p)).to(torch.float32)
+
+
+def concrete_keep_mask(u, p_logit, temperature=0.1):
+    """BNN_CDropout.py:18-19, :59-65 + torch relaxed_bernoulli.py (LogitRelaxed
+    Bernoulli.rsample) + transforms._clipped_sigmoid.
+
+    p = clamp(sigmoid(p_logit)), q = clamp(1 - p), u = clamp(u);
+    z = clip(sigmoid((log u - log1p(-u) + log q - log1p(-q)) / T), tiny, 1-eps).
+    """
+    p = torch.sigmoid(torch.as_tensor(p_logit, dtype=torch.float32)).clamp(F32_EPS, 1 - F32_EPS)
+    q = (1 - p).clamp(F32_EPS, 1 - F32_EPS)
+    u = u.clamp(F32_EPS, 1 - F32_EPS)
+    logits = (u.log() - (-u).log1p() + q.log() - (-q).log1p()) / temperature
+    return torch.clamp(torch.sigmoid(logits), min=F32_TINY, max=1.0 - F32_EPS)
+
+
+# --------------------------------------------------------------------------- #
+# a12: pSGLD update (UNPINNED -- pybnn absent; Li et al. 2016 Alg. 1, no Gamma term)
+# --------------------------------------------------------------------------- #
+def psgld_step(theta, grad, V, lr, noise, alpha=0.99, lam=1e-5):
+    """V <- a V + (1-a) g^2 ; G = 1/(lam + sqrt(V)) ;
+    theta <- theta - (0.5 lr G g + sqrt(lr G) xi).   SURVEY.md App. C."""
+    V = alpha * V + (1.0 - alpha) * grad * grad
+    G = 1.0 / (lam + V.sqrt())
+    theta = theta - (0.5 * lr * G * grad + (lr * G).sqrt() * noise)
+    return theta, V
+
+
+def lr_factor(t):
+    """BNN_SGDMC.py:101: np.float32((1 + it) ** -0.33)."""
+    return np.float32((1 + t) ** -0.33)
+
+
+def sgdmc_neg_log_post(net, log_precs, X, y, act, num_train, alpha_n, beta_n, gain=5. / 3):
+    """U = -(loglik * N/|b| + logprior): BNN_SGDMC.py:61-74, :83.
+
+    log p(l) for l = log-precision: Gamma(alpha, beta).log_prob(exp(l)) + l
+    (TransformedDistribution with ExpTransform().inv, BNN_SGDMC.py:47);
+    weights only get a Normal(0, gain*sqrt(2/(fan_in+fan_out))) prior.
+    """
+    nout = log_precs.shape[0]
+    yv = y.view(-1, nout)
+    out = mlp_forward(net, X, act).view(-1, nout)
+    precs = log_precs.exp()
+    log_lik = (-0.5 * precs * (yv - out) ** 2 + 0.5 * log_precs - 0.5 * np.log(2 * np.pi)).sum()
+    a, b = torch.as_tensor(alpha_n, dtype=torch.float32), torch.as_tensor(beta_n, dtype=torch.float32)
+    x = log_precs.exp()
+    log_gamma = a * b.log() + (a - 1) * x.log() - b * x - torch.lgamma(a)
+    log_p = (log_gamma + log_precs).sum()
+    for (W, _) in net:
+        std = gain * np.sqrt(2. / (W.shape[0] + W.shape[1]))
+        log_p = log_p + normal_log_prob(W, torch.zeros(()), torch.as_tensor(std, dtype=torch.float32)).sum()
+    return -1 * (log_lik * (num_train / X.shape[0]) + log_p)
+
+
+# --------------------------------------------------------------------------- #
+# multi-GPU merge of per-shard moments (Chan et al.); float64 on purpose
+# --------------------------------------------------------------------------- #
+def shard_moments(pred64):
+    """(count, mean, M2) of one shard of samples; pred64 is [S_shard, M] float64."""
+    n = pred64.shape[0]
+    mean = pred64.mean(axis=0)
+    m2 = ((pred64 - mean) ** 2).sum(axis=0)
+    return n, mean, m2
+
+
+def merge_moments(parts):
+    """Pairwise Chan merge of (n, mean, M2) triples, left to right."""
+    n, mean, m2 = parts[0]
+    for (nb, mb, m2b) in parts[1:]:
+        d = mb - mean
+        nn = n + nb
+        mean = mean + d * (nb / nn)
+        m2 = m2 + m2b + d * d * (n * nb / nn)
+        n = nn
+    return n, mean, m2

@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference at /root/reference.
+
+Run in the authoring container only (the reference does not travel to the GPU
+box):   python tests/golden/make_golden.py
+
+What is recorded: inputs (weights / mu,rho / base weights, data rows), the
+random draws the reference consumed (captured by wrapping torch.randn /
+torch.rand / F.dropout while the reference's own ``sample()`` runs -- the
+reference code itself is not modified), and the reference's outputs
+(sample_predict, predict_mv, validate, KL).  While generating, the CPU oracle is
+checked against the reference (asserts below), which is what pins it.
+
+``pybnn`` is absent offline; BNN_SGDMC imports it at module import only
+(BNN_SGDMC.py:14-17), so four empty stand-in classes are registered -- no
+arithmetic is stubbed; ``train()`` (the only user) is never called here.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+for name, cls in [("pybnn", None), ("pybnn.sampler", None),
+                  ("pybnn.sampler.sgld", "SGLD"),
+                  ("pybnn.sampler.preconditioned_sgld", "PreconditionedSGLD"),
+                  ("pybnn.sampler.sghmc", "SGHMC"),
+                  ("pybnn.sampler.adaptive_sghmc", "AdaptiveSGHMC")]:
+    m = types.ModuleType(name)
+    if cls:
+        setattr(m, cls, type(cls, (), {}))
+    sys.modules[name] = m
+
+import BNN_SGDMC as ref_sgdmc      # noqa: E402
+import BNN_BBB as ref_bbb          # noqa: E402
+import BNN_Dropout as ref_do       # noqa: E402
+import BNN_CDropout as ref_cdo     # noqa: E402
+from util import normalize         # noqa: E402
+
+from oracle import bnn_oracle as O  # noqa: E402
+
+
+def seq_to_net(seq):
+    return [(l.weight.detach().clone(), l.bias.detach().clone()) for l in seq if isinstance(l, nn.Linear)]
+
+
+def flat(net):
+    return np.concatenate([np.concatenate([W.numpy().ravel(), b.numpy().ravel()]) for W, b in net]).astype(np.float32)
+
+
+def uci_split(dataset, split):
+    d = np.loadtxt(f"{REF}/UCI_Datasets/{dataset}/data/data.txt")
+    tr = np.loadtxt(f"{REF}/UCI_Datasets/{dataset}/data/index_train_{split}.txt", dtype=np.int64)
+    te = np.loadtxt(f"{REF}/UCI_Datasets/{dataset}/data/index_test_{split}.txt", dtype=np.int64)
+    f = lambda a: torch.FloatTensor(a)
+    return f(d[tr, :-1]), f(d[tr, -1]), f(d[te, :-1]), f(d[te, -1])
+
+
+def save(name, **kw):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in kw.items()})
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+# --------------------------------------------------------------------------- #
+def gen_sgdmc_boston():
+    """cfg 1: BNN_SGDMC, bostonHousing split 0, 1x50 ReLU, 100 posterior samples."""
+    torch.manual_seed(11); np.random.seed(11)
+    trx, try_, tex, tey = uci_split("bostonHousing", 0)
+    xm, xs, ym, ys = normalize(trx, try_)                       # experiments/SGDMC.py:55-58
+    tex_n = (tex - xm) / xs
+    model = ref_sgdmc.BNN_SGDMC(13, nn.ReLU(), [50], nout=1, conf={})
+    model.nns = []
+    from copy import deepcopy
+    for _ in range(100):                                        # stand-in for a thinned chain
+        net = deepcopy(model.nn)
+        for p in net.parameters():
+            p.data += 0.05 * torch.randn_like(p)
+        model.nns.append(net)
+    model.log_precs.data.fill_(1.3)
+    nets = [seq_to_net(n.nn) for n in model.nns]
+    with torch.no_grad():
+        pred = model.sample_predict(model.nns, tex_n)           # [100,51,1]
+        py, pv = model.predict_mv(tex_n, model.nns)
+        # BNN.validate with a recorded permutation (BNN_SGDMC.py:127-129 uses numpy's global RNG)
+        np.random.seed(5)
+        perm = np.random.permutation(100)[:40]
+        np.random.seed(5)
+        rmse, nll = model.validate(tex_n, (tey - ym) / ys, num_samples=40)
+        # experiments/SGDMC.py:81-93 variant
+        preds_d = pred * ys + ym
+        py_d = preds_d.mean(dim=0).squeeze()
+        pv_d = preds_d.var(dim=0).squeeze() + ys ** 2 / model.log_precs.exp().squeeze().detach()
+        rmse_d = torch.mean((py_d - tey) ** 2).sqrt()
+        nll_d = -1 * torch.distributions.Normal(py_d, pv_d.sqrt()).log_prob(tey.squeeze()).mean()
+        # pin the oracle
+        o_pred = O.sample_predict(nets, tex_n, "relu", nout=1)
+        assert torch.equal(o_pred, pred)
+        o_py, o_pv = O.predict_mv(o_pred, 51)
+        assert torch.equal(o_py, py) and torch.equal(o_pv, pv)
+        sub = [nets[i] for i in perm]
+        s_py, s_pv = O.predict_mv(O.sample_predict(sub, tex_n, "relu", nout=1), 51)
+        o_rmse, o_nll = O.validate_metrics(s_py, s_pv, (tey - ym) / ys)
+        assert torch.allclose(o_rmse, rmse, rtol=1e-6) and torch.allclose(o_nll, nll, rtol=1e-6)
+    save("sgdmc_boston.npz", dims=[13, 50, 1], act="relu",
+         W=np.stack([flat(n) for n in nets]), X=tex_n, y_norm=(tey - ym) / ys, y_raw=tey,
+         ym=ym, ys=ys, log_prec=model.log_precs.detach(),
+         pred=pred, mean=py, var=pv, perm=perm, rmse=rmse, nll=nll,
+         mean_denorm=py_d, var_denorm=pv_d, rmse_denorm=rmse_d, nll_denorm=nll_d)
+
+
+def gen_sgdmc_multiout():
+    """nout > 1 (experiments/MO_SGDMC.py shape family): 10 -> 30 -> 30 -> 15, tanh."""
+    torch.manual_seed(12)
+    model = ref_sgdmc.BNN_SGDMC(10, nn.Tanh(), [30, 30], nout=15, conf={})
+    from copy import deepcopy
+    model.nns = []
+    for _ in range(12):
+        net = deepcopy(model.nn)
+        for p in net.parameters():
+            p.data += 0.1 * torch.randn_like(p)
+        model.nns.append(net)
+    X = torch.randn(37, 10)
+    y = torch.randn(37, 15)
+    nets = [seq_to_net(n.nn) for n in model.nns]
+    with torch.no_grad():
+        pred = model.sample_predict(model.nns, X)
+        py, pv = model.predict_mv(X, model.nns)
+        rmse = torch.mean((py - y) ** 2, dim=0).sqrt()                       # BNN.py:30
+        nll = -1 * torch.distributions.Normal(py, pv.sqrt()).log_prob(y).mean(dim=0)  # BNN.py:31
+        o_pred = O.sample_predict(nets, X, "tanh", nout=15)
+        assert torch.equal(o_pred, pred)
+        o_rmse, o_nll = O.validate_metrics(*O.predict_mv(o_pred, 37), y)
+        assert torch.allclose(o_rmse, rmse, rtol=1e-6) and torch.allclose(o_nll, nll, rtol=1e-6)
+    save("sgdmc_multiout.npz", dims=[10, 30, 30, 15], act="tanh",
+         W=np.stack([flat(n) for n in nets]), X=X, y=y, pred=pred, mean=py, var=pv, rmse=rmse, nll=nll)
+
+
+def gen_bbb_sinc():
+    """cfg 2: BNN_BBB, 1-D sinc toy, 2x50 tanh; eps captured from torch.randn."""
+    torch.manual_seed(13)
+    model = ref_bbb.BNN_BBB(1, nn.Tanh(), [50, 50], conf={"weight_std": 0.1})
+    gls = [l for l in model.nn.nn if isinstance(l, ref_bbb.GaussianLinear)]
+    for l in gls:                                   # move off the init point; cover the clamp and the threshold
+        l.mu.data += 0.3 * torch.randn_like(l.mu)
+        l.rho.data += 1.5 * torch.randn_like(l.rho)
+    gls[0].rho.data[0, 0] = -50.                    # exercises clamp(min=-35)
+    gls[0].rho.data[1, 0] = 25.                     # exercises softplus threshold 20
+    gls[1].rho.data[3, 4] = 19.5
+    S = 8
+    rec = []
+    orig = torch.randn
+    torch.randn = lambda *a, **k: (rec.append(orig(*a, **k)) or rec[-1])
+    try:
+        torch.manual_seed(99)
+        nns = model.sample(S)                       # BNN_BBB.py:139-141
+    finally:
+        torch.randn = orig
+    assert len(rec) == S * len(gls)
+    X = torch.linspace(-3, 3, 64).view(-1, 1)
+    y = torch.sin(3 * X) / (3 * X)
+    with torch.no_grad():
+        pred = model.sample_predict(nns, X)         # [S,64]
+        py, pv = model.predict_mv(X, nns)
+        mse, kld = model.loss(X, y)                 # kld is deterministic (BNN_BBB.py:107-110)
+        # pin the oracle draw + KL + forward
+        nets = []
+        for s in range(S):
+            net = []
+            for li, l in enumerate(gls):
+                wb = O.bbb_rsample(l.mu.detach(), l.rho.detach(), rec[s * len(gls) + li])
+                net.append(O.bbb_split(wb))
+            nets.append(net)
+        ref_nets = [seq_to_net(n) for n in nns]
+        for a, b in zip(nets, ref_nets):
+            for (W1, b1), (W2, b2) in zip(a, b):
+                assert torch.equal(W1, W2) and torch.equal(b1, b2)
+        assert torch.equal(O.sample_predict(nets, X, "tanh"), pred)
+        o_kl = O.bbb_kl([l.mu.detach() for l in gls], [l.rho.detach() for l in gls], 0.1)
+        assert torch.allclose(o_kl, kld.detach(), rtol=1e-6), (o_kl, kld)
+    kw = {}
+    for li, l in enumerate(gls):
+        kw[f"mu{li}"] = l.mu.detach()
+        kw[f"rho{li}"] = l.rho.detach()
+        kw[f"eps{li}"] = torch.stack([rec[s * len(gls) + li] for s in range(S)])
+        kw[f"wb{li}"] = torch.stack([torch.cat([ref_nets[s][li][0], ref_nets[s][li][1][:, None]], dim=1) for s in range(S)])
+    save("bbb_sinc.npz", dims=[1, 50, 50, 1], act="tanh", weight_std=0.1, X=X, y=y,
+         pred=pred, mean=py, var=pv, kl=kld.detach(), **kw)
+
+
+def gen_dropout_protein():
+    """cfg 3a: BNN_Dropout, protein split 0 rows, 2x100 tanh, p = 0.05; masks captured from F.dropout."""
+    torch.manual_seed(14)
+    trx, try_, tex, tey = uci_split("protein-tertiary-structure", 0)
+    xm, xs, _, _ = normalize(trx, try_)
+    X = ((tex - xm) / xs)[:96]
+    y = tey[:96]
+    p = 0.05
+    model = ref_do.BNN_Dropout(9, nn.Tanh(), [100, 100], conf={"dropout_rate": p})
+    for q in model.nn.parameters():
+        q.data += 0.05 * torch.randn_like(q)
+    S = 6
+    rec = []
+    orig = F.dropout
+    F.dropout = lambda *a, **k: (rec.append(orig(*a, **k)) or rec[-1])
+    try:
+        torch.manual_seed(77)
+        nns = model.sample(S)                       # BNN_Dropout.py:67-76
+    finally:
+        F.dropout = orig
+    assert len(rec) == 3 * S                        # every Linear has in > 1 here
+    masks = [[(rec[3 * s + l] * (1 - p)) for l in range(3)] for s in range(S)]
+    for s in range(S):
+        for m in masks[s]:
+            assert set(np.unique(m.numpy())).issubset({0.0, 1.0})
+    base = seq_to_net(model.nn.nn)
+    with torch.no_grad():
+        pred = model.sample_predict(nns, X)
+        py, pv = model.predict_mv(X, nns)
+        nets = [O.scale_columns(base, masks[s], skip_unit_inputs=True) for s in range(S)]
+        for a, b in zip(nets, [seq_to_net(n) for n in nns]):
+            for (W1, b1), (W2, b2) in zip(a, b):
+                assert torch.equal(W1, W2) and torch.equal(b1, b2)
+        assert torch.equal(O.sample_predict(nets, X, "tanh"), pred)
+    save("dropout_protein.npz", dims=[9, 100, 100, 1], act="tanh", p=p, base=flat(base), X=X, y=y,
+         masks=np.stack([np.concatenate([m.numpy() for m in masks[s]]) for s in range(S)]),
+         pred=pred, mean=py, var=pv)
+
+
+def gen_cdropout_protein():
+    """cfg 3b: BNN_CDropout, 2x100 tanh; uniforms captured from torch.rand."""
+    torch.manual_seed(15)
+    trx, try_, tex, _ = uci_split("protein-tertiary-structure", 0)
+    xm, xs, _, _ = normalize(trx, try_)
+    X = ((tex - xm) / xs)[100:180]
+    model = ref_cdo.BNN_CDropout(9, nn.Tanh(), [100, 100], conf={})
+    cls = [l for l in model.nn.nn if isinstance(l, ref_cdo.CDropoutLinear)]
+    for i, l in enumerate(cls):
+        l.layer[0].p_logit.data.fill_([-2.0, 0.0, 1.0][i])
+        l.layer[1].weight.data += 0.05 * torch.randn_like(l.layer[1].weight)
+    S = 5
+    rec = []
+    orig = torch.rand
+    torch.rand = lambda *a, **k: (rec.append(orig(*a, **k)) or rec[-1])
+    try:
+        torch.manual_seed(55)
+        nns = model.sample(S)                       # BNN_CDropout.py:154-156
+    finally:
+        torch.rand = orig
+    assert len(rec) == 3 * S
+    base = [(l.layer[1].weight.detach().clone(), l.layer[1].bias.detach().clone()) for l in cls]
+    p_logits = [float(l.layer[0].p_logit) for l in cls]
+    with torch.no_grad():
+        pred = model.sample_predict(nns, X)
+        py, pv = model.predict_mv(X, nns)
+        masks = [[O.concrete_keep_mask(rec[3 * s + l], p_logits[l]) for l in range(3)] for s in range(S)]
+        nets = [O.scale_columns(base, masks[s], skip_unit_inputs=False) for s in range(S)]
+        for a, b in zip(nets, [seq_to_net(n) for n in nns]):
+            for (W1, b1), (W2, b2) in zip(a, b):
+                assert torch.equal(W1, W2) and torch.equal(b1, b2)
+        assert torch.equal(O.sample_predict(nets, X, "tanh"), pred)
+    save("cdropout_protein.npz", dims=[9, 100, 100, 1], act="tanh", p_logits=p_logits, base=flat(base), X=X,
+         uniforms=np.stack([np.concatenate([rec[3 * s + l].numpy() for l in range(3)]) for s in range(S)]),
+         masks=np.stack([np.concatenate([m.numpy() for m in masks[s]]) for s in range(S)]),
+         pred=pred, mean=py, var=pv)
+
+
+if __name__ == "__main__":
+    gen_sgdmc_boston()
+    gen_sgdmc_multiout()
+    gen_bbb_sinc()
+    gen_dropout_protein()
+    gen_cdropout_protein()

@@ -1,0 +1,230 @@
+"""GPU parity of kernels (b) reparam+KL, (c) pSGLD, (d) dropout masks, and the Philox streams.
+Bit-exact: Philox words, Bernoulli masks, mask application; float functions: stated tolerances."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, max_rel, random_nets
+from oracle import bnn_oracle as O
+from oracle import philox as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _arch(dims, act):
+    from bnn_b200.layout import Arch
+    return Arch(dims, act)
+
+
+# ---- Philox ------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,sub,tag,n", [(0, 0, 0, 4), (1234567890123, 7, 1, 1001), (2**63 + 5, 2**31 + 3, 4, 4096)])
+def test_philox_words_bit_exact(seed, sub, tag, n):
+    from bnn_b200 import ops
+    dev = ops.philox_words(seed, sub, tag, n, "cuda").cpu().numpy().view(np.uint32)
+    assert np.array_equal(dev, P.stream_words(seed, sub, tag, n))
+
+
+def test_philox_normals():
+    from bnn_b200 import ops
+    n = 100003
+    dev = ops.philox_normals(42, 3, P.STREAM_REPARAM, n, "cuda").cpu().numpy()
+    ref = P.stream_normal(42, 3, P.STREAM_REPARAM, n)
+    # float32 logf/sincospif vs float64 twin: a few ulp of the result, plus cancellation near cos/sin zeros
+    assert np.max(np.abs(dev - ref) / (1e-6 + np.abs(ref))) < 1e-3
+    assert np.max(np.abs(dev - ref)) < 4e-6
+    assert abs(dev.mean()) < 0.02 and abs(dev.std() - 1) < 0.02
+
+
+# ---- (b) reparam + KL -------------------------------------------------------------------
+def test_bbb_draw_and_kl_golden():
+    from bnn_b200 import ops
+    g = golden("bbb_sinc.npz")
+    dims = [int(d) for d in g["dims"]]
+    arch = _arch(dims, "tanh")
+    t = lambda k: torch.from_numpy(g[k])
+    mu = arch.pack_bias_last([t(f"mu{l}") for l in range(3)]).cuda()
+    rho = arch.pack_bias_last([t(f"rho{l}") for l in range(3)]).cuda()
+    eps = arch.pack_bias_last([t(f"eps{l}") for l in range(3)]).cuda()
+    S = eps.shape[0]
+    W, kl = ops.reparam_kl(arch, mu, rho, S, mode="bbb", eps=eps, weight_std=float(g["weight_std"]))
+    wb_ref = arch.pack_bias_last([t(f"wb{l}") for l in range(3)])
+    # softplus/sqrt on device (libdevice) vs Sleef on CPU: <= 2 ulp on sigma
+    err = (W.cpu() - wb_ref).abs().max() / wb_ref.abs().max()
+    assert float(err) < 1e-6
+    assert not bool((W.cpu()[:, ~arch.valid_mask()] != 0).any())          # padding stays zero
+    assert abs(float(kl) - float(g["kl"])) <= 1e-5 * abs(float(g["kl"]))
+    # and the drawn bank reproduces the reference's predictions
+    X = t("X").cuda()
+    out = ops.forward(arch, X, W, want_pred=True)
+    assert max_rel(out["pred"].cpu().squeeze(-1), g["pred"]) <= 1e-5
+    assert max_rel(out["mean"].cpu().squeeze(-1), g["mean"].squeeze(-1)) <= 1e-5
+
+
+@pytest.mark.parametrize("mode", ["bbb", "svi"])
+def test_reparam_philox_matches_twin(mode):
+    from bnn_b200 import ops
+    dims = [3, 17, 6, 2]
+    arch = _arch(dims, "relu")
+    g = torch.Generator().manual_seed(5)
+    mu = torch.zeros(arch.stride); rho = torch.zeros(arch.stride)
+    vm = arch.valid_mask()
+    mu[vm] = torch.randn(int(vm.sum()), generator=g)
+    rho[vm] = torch.randn(int(vm.sum()), generator=g) * 3 - 2
+    S, seed, off = 5, 99, 1000
+    W, _ = ops.reparam_kl(arch, mu.cuda(), rho.cuda(), S, mode=mode, seed=seed, sample_offset=off)
+    for s in range(S):
+        z = torch.from_numpy(P.stream_normal(seed, off + s, P.STREAM_REPARAM, arch.stride))
+        ref = O.bbb_rsample(mu, rho, z) if mode == "bbb" else O.svi_draw(mu, rho, z)
+        ref[~vm] = 0
+        assert float((W[s].cpu() - ref).abs().max()) < 2e-5        # normals differ by a few ulp (see test_philox_normals)
+    # independent of how samples are sharded: shard [2,5) alone gives the same rows
+    W2, _ = ops.reparam_kl(arch, mu.cuda(), rho.cuda(), 3, mode=mode, seed=seed, sample_offset=off + 2)
+    assert torch.equal(W2, W[2:])
+
+
+def test_kl_only():
+    from bnn_b200 import ops
+    arch = _arch([4, 9, 1], "tanh")
+    vm = arch.valid_mask()
+    g = torch.Generator().manual_seed(1)
+    mu = torch.zeros(arch.stride); rho = torch.zeros(arch.stride)
+    mu[vm] = torch.randn(int(vm.sum()), generator=g); rho[vm] = torch.randn(int(vm.sum()), generator=g)
+    _, kl = ops.reparam_kl(arch, mu.cuda(), rho.cuda(), 0, weight_std=0.3)
+    mus = [arch.layer_view(mu, l)[:, :arch.ins[l] + 1] for l in range(2)]
+    rhos = [arch.layer_view(rho, l)[:, :arch.ins[l] + 1] for l in range(2)]
+    assert abs(float(kl) - float(O.bbb_kl(mus, rhos, 0.3))) <= 1e-5 * abs(float(O.bbb_kl(mus, rhos, 0.3)))
+
+
+# ---- (d) masks ---------------------------------------------------------------------------
+def test_bernoulli_masks_bit_exact_and_sharding():
+    from bnn_b200 import ops
+    arch = _arch([9, 100, 100, 1], "tanh")
+    cfg = ops.MaskConfig("bernoulli", [True, True, True], p_drop=[0.05, 0.3, 0.5], seed=17, sample_offset=4)
+    S = 11
+    m = ops.dropout_masks(arch, cfg, S, "cuda").cpu().numpy()
+    offs, mlen = arch.mask_layout([True, True, True])
+    assert mlen == 209
+    for s in range(S):
+        u = P.stream_uniform(17, 4 + s, P.STREAM_BERNOULLI, mlen)
+        ref = np.concatenate([(u[o:o + n] < np.float32(1) - np.float32(p)).astype(np.float32)
+                              for o, n, p in zip(offs, arch.ins, [0.05, 0.3, 0.5])])
+        assert np.array_equal(m[s], ref)
+    assert set(np.unique(m)) <= {0.0, 1.0}
+
+
+def test_concrete_masks_golden_uniforms():
+    from bnn_b200 import ops
+    g = golden("cdropout_protein.npz")
+    arch = _arch([int(d) for d in g["dims"]], "tanh")
+    p = [float(torch.sigmoid(torch.tensor(v, dtype=torch.float32)).clamp(O.F32_EPS, 1 - O.F32_EPS)) for v in g["p_logits"]]
+    cfg = ops.MaskConfig("concrete", [True, True, True], p_drop=p, temperature=0.1)
+    u = torch.from_numpy(g["uniforms"]).cuda()
+    m = ops.dropout_masks(arch, cfg, u.shape[0], "cuda", uniforms=u).cpu()
+    ref = torch.from_numpy(g["masks"])
+    # logit/T amplifies 1-ulp differences of logf/log1pf by 1/T = 10 before the sigmoid
+    assert float((m - ref).abs().max()) < 2e-5
+    assert float(m.min()) >= O.F32_TINY and float(m.max()) <= 1 - O.F32_EPS
+
+
+def test_apply_masks_matches_reference_weights():
+    from bnn_b200 import ops
+    from helpers import flat_to_nets
+    g = golden("dropout_protein.npz")
+    dims = [int(d) for d in g["dims"]]
+    arch = _arch(dims, "tanh")
+    base_net = flat_to_nets(g["base"][None], dims)[0]
+    base = arch.pack([base_net])[0].cuda()
+    masks = torch.from_numpy(g["masks"]).cuda()
+    W = ops.apply_masks(arch, [True, True, True], base, masks).cpu()
+    for s in range(masks.shape[0]):
+        ms = [torch.from_numpy(g["masks"][s, o:o + n]) for o, n in zip([0, 9, 109], [9, 100, 100])]
+        ref = arch.pack([O.scale_columns(base_net, ms, True)])[0]
+        assert torch.equal(W[s], ref)
+
+
+@pytest.mark.parametrize("fixture,skip_unit", [("dropout_protein.npz", True), ("cdropout_protein.npz", False)])
+def test_masked_forward_golden(fixture, skip_unit):
+    """Shared base weights + per-sample input-unit masks == the reference's S scaled deep copies."""
+    from bnn_b200 import ops
+    from helpers import flat_to_nets
+    g = golden(fixture)
+    dims = [int(d) for d in g["dims"]]
+    arch = _arch(dims, "tanh")
+    base = arch.pack(flat_to_nets(g["base"][None], dims))[0].cuda()
+    masks = torch.from_numpy(g["masks"]).cuda()
+    S = masks.shape[0]
+    X = torch.from_numpy(g["X"]).cuda()
+    cfg = ops.MaskConfig("external", [True, True, True], mask=masks)
+    out = ops.forward(arch, X, base, S=S, mask=cfg, want_pred=True)
+    assert max_rel(out["pred"].cpu().squeeze(-1), g["pred"]) <= 1e-5
+    assert max_rel(out["mean"].cpu().squeeze(-1), g["mean"].squeeze(-1)) <= 1e-5
+    # materialised-bank route (the reference's own arithmetic order) agrees too
+    Wb = ops.apply_masks(arch, [True, True, True], base, masks)
+    out2 = ops.forward(arch, X, Wb, want_pred=True)
+    assert max_rel(out2["pred"].cpu().squeeze(-1), g["pred"]) <= 1e-5
+
+
+@pytest.mark.parametrize("kind", ["bernoulli", "concrete"])
+def test_inkernel_masks_equal_standalone(kind):
+    """bnn_forward's in-kernel Philox masks == bnn_dropout_masks fed back as an external tensor, bit for bit."""
+    from bnn_b200 import ops
+    dims = [5, 24, 24, 2]
+    arch = _arch(dims, "relu")
+    lm = [True, True, True] if kind == "concrete" else [True, True, True]
+    base = arch.pack(random_nets(dims, 1, seed=8))[0].cuda()
+    X = torch.randn(70, 5, generator=torch.Generator().manual_seed(3)).cuda()
+    S = 37
+    cfg = ops.MaskConfig(kind, lm, p_drop=[0.2, 0.4, 0.1], temperature=0.1, seed=123, sample_offset=50)
+    a = ops.forward(arch, X, base, S=S, mask=cfg, want_pred=True)
+    masks = ops.dropout_masks(arch, cfg, S, "cuda")
+    b = ops.forward(arch, X, base, S=S, mask=ops.MaskConfig("external", lm, mask=masks), want_pred=True)
+    assert torch.equal(a["pred"], b["pred"])
+    assert torch.equal(a["mean"], b["mean"]) and torch.equal(a["var"], b["var"])
+    # layer with in == 1 unmasked (BNN_Dropout.py:73 skips in <= 1)
+    arch1 = _arch([1, 16, 1], "tanh")
+    cfg1 = ops.MaskConfig("bernoulli", [False, True], p_drop=[0.0, 0.5], seed=1)
+    m1 = ops.dropout_masks(arch1, cfg1, 4, "cuda")
+    assert m1.shape == (4, 16)
+
+
+# ---- (c) pSGLD ----------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [572417 + 1, 751, 5])
+def test_psgld_step_matches_oracle(n):
+    from bnn_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    theta = torch.randn(n, generator=g); grad = torch.randn(n, generator=g) * 3
+    V = torch.rand(n, generator=g) + 0.1; noise = torch.randn(n, generator=g)
+    n_head = n - 1
+    lr_w, lr_n = 2e-2 * float(O.lr_factor(10)), 1e-1 * float(O.lr_factor(10))
+    th_d, V_d = theta.cuda().clone(), V.cuda().clone()
+    ops.psgld_step(th_d, grad.cuda(), V_d, lr_w, lr_tail=lr_n, n_head=n_head, alpha=0.99, lam=1e-5, noise=noise.cuda())
+    th_h, V_h = O.psgld_step(theta[:n_head], grad[:n_head], V[:n_head], lr_w, noise[:n_head])
+    th_t, V_t = O.psgld_step(theta[n_head:], grad[n_head:], V[n_head:], lr_n, noise[n_head:])
+    assert torch.allclose(th_d.cpu(), torch.cat([th_h, th_t]), rtol=2e-6, atol=1e-7)
+    assert torch.allclose(V_d.cpu(), torch.cat([V_h, V_t]), rtol=2e-6, atol=1e-9)
+
+
+def test_psgld_philox_noise_matches_twin():
+    from bnn_b200 import ops
+    n = 1003
+    theta = torch.zeros(n); grad = torch.zeros(n); V = torch.ones(n)
+    th = theta.cuda()
+    ops.psgld_step(th, grad.cuda(), V.cuda(), 1e-2, alpha=0.99, lam=1e-5, seed=5, step=77)
+    z = torch.from_numpy(P.stream_normal(5, 77, P.STREAM_SGLD, n))
+    ref, _ = O.psgld_step(theta, grad, V, 1e-2, z)
+    assert float((th.cpu() - ref).abs().max()) < 1e-6
+
+
+def test_psgld_stationary_variance():
+    """Sanity of the restated update (UNPINNED vs pybnn): on U = theta^2 / (2 s^2) the chain's
+    stationary variance approaches s^2 as lr -> 0."""
+    from bnn_b200 import ops
+    n, s2 = 4096, 0.25
+    theta = torch.zeros(n).cuda(); V = torch.ones(n).cuda()
+    acc = torch.zeros((), dtype=torch.float64); cnt = 0
+    for t in range(3000):
+        grad = theta / s2
+        ops.psgld_step(theta, grad, V, 5e-3, alpha=0.99, lam=1e-5, seed=3, step=t)
+        if t >= 1000 and t % 10 == 0:
+            acc += float((theta.double() ** 2).mean()); cnt += 1
+    assert abs(float(acc / cnt) - s2) < 0.1 * s2
