@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Headline benchmark: posterior-predictive sample.point MLP evals/s (BASELINE.json metric).
+
+Workload (BASELINE.json configs[3], "synthetic predictive sweep"): N = 1M points, 2x200 ReLU
+MLP (D = 16), SGLD samples sharded over the GPUs -- 1250 samples per GPU, so 8 GPUs are the
+full S = 10k config and every N runs the same per-GPU shard (weak scaling).  One "step" is one
+predict_mv over the whole shard: fused forward + Welford reduction (+ the NCCL all-gather and
+Chan merge of the per-point moments when N > 1).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]           # our CUDA path
+    python bench.py --impl reference ...                          # the reference's CPU torch loop
+
+Prints ONE JSON line (see the field notes in DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIMS = [16, 200, 200, 1]
+ACT = "relu"
+N_POINTS = 1_000_000
+S_PER_GPU = 1250
+METRIC = "posterior-predictive sample.point MLP evals/sec"
+UNIT = "evals/s"
+FLOP_PER_EVAL = 2 * sum(i * o for i, o in zip(DIMS[:-1], DIMS[1:]))   # 86,800
+
+
+def workload_name(n_gpus):
+    return (f"cfg4 synthetic predictive sweep: N={N_POINTS} points x S={S_PER_GPU * n_gpus} SGLD samples "
+            f"({S_PER_GPU}/GPU; 8 GPUs = the S=10k config), {DIMS[0]}-{DIMS[1]}-{DIMS[2]}-{DIMS[3]} {ACT} MLP")
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the reference's own per-sample torch loop (oracle port)
+# --------------------------------------------------------------------------------------
+def cpu_nets(S, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    base = []
+    for i, o in zip(DIMS[:-1], DIMS[1:]):
+        bound = (6.0 / (i + o)) ** 0.5                          # xavier-uniform, util.py:19
+        base.append(((torch.rand(o, i, generator=g) * 2 - 1) * bound, (torch.rand(o, generator=g) * 2 - 1) / i ** 0.5))
+    return [[(W + 0.05 * torch.randn(W.shape, generator=g), b + 0.05 * torch.randn(b.shape, generator=g)) for W, b in base]
+            for _ in range(S)]
+
+
+def time_cpu_sample(S, N, reps=1):
+    """Time predict_mv of the reference's loop (sample_predict + mean/var) on S x N evals."""
+    import torch
+    from oracle import bnn_oracle as O           # bench's cpu_baseline leg may execute the oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    nets = cpu_nets(S, 1)
+    X = torch.randn(N, DIMS[0], generator=torch.Generator().manual_seed(2))
+    best = float("inf")
+    with torch.no_grad():
+        O.sample_predict(nets[:1], X[:1000], ACT, nout=1)      # warm-up
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            pred = O.sample_predict(nets, X, ACT, nout=1)
+            O.predict_mv(pred, N)
+            best = min(best, time.perf_counter() - t0)
+    return S * N / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    S, N = 8, 250_000                                            # bounded sample of the workload per step
+    for _ in range(args.warmup):
+        time_cpu_sample(2, 50_000)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        time_cpu_sample(S, N)
+    dt = time.perf_counter() - t0
+    value = args.steps * S * N / dt
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus), "sample_per_step": f"S={S} x N={N} of the workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x (S={S} samples x N={N} points), torch CPU, {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.path = None, f"/tmp/bnn_clocks_{os.getpid()}.csv"
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            # median over the upper half = samples taken under load
+            hi = sorted(sm)[len(sm) // 2:]
+            out.update(sm_mhz=statistics.median(hi), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bnn_b200 import _lib, ops
+    from bnn_b200.layout import Arch
+    from bnn_b200.distributed import merge_shards
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    arch = Arch(DIMS, ACT)
+    S = S_PER_GPU
+    # synthetic inputs: X ~ N(0,1); nets = xavier base + 0.05 N(0,1), one chain shard per rank
+    g = torch.Generator(device=dev).manual_seed(1234 + 4)
+    X = torch.randn(N_POINTS, DIMS[0], generator=g, device=dev)
+    base = arch.pack(cpu_nets(1, 0)[:1])[0].to(dev)
+    gw = torch.Generator(device=dev).manual_seed(100 + rank)
+    bank = (base[None, :] + 0.05 * torch.randn(S, arch.stride, generator=gw, device=dev)) * arch.valid_mask().to(dev)
+    bank = bank.contiguous()
+    X_host = X.cpu().pin_memory()
+    bank_host = bank.cpu().pin_memory()
+
+    def step_device():
+        out = ops.forward(arch, X, bank, want_pred=False, want_moments=(world == 1), want_partials=(world > 1))
+        if world > 1:
+            return merge_shards(out["part_mean"], out["part_m2"], S)
+        return out["mean"], out["var"]
+
+    def step_e2e():
+        Xd = X_host.to(dev, non_blocking=True)
+        Wd = bank_host.to(dev, non_blocking=True)
+        out = ops.forward(arch, Xd, Wd, want_pred=False, want_moments=(world == 1), want_partials=(world > 1))
+        mean, var = merge_shards(out["part_mean"], out["part_m2"], S) if world > 1 else (out["mean"], out["var"])
+        return mean.cpu(), var.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, r
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    ms, (mean, var) = timed(step_device, args.steps, max(args.warmup, 3))
+    clk = clocks.stop() if clocks else None
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e, _ = timed(step_e2e, e2e_steps, 1)
+
+    evals_per_step = float(S) * n_gpus * N_POINTS
+    value = evals_per_step * args.steps / (ms * 1e-3)
+    e2e_value = evals_per_step * e2e_steps / (ms_e2e * 1e-3)
+    finite = bool(torch.isfinite(mean).all() and torch.isfinite(var).all())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf16_peak, peak_src = (peaks.get("bf16_tflops_sustained"), "measured (MEASURED_PEAKS.json, sustained)") \
+            if peaks.get("bf16_tflops_sustained") else (1400.0, "fallback (B200_PROFILING.md sustained)")
+        fp32_peak = float(_lib.lib().bnn_measure_fp32_tflops())
+        per_gpu_tflops = FLOP_PER_EVAL * float(S) * N_POINTS * args.steps / (ms * 1e-3) / 1e12
+        cpu_val, cpu_t = time_cpu_sample(16, 250_000)
+        cores = os.cpu_count() or 1
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(n_gpus), "precision": "fp32-simt",
+                       "l2": f"inputs {(bank.numel() + X.numel()) * 4 / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)",
+                       "parallelism": f"samples sharded x{n_gpus}, all-gather of float64 (mean, M2) + Chan merge"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((bank.numel() + X.numel()) * 4),
+                    "d2h_bytes_per_step": int(2 * N_POINTS * DIMS[-1] * 4), "ms_per_step": ms_e2e / e2e_steps,
+                    "steps": e2e_steps, "api": "bnn_b200.ops.forward on pinned host tensors (H2D + launch + D2H per step)"},
+            "gpu_launches": args.steps * (3 if world > 1 else 2),
+            "roofline": {"bound": "fp32", "achieved": per_gpu_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": per_gpu_tflops / fp32_peak if fp32_peak > 0 else None, "traffic": None,
+                         "kernel": "fwd_simt_kernel<8>", "flop_per_eval": FLOP_PER_EVAL,
+                         "peak_source": "FP32 FFMA microbenchmark measured live (bnn_measure_fp32_tflops); "
+                                        "MEASURED_PEAKS.json has no FP32-SIMT figure",
+                         "frac_of_bf16_tensor_peak": per_gpu_tflops / bf16_peak, "bf16_peak": bf16_peak,
+                         "bf16_peak_source": peak_src},
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"S=16 samples x N=250000 points of the same workload, torch CPU loop, "
+                                       f"{cores} threads, {cpu_t:.1f} s"},
+            "clocks": clk, "outputs_finite": finite,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,7 @@ PROTOTYPES = {
                                    C.c_float, C.c_float, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p]),
     "bnn_philox_words": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]),
     "bnn_philox_normals": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "bnn_measure_fp32_tflops": (C.c_double, []),
     "bnn_forward_host": (C.c_int32, [C.POINTER(ForwardArgs)]),
     "bnn_release_workspace": (None, []),
 }

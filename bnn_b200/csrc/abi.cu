@@ -180,3 +180,48 @@ extern "C" int32_t bnn_forward_host(const BnnForwardArgs* ah) {
   BNN_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
+
+// ---- measurement helper: FP32 FFMA peak of this device (roofline denominator for the SIMT forward)
+namespace bnn {
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-3f + i;
+  const float b = 1.0000001f, c = 1e-7f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678f) out[0] = s;
+}
+}  // namespace bnn
+
+extern "C" double bnn_measure_fp32_tflops(void) {
+  float* d = nullptr;
+  if (cudaMalloc(&d, 4) != cudaSuccess) return -1.0;
+  const int iters = 4096, blocks = sm_count() * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    ffma_peak_kernel<<<blocks, 256>>>(d, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 16 * 8 * (double)iters * 256.0 * blocks;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+}

@@ -14,15 +14,18 @@
 // 8 consumer warps do register-tiled FP32 FFMA (thread tile (4*NI/4.. rows) x RN points,
 // lane grid 4 x 8).  The last layer's outputs feed per-point FP64 Welford state kept in
 // shared memory; only (mean, M2) per point leave the CTA (and pred[S,N,O] if asked).
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
+
 #include "common.cuh"
 #include "philox.cuh"
 
 namespace bnn {
 
 constexpr int kComputeWarps = 8;
+constexpr int kKC = 32;  // K-chunk: 32 floats = one 128-byte swizzle row
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kThreads = kComputeThreads + 32;  // + producer warp
-constexpr int kStages = 3;
+constexpr int kMaxStages = 3;
 constexpr int kSmemBudget = 227 * 1024;
 
 struct FwdLayer {
@@ -32,12 +35,14 @@ struct FwdLayer {
   int rounds;    // ceil(tiles / kComputeWarps)
   int chunks;    // ceil(in / KC)
   int mask_off;  // offset of this layer's INPUT mask, -1 = none
+  int box_rows;  // rows of one staged block (TMA box height)
   long long off;
 };
 
 struct FwdParams {
-  int n_lin, act, KC, stage_floats, nout, d4, hrows;
+  int n_lin, act, nstages, stage_floats, nout, d4, hrows;
   FwdLayer L[BNN_MAX_LINEAR];
+  alignas(64) CUtensorMap tmap[BNN_MAX_LINEAR];  // per layer: dims (in, out, S), box (32, stage rows, 1), 128B swizzle
   const float* X;
   long long N;
   const float* W;
@@ -56,31 +61,35 @@ struct FwdParams {
 };
 
 // acc[i][j] += W[row_i][k] * h[k][n_j] over one staged K-chunk
+// The staged block is dense [rows][32 floats] written by TMA with the 128-byte swizzle: the 16-byte
+// granule g of row r sits at granule g ^ (r & 7), which makes the 4 rows a warp reads per LDS.128
+// (r, r+1, r+2, r+3) land in distinct banks.  All addresses are 32-bit shared-space byte addresses.
 template <int NI, int RN>
-__device__ __forceinline__ void tile_fma(float (&acc)[NI][RN], const float* __restrict__ wst, const float* __restrict__ h,
-                                         int kq_count, int wstride, int lo, int ln) {
+__device__ __forceinline__ void tile_fma(float (&acc)[NI][RN], uint32_t wst, uint32_t h, int kq_count, int row0, int ln) {
   constexpr int TN = 8 * RN;
-  const float* wrow = wst + lo * wstride;
-  const float* hcol = h + (RN == 2 ? ln * 2 : ln * 4);
+  const uint32_t wrow = wst + (uint32_t)row0 * (kKC * 4);  // row0 = first staged row of this thread (stage_row + lo)
+  const uint32_t swz0 = (uint32_t)(row0 & 7);
+  const uint32_t hcol = h + (RN == 2 ? ln * 8 : ln * 16);
 #pragma unroll 2
   for (int kq = 0; kq < kq_count; ++kq) {
     float4 w[NI];
+    const uint32_t g0 = (((uint32_t)kq ^ swz0) << 4), g1 = (((uint32_t)kq ^ swz0 ^ 4u) << 4);  // rows r and r+4
 #pragma unroll
-    for (int i = 0; i < NI; ++i) w[i] = *reinterpret_cast<const float4*>(wrow + i * 4 * wstride + kq * 4);
+    for (int i = 0; i < NI; ++i) w[i] = lds128(wrow + i * 4 * (kKC * 4) + ((i & 1) ? g1 : g0));
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       float a[RN];
-      const float* hp = hcol + (kq * 4 + kk) * TN;
+      const uint32_t hp = hcol + (uint32_t)(kq * 4 + kk) * (TN * 4);
       if constexpr (RN == 8) {
-        const float4 a0 = *reinterpret_cast<const float4*>(hp);
-        const float4 a1 = *reinterpret_cast<const float4*>(hp + 32);
+        const float4 a0 = lds128(hp);
+        const float4 a1 = lds128(hp + 128);
         a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
         a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
       } else if constexpr (RN == 4) {
-        const float4 a0 = *reinterpret_cast<const float4*>(hp);
+        const float4 a0 = lds128(hp);
         a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
       } else {
-        const float2 a0 = *reinterpret_cast<const float2*>(hp);
+        const float2 a0 = lds64(hp);
         a[0] = a0.x; a[1] = a0.y;
       }
 #pragma unroll
@@ -96,19 +105,27 @@ __device__ __forceinline__ void tile_fma(float (&acc)[NI][RN], const float* __re
 struct PipeState {
   int stage;
   uint32_t phase;
-  __device__ __forceinline__ void advance() {
-    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+  __device__ __forceinline__ void advance(int nstages) {
+    if (++stage == nstages) { stage = 0; phase ^= 1u; }
   }
 };
+
+// one TMA tile load: box of the layer's tensor map at (k0, row0, sample) -> smem, completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
 
 // one (layer, round): this warp's tile over all K-chunks, then bias/act/mask epilogue into hout
 template <int NI, int RN>
 __device__ __forceinline__ void layer_round(const FwdParams& p, const FwdLayer& L, int l, int round, const float* __restrict__ Ws,
                                             const float* __restrict__ hin, float* __restrict__ hout, const float* __restrict__ msk,
-                                            float* ring, uint64_t* full, uint64_t* empty, PipeState& ps, int warp, int lane) {
+                                            const float* ring, uint64_t* full, uint64_t* empty, PipeState& ps, int warp, int lane) {
   constexpr int TN = 8 * RN;
   const int lo = lane >> 3, ln = lane & 7;
-  const int wstride = p.KC + 4;
   const int tile = round * kComputeWarps + warp;
   const bool valid = tile < L.tiles;
   const int row_base = tile * 4 * NI;                        // first row of this warp's tile
@@ -125,15 +142,15 @@ __device__ __forceinline__ void layer_round(const FwdParams& p, const FwdLayer& 
   }
 
   for (int c = 0; c < L.chunks; ++c) {
-    const int k0 = c * p.KC;
-    const int kw = min(p.KC, roundup4(L.in - k0));
+    const int k0 = c * kKC;
+    const int kw = min(kKC, roundup4(L.in - k0));
     mbar_wait(&full[ps.stage], ps.phase);
     if (valid)
-      tile_fma<NI, RN>(acc, ring + (size_t)ps.stage * p.stage_floats + stage_row * wstride, hin + (size_t)k0 * TN, kw >> 2,
-                       wstride, lo, ln);
+      tile_fma<NI, RN>(acc, smem_u32(ring) + (uint32_t)ps.stage * (uint32_t)(p.stage_floats * 4),
+                       smem_u32(hin) + (uint32_t)k0 * (TN * 4), kw >> 2, stage_row + lo, ln);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[ps.stage]);
-    ps.advance();
+    ps.advance(p.nstages);
   }
 
   if (valid) {
@@ -151,14 +168,14 @@ __device__ __forceinline__ void layer_round(const FwdParams& p, const FwdLayer& 
           if (!last) t = apply_act(t, p.act);
           v[j] = next_mask >= 0 ? t * m : t;
         }
-        float* dst = hout + (size_t)row * TN;
+        const uint32_t dst = smem_u32(hout) + (uint32_t)row * (TN * 4);
         if constexpr (RN == 8) {
-          *reinterpret_cast<float4*>(dst + ln * 4) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(dst + 32 + ln * 4) = make_float4(v[4], v[5], v[6], v[7]);
+          sts128(dst + ln * 16, make_float4(v[0], v[1], v[2], v[3]));
+          sts128(dst + 128 + ln * 16, make_float4(v[4], v[5], v[6], v[7]));
         } else if constexpr (RN == 4) {
-          *reinterpret_cast<float4*>(dst + ln * 4) = make_float4(v[0], v[1], v[2], v[3]);
+          sts128(dst + ln * 16, make_float4(v[0], v[1], v[2], v[3]));
         } else {
-          *reinterpret_cast<float2*>(dst + ln * 2) = make_float2(v[0], v[1]);
+          sts64(dst + ln * 8, make_float2(v[0], v[1]));
         }
       }
     }
@@ -176,9 +193,9 @@ __device__ __forceinline__ float mask_value(const FwdParams& p, long long s_glob
 template <int RN>
 __global__ void __launch_bounds__(kThreads, 1) fwd_simt_kernel(const __grid_constant__ FwdParams p) {
   constexpr int TN = 8 * RN;
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* empty = full + kStages;
+  uint64_t* empty = full + kMaxStages;
   float* msk = reinterpret_cast<float*>(smem + p.sm_msk);
   double* wf_mean = reinterpret_cast<double*>(smem + p.sm_wf);
   double* wf_m2 = wf_mean + p.nout * TN;
@@ -192,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_simt_kernel(const __grid_cons
   const int s0 = g * p.Sg, s1 = min(p.S, s0 + p.Sg);
 
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < p.nstages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], kComputeWarps);
     }
@@ -201,28 +218,23 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_simt_kernel(const __grid_cons
   __syncthreads();
 
   if (warp == kComputeWarps) {
-    // ===================== producer warp: weights -> smem ring =====================
-    PipeState ps{0, 0};
-    const int wstride = p.KC + 4;
-    for (int s = s0; s < s1; ++s) {
-      const float* Ws = p.W + (long long)s * p.w_stride;
-      for (int l = 0; l < p.n_lin; ++l) {
-        const FwdLayer& L = p.L[l];
-        const int rows_per_round = kComputeWarps * 4 * L.ni;
-        for (int r = 0; r < L.rounds; ++r) {
-          const int row0 = r * rows_per_round;
-          const int nrows = min(L.out - row0, rows_per_round);
-          for (int c = 0; c < L.chunks; ++c) {
-            const int k0 = c * p.KC;
-            const int kw = min(p.KC, roundup4(L.in - k0));
-            mbar_wait(&empty[ps.stage], ps.phase ^ 1u);
-            if (lane == 0) mbar_arrive_expect_tx(&full[ps.stage], (uint32_t)(nrows * kw * 4));
-            __syncwarp();
-            float* dst = ring + (size_t)ps.stage * p.stage_floats;
-            const float* src = Ws + L.off + (long long)row0 * L.ld + k0;
-            for (int row = lane; row < nrows; row += 32)
-              bulk_g2s(dst + row * wstride, src + (long long)row * L.ld, (uint32_t)(kw * 4), &full[ps.stage]);
-            ps.advance();
+    // ===================== producer warp: weights -> smem ring (one TMA per stage) =====================
+    if (lane == 0) {
+      PipeState ps{0, 0};
+      const bool shared_w = (p.w_stride == 0);
+      for (int s = s0; s < s1; ++s) {
+        for (int l = 0; l < p.n_lin; ++l) {
+          const FwdLayer& L = p.L[l];
+          const uint32_t stage_bytes = (uint32_t)(L.box_rows * kKC * 4);
+          for (int r = 0; r < L.rounds; ++r) {
+            const int row0 = r * L.box_rows;
+            for (int c = 0; c < L.chunks; ++c) {
+              mbar_wait_backoff(&empty[ps.stage], ps.phase ^ 1u);
+              mbar_arrive_expect_tx(&full[ps.stage], stage_bytes);  // OOB rows/cols are zero-filled and counted
+              tma_load_3d(ring + (size_t)ps.stage * p.stage_floats, &p.tmap[l], c * kKC, row0, shared_w ? 0 : s,
+                          &full[ps.stage]);
+              ps.advance(p.nstages);
+            }
           }
         }
       }
@@ -322,17 +334,17 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_simt_kernel(const __grid_cons
 }
 
 // ---- host side ---------------------------------------------------------------
+// Thread-tile height.  Tall tiles (NI = 8: 8 rows x RN points per thread) are what keeps the loop FMA-bound:
+// per 4-wide K step a warp issues NI*32 FFMA against NI + 8 LDS.128, so NI = 1 is shared-memory-bound by ~4x.
+// Only shrink the tile when the layer is too narrow to give every compute warp a tile.
 static int choose_ni(int out) {
-  int best = 1, best_cost = 1 << 30;
   const int cand[4] = {8, 4, 2, 1};
   for (int c = 0; c < 4; ++c) {
     const int ni = cand[c];
     const int tiles = (out + 4 * ni - 1) / (4 * ni);
-    const int rounds = (tiles + kComputeWarps - 1) / kComputeWarps;
-    const int cost = rounds * ni;
-    if (cost < best_cost) { best_cost = cost; best = ni; }
+    if (tiles >= kComputeWarps - 1 || ni == 1) return ni;  // (almost) every warp busy
   }
-  return best;
+  return 1;
 }
 
 struct FwdPlan {
@@ -364,6 +376,7 @@ static int plan_forward(const BnnForwardArgs* a, const Layout& L, FwdPlan* plan)
     if (roundup4(f.out) > hrows) hrows = roundup4(f.out);
     // rows a consumer may touch in one staged block: whole tiles, even if the last one is ragged
     const int rr = (f.tiles < kComputeWarps ? f.tiles : kComputeWarps) * 4 * f.ni;
+    f.box_rows = rr;
     if (rr > stage_rows) stage_rows = rr;
     p.p_drop[l] = a->mask.p_drop[l];
   }
@@ -371,13 +384,14 @@ static int plan_forward(const BnnForwardArgs* a, const Layout& L, FwdPlan* plan)
   p.hrows = hrows;
   if (p.nout > BNN_MAX_FUSED_NOUT) BNN_FAIL("nout=%d exceeds BNN_MAX_FUSED_NOUT=%d", p.nout, BNN_MAX_FUSED_NOUT);
 
-  // pick the largest point tile (and K-chunk) that fits the 227 KB shared-memory budget
+  // pick the largest point tile (and ring depth) that fits the 227 KB shared-memory budget
+  stage_rows = (stage_rows + 7) & ~7;  // whole 1024-byte swizzle atoms
+  p.stage_floats = stage_rows * kKC;
   const int tn_cand[3] = {64, 32, 16};
-  const int kc_cand[2] = {32, 16};
   bool ok = false;
   for (int ti = 0; ti < 3 && !ok; ++ti) {
-    for (int ki = 0; ki < 2 && !ok; ++ki) {
-      const int TN = tn_cand[ti], KC = kc_cand[ki];
+    for (int nst = kMaxStages; nst >= 2 && !ok; --nst) {
+      const int TN = tn_cand[ti];
       size_t o = 128;  // barriers
       p.sm_msk = (int)o; o += (size_t)((p.mask_len + 3) & ~3) * 4;
       o = (o + 15) & ~(size_t)15;
@@ -385,20 +399,19 @@ static int plan_forward(const BnnForwardArgs* a, const Layout& L, FwdPlan* plan)
       p.sm_xs = (int)o; o += (size_t)p.d4 * TN * 4;
       p.sm_h0 = (int)o; o += (size_t)hrows * TN * 4;
       p.sm_h1 = (int)o; o += (size_t)hrows * TN * 4;
-      o = (o + 127) & ~(size_t)127;
+      o = (o + 1023) & ~(size_t)1023;  // 128B-swizzled TMA destinations need 1024-byte alignment
       p.sm_ring = (int)o;
-      p.stage_floats = stage_rows * (KC + 4);
-      o += (size_t)kStages * p.stage_floats * 4;
+      o += (size_t)nst * p.stage_floats * 4;
       if (o <= (size_t)kSmemBudget) {
         ok = true;
         plan->RN = TN / 8;
         plan->smem = o;
-        p.KC = KC;
+        p.nstages = nst;
       }
     }
   }
   if (!ok) BNN_FAIL("network too wide for the SIMT forward (shared-memory budget exceeded)");
-  for (int l = 0; l < L.n_lin; ++l) p.L[l].chunks = (p.L[l].in + p.KC - 1) / p.KC;
+  for (int l = 0; l < L.n_lin; ++l) p.L[l].chunks = (p.L[l].in + kKC - 1) / kKC;
 
   const int TN = plan->RN * 8;
   plan->tiles = (a->N + TN - 1) / TN;
@@ -417,6 +430,43 @@ static int plan_forward(const BnnForwardArgs* a, const Layout& L, FwdPlan* plan)
   p.mask = a->mask.mask; p.mask_stride = a->mask.mask_stride;
   p.temperature = a->mask.temperature; p.seed = a->mask.seed; p.sample_offset = a->mask.sample_offset;
   p.pred = a->pred;
+  return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// per layer: 3-D view (k, row, sample) of the bank; K beyond `in` (bias + padding columns) and rows beyond
+// `out` are out of bounds for the map, so TMA zero-fills them and the FMA loop needs no tail handling
+static int make_tensor_maps(const BnnForwardArgs* a, FwdParams& p) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) BNN_FAIL("cuTensorMapEncodeTiled is not available from this driver");
+  for (int l = 0; l < p.n_lin; ++l) {
+    const FwdLayer& L = p.L[l];
+    const bool shared_w = a->w_stride == 0;
+    cuuint64_t gdim[3] = {(cuuint64_t)L.in, (cuuint64_t)L.out, (cuuint64_t)(shared_w ? 1 : a->S)};
+    cuuint64_t gstr[2] = {(cuuint64_t)L.ld * 4, (cuuint64_t)(shared_w ? (long long)L.out * L.ld : a->w_stride) * 4};
+    cuuint32_t box[3] = {(cuuint32_t)kKC, (cuuint32_t)L.box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    void* base = const_cast<float*>(a->W) + L.off;
+    const CUresult r = enc(&p.tmap[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) BNN_FAIL("cuTensorMapEncodeTiled failed for layer %d (CUresult %d)", l, (int)r);
+  }
   return 0;
 }
 
@@ -447,6 +497,7 @@ int forward_simt(const BnnForwardArgs* a, cudaStream_t st) {
   } else {
     p.part = nullptr;
   }
+  if (make_tensor_maps(a, p)) return -1;
   dim3 grid((unsigned)plan.tiles, (unsigned)p.G);
   auto launch = [&](auto kern) -> int {
     BNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));

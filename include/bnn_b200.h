@@ -180,6 +180,10 @@ int32_t bnn_psgld_step(float* theta, const float* grad, float* V, int64_t n, int
 int32_t bnn_philox_words(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, uint32_t* out, void* stream);
 int32_t bnn_philox_normals(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, float* out, void* stream);
 
+/* measurement helper: sustained FP32 FFMA TFLOP/s of the current device (dependent-chain
+ * microbenchmark, best of 4) -- the roofline denominator of the SIMT forward */
+double bnn_measure_fp32_tflops(void);
+
 /* ---- host-buffer convenience (end-to-end path) --------------------------- */
 /* Same as bnn_forward but X / W / mask and all outputs are HOST pointers
  * (pinned for full PCIe speed); copies in, runs, copies out, synchronises.   */

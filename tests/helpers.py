@@ -46,7 +46,7 @@ def max_rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-def var_bound(pred_ref, rel=1e-5, c=32.0):
+def var_bound(pred_ref, rel=1e-5, c=32.0, depth=2):
     """Per-point bound on |dvar|:  rel*var + c*eps_f32*max_s|pred|*sqrt(var)  (+ the same in var).
 
     The forward's own rounding (~eps*|pred| per sample, more for deep nets) enters the variance as
@@ -55,4 +55,5 @@ def var_bound(pred_ref, rel=1e-5, c=32.0):
     p = torch.as_tensor(pred_ref, dtype=torch.float64)
     var = p.var(dim=0) if p.shape[0] > 1 else torch.zeros_like(p[0])
     scale = p.abs().amax(dim=0)
+    c = c * max(1.0, depth / 2.0)      # forward rounding accumulates layer by layer
     return rel * var + c * eps * (scale * var.sqrt() + var) + 1e-30

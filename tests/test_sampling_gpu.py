@@ -216,15 +216,18 @@ def test_psgld_philox_noise_matches_twin():
 
 
 def test_psgld_stationary_variance():
-    """Sanity of the restated update (UNPINNED vs pybnn): on U = theta^2 / (2 s^2) the chain's
-    stationary variance approaches s^2 as lr -> 0."""
+    """Sanity of the restated update (UNPINNED vs pybnn): with the preconditioner frozen (alpha = 1, V = 1)
+    the update is plain Langevin dynamics, whose stationary variance on U = theta^2 / (2 s^2) is s^2
+    (+ O(lr) discretisation bias).  With alpha < 1 the Gamma-less pSGLD of Li et al. is biased (the oracle
+    gives ~0.37 here), so the adaptive case is only compared against the oracle (tests above)."""
     from bnn_b200 import ops
     n, s2 = 4096, 0.25
     theta = torch.zeros(n).cuda(); V = torch.ones(n).cuda()
-    acc = torch.zeros((), dtype=torch.float64); cnt = 0
+    acc, cnt = 0.0, 0
     for t in range(3000):
         grad = theta / s2
-        ops.psgld_step(theta, grad, V, 5e-3, alpha=0.99, lam=1e-5, seed=3, step=t)
+        ops.psgld_step(theta, grad, V, 5e-3, alpha=1.0, lam=1e-5, seed=3, step=t)
         if t >= 1000 and t % 10 == 0:
             acc += float((theta.double() ** 2).mean()); cnt += 1
-    assert abs(float(acc / cnt) - s2) < 0.1 * s2
+    assert abs(acc / cnt - s2) < 0.1 * s2
+    assert bool((V == 1).all())
