@@ -30,10 +30,14 @@ def merge_shards(part_mean, part_m2, count, group=None, merge_fn=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return merge_fn(part_mean.unsqueeze(0), part_m2.unsqueeze(0), [int(count)])
     R = dist.get_world_size(group)
-    packed = torch.stack([part_mean, part_m2]).contiguous()             # [2, ...] float64
-    gathered = torch.empty((R,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+    shape = tuple(part_mean.shape)
+    packed = torch.cat([part_mean.reshape(-1), part_m2.reshape(-1)]).contiguous()      # [2*M] float64
+    gathered = torch.empty(R * packed.numel(), dtype=packed.dtype, device=packed.device)
     dist.all_gather_into_tensor(gathered, packed, group=group)
+    gathered = gathered.view(R, 2, -1)
     cnt = torch.tensor([int(count)], dtype=torch.int64, device=packed.device)
     cnts = torch.empty(R, dtype=torch.int64, device=packed.device)
     dist.all_gather_into_tensor(cnts, cnt, group=group)
-    return merge_fn(gathered[:, 0].contiguous(), gathered[:, 1].contiguous(), cnts.tolist())
+    pm = gathered[:, 0].contiguous().view((R,) + shape)
+    pm2 = gathered[:, 1].contiguous().view((R,) + shape)
+    return merge_fn(pm, pm2, cnts.tolist())
