@@ -47,6 +47,8 @@ PROTOTYPES = {
     "bnn_mask_len": (C.c_int64, [C.POINTER(MlpDesc), C.POINTER(C.c_int32)]),
     "bnn_forward_workspace_bytes": (C.c_int64, [C.POINTER(ForwardArgs)]),
     "bnn_forward": (C.c_int32, [C.POINTER(ForwardArgs), C.c_void_p]),
+    "bnn_forward_tc_supported": (C.c_int32, [C.POINTER(ForwardArgs)]),
+    "bnn_tc_selftest": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bnn_moments": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int64, C.c_void_p]),
     "bnn_moments_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),

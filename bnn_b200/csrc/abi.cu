@@ -29,6 +29,11 @@ int sm_count() {
 
 int forward_simt(const BnnForwardArgs* a, cudaStream_t st);
 long long forward_simt_workspace_bytes(const BnnForwardArgs* a);
+int forward_tc(const BnnForwardArgs* a, cudaStream_t st);
+long long forward_tc_workspace_bytes(const BnnForwardArgs* a);
+int forward_tc_supported(const BnnForwardArgs* a);
+
+static bool use_tc(const BnnForwardArgs* a) { return a->precision == BNN_PREC_TF32X3 || a->precision == BNN_PREC_TF32; }
 
 static int check_forward_args(const BnnForwardArgs* a, bool host) {
   if (!a) BNN_FAIL("bnn_forward: null args");
@@ -43,7 +48,7 @@ static int check_forward_args(const BnnForwardArgs* a, bool host) {
   if (!host && (((uintptr_t)a->W) & 15)) BNN_FAIL("bnn_forward: W must be 16-byte aligned");
   if (a->mask.mode < BNN_MASK_NONE || a->mask.mode > BNN_MASK_CONCRETE) BNN_FAIL("bnn_forward: bad mask mode %d", a->mask.mode);
   if (a->mask.mode == BNN_MASK_EXTERNAL && !a->mask.mask) BNN_FAIL("bnn_forward: BNN_MASK_EXTERNAL without a mask tensor");
-  if (a->precision != BNN_PREC_FP32) BNN_FAIL("bnn_forward: precision %d not available in this build", a->precision);
+  if (a->precision < BNN_PREC_FP32 || a->precision > BNN_PREC_TF32) BNN_FAIL("bnn_forward: unknown precision %d", a->precision);
   if (!a->pred && !a->mean && !a->var && !a->part_mean && !a->part_m2) BNN_FAIL("bnn_forward: no output requested");
   return 0;
 }
@@ -55,6 +60,10 @@ using namespace bnn;
 extern "C" int32_t bnn_abi_version(void) { return BNN_ABI_VERSION; }
 extern "C" const char* bnn_last_error(void) { return g_err; }
 extern "C" int32_t bnn_sm_count(void) { return sm_count(); }
+extern "C" int32_t bnn_forward_tc_supported(const BnnForwardArgs* a) {
+  if (!a) { set_error("null args"); return 0; }
+  return forward_tc_supported(a);
+}
 extern "C" int32_t bnn_set_device(int32_t device) {
   BNN_CUDA(cudaSetDevice(device));
   return 0;
@@ -86,12 +95,12 @@ extern "C" int64_t bnn_mask_len(const BnnMlpDesc* d, const int32_t* layer_masked
 
 extern "C" int64_t bnn_forward_workspace_bytes(const BnnForwardArgs* a) {
   if (!a) { set_error("null args"); return -1; }
-  return forward_simt_workspace_bytes(a);
+  return use_tc(a) ? forward_tc_workspace_bytes(a) : forward_simt_workspace_bytes(a);
 }
 
 extern "C" int32_t bnn_forward(const BnnForwardArgs* a, void* stream) {
   if (check_forward_args(a, false)) return -1;
-  return forward_simt(a, (cudaStream_t)stream);
+  return use_tc(a) ? forward_tc(a, (cudaStream_t)stream) : forward_simt(a, (cudaStream_t)stream);
 }
 
 // ---- host-buffer path ---------------------------------------------------------
@@ -165,12 +174,12 @@ extern "C" int32_t bnn_forward_host(const BnnForwardArgs* ah) {
     a.part_mean = ah->part_mean ? (double*)g_ws.buf[BPART] : nullptr;
     a.part_m2 = ah->part_m2 ? (double*)g_ws.buf[BPART] + M : nullptr;
   }
-  const long long wsb = forward_simt_workspace_bytes(&a);
+  const long long wsb = use_tc(&a) ? forward_tc_workspace_bytes(&a) : forward_simt_workspace_bytes(&a);
   if (wsb < 0) return -1;
   if (g_ws.ensure(BWS, (size_t)(wsb > 16 ? wsb : 16))) return -2;
   a.workspace = g_ws.buf[BWS];
   a.workspace_bytes = wsb;
-  const int rc = forward_simt(&a, st);
+  const int rc = use_tc(&a) ? forward_tc(&a, st) : forward_simt(&a, st);
   if (rc) return rc;
   if (ah->pred) BNN_CUDA(cudaMemcpyAsync(ah->pred, a.pred, (size_t)a.S * M * 4, cudaMemcpyDeviceToHost, st));
   if (ah->mean) BNN_CUDA(cudaMemcpyAsync(ah->mean, a.mean, (size_t)M * 4, cudaMemcpyDeviceToHost, st));

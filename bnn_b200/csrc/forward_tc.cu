@@ -1,0 +1,622 @@
+// Kernel (a)+(e), tensor-core variant: fused S x N batched MLP forward on tcgen05 (5th-gen tensor cores),
+// accumulators in TMEM, FP32-grade accuracy through 3xTF32 error compensation
+//     A*B ~= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo          (hi = tf32(x) rounded to nearest, lo = x - hi exactly)
+// or a single TF32 pass (BNN_PREC_TF32, looser bound).  Replaces the same reference code as forward_simt.cu
+// (the `for i in range(S): pred[i] = nns[i](X)` loops + BNN.py:36-37) for the wide configs where the layers are
+// real contractions (M = 128/256 points, N = hidden width, K = previous width).
+//
+// Shape family: dims = [D, H1, H2, O] with D <= 64, H1, H2 <= 256, O <= 4 (the last Linear is a dot product in
+// the epilogue).  One CTA (kPair = 1) or one CTA pair on two SMs (kPair = 2, cta_group::2, M = 256) owns a range
+// of 128-point tiles and walks the posterior samples in the outer loop:
+//   per sample : the sample's weights, pre-split into hi/lo UMMA operand images by tc_prep_kernel, are bulk-copied
+//                (TMA bulk engine) into shared memory ONCE and stay resident for all tiles (pair mode: each CTA
+//                holds half of the N rows of every B operand, the tensor core reads both halves);
+//   per tile   : X tile -> A1 (hi/lo) -> MMA1 -> D1[TMEM] -> epilogue-1 (bias, activation, hi/lo split) writes the
+//                layer-2 A operand K-step by K-step into a shared-memory ring -> MMA2 consumes the ring into
+//                D2[TMEM] -> epilogue-2 (bias, activation, dot with w3) -> y -> FP64 Welford update of the
+//                per-point state (global, owned by this CTA; finalised by finalize_moments()).
+// Roles: warps 0-3 = epilogue/compute (TMEM lane quarter = warp id), warp 4 = MMA issuer + weight loader.
+#include "common.cuh"
+#include "philox.cuh"
+#include "tc_common.cuh"
+
+namespace bnn {
+
+constexpr int kTcThreads = 160;       // 4 epilogue warps + 1 MMA/loader warp
+constexpr int kTcEpiThreads = 128;
+constexpr int kTcRing = 4;            // A2 ring stages (one K = 8 step each)
+constexpr int kTcStageBytes = 2 * 2 * 128 * 16;  // hi + lo, 2 granule columns x 128 rows x 16 B = 8 KB
+
+struct TcParams {
+  int D, H1, H2, O, act;
+  int Dp, N1, N2;          // padded: K of layer 1 (mult of 8), N of layer 1 = K of layer 2, N of layer 2 (mult of 16)
+  int passes;              // 3 (tf32x3) or 1 (tf32)
+  long long part_stride;   // floats per (sample, part) of the operand image
+  long long img_stride;    // floats per sample of the operand image
+  int vec_len;             // floats: b1[N1] b2[N2] w3[O*N2] b3[4]
+  const float* img;        // [S][img_stride]
+  const float* X;
+  long long N;
+  int S, G, Sg;
+  int tiles_per_slot, n_tiles;   // pair-tiles (128 * kPair points each)
+  float* pred;
+  double* part;            // [G][2][M]  Welford state = shard moments
+  int tmem_cols;
+  // shared memory offsets (bytes)
+  int sm_b1, sm_b2, sm_vec, sm_a1, sm_ring, sm_bar;
+};
+
+// ---- operand image builder -------------------------------------------------------------------------
+struct TcPrepParams {
+  int D, H1, H2, O, Dp, N1, N2, kpair;
+  int ld0, ld1, ld2;
+  long long off0, off1, off2, w_stride, part_stride, img_stride;
+  int vec_len;
+};
+
+__global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ TcPrepParams q, const float* __restrict__ W,
+                                                      float* __restrict__ img) {
+  const long long s = blockIdx.y;
+  const float* Ws = W + s * q.w_stride;
+  float* out = img + s * q.img_stride;
+  const int N1h = q.N1 / q.kpair, N2h = q.N2 / q.kpair;
+  const long long b1_sz = (long long)q.Dp * N1h, b2_sz = (long long)q.N1 * N2h;
+  const long long total = q.img_stride;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v = 0.0f;
+    long long r = i;
+    if (r < q.part_stride * q.kpair) {
+      const int part = (int)(r / q.part_stride);
+      r -= part * q.part_stride;
+      // regions: [B1 hi][B1 lo][B2 hi][B2 lo], each [kc][n][4]
+      int layer, hl;
+      if (r < 2 * b1_sz) { layer = 0; hl = r >= b1_sz; r -= hl * b1_sz; }
+      else { r -= 2 * b1_sz; layer = 1; hl = r >= b2_sz; r -= hl * b2_sz; }
+      const int rows = layer == 0 ? N1h : N2h;
+      const int e = (int)(r & 3);
+      const long long g = r >> 2;
+      const int kc = (int)(g / rows), n = (int)(g - (long long)kc * rows);
+      const int k = kc * 4 + e;
+      const int ng = part * rows + n;
+      float w = 0.0f;
+      if (layer == 0) { if (ng < q.H1 && k < q.D) w = Ws[q.off0 + (long long)ng * q.ld0 + k]; }
+      else            { if (ng < q.H2 && k < q.H1) w = Ws[q.off1 + (long long)ng * q.ld1 + k]; }
+      const float hi = tc::tf32_hi(w);
+      v = hl ? (w - hi) : hi;
+    } else {
+      int j = (int)(r - q.part_stride * q.kpair);
+      if (j < q.N1) { if (j < q.H1) v = Ws[q.off0 + (long long)j * q.ld0 + q.D]; }           // b1
+      else if ((j -= q.N1) < q.N2) { if (j < q.H2) v = Ws[q.off1 + (long long)j * q.ld1 + q.H1]; }  // b2
+      else if ((j -= q.N2) < q.O * q.N2) {                                                          // w3[o][j]
+        const int o = j / q.N2, c = j - o * q.N2;
+        if (c < q.H2) v = Ws[q.off2 + (long long)o * q.ld2 + c];
+      } else if ((j -= q.O * q.N2) < q.O) v = Ws[q.off2 + (long long)j * q.ld2 + q.H2];            // b3
+    }
+    out[i] = v;
+  }
+}
+
+// ---- cluster helpers (pair mode) ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+
+template <int kPair>
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kPair == 1) {
+    tc::mma_tf32_ss(tmem_d, adesc, bdesc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// MMA completion -> arrival on the barrier at this offset in every CTA of the pair
+template <int kPair>
+__device__ __forceinline__ void mma_commit_all(uint64_t* bar) {
+  if constexpr (kPair == 1) {
+    tc::mma_commit(bar);
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
+}
+template <int kPair>
+__device__ __forceinline__ void tmem_alloc_n(uint32_t* dst, uint32_t ncols) {
+  if constexpr (kPair == 1) {
+    tc::tmem_alloc(dst, ncols);
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int kPair>
+__device__ __forceinline__ void tmem_dealloc_n(uint32_t addr, uint32_t ncols) {
+  if constexpr (kPair == 1) tc::tmem_dealloc(addr, ncols);
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+
+// barrier slots in shared memory
+enum { BAR_W_FULL = 0, BAR_A1_FULL, BAR_D1_FULL, BAR_D2_FULL, BAR_D2_EMPTY, BAR_A2_FULL, BAR_A2_EMPTY = BAR_A2_FULL + kTcRing,
+       BAR_COUNT = BAR_A2_EMPTY + kTcRing };
+
+// one warp signals "my part is done" to the MMA issuer (leader CTA): writers fence their generic-proxy
+// stores for the async proxy, the warp converges, one lane arrives
+template <int kPair>
+__device__ __forceinline__ void warp_signal_leader(uint64_t* bar, int lane) {
+  fence_proxy_async();
+  tc::fence_before_thread_sync();
+  __syncwarp();
+  if (lane == 0) {
+    if constexpr (kPair == 1) mbar_arrive(bar);
+    else mbar_arrive_cluster(bar, 0);
+  }
+}
+
+template <int kPair>
+__global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.sm_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+  const uint32_t s_b1 = smem_u32(smem + p.sm_b1), s_b2 = smem_u32(smem + p.sm_b2);
+  const uint32_t s_a1 = smem_u32(smem + p.sm_a1), s_ring = smem_u32(smem + p.sm_ring);
+  const float* vecs = reinterpret_cast<const float*>(smem + p.sm_vec);  // double buffered by sample parity
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = kPair == 1 ? 0u : cluster_ctarank();
+  const bool leader = rank == 0;
+  const int slot = blockIdx.x / kPair;
+  const int g = blockIdx.y;
+  const int s0 = g * p.Sg, s1 = min(p.S, s0 + p.Sg);
+  const int pt0 = slot * p.tiles_per_slot, pt1 = min(p.n_tiles, pt0 + p.tiles_per_slot);
+  const int N1h = p.N1 / kPair, N2h = p.N2 / kPair;
+  const int n_k1 = p.Dp >> 3, n_k2 = p.N1 >> 3;
+  const uint32_t b1_hl_bytes = (uint32_t)p.Dp * N1h * 4, b2_hl_bytes = (uint32_t)p.N1 * N2h * 4;
+  const uint32_t a1_hl_bytes = (uint32_t)p.Dp * 128 * 4;
+  const int vec_pad = (p.vec_len + 3) & ~3;
+
+  if (tid == 0) {
+    mbar_init(&bars[BAR_W_FULL], 1);
+    mbar_init(&bars[BAR_A1_FULL], 4 * kPair);
+    mbar_init(&bars[BAR_D1_FULL], 1);
+    mbar_init(&bars[BAR_D2_FULL], 1);
+    mbar_init(&bars[BAR_D2_EMPTY], 4 * kPair);
+    for (int i = 0; i < kTcRing; ++i) {
+      mbar_init(&bars[BAR_A2_FULL + i], 4 * kPair);
+      mbar_init(&bars[BAR_A2_EMPTY + i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc_n<kPair>(tmem_slot, (uint32_t)p.tmem_cols);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if constexpr (kPair == 2) cluster_sync_all();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + (uint32_t)p.N1;
+
+  if (warp == 4) {
+    // ===================== weight loader + MMA issuer (one lane) ==========================================
+    if (lane == 0) {
+      const uint32_t idesc1 = tc::make_idesc_tf32(128 * kPair, p.N1), idesc2 = tc::make_idesc_tf32(128 * kPair, p.N2);
+      uint32_t tile_cnt = 0, ring_it = 0;
+      for (int s = s0; s < s1; ++s) {
+        // previous sample's MMAs have all completed (its last d2_full was observed below): reload the operands
+        {
+          const float* src = p.img + (long long)s * p.img_stride + (long long)rank * p.part_stride;
+          const uint32_t b1_bytes = p.passes == 3 ? 2 * b1_hl_bytes : b1_hl_bytes;
+          const uint32_t b2_bytes = p.passes == 3 ? 2 * b2_hl_bytes : b2_hl_bytes;
+          mbar_arrive_expect_tx(&bars[BAR_W_FULL], b1_bytes + b2_bytes + (uint32_t)vec_pad * 4);
+          bulk_g2s(smem + p.sm_b1, src, b1_bytes, &bars[BAR_W_FULL]);
+          bulk_g2s(smem + p.sm_b2, src + 2 * (long long)(b1_hl_bytes / 4), b2_bytes, &bars[BAR_W_FULL]);
+          bulk_g2s(smem + p.sm_vec + ((s - s0) & 1) * vec_pad * 4, p.img + (long long)s * p.img_stride + p.part_stride * kPair,
+                   (uint32_t)vec_pad * 4, &bars[BAR_W_FULL]);
+        }
+        if (leader) mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
+        for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
+          const uint32_t tpar = tile_cnt & 1u;
+          if (leader) {
+            // ---- layer 1: D1 = A1 * B1^T
+            mbar_wait(&bars[BAR_A1_FULL], tpar);
+            tc::fence_after_thread_sync();
+            for (int ks = 0; ks < n_k1; ++ks) {
+              const uint64_t a_hi = tc::make_smem_desc(s_a1 + (uint32_t)(2 * ks) * 2048u, 2048u, 128u);
+              const uint64_t a_lo = tc::make_smem_desc(s_a1 + a1_hl_bytes + (uint32_t)(2 * ks) * 2048u, 2048u, 128u);
+              const uint64_t b_hi = tc::make_smem_desc(s_b1 + (uint32_t)(2 * ks) * (uint32_t)N1h * 16u, (uint32_t)N1h * 16u, 128u);
+              const uint64_t b_lo = tc::make_smem_desc(s_b1 + b1_hl_bytes + (uint32_t)(2 * ks) * (uint32_t)N1h * 16u, (uint32_t)N1h * 16u, 128u);
+              mma_tf32<kPair>(tmem_d1, a_hi, b_hi, idesc1, ks > 0);
+              if (p.passes == 3) {
+                mma_tf32<kPair>(tmem_d1, a_lo, b_hi, idesc1, 1);
+                mma_tf32<kPair>(tmem_d1, a_hi, b_lo, idesc1, 1);
+              }
+            }
+            mma_commit_all<kPair>(&bars[BAR_D1_FULL]);
+            // ---- layer 2: D2 = A2 * B2^T, A2 produced K-step by K-step by epilogue-1
+            for (int ks = 0; ks < n_k2; ++ks, ++ring_it) {
+              const uint32_t st = ring_it % kTcRing, rpar = (ring_it / kTcRing) & 1u;
+              mbar_wait(&bars[BAR_A2_FULL + st], rpar);
+              if (ks == 0) mbar_wait(&bars[BAR_D2_EMPTY], tpar ^ 1u);   // epilogue-2 of the previous tile drained D2
+              tc::fence_after_thread_sync();
+              const uint32_t sa = s_ring + st * kTcStageBytes;
+              const uint64_t a_hi = tc::make_smem_desc(sa, 2048u, 128u);
+              const uint64_t a_lo = tc::make_smem_desc(sa + kTcStageBytes / 2, 2048u, 128u);
+              const uint64_t b_hi = tc::make_smem_desc(s_b2 + (uint32_t)(2 * ks) * (uint32_t)N2h * 16u, (uint32_t)N2h * 16u, 128u);
+              const uint64_t b_lo = tc::make_smem_desc(s_b2 + b2_hl_bytes + (uint32_t)(2 * ks) * (uint32_t)N2h * 16u, (uint32_t)N2h * 16u, 128u);
+              mma_tf32<kPair>(tmem_d2, a_hi, b_hi, idesc2, ks > 0);
+              if (p.passes == 3) {
+                mma_tf32<kPair>(tmem_d2, a_lo, b_hi, idesc2, 1);
+                mma_tf32<kPair>(tmem_d2, a_hi, b_lo, idesc2, 1);
+              }
+              mma_commit_all<kPair>(&bars[BAR_A2_EMPTY + st]);
+            }
+            mma_commit_all<kPair>(&bars[BAR_D2_FULL]);
+          } else {
+            ring_it += n_k2;
+          }
+          // every CTA's loader observes the end of the tile (keeps its phase in step; the last one per
+          // sample also licenses the operand reload above)
+          mbar_wait(&bars[BAR_D2_FULL], tpar);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue / compute warps: thread = one point (TMEM lane) ===============================
+    const int row = warp * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    uint32_t tile_cnt = 0, ring_it = 0;
+    const long long M = p.N * p.O;
+    double* st_mean = p.part ? p.part + (long long)g * 2 * M : nullptr;
+    double* st_m2 = p.part ? st_mean + M : nullptr;
+    for (int s = s0; s < s1; ++s) {
+      const float* vec = vecs + ((s - s0) & 1) * vec_pad;
+      const float* b1 = vec;
+      const float* b2 = vec + p.N1;
+      const float* w3 = b2 + p.N2;
+      const float* b3 = w3 + p.O * p.N2;
+      const double inv_cnt = 1.0 / (double)(s - s0 + 1);
+      bool w_ready = false;
+      for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
+        const uint32_t tpar = tile_cnt & 1u;
+        const long long n = ((long long)pt * kPair + rank) * 128 + row;
+        const bool in_range = n < p.N;
+        // ---- A1: this point's input row, hi/lo split, as K-major granules
+        {
+          const float* xr = p.X + n * p.D;
+          for (int kc = 0; kc < (p.Dp >> 2); ++kc) {
+            float x[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int k = kc * 4 + e;
+              x[e] = (in_range && k < p.D) ? __ldg(xr + k) : 0.0f;
+            }
+            float4 hi, lo;
+            hi.x = tc::tf32_hi(x[0]); hi.y = tc::tf32_hi(x[1]); hi.z = tc::tf32_hi(x[2]); hi.w = tc::tf32_hi(x[3]);
+            lo.x = x[0] - hi.x; lo.y = x[1] - hi.y; lo.z = x[2] - hi.z; lo.w = x[3] - hi.w;
+            const uint32_t a = s_a1 + (uint32_t)(kc * 128 + row) * 16u;
+            sts128(a, hi);
+            sts128(a + a1_hl_bytes, lo);
+          }
+        }
+        if (!w_ready) {   // biases / w3 of this sample (also: this CTA's operand images have landed)
+          mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
+          w_ready = true;
+        }
+        warp_signal_leader<kPair>(&bars[BAR_A1_FULL], lane);
+
+        // ---- epilogue 1: D1 -> h1 = act(d + b1) -> hi/lo -> A2 ring, one K = 8 step per stage
+        mbar_wait(&bars[BAR_D1_FULL], tpar);
+        tc::fence_after_thread_sync();
+        for (int c0 = 0; c0 < p.N1; c0 += 16) {
+          float d[16];
+          tc::tmem_ld16(tmem_d1 + lane_sel + (uint32_t)c0, d);
+#pragma unroll
+          for (int half = 0; half < 2; ++half, ++ring_it) {
+            const uint32_t st = ring_it % kTcRing, rpar = (ring_it / kTcRing) & 1u;
+            mbar_wait(&bars[BAR_A2_EMPTY + st], rpar ^ 1u);
+            const uint32_t sa = s_ring + st * kTcStageBytes + (uint32_t)row * 16u;
+#pragma unroll
+            for (int q4 = 0; q4 < 2; ++q4) {
+              float h[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = half * 8 + q4 * 4 + e;
+                h[e] = apply_act(d[j] + b1[c0 + j], p.act);
+              }
+              float4 hi, lo;
+              hi.x = tc::tf32_hi(h[0]); hi.y = tc::tf32_hi(h[1]); hi.z = tc::tf32_hi(h[2]); hi.w = tc::tf32_hi(h[3]);
+              lo.x = h[0] - hi.x; lo.y = h[1] - hi.y; lo.z = h[2] - hi.z; lo.w = h[3] - hi.w;
+              sts128(sa + (uint32_t)q4 * 2048u, hi);
+              sts128(sa + kTcStageBytes / 2 + (uint32_t)q4 * 2048u, lo);
+            }
+            warp_signal_leader<kPair>(&bars[BAR_A2_FULL + st], lane);
+          }
+        }
+
+        // ---- epilogue 2: D2 -> y[o] = b3[o] + sum_j w3[o][j] * act(d + b2[j])
+        mbar_wait(&bars[BAR_D2_FULL], tpar);
+        tc::fence_after_thread_sync();
+        float y[4] = {b3[0], p.O > 1 ? b3[1] : 0.f, p.O > 2 ? b3[2] : 0.f, p.O > 3 ? b3[3] : 0.f};
+        for (int c0 = 0; c0 < p.N2; c0 += 16) {
+          float d[16];
+          tc::tmem_ld16(tmem_d2 + lane_sel + (uint32_t)c0, d);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float t = apply_act(d[j] + b2[c0 + j], p.act);
+            y[0] = fmaf(w3[c0 + j], t, y[0]);
+            if (p.O > 1) y[1] = fmaf(w3[p.N2 + c0 + j], t, y[1]);
+            if (p.O > 2) y[2] = fmaf(w3[2 * p.N2 + c0 + j], t, y[2]);
+            if (p.O > 3) y[3] = fmaf(w3[3 * p.N2 + c0 + j], t, y[3]);
+          }
+        }
+        // D2 is drained: let the next tile's layer-2 MMAs overwrite it
+        tc::fence_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kPair == 1) mbar_arrive(&bars[BAR_D2_EMPTY]);
+          else mbar_arrive_cluster(&bars[BAR_D2_EMPTY], 0);
+        }
+        // ---- predictive reduction: FP64 Welford state of this point (only this thread ever touches it)
+        if (in_range) {
+          for (int o = 0; o < p.O; ++o) {
+            const long long m = n * p.O + o;
+            if (p.pred) p.pred[((long long)s * p.N + n) * p.O + o] = y[o];
+            if (st_mean) {
+              const double mu0 = s == s0 ? 0.0 : st_mean[m];
+              const double q0 = s == s0 ? 0.0 : st_m2[m];
+              const double dlt = (double)y[o] - mu0;
+              const double mu = mu0 + dlt * inv_cnt;
+              st_mean[m] = mu;
+              st_m2[m] = q0 + dlt * ((double)y[o] - mu);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if constexpr (kPair == 2) cluster_sync_all();
+  if (warp == 4) tmem_dealloc_n<kPair>(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---- self-test GEMM: D[128, N] = A[128, K] * B[N, K]^T through the same descriptors / split -----------------
+__global__ void __launch_bounds__(160, 1) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                             float* __restrict__ Dout, int K, int N, int passes) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_hl = (uint32_t)K * 128 * 4, b_hl = (uint32_t)K * N * 4;
+  const uint32_t s_a = smem_u32(smem), s_b = s_a + 2 * a_hl;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 4) tc::tmem_alloc(&tmem_slot, 256);
+  // operands -> K-major granules, hi/lo
+  for (int i = tid; i < (K / 4) * 128; i += blockDim.x) {
+    const int kc = i / 128, r = i % 128;
+    float4 x = *reinterpret_cast<const float4*>(A + (size_t)r * K + kc * 4);
+    float4 hi = make_float4(tc::tf32_hi(x.x), tc::tf32_hi(x.y), tc::tf32_hi(x.z), tc::tf32_hi(x.w));
+    float4 lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+    sts128(s_a + (uint32_t)i * 16u, hi);
+    sts128(s_a + a_hl + (uint32_t)i * 16u, lo);
+  }
+  for (int i = tid; i < (K / 4) * N; i += blockDim.x) {
+    const int kc = i / N, r = i % N;
+    float4 x = *reinterpret_cast<const float4*>(B + (size_t)r * K + kc * 4);
+    float4 hi = make_float4(tc::tf32_hi(x.x), tc::tf32_hi(x.y), tc::tf32_hi(x.z), tc::tf32_hi(x.w));
+    float4 lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+    sts128(s_b + (uint32_t)i * 16u, hi);
+    sts128(s_b + b_hl + (uint32_t)i * 16u, lo);
+  }
+  fence_proxy_async();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 4 && lane == 0) {
+    const uint32_t idesc = tc::make_idesc_tf32(128, N);
+    for (int ks = 0; ks < K / 8; ++ks) {
+      const uint64_t a_hi = tc::make_smem_desc(s_a + (uint32_t)(2 * ks) * 2048u, 2048u, 128u);
+      const uint64_t a_lo = tc::make_smem_desc(s_a + a_hl + (uint32_t)(2 * ks) * 2048u, 2048u, 128u);
+      const uint64_t b_hi = tc::make_smem_desc(s_b + (uint32_t)(2 * ks) * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
+      const uint64_t b_lo = tc::make_smem_desc(s_b + b_hl + (uint32_t)(2 * ks) * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
+      tc::mma_tf32_ss(tmem, a_hi, b_hi, idesc, ks > 0);
+      if (passes == 3) {
+        tc::mma_tf32_ss(tmem, a_lo, b_hi, idesc, 1);
+        tc::mma_tf32_ss(tmem, a_hi, b_lo, idesc, 1);
+      }
+    }
+    tc::mma_commit(&bar);
+  }
+  if (warp < 4) {
+    mbar_wait(&bar, 0);
+    tc::fence_after_thread_sync();
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float d[16];
+      tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, d);
+      for (int j = 0; j < 16; ++j) Dout[(size_t)row * N + c0 + j] = d[j];
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem, 256);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+static inline int roundup(int v, int m) { return (v + m - 1) / m * m; }
+
+struct TcPlan {
+  TcParams p;
+  TcPrepParams q;
+  int kpair;
+  size_t smem;
+  long long img_bytes, part_bytes;
+  int slots;
+};
+
+int finalize_moments(const double* part, const int*, int G, int Sg, long long S, long long M, float* mean, float* var,
+                     double* part_mean, double* part_m2, cudaStream_t st);
+
+// 0 = ok, 1 = shape not supported by the tensor-core path (message set), <0 = error
+static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
+  Layout L;
+  if (make_layout(&a->desc, &L)) return -1;
+  if (L.n_lin != 3) { set_error("tensor-core forward needs exactly 2 hidden layers (got %d Linear layers)", L.n_lin); return 1; }
+  if (a->mask.mode != BNN_MASK_NONE) { set_error("tensor-core forward does not take dropout masks yet"); return 1; }
+  if (a->w_stride == 0) { set_error("tensor-core forward needs a per-sample bank"); return 1; }
+  const int D = L.in[0], H1 = L.out[0], H2 = L.out[1], O = L.out[2];
+  if (D > 64 || H1 > 256 || H2 > 256 || O > 4) { set_error("tensor-core forward: shape outside D<=64, H<=256, O<=4"); return 1; }
+  TcParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  p.D = D; p.H1 = H1; p.H2 = H2; p.O = O; p.act = L.act;
+  p.Dp = roundup(D, 8); p.N1 = roundup(H1, 16); p.N2 = roundup(H2, 16);
+  p.passes = a->precision == BNN_PREC_TF32 ? 1 : 3;
+  p.vec_len = p.N1 + p.N2 + O * p.N2 + 4;
+  const int vec_pad = (p.vec_len + 3) & ~3;
+  // try one CTA per tile first (weights fully resident in one SM's shared memory), else a CTA pair
+  int kpair = 0;
+  for (int kp = 1; kp <= 2 && !kpair; ++kp) {
+    const int N1h = p.N1 / kp, N2h = p.N2 / kp;
+    if ((N1h & 7) || (N2h & 7)) continue;
+    size_t o = 0;
+    p.sm_b1 = (int)o; o += (size_t)2 * p.Dp * N1h * 4;
+    p.sm_b2 = (int)o; o += (size_t)2 * p.N1 * N2h * 4;
+    p.sm_a1 = (int)o; o += (size_t)2 * p.Dp * 128 * 4;
+    p.sm_ring = (int)o; o += (size_t)kTcRing * kTcStageBytes;
+    p.sm_vec = (int)o; o += (size_t)2 * vec_pad * 4;
+    o = (o + 15) & ~(size_t)15;
+    p.sm_bar = (int)o; o += (size_t)BAR_COUNT * 8 + 16;
+    if (o <= (size_t)227 * 1024) { kpair = kp; plan->smem = o; }
+  }
+  if (!kpair) { set_error("tensor-core forward: weights do not fit shared memory even as a CTA pair"); return 1; }
+  plan->kpair = kpair;
+  const int N1h = p.N1 / kpair, N2h = p.N2 / kpair;
+  p.part_stride = 2LL * p.Dp * N1h + 2LL * p.N1 * N2h;
+  p.img_stride = p.part_stride * kpair + vec_pad;
+  int cols = p.N1 + p.N2, tc = 32;
+  while (tc < cols) tc <<= 1;
+  if (tc > 512) { set_error("tensor-core forward: accumulators exceed TMEM"); return 1; }
+  p.tmem_cols = tc;
+  p.X = a->X; p.N = a->N; p.S = (int)a->S; p.pred = a->pred;
+  // work split: slots over pair-tiles, sample groups when there are too few tiles
+  const int tile_pts = 128 * kpair;
+  p.n_tiles = (int)((a->N + tile_pts - 1) / tile_pts);
+  const int max_slots = sm_count() / kpair;
+  int slots = p.n_tiles < max_slots ? p.n_tiles : max_slots;
+  p.tiles_per_slot = (p.n_tiles + slots - 1) / slots;
+  slots = (p.n_tiles + p.tiles_per_slot - 1) / p.tiles_per_slot;
+  plan->slots = slots;
+  long long G = 1;
+  if (slots < max_slots) G = max_slots / slots;
+  if (G > a->S) G = a->S;
+  if (G < 1) G = 1;
+  if (G > 65535) G = 65535;
+  const long long Sg = (a->S + G - 1) / G;
+  G = (a->S + Sg - 1) / Sg;
+  p.G = (int)G; p.Sg = (int)Sg;
+  plan->img_bytes = ((long long)a->S * p.img_stride * 4 + 255) & ~255LL;
+  plan->part_bytes = (long long)G * 2 * a->N * O * (long long)sizeof(double);
+  TcPrepParams& q = plan->q;
+  q.D = D; q.H1 = H1; q.H2 = H2; q.O = O; q.Dp = p.Dp; q.N1 = p.N1; q.N2 = p.N2; q.kpair = kpair;
+  q.ld0 = L.ld[0]; q.ld1 = L.ld[1]; q.ld2 = L.ld[2];
+  q.off0 = L.off[0]; q.off1 = L.off[1]; q.off2 = L.off[2];
+  q.w_stride = a->w_stride; q.part_stride = p.part_stride; q.img_stride = p.img_stride; q.vec_len = p.vec_len;
+  return 0;
+}
+
+long long forward_tc_workspace_bytes(const BnnForwardArgs* a) {
+  TcPlan plan;
+  const int rc = plan_tc(a, &plan);
+  if (rc) return -1;
+  return plan.img_bytes + plan.part_bytes;
+}
+
+int forward_tc_supported(const BnnForwardArgs* a) {
+  TcPlan plan;
+  return plan_tc(a, &plan) == 0;
+}
+
+int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
+  TcPlan plan;
+  const int rc = plan_tc(a, &plan);
+  if (rc) return -1;
+  TcParams& p = plan.p;
+  const long long need = plan.img_bytes + plan.part_bytes;
+  if (!a->workspace || a->workspace_bytes < need)
+    BNN_FAIL("workspace too small: need %lld bytes, got %lld", need, (long long)a->workspace_bytes);
+  float* img = reinterpret_cast<float*>(a->workspace);
+  p.img = img;
+  const bool want_moments = a->mean || a->var || a->part_mean || a->part_m2;
+  p.part = want_moments ? reinterpret_cast<double*>(reinterpret_cast<char*>(a->workspace) + plan.img_bytes) : nullptr;
+  {
+    long long bx = (p.img_stride + 255) / 256;
+    if (bx > 64) bx = 64;
+    dim3 grid((unsigned)bx, (unsigned)a->S);
+    tc_prep_kernel<<<grid, 256, 0, st>>>(plan.q, a->W, img);
+    BNN_CUDA(cudaGetLastError());
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(plan.slots * plan.kpair), (unsigned)p.G, 1);
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)plan.kpair;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (plan.kpair == 1) {
+    BNN_CUDA(cudaFuncSetAttribute(fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    BNN_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc_kernel<1>, p));
+  } else {
+    BNN_CUDA(cudaFuncSetAttribute(fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    BNN_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc_kernel<2>, p));
+  }
+  BNN_CUDA(cudaGetLastError());
+  if (want_moments)
+    return finalize_moments(p.part, nullptr, p.G, p.Sg, a->S, a->N * p.O, a->mean, a->var, a->part_mean, a->part_m2, st);
+  return 0;
+}
+
+}  // namespace bnn
+
+using namespace bnn;
+
+// D[128, N] = A[128, K] * B[N, K]^T on tcgen05 (device pointers; K % 8 == 0, K <= 64; N % 16 == 0, N <= 256)
+extern "C" int32_t bnn_tc_selftest(const float* A, const float* B, float* D, int32_t K, int32_t N, int32_t passes, void* stream) {
+  if (!A || !B || !D || K < 8 || K > 64 || (K & 7) || N < 16 || N > 256 || (N & 15) || (passes != 1 && passes != 3))
+    BNN_FAIL("bnn_tc_selftest: bad arguments");
+  const size_t smem = (size_t)2 * K * 128 * 4 + (size_t)2 * K * N * 4;
+  BNN_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(A, B, D, K, N, passes);
+  BNN_CUDA(cudaGetLastError());
+  return 0;
+}

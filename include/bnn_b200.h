@@ -120,6 +120,12 @@ int64_t bnn_forward_workspace_bytes(const BnnForwardArgs* a);
  * `preds.mean(0), preds.var(0)` of BNN.predict_mv (BNN.py:34-37), in one
  * launch; pred[S,N,nout] is only written when asked for.                   */
 int32_t bnn_forward(const BnnForwardArgs* a, void* stream);
+/* 1 if the tensor-core (tcgen05) forward takes this shape (2 hidden layers, D <= 64, H <= 256, nout <= 4,
+ * per-sample bank, no masks), else 0 with the reason in bnn_last_error(); BNN_PREC_FP32 takes every shape */
+int32_t bnn_forward_tc_supported(const BnnForwardArgs* a);
+/* tcgen05 self-test: D[128, N] = A[128, K] * B[N, K]^T (row-major device buffers, K % 8 == 0, K <= 64,
+ * N % 16 == 0, N <= 256, passes = 1 (TF32) or 3 (3xTF32)) through the kernels' own operand layout */
+int32_t bnn_tc_selftest(const float* A, const float* B, float* D, int32_t K, int32_t N, int32_t passes, void* stream);
 
 /* ---- (e) standalone reduction and metrics ------------------------------- */
 /* replaces: BNN.predict_mv's `preds.mean(dim=0), preds.var(dim=0)` (BNN.py:37)
