@@ -29,7 +29,8 @@ constexpr int kTcStageBytes = 2 * 2 * 128 * 16;  // hi + lo, 2 granule columns x
 
 struct TcParams {
   int D, H1, H2, O, act;
-  int Dp, N1, N2;          // padded: K of layer 1 (mult of 8), N of layer 1 = K of layer 2, N of layer 2 (mult of 16)
+  int Dp, N1, N2, K2;      // padded: K of layer 1 (mult of 8), N of layers 1/2 (mult of 16), K of layer 2 (mult of 8, <= N1)
+  int ring;                // A2 ring depth (2..kTcRing)
   int passes;              // 3 (tf32x3) or 1 (tf32)
   long long part_stride;   // floats per (sample, part) of the operand image
   long long img_stride;    // floats per sample of the operand image
@@ -48,7 +49,7 @@ struct TcParams {
 
 // ---- operand image builder -------------------------------------------------------------------------
 struct TcPrepParams {
-  int D, H1, H2, O, Dp, N1, N2, kpair;
+  int D, H1, H2, O, Dp, N1, N2, K2, kpair;
   int ld0, ld1, ld2;
   long long off0, off1, off2, w_stride, part_stride, img_stride;
   int vec_len;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Tc
   const float* Ws = W + s * q.w_stride;
   float* out = img + s * q.img_stride;
   const int N1h = q.N1 / q.kpair, N2h = q.N2 / q.kpair;
-  const long long b1_sz = (long long)q.Dp * N1h, b2_sz = (long long)q.N1 * N2h;
+  const long long b1_sz = (long long)q.Dp * N1h, b2_sz = (long long)q.K2 * N2h;
   const long long total = q.img_stride;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float v = 0.0f;
@@ -193,8 +194,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
   const int s0 = g * p.Sg, s1 = min(p.S, s0 + p.Sg);
   const int pt0 = slot * p.tiles_per_slot, pt1 = min(p.n_tiles, pt0 + p.tiles_per_slot);
   const int N1h = p.N1 / kPair, N2h = p.N2 / kPair;
-  const int n_k1 = p.Dp >> 3, n_k2 = p.N1 >> 3;
-  const uint32_t b1_hl_bytes = (uint32_t)p.Dp * N1h * 4, b2_hl_bytes = (uint32_t)p.N1 * N2h * 4;
+  const int n_k1 = p.Dp >> 3, n_k2 = p.K2 >> 3;
+  const uint32_t b1_hl_bytes = (uint32_t)p.Dp * N1h * 4, b2_hl_bytes = (uint32_t)p.K2 * N2h * 4;
   const uint32_t a1_hl_bytes = (uint32_t)p.Dp * 128 * 4;
   const int vec_pad = (p.vec_len + 3) & ~3;
 
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             mma_commit_all<kPair>(&bars[BAR_D1_FULL]);
             // ---- layer 2: D2 = A2 * B2^T, A2 produced K-step by K-step by epilogue-1
             for (int ks = 0; ks < n_k2; ++ks, ++ring_it) {
-              const uint32_t st = ring_it % kTcRing, rpar = (ring_it / kTcRing) & 1u;
+              const uint32_t st = ring_it % (uint32_t)p.ring, rpar = (ring_it / (uint32_t)p.ring) & 1u;
               mbar_wait(&bars[BAR_A2_FULL + st], rpar);
               if (ks == 0) mbar_wait(&bars[BAR_D2_EMPTY], tpar ^ 1u);   // epilogue-2 of the previous tile drained D2
               tc::fence_after_thread_sync();
@@ -329,12 +330,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         // ---- epilogue 1: D1 -> h1 = act(d + b1) -> hi/lo -> A2 ring, one K = 8 step per stage
         mbar_wait(&bars[BAR_D1_FULL], tpar);
         tc::fence_after_thread_sync();
-        for (int c0 = 0; c0 < p.N1; c0 += 16) {
+        for (int c0 = 0; c0 < p.K2; c0 += 16) {
           float d[16];
           tc::tmem_ld16(tmem_d1 + lane_sel + (uint32_t)c0, d);
 #pragma unroll
-          for (int half = 0; half < 2; ++half, ++ring_it) {
-            const uint32_t st = ring_it % kTcRing, rpar = (ring_it / kTcRing) & 1u;
+          for (int half = 0; half < 2; ++half) {
+            if (c0 + half * 8 >= p.K2) break;      // K2 is a multiple of 8, not necessarily of 16
+            const uint32_t st = ring_it % (uint32_t)p.ring, rpar = (ring_it / (uint32_t)p.ring) & 1u;
+            ++ring_it;
             mbar_wait(&bars[BAR_A2_EMPTY + st], rpar ^ 1u);
             const uint32_t sa = s_ring + st * kTcStageBytes + (uint32_t)row * 16u;
 #pragma unroll
@@ -494,7 +497,7 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   TcParams& p = plan->p;
   memset(&p, 0, sizeof(p));
   p.D = D; p.H1 = H1; p.H2 = H2; p.O = O; p.act = L.act;
-  p.Dp = roundup(D, 8); p.N1 = roundup(H1, 16); p.N2 = roundup(H2, 16);
+  p.Dp = roundup(D, 8); p.N1 = roundup(H1, 16); p.N2 = roundup(H2, 16); p.K2 = roundup(H1, 8);
   p.passes = a->precision == BNN_PREC_TF32 ? 1 : 3;
   p.vec_len = p.N1 + p.N2 + O * p.N2 + 4;
   const int vec_pad = (p.vec_len + 3) & ~3;
@@ -503,20 +506,22 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   for (int kp = 1; kp <= 2 && !kpair; ++kp) {
     const int N1h = p.N1 / kp, N2h = p.N2 / kp;
     if ((N1h & 7) || (N2h & 7)) continue;
-    size_t o = 0;
-    p.sm_b1 = (int)o; o += (size_t)2 * p.Dp * N1h * 4;
-    p.sm_b2 = (int)o; o += (size_t)2 * p.N1 * N2h * 4;
-    p.sm_a1 = (int)o; o += (size_t)2 * p.Dp * 128 * 4;
-    p.sm_ring = (int)o; o += (size_t)kTcRing * kTcStageBytes;
-    p.sm_vec = (int)o; o += (size_t)2 * vec_pad * 4;
-    o = (o + 15) & ~(size_t)15;
-    p.sm_bar = (int)o; o += (size_t)BAR_COUNT * 8 + 16;
-    if (o <= (size_t)227 * 1024) { kpair = kp; plan->smem = o; }
+    for (int ring = kTcRing; ring >= 2 && !kpair; --ring) {
+      size_t o = 0;
+      p.sm_b1 = (int)o; o += (size_t)2 * p.Dp * N1h * 4;
+      p.sm_b2 = (int)o; o += (size_t)2 * p.K2 * N2h * 4;
+      p.sm_a1 = (int)o; o += (size_t)2 * p.Dp * 128 * 4;
+      p.sm_ring = (int)o; o += (size_t)ring * kTcStageBytes;
+      p.sm_vec = (int)o; o += (size_t)2 * vec_pad * 4;
+      o = (o + 15) & ~(size_t)15;
+      p.sm_bar = (int)o; o += (size_t)BAR_COUNT * 8 + 16;
+      if (o <= (size_t)227 * 1024) { kpair = kp; plan->smem = o; p.ring = ring; }
+    }
   }
   if (!kpair) { set_error("tensor-core forward: weights do not fit shared memory even as a CTA pair"); return 1; }
   plan->kpair = kpair;
   const int N1h = p.N1 / kpair, N2h = p.N2 / kpair;
-  p.part_stride = 2LL * p.Dp * N1h + 2LL * p.N1 * N2h;
+  p.part_stride = 2LL * p.Dp * N1h + 2LL * p.K2 * N2h;
   p.img_stride = p.part_stride * kpair + vec_pad;
   int cols = p.N1 + p.N2, tc = 32;
   while (tc < cols) tc <<= 1;
@@ -542,7 +547,7 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   plan->img_bytes = ((long long)a->S * p.img_stride * 4 + 255) & ~255LL;
   plan->part_bytes = (long long)G * 2 * a->N * O * (long long)sizeof(double);
   TcPrepParams& q = plan->q;
-  q.D = D; q.H1 = H1; q.H2 = H2; q.O = O; q.Dp = p.Dp; q.N1 = p.N1; q.N2 = p.N2; q.kpair = kpair;
+  q.D = D; q.H1 = H1; q.H2 = H2; q.O = O; q.Dp = p.Dp; q.N1 = p.N1; q.N2 = p.N2; q.K2 = p.K2; q.kpair = kpair;
   q.ld0 = L.ld[0]; q.ld1 = L.ld[1]; q.ld2 = L.ld[2];
   q.off0 = L.off[0]; q.off1 = L.off[1]; q.off2 = L.off[2];
   q.w_stride = a->w_stride; q.part_stride = p.part_stride; q.img_stride = p.img_stride; q.vec_len = p.vec_len;
