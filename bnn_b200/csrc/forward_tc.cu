@@ -22,7 +22,7 @@
 
 namespace bnn {
 
-constexpr int kTcThreads = 160;       // 4 epilogue warps + 1 MMA/loader warp
+constexpr int kTcThreads = 288;       // WG-A (4 warps) + WG-B (4 warps) + 1 MMA/loader warp
 constexpr int kTcEpiThreads = 128;
 constexpr int kTcRing = 4;            // A2 ring stages (one K = 8 step each)
 constexpr int kTcStageBytes = 2 * 2 * 128 * 16;  // hi + lo, 2 granule columns x 128 rows x 16 B = 8 KB
@@ -112,7 +112,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       "{\n"
       ".reg .b32 ra;\n"
       "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"   // default .release.cta: a cluster-scope release costs a MEMBAR.ALL.GPU per hand-off
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
@@ -177,14 +177,25 @@ __device__ __forceinline__ void warp_signal_leader(uint64_t* bar, int lane) {
   }
 }
 
-template <int kPair>
+template <int kAct>
+__device__ __forceinline__ float act_ct(float v) {
+  if constexpr (kAct == BNN_ACT_RELU) return fmaxf(v, 0.0f);
+  else if constexpr (kAct == BNN_ACT_TANH) return tanhf(v);
+  else if constexpr (kAct == BNN_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+  else return v;
+}
+
+// Roles: warps 0-3 (WG-A) build A1 and run epilogue-1; warps 4-7 (WG-B) run epilogue-2 + the Welford update, so
+// that epilogue-2 of tile t overlaps layer 1 / epilogue-1 of tile t+1; warp 8 = MMA issuer + weight loader.
+// A warp may only touch TMEM lanes [32 * (warp % 4), +32), which is why both groups are 4 warps.
+template <int kPair, int kAct>
 __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.sm_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   const uint32_t s_b1 = smem_u32(smem + p.sm_b1), s_b2 = smem_u32(smem + p.sm_b2);
   const uint32_t s_a1 = smem_u32(smem + p.sm_a1), s_ring = smem_u32(smem + p.sm_ring);
-  const float* vecs = reinterpret_cast<const float*>(smem + p.sm_vec);  // double buffered by sample parity
+  const uint32_t s_vec = smem_u32(smem + p.sm_vec);   // double buffered by sample parity
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = kPair == 1 ? 0u : cluster_ctarank();
@@ -211,7 +222,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc_n<kPair>(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 8) tmem_alloc_n<kPair>(tmem_slot, (uint32_t)p.tmem_cols);
   tc::fence_before_thread_sync();
   __syncthreads();
   if constexpr (kPair == 2) cluster_sync_all();
@@ -219,7 +230,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + (uint32_t)p.N1;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== weight loader + MMA issuer (one lane) ==========================================
     if (lane == 0) {
       const uint32_t idesc1 = tc::make_idesc_tf32(128 * kPair, p.N1), idesc2 = tc::make_idesc_tf32(128 * kPair, p.N2);
@@ -274,8 +285,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
               mma_commit_all<kPair>(&bars[BAR_A2_EMPTY + st]);
             }
             mma_commit_all<kPair>(&bars[BAR_D2_FULL]);
-          } else {
-            ring_it += n_k2;
           }
           // every CTA's loader observes the end of the tile (keeps its phase in step; the last one per
           // sample also licenses the operand reload above)
@@ -283,21 +292,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         }
       }
     }
-  } else {
-    // ===================== epilogue / compute warps: thread = one point (TMEM lane) ===============================
+  } else if (warp < 4) {
+    // ===================== WG-A: A1 + epilogue 1; thread = one point (TMEM lane) ===============================
     const int row = warp * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
     uint32_t tile_cnt = 0, ring_it = 0;
-    const long long M = p.N * p.O;
-    double* st_mean = p.part ? p.part + (long long)g * 2 * M : nullptr;
-    double* st_m2 = p.part ? st_mean + M : nullptr;
     for (int s = s0; s < s1; ++s) {
-      const float* vec = vecs + ((s - s0) & 1) * vec_pad;
-      const float* b1 = vec;
-      const float* b2 = vec + p.N1;
-      const float* w3 = b2 + p.N2;
-      const float* b3 = w3 + p.O * p.N2;
-      const double inv_cnt = 1.0 / (double)(s - s0 + 1);
+      const uint32_t b1v = s_vec + (uint32_t)(((s - s0) & 1) * vec_pad) * 4u;
       bool w_ready = false;
       for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
         const uint32_t tpar = tile_cnt & 1u;
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             sts128(a + a1_hl_bytes, lo);
           }
         }
-        if (!w_ready) {   // biases / w3 of this sample (also: this CTA's operand images have landed)
+        if (!w_ready) {   // this CTA's operand images + biases of this sample have landed
           mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
           w_ready = true;
         }
@@ -333,6 +334,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         for (int c0 = 0; c0 < p.K2; c0 += 16) {
           float d[16];
           tc::tmem_ld16(tmem_d1 + lane_sel + (uint32_t)c0, d);
+          float bb[16];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 t = lds128(b1v + (uint32_t)(c0 + q4 * 4) * 4u);
+            bb[q4 * 4 + 0] = t.x; bb[q4 * 4 + 1] = t.y; bb[q4 * 4 + 2] = t.z; bb[q4 * 4 + 3] = t.w;
+          }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             if (c0 + half * 8 >= p.K2) break;      // K2 is a multiple of 8, not necessarily of 16
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int j = half * 8 + q4 * 4 + e;
-                h[e] = apply_act(d[j] + b1[c0 + j], p.act);
+                h[e] = act_ct<kAct>(d[j] + bb[j]);
               }
               float4 hi, lo;
               hi.x = tc::tf32_hi(h[0]); hi.y = tc::tf32_hi(h[1]); hi.z = tc::tf32_hi(h[2]); hi.w = tc::tf32_hi(h[3]);
@@ -357,7 +364,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             warp_signal_leader<kPair>(&bars[BAR_A2_FULL + st], lane);
           }
         }
-
+      }
+    }
+  } else {
+    // ===================== WG-B: epilogue 2 + predictive reduction; thread = one point ===============================
+    const int wq = warp - 4;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
+    uint32_t tile_cnt = 0;
+    const long long M = p.N * p.O;
+    double* st_mean = p.part ? p.part + (long long)g * 2 * M : nullptr;
+    double* st_m2 = p.part ? st_mean + M : nullptr;
+    for (int s = s0; s < s1; ++s) {
+      const uint32_t vb = s_vec + (uint32_t)(((s - s0) & 1) * vec_pad) * 4u;
+      const uint32_t b2v = vb + (uint32_t)p.N1 * 4u, w3v = b2v + (uint32_t)p.N2 * 4u;
+      const float* b3 = reinterpret_cast<const float*>(smem + p.sm_vec) + ((s - s0) & 1) * vec_pad + p.N1 + p.N2 + p.O * p.N2;
+      const double inv_cnt = 1.0 / (double)(s - s0 + 1);
+      mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
+      for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
+        const uint32_t tpar = tile_cnt & 1u;
+        const long long n = ((long long)pt * kPair + rank) * 128 + row;
+        const bool in_range = n < p.N;
         // ---- epilogue 2: D2 -> y[o] = b3[o] + sum_j w3[o][j] * act(d + b2[j])
         mbar_wait(&bars[BAR_D2_FULL], tpar);
         tc::fence_after_thread_sync();
@@ -365,13 +392,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         for (int c0 = 0; c0 < p.N2; c0 += 16) {
           float d[16];
           tc::tmem_ld16(tmem_d2 + lane_sel + (uint32_t)c0, d);
+          float t[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float t = apply_act(d[j] + b2[c0 + j], p.act);
-            y[0] = fmaf(w3[c0 + j], t, y[0]);
-            if (p.O > 1) y[1] = fmaf(w3[p.N2 + c0 + j], t, y[1]);
-            if (p.O > 2) y[2] = fmaf(w3[2 * p.N2 + c0 + j], t, y[2]);
-            if (p.O > 3) y[3] = fmaf(w3[3 * p.N2 + c0 + j], t, y[3]);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 bq = lds128(b2v + (uint32_t)(c0 + q4 * 4) * 4u);
+            t[q4 * 4 + 0] = act_ct<kAct>(d[q4 * 4 + 0] + bq.x);
+            t[q4 * 4 + 1] = act_ct<kAct>(d[q4 * 4 + 1] + bq.y);
+            t[q4 * 4 + 2] = act_ct<kAct>(d[q4 * 4 + 2] + bq.z);
+            t[q4 * 4 + 3] = act_ct<kAct>(d[q4 * 4 + 3] + bq.w);
+          }
+          for (int o = 0; o < p.O; ++o) {
+            float acc = y[o];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 wq4 = lds128(w3v + (uint32_t)(o * p.N2 + c0 + q4 * 4) * 4u);
+              acc = fmaf(wq4.x, t[q4 * 4 + 0], acc);
+              acc = fmaf(wq4.y, t[q4 * 4 + 1], acc);
+              acc = fmaf(wq4.z, t[q4 * 4 + 2], acc);
+              acc = fmaf(wq4.w, t[q4 * 4 + 3], acc);
+            }
+            y[o] = acc;
           }
         }
         // D2 is drained: let the next tile's layer-2 MMAs overwrite it
@@ -404,7 +444,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
   tc::fence_before_thread_sync();
   __syncthreads();
   if constexpr (kPair == 2) cluster_sync_all();
-  if (warp == 4) tmem_dealloc_n<kPair>(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == 8) tmem_dealloc_n<kPair>(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ---- self-test GEMM: D[128, N] = A[128, K] * B[N, K]^T through the same descriptors / split -----------------
@@ -598,13 +638,22 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (plan.kpair == 1) {
-    BNN_CUDA(cudaFuncSetAttribute(fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    BNN_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc_kernel<1>, p));
-  } else {
-    BNN_CUDA(cudaFuncSetAttribute(fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    BNN_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc_kernel<2>, p));
+  auto launch = [&](auto kern) -> int {
+    BNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    BNN_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    return 0;
+  };
+  int lrc = 0;
+#define BNN_TC_LAUNCH(ACT)                                                         \
+  case ACT: lrc = plan.kpair == 1 ? launch(fwd_tc_kernel<1, ACT>) : launch(fwd_tc_kernel<2, ACT>); break;
+  switch (p.act) {
+    BNN_TC_LAUNCH(BNN_ACT_RELU)
+    BNN_TC_LAUNCH(BNN_ACT_TANH)
+    BNN_TC_LAUNCH(BNN_ACT_SIGMOID)
+    default: lrc = plan.kpair == 1 ? launch(fwd_tc_kernel<1, BNN_ACT_IDENTITY>) : launch(fwd_tc_kernel<2, BNN_ACT_IDENTITY>); break;
   }
+#undef BNN_TC_LAUNCH
+  if (lrc) return lrc;
   BNN_CUDA(cudaGetLastError());
   if (want_moments)
     return finalize_moments(p.part, nullptr, p.G, p.Sg, a->S, a->N * p.O, a->mean, a->var, a->part_mean, a->part_m2, st);
