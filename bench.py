@@ -175,7 +175,8 @@ def run_ours(args):
     bank_host = bank.cpu().pin_memory()
 
     def step_device():
-        out = ops.forward(arch, X, bank, want_pred=False, want_moments=(world == 1), want_partials=(world > 1))
+        out = ops.forward(arch, X, bank, want_pred=False, want_moments=(world == 1), want_partials=(world > 1),
+                          precision=args.precision)
         if world > 1:
             return merge_shards(out["part_mean"], out["part_m2"], S)
         return out["mean"], out["var"]
@@ -183,7 +184,8 @@ def run_ours(args):
     def step_e2e():
         Xd = X_host.to(dev, non_blocking=True)
         Wd = bank_host.to(dev, non_blocking=True)
-        out = ops.forward(arch, Xd, Wd, want_pred=False, want_moments=(world == 1), want_partials=(world > 1))
+        out = ops.forward(arch, Xd, Wd, want_pred=False, want_moments=(world == 1), want_partials=(world > 1),
+                          precision=args.precision)
         mean, var = merge_shards(out["part_mean"], out["part_m2"], S) if world > 1 else (out["mean"], out["var"])
         return mean.cpu(), var.cpu()
 
@@ -232,24 +234,40 @@ def run_ours(args):
         per_gpu_tflops = FLOP_PER_EVAL * float(S) * N_POINTS * args.steps / (ms * 1e-3) / 1e12
         cpu_val, cpu_t = time_cpu_sample(16, 250_000)
         cores = os.cpu_count() or 1
+        tc = args.precision in ("tf32x3", "tf32")
+        passes = 3 if args.precision == "tf32x3" else 1
+        if tc:
+            # bf16-equivalent tensor work actually executed: `passes` TF32 MMAs per algorithmic MAC, TF32 = half the bf16 rate
+            roof = {"bound": "tensor", "achieved": per_gpu_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
+                    "frac": per_gpu_tflops / bf16_peak, "traffic": None,
+                    "kernel": "fwd_tc_kernel<2,relu> (tcgen05 kind::tf32, cta_group::2)", "flop_per_eval": FLOP_PER_EVAL,
+                    "peak_source": peak_src + "; dense bf16",
+                    "note": f"achieved = ALGORITHMIC flop/s (2*sum in*out per eval).  {args.precision} issues {passes} TF32 MMA pass(es) per "
+                            f"algorithmic MAC and TF32 runs at half the bf16 rate, so frac is capped at {1.0 / (2 * passes):.3f}; "
+                            "tensor_pipe_frac below is the share of the bf16-equivalent peak the issued MMAs occupy",
+                    "tensor_pipe_frac": 2 * passes * per_gpu_tflops / bf16_peak}
+        else:
+            roof = {"bound": "fp32", "achieved": per_gpu_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": per_gpu_tflops / fp32_peak if fp32_peak > 0 else None, "traffic": None,
+                    "kernel": "fwd_simt_kernel<8>", "flop_per_eval": FLOP_PER_EVAL,
+                    "peak_source": "FP32 FFMA microbenchmark measured live (bnn_measure_fp32_tflops); "
+                                   "MEASURED_PEAKS.json has no FP32-SIMT figure",
+                    "frac_of_bf16_tensor_peak": per_gpu_tflops / bf16_peak, "bf16_peak": bf16_peak}
+        launches_per_step = (3 if tc else 2) + (1 if world > 1 else 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(n_gpus), "precision": "fp32-simt",
+            "vs_baseline": None, "dtype": {"tf32x3": "tf32x3 (3-pass error-compensated TF32, FP32 accumulate; parity 1e-5)",
+                                           "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "config": {"workload": workload_name(n_gpus), "precision": args.precision,
                        "l2": f"inputs {(bank.numel() + X.numel()) * 4 / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)",
                        "parallelism": f"samples sharded x{n_gpus}, all-gather of float64 (mean, M2) + Chan merge"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((bank.numel() + X.numel()) * 4),
                     "d2h_bytes_per_step": int(2 * N_POINTS * DIMS[-1] * 4), "ms_per_step": ms_e2e / e2e_steps,
                     "steps": e2e_steps, "api": "bnn_b200.ops.forward on pinned host tensors (H2D + launch + D2H per step)"},
-            "gpu_launches": args.steps * (3 if world > 1 else 2),
-            "roofline": {"bound": "fp32", "achieved": per_gpu_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": per_gpu_tflops / fp32_peak if fp32_peak > 0 else None, "traffic": None,
-                         "kernel": "fwd_simt_kernel<8>", "flop_per_eval": FLOP_PER_EVAL,
-                         "peak_source": "FP32 FFMA microbenchmark measured live (bnn_measure_fp32_tflops); "
-                                        "MEASURED_PEAKS.json has no FP32-SIMT figure",
-                         "frac_of_bf16_tensor_peak": per_gpu_tflops / bf16_peak, "bf16_peak": bf16_peak,
-                         "bf16_peak_source": peak_src},
+            "gpu_launches": args.steps * launches_per_step,
+            "roofline": roof,
+            "fp32_ffma_peak_tflops": fp32_peak,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"S=16 samples x N=250000 points of the same workload, torch CPU loop, "
                                        f"{cores} threads, {cpu_t:.1f} s"},
@@ -266,6 +284,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "fp32", "tf32"],
+                    help="tf32x3: tcgen05 3-pass error-compensated (FP32-grade, default); fp32: SIMT FFMA; tf32: single pass (looser)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -48,6 +48,7 @@ PROTOTYPES = {
     "bnn_forward_workspace_bytes": (C.c_int64, [C.POINTER(ForwardArgs)]),
     "bnn_forward": (C.c_int32, [C.POINTER(ForwardArgs), C.c_void_p]),
     "bnn_forward_tc_supported": (C.c_int32, [C.POINTER(ForwardArgs)]),
+    "bnn_tc_trace_dump": (C.c_int32, [C.c_void_p]),
     "bnn_tc_selftest": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bnn_moments": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int64, C.c_void_p]),

@@ -16,21 +16,24 @@
 //                D2[TMEM] -> epilogue-2 (bias, activation, dot with w3) -> y -> FP64 Welford update of the
 //                per-point state (global, owned by this CTA; finalised by finalize_moments()).
 // Roles: warps 0-3 = epilogue/compute (TMEM lane quarter = warp id), warp 4 = MMA issuer + weight loader.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 #include "tc_common.cuh"
 
 namespace bnn {
 
-constexpr int kTcThreads = 288;       // WG-A (4 warps) + WG-B (4 warps) + 1 MMA/loader warp
+constexpr int kTcThreads = 416;       // WG-A (8 warps) + WG-B (4 warps) + 1 MMA/loader warp
+constexpr int kTcMmaWarp = 12;
 constexpr int kTcEpiThreads = 128;
-constexpr int kTcRing = 4;            // A2 ring stages (one K = 8 step each)
+constexpr int kTcRing = 8;            // max A2 ring stages (one K = 8 step each)
 constexpr int kTcStageBytes = 2 * 2 * 128 * 16;  // hi + lo, 2 granule columns x 128 rows x 16 B = 8 KB
 
 struct TcParams {
   int D, H1, H2, O, act;
   int Dp, N1, N2, K2;      // padded: K of layer 1 (mult of 8), N of layers 1/2 (mult of 16), K of layer 2 (mult of 8, <= N1)
-  int ring;                // A2 ring depth (2..kTcRing)
+  int ring;                // A2 ring depth (3..kTcRing)
   int passes;              // 3 (tf32x3) or 1 (tf32)
   long long part_stride;   // floats per (sample, part) of the operand image
   long long img_stride;    // floats per sample of the operand image
@@ -43,6 +46,7 @@ struct TcParams {
   float* pred;
   double* part;            // [G][2][M]  Welford state = shard moments
   int tmem_cols;
+  unsigned long long* trace;   // debug timeline (BNN_TC_TRACE), null in production
   // shared memory offsets (bytes)
   int sm_b1, sm_b2, sm_vec, sm_a1, sm_ring, sm_bar;
 };
@@ -160,6 +164,15 @@ __device__ __forceinline__ void tmem_dealloc_n(uint32_t addr, uint32_t ncols) {
   else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
 
+// debug timeline: CTA (0,0) only; each traced warp owns 4096 (tag, clock) slots
+__device__ __forceinline__ void trace_ev(unsigned long long* tr, int who, uint32_t& n, uint32_t tag, uint32_t it) {
+  if (tr && n < 4096) {
+    tr[((size_t)who * 4096 + n) * 2] = ((unsigned long long)tag << 32) | it;
+    tr[((size_t)who * 4096 + n) * 2 + 1] = (unsigned long long)clock64();
+    ++n;
+  }
+}
+
 // barrier slots in shared memory
 enum { BAR_W_FULL = 0, BAR_A1_FULL, BAR_D1_FULL, BAR_D2_FULL, BAR_D2_EMPTY, BAR_A2_FULL, BAR_A2_EMPTY = BAR_A2_FULL + kTcRing,
        BAR_COUNT = BAR_A2_EMPTY + kTcRing };
@@ -185,9 +198,10 @@ __device__ __forceinline__ float act_ct(float v) {
   else return v;
 }
 
-// Roles: warps 0-3 (WG-A) build A1 and run epilogue-1; warps 4-7 (WG-B) run epilogue-2 + the Welford update, so
-// that epilogue-2 of tile t overlaps layer 1 / epilogue-1 of tile t+1; warp 8 = MMA issuer + weight loader.
-// A warp may only touch TMEM lanes [32 * (warp % 4), +32), which is why both groups are 4 warps.
+// Roles: warps 0-7 (WG-A) run epilogue-1, two warps per TMEM lane quarter taking alternate 16-column batches
+// (warps 0-3 also build A1); warps 8-11 (WG-B) run epilogue-2 + the Welford update, so that epilogue-2 of tile t
+// overlaps layer 1 / epilogue-1 of tile t+1; warp 12 = MMA issuer + weight loader.
+// A warp may only touch TMEM lanes [32 * (warp % 4), +32).
 template <int kPair, int kAct>
 __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -222,7 +236,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc_n<kPair>(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == kTcMmaWarp) tmem_alloc_n<kPair>(tmem_slot, (uint32_t)p.tmem_cols);
   tc::fence_before_thread_sync();
   __syncthreads();
   if constexpr (kPair == 2) cluster_sync_all();
@@ -230,145 +244,239 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + (uint32_t)p.N1;
 
-  if (warp == 8) {
-    // ===================== weight loader + MMA issuer (one lane) ==========================================
-    if (lane == 0) {
-      const uint32_t idesc1 = tc::make_idesc_tf32(128 * kPair, p.N1), idesc2 = tc::make_idesc_tf32(128 * kPair, p.N2);
-      uint32_t tile_cnt = 0, ring_it = 0;
-      for (int s = s0; s < s1; ++s) {
-        // previous sample's MMAs have all completed (its last d2_full was observed below): reload the operands
-        {
-          const float* src = p.img + (long long)s * p.img_stride + (long long)rank * p.part_stride;
-          const uint32_t b1_bytes = p.passes == 3 ? 2 * b1_hl_bytes : b1_hl_bytes;
-          const uint32_t b2_bytes = p.passes == 3 ? 2 * b2_hl_bytes : b2_hl_bytes;
-          mbar_arrive_expect_tx(&bars[BAR_W_FULL], b1_bytes + b2_bytes + (uint32_t)vec_pad * 4);
-          bulk_g2s(smem + p.sm_b1, src, b1_bytes, &bars[BAR_W_FULL]);
-          bulk_g2s(smem + p.sm_b2, src + 2 * (long long)(b1_hl_bytes / 4), b2_bytes, &bars[BAR_W_FULL]);
-          bulk_g2s(smem + p.sm_vec + ((s - s0) & 1) * vec_pad * 4, p.img + (long long)s * p.img_stride + p.part_stride * kPair,
-                   (uint32_t)vec_pad * 4, &bars[BAR_W_FULL]);
-        }
-        if (leader) mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
-        for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
-          const uint32_t tpar = tile_cnt & 1u;
-          if (leader) {
-            // ---- layer 1: D1 = A1 * B1^T
-            mbar_wait(&bars[BAR_A1_FULL], tpar);
-            tc::fence_after_thread_sync();
-            for (int ks = 0; ks < n_k1; ++ks) {
-              const uint64_t a_hi = tc::make_smem_desc(s_a1 + (uint32_t)(2 * ks) * 2048u, 2048u, 128u);
-              const uint64_t a_lo = tc::make_smem_desc(s_a1 + a1_hl_bytes + (uint32_t)(2 * ks) * 2048u, 2048u, 128u);
-              const uint64_t b_hi = tc::make_smem_desc(s_b1 + (uint32_t)(2 * ks) * (uint32_t)N1h * 16u, (uint32_t)N1h * 16u, 128u);
-              const uint64_t b_lo = tc::make_smem_desc(s_b1 + b1_hl_bytes + (uint32_t)(2 * ks) * (uint32_t)N1h * 16u, (uint32_t)N1h * 16u, 128u);
-              mma_tf32<kPair>(tmem_d1, a_hi, b_hi, idesc1, ks > 0);
-              if (p.passes == 3) {
-                mma_tf32<kPair>(tmem_d1, a_lo, b_hi, idesc1, 1);
-                mma_tf32<kPair>(tmem_d1, a_hi, b_lo, idesc1, 1);
-              }
-            }
-            mma_commit_all<kPair>(&bars[BAR_D1_FULL]);
-            // ---- layer 2: D2 = A2 * B2^T, A2 produced K-step by K-step by epilogue-1
-            for (int ks = 0; ks < n_k2; ++ks, ++ring_it) {
-              const uint32_t st = ring_it % (uint32_t)p.ring, rpar = (ring_it / (uint32_t)p.ring) & 1u;
-              mbar_wait(&bars[BAR_A2_FULL + st], rpar);
-              if (ks == 0) mbar_wait(&bars[BAR_D2_EMPTY], tpar ^ 1u);   // epilogue-2 of the previous tile drained D2
-              tc::fence_after_thread_sync();
-              const uint32_t sa = s_ring + st * kTcStageBytes;
-              const uint64_t a_hi = tc::make_smem_desc(sa, 2048u, 128u);
-              const uint64_t a_lo = tc::make_smem_desc(sa + kTcStageBytes / 2, 2048u, 128u);
-              const uint64_t b_hi = tc::make_smem_desc(s_b2 + (uint32_t)(2 * ks) * (uint32_t)N2h * 16u, (uint32_t)N2h * 16u, 128u);
-              const uint64_t b_lo = tc::make_smem_desc(s_b2 + b2_hl_bytes + (uint32_t)(2 * ks) * (uint32_t)N2h * 16u, (uint32_t)N2h * 16u, 128u);
-              mma_tf32<kPair>(tmem_d2, a_hi, b_hi, idesc2, ks > 0);
-              if (p.passes == 3) {
-                mma_tf32<kPair>(tmem_d2, a_lo, b_hi, idesc2, 1);
-                mma_tf32<kPair>(tmem_d2, a_hi, b_lo, idesc2, 1);
-              }
-              mma_commit_all<kPair>(&bars[BAR_A2_EMPTY + st]);
-            }
-            mma_commit_all<kPair>(&bars[BAR_D2_FULL]);
-          }
-          // every CTA's loader observes the end of the tile (keeps its phase in step; the last one per
-          // sample also licenses the operand reload above)
-          mbar_wait(&bars[BAR_D2_FULL], tpar);
-        }
-      }
-    }
-  } else if (warp < 4) {
-    // ===================== WG-A: A1 + epilogue 1; thread = one point (TMEM lane) ===============================
-    const int row = warp * 32 + lane;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    uint32_t tile_cnt = 0, ring_it = 0;
+  if (warp == kTcMmaWarp) {
+    // ===================== weight loader + MMA issuer =========================================================
+    // The whole warp runs this loop CONVERGED with warp-uniform variables; only the tcgen05 / bulk-copy issue is
+    // done by one elected lane.  (Running the loop inside `if (lane == 0)` makes ptxas treat it as divergent code
+    // and wrap every uniform-datapath instruction -- UTCHMMA, UTCBAR -- in an ELECT/BRA.U.ANY loop with R2UR
+    // transfers: ~90 instructions and ~700 cycles per K-step, which starved the tensor pipe.)
+    const uint32_t idesc1 = tc::make_idesc_tf32(128 * kPair, p.N1), idesc2 = tc::make_idesc_tf32(128 * kPair, p.N2);
+    uint32_t tile_cnt = 0, ring_it = 0, tn = 0, ring_st = 0, ring_par = 0;
+    unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? p.trace : nullptr;
+    const uint64_t a1_desc0 = tc::make_smem_desc(s_a1, 2048u, 128u);
+    const uint64_t b1_desc0 = tc::make_smem_desc(s_b1, (uint32_t)N1h * 16u, 128u);
+    const uint64_t a2_desc0 = tc::make_smem_desc(s_ring, 2048u, 128u);
+    const uint64_t b2_desc0 = tc::make_smem_desc(s_b2, (uint32_t)N2h * 16u, 128u);
+    const uint64_t b1_step = (uint64_t)(2 * N1h), b2_step = (uint64_t)(2 * N2h);   // 16-byte units per K = 8 step
+    const uint64_t a1_step = (uint64_t)(2 * 128);
+    const bool three = p.passes == 3;
+    trace_ev(tr, 0, tn, 20, 0);
     for (int s = s0; s < s1; ++s) {
-      const uint32_t b1v = s_vec + (uint32_t)(((s - s0) & 1) * vec_pad) * 4u;
-      bool w_ready = false;
+      // previous sample's MMAs have all completed (its last d2_full was observed below): reload the operands
+      if (tc::elect_one()) {
+        const float* src = p.img + (long long)s * p.img_stride + (long long)rank * p.part_stride;
+        const uint32_t b1_bytes = three ? 2 * b1_hl_bytes : b1_hl_bytes;
+        const uint32_t b2_bytes = three ? 2 * b2_hl_bytes : b2_hl_bytes;
+        mbar_arrive_expect_tx(&bars[BAR_W_FULL], b1_bytes + b2_bytes + (uint32_t)vec_pad * 4);
+        bulk_g2s(smem + p.sm_b1, src, b1_bytes, &bars[BAR_W_FULL]);
+        bulk_g2s(smem + p.sm_b2, src + 2 * (long long)(b1_hl_bytes / 4), b2_bytes, &bars[BAR_W_FULL]);
+        bulk_g2s(smem + p.sm_vec + ((s - s0) & 1) * vec_pad * 4, p.img + (long long)s * p.img_stride + p.part_stride * kPair,
+                 (uint32_t)vec_pad * 4, &bars[BAR_W_FULL]);
+      }
+      __syncwarp();
+      if (leader) mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
       for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
         const uint32_t tpar = tile_cnt & 1u;
-        const long long n = ((long long)pt * kPair + rank) * 128 + row;
-        const bool in_range = n < p.N;
-        // ---- A1: this point's input row, hi/lo split, as K-major granules
-        {
-          const float* xr = p.X + n * p.D;
-          for (int kc = 0; kc < (p.Dp >> 2); ++kc) {
-            float x[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int k = kc * 4 + e;
-              x[e] = (in_range && k < p.D) ? __ldg(xr + k) : 0.0f;
+        if (leader) {
+          // ---- layer 1: D1 = A1 * B1^T
+          mbar_wait(&bars[BAR_A1_FULL], tpar);
+          tc::fence_after_thread_sync();
+          if (tc::elect_one()) {
+            uint64_t a_hi = a1_desc0, b_hi = b1_desc0;
+            const uint64_t a_lo_off = (uint64_t)(a1_hl_bytes >> 4), b_lo_off = (uint64_t)(b1_hl_bytes >> 4);
+            for (int ks = 0; ks < n_k1; ++ks) {
+              mma_tf32<kPair>(tmem_d1, a_hi, b_hi, idesc1, ks > 0);
+              if (three) {
+                mma_tf32<kPair>(tmem_d1, a_hi + a_lo_off, b_hi, idesc1, 1);
+                mma_tf32<kPair>(tmem_d1, a_hi, b_hi + b_lo_off, idesc1, 1);
+              }
+              a_hi += a1_step;
+              b_hi += b1_step;
             }
-            float4 hi, lo;
-            hi.x = tc::tf32_hi(x[0]); hi.y = tc::tf32_hi(x[1]); hi.z = tc::tf32_hi(x[2]); hi.w = tc::tf32_hi(x[3]);
-            lo.x = x[0] - hi.x; lo.y = x[1] - hi.y; lo.z = x[2] - hi.z; lo.w = x[3] - hi.w;
-            const uint32_t a = s_a1 + (uint32_t)(kc * 128 + row) * 16u;
-            sts128(a, hi);
-            sts128(a + a1_hl_bytes, lo);
+            mma_commit_all<kPair>(&bars[BAR_D1_FULL]);
           }
+          __syncwarp();
+          // ---- layer 2: D2 = A2 * B2^T, A2 produced K-step by K-step by epilogue-1.  Software pipelined: the
+          //      (100+ cycle) barrier probe for stage k+1 runs while the tensor pipe executes the MMAs of stage k;
+          //      the commit of stage k is issued after it (it still only covers MMAs <= k).
+          uint64_t b_hi = b2_desc0;
+          const uint64_t b_lo_off = (uint64_t)(b2_hl_bytes >> 4);
+          mbar_wait(&bars[BAR_A2_FULL + ring_st], ring_par);
+          mbar_wait(&bars[BAR_D2_EMPTY], tpar ^ 1u);   // epilogue-2 of the previous tile drained D2
+          tc::fence_after_thread_sync();
+          for (int ks = 0; ks < n_k2; ++ks, ++ring_it) {
+            trace_ev(tr, 0, tn, 2, ring_it);
+            const uint32_t cur_st = ring_st;
+            const uint64_t a_hi = a2_desc0 + (uint64_t)(cur_st * (kTcStageBytes >> 4));
+            if (tc::elect_one()) {
+              mma_tf32<kPair>(tmem_d2, a_hi, b_hi, idesc2, ks > 0);
+              if (three) {
+                mma_tf32<kPair>(tmem_d2, a_hi + (uint64_t)(kTcStageBytes >> 5), b_hi, idesc2, 1);
+                mma_tf32<kPair>(tmem_d2, a_hi, b_hi + b_lo_off, idesc2, 1);
+              }
+            }
+            __syncwarp();
+            b_hi += b2_step;
+            if (++ring_st == (uint32_t)p.ring) { ring_st = 0; ring_par ^= 1u; }
+            if (ks + 1 < n_k2) {
+              trace_ev(tr, 0, tn, 1, ring_it + 1);
+              mbar_wait(&bars[BAR_A2_FULL + ring_st], ring_par);
+              tc::fence_after_thread_sync();
+            }
+            if (tc::elect_one()) mma_commit_all<kPair>(&bars[BAR_A2_EMPTY + cur_st]);
+            __syncwarp();
+            trace_ev(tr, 0, tn, 3, ring_it);
+          }
+          if (tc::elect_one()) mma_commit_all<kPair>(&bars[BAR_D2_FULL]);
+          __syncwarp();
         }
-        if (!w_ready) {   // this CTA's operand images + biases of this sample have landed
-          mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
-          w_ready = true;
+        // every CTA's loader observes the end of the tile (keeps its phase in step; the last one per
+        // sample also licenses the operand reload above)
+        mbar_wait(&bars[BAR_D2_FULL], tpar);
+        trace_ev(tr, 0, tn, 21, tile_cnt);
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== WG-A: A1 + epilogue 1; thread = one point (TMEM lane) ===============================
+    const int quarter = warp & 3, set = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+    uint32_t tile_cnt = 0, tn = 0;
+    // ring position of this warp's next K-step (K-step index it -> stage it % ring, phase (it / ring) & 1), kept
+    // incrementally: the two sets leapfrog each other in 16-column batches
+    uint32_t my_st = 0, my_par = 0;
+    auto ring_advance = [&](uint32_t k) {
+      my_st += k;
+      while (my_st >= (uint32_t)p.ring) { my_st -= (uint32_t)p.ring; my_par ^= 1u; }
+    };
+    unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quarter == 0) ? p.trace : nullptr;
+    const int who = 1 + set;
+    // A1 granule kc of point n: hi/lo split of X[n][4kc .. 4kc+3] (zero beyond D / N)
+    auto store_a1 = [&](int kc, const float (&x)[4]) {
+      float4 hi, lo;
+      hi.x = tc::tf32_hi(x[0]); hi.y = tc::tf32_hi(x[1]); hi.z = tc::tf32_hi(x[2]); hi.w = tc::tf32_hi(x[3]);
+      lo.x = x[0] - hi.x; lo.y = x[1] - hi.y; lo.z = x[2] - hi.z; lo.w = x[3] - hi.w;
+      const uint32_t a = s_a1 + (uint32_t)(kc * 128 + row) * 16u;
+      sts128(a, hi);
+      sts128(a + a1_hl_bytes, lo);
+    };
+    auto load_x = [&](long long n, int kc, float (&x)[4]) {
+      const float* xr = p.X + n * p.D;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = kc * 4 + e;
+        x[e] = (n < p.N && k < p.D) ? __ldg(xr + k) : 0.0f;
+      }
+    };
+    constexpr int kPre = 4;   // granules of the next tile's input row prefetched into registers (D <= 16 fully)
+    const int n_kc = p.Dp >> 2;
+    for (int s = s0; s < s1; ++s) {
+      const uint32_t b1v = s_vec + (uint32_t)(((s - s0) & 1) * vec_pad) * 4u;
+      for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
+        const uint32_t tpar = tile_cnt & 1u;
+        const uint32_t it_base = tile_cnt * (uint32_t)n_k2;
+        float xn[kPre][4];
+        const bool have_next = (pt + 1 < pt1);
+        const long long n_next = ((long long)(pt + 1) * kPair + rank) * 128 + row;
+        if (set == 0) {
+          if (pt == pt0) {
+            // first tile of a sample: build A1 on the critical path; the operands of this sample must have
+            // landed in THIS CTA before the leader may use them, so wait for them before signalling
+            const long long n = ((long long)pt * kPair + rank) * 128 + row;
+            for (int kc = 0; kc < n_kc; ++kc) {
+              float x[4];
+              load_x(n, kc, x);
+              store_a1(kc, x);
+            }
+            mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
+            warp_signal_leader<kPair>(&bars[BAR_A1_FULL], lane);
+          }
+          if (have_next) {
+#pragma unroll
+            for (int kc = 0; kc < kPre; ++kc)
+              if (kc < n_kc) load_x(n_next, kc, xn[kc]);
+          }
+        } else if (pt == pt0) {
+          mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);   // b1 of this sample
         }
-        warp_signal_leader<kPair>(&bars[BAR_A1_FULL], lane);
 
-        // ---- epilogue 1: D1 -> h1 = act(d + b1) -> hi/lo -> A2 ring, one K = 8 step per stage
         mbar_wait(&bars[BAR_D1_FULL], tpar);
         tc::fence_after_thread_sync();
-        for (int c0 = 0; c0 < p.K2; c0 += 16) {
+        // MMA1 of this tile has consumed A1: build the next tile's A1 now, so that MMA1(t+1) can run right behind
+        // MMA2(t) (by then epilogue-1 of this tile has finished reading D1)
+        if (set == 0 && have_next) {
+#pragma unroll
+          for (int kc = 0; kc < kPre; ++kc)
+            if (kc < n_kc) store_a1(kc, xn[kc]);
+          for (int kc = kPre; kc < n_kc; ++kc) {
+            float x[4];
+            load_x(n_next, kc, x);
+            store_a1(kc, x);
+          }
+          warp_signal_leader<kPair>(&bars[BAR_A1_FULL], lane);
+        }
+
+        // ---- epilogue 1: D1 -> h1 = act(d + b1) -> hi/lo -> A2 ring, one K = 8 step per stage; this warp takes
+        //      the 16-column batches whose index parity equals `set`
+        // K-steps of this tile before this warp's first batch belong to the other set
+        {
+          const int first = set * 2 < n_k2 ? set * 2 : n_k2;
+          ring_advance((uint32_t)first);
+        }
+        int ks_done = set * 2 < n_k2 ? set * 2 : n_k2;   // K-steps of this tile accounted for in (my_st, my_par)
+        for (int c0 = set * 16; c0 < p.K2; c0 += 32) {
           float d[16];
+          trace_ev(tr, who, tn, 10, it_base + (uint32_t)(c0 >> 3));
           tc::tmem_ld16(tmem_d1 + lane_sel + (uint32_t)c0, d);
+          trace_ev(tr, who, tn, 11, it_base + (uint32_t)(c0 >> 3));
           float bb[16];
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             const float4 t = lds128(b1v + (uint32_t)(c0 + q4 * 4) * 4u);
             bb[q4 * 4 + 0] = t.x; bb[q4 * 4 + 1] = t.y; bb[q4 * 4 + 2] = t.z; bb[q4 * 4 + 3] = t.w;
           }
+          // hi/lo of all 16 activations first, so that after a stage frees up only stores + the hand-off remain
+          float4 hi4[4], lo4[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = act_ct<kAct>(d[q4 * 4 + e] + bb[q4 * 4 + e]);
+            hi4[q4] = make_float4(tc::tf32_hi(h[0]), tc::tf32_hi(h[1]), tc::tf32_hi(h[2]), tc::tf32_hi(h[3]));
+            lo4[q4] = make_float4(h[0] - hi4[q4].x, h[1] - hi4[q4].y, h[2] - hi4[q4].z, h[3] - hi4[q4].w);
+          }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             if (c0 + half * 8 >= p.K2) break;      // K2 is a multiple of 8, not necessarily of 16
-            const uint32_t st = ring_it % (uint32_t)p.ring, rpar = (ring_it / (uint32_t)p.ring) & 1u;
-            ++ring_it;
+            const uint32_t it = it_base + (uint32_t)(c0 >> 3) + (uint32_t)half;
+            const uint32_t st = my_st, rpar = my_par;
+            trace_ev(tr, who, tn, 12, it);
             mbar_wait(&bars[BAR_A2_EMPTY + st], rpar ^ 1u);
+            trace_ev(tr, who, tn, 13, it);
             const uint32_t sa = s_ring + st * kTcStageBytes + (uint32_t)row * 16u;
 #pragma unroll
             for (int q4 = 0; q4 < 2; ++q4) {
-              float h[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = half * 8 + q4 * 4 + e;
-                h[e] = act_ct<kAct>(d[j] + bb[j]);
-              }
-              float4 hi, lo;
-              hi.x = tc::tf32_hi(h[0]); hi.y = tc::tf32_hi(h[1]); hi.z = tc::tf32_hi(h[2]); hi.w = tc::tf32_hi(h[3]);
-              lo.x = h[0] - hi.x; lo.y = h[1] - hi.y; lo.z = h[2] - hi.z; lo.w = h[3] - hi.w;
-              sts128(sa + (uint32_t)q4 * 2048u, hi);
-              sts128(sa + kTcStageBytes / 2 + (uint32_t)q4 * 2048u, lo);
+              sts128(sa + (uint32_t)q4 * 2048u, hi4[half * 2 + q4]);
+              sts128(sa + kTcStageBytes / 2 + (uint32_t)q4 * 2048u, lo4[half * 2 + q4]);
             }
             warp_signal_leader<kPair>(&bars[BAR_A2_FULL + st], lane);
+            trace_ev(tr, who, tn, 14, it);
+            ring_advance(1);
+            ++ks_done;
+          }
+          // skip the other set's batch (up to 2 K-steps), staying inside this tile
+          {
+            const int skip = n_k2 - ks_done < 2 ? n_k2 - ks_done : 2;
+            ring_advance((uint32_t)skip);
+            ks_done += skip;
           }
         }
+        if (ks_done < n_k2) ring_advance((uint32_t)(n_k2 - ks_done));   // (only when this warp had no batch at all)
       }
     }
   } else {
     // ===================== WG-B: epilogue 2 + predictive reduction; thread = one point ===============================
-    const int wq = warp - 4;
+    const int wq = warp - 8;
     const int row = wq * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
     uint32_t tile_cnt = 0;
@@ -385,6 +493,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         const uint32_t tpar = tile_cnt & 1u;
         const long long n = ((long long)pt * kPair + rank) * 128 + row;
         const bool in_range = n < p.N;
+        // this point's Welford state, fetched before the wait so that its latency hides behind the MMAs
+        double mu0[4] = {0.0, 0.0, 0.0, 0.0}, q0[4] = {0.0, 0.0, 0.0, 0.0};
+        if (in_range && st_mean && s != s0) {
+          for (int o = 0; o < p.O; ++o) {
+            mu0[o] = st_mean[n * p.O + o];
+            q0[o] = st_m2[n * p.O + o];
+          }
+        }
         // ---- epilogue 2: D2 -> y[o] = b3[o] + sum_j w3[o][j] * act(d + b2[j])
         mbar_wait(&bars[BAR_D2_FULL], tpar);
         tc::fence_after_thread_sync();
@@ -427,12 +543,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             const long long m = n * p.O + o;
             if (p.pred) p.pred[((long long)s * p.N + n) * p.O + o] = y[o];
             if (st_mean) {
-              const double mu0 = s == s0 ? 0.0 : st_mean[m];
-              const double q0 = s == s0 ? 0.0 : st_m2[m];
-              const double dlt = (double)y[o] - mu0;
-              const double mu = mu0 + dlt * inv_cnt;
+              const double dlt = (double)y[o] - mu0[o];
+              const double mu = mu0[o] + dlt * inv_cnt;
               st_mean[m] = mu;
-              st_m2[m] = q0 + dlt * ((double)y[o] - mu);
+              st_m2[m] = q0[o] + dlt * ((double)y[o] - mu);
             }
           }
         }
@@ -444,7 +558,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
   tc::fence_before_thread_sync();
   __syncthreads();
   if constexpr (kPair == 2) cluster_sync_all();
-  if (warp == 8) tmem_dealloc_n<kPair>(tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == kTcMmaWarp) tmem_dealloc_n<kPair>(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ---- self-test GEMM: D[128, N] = A[128, K] * B[N, K]^T through the same descriptors / split -----------------
@@ -546,7 +660,9 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   for (int kp = 1; kp <= 2 && !kpair; ++kp) {
     const int N1h = p.N1 / kp, N2h = p.N2 / kp;
     if ((N1h & 7) || (N2h & 7)) continue;
-    for (int ring = kTcRing; ring >= 2 && !kpair; --ring) {
+    int ring_max = kTcRing;
+    if (const char* e = getenv("BNN_TC_RING")) { const int v = atoi(e); if (v >= 3 && v <= kTcRing) ring_max = v; }  // tuning knob
+    for (int ring = ring_max; ring >= 3 && !kpair; --ring) {   // ring = 2 hung in testing: not used
       size_t o = 0;
       p.sm_b1 = (int)o; o += (size_t)2 * p.Dp * N1h * 4;
       p.sm_b2 = (int)o; o += (size_t)2 * p.K2 * N2h * 4;
@@ -594,6 +710,9 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   return 0;
 }
 
+static unsigned long long* g_tc_trace = nullptr;
+unsigned long long* tc_trace_buffer() { return g_tc_trace; }
+
 long long forward_tc_workspace_bytes(const BnnForwardArgs* a) {
   TcPlan plan;
   const int rc = plan_tc(a, &plan);
@@ -616,6 +735,11 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
     BNN_FAIL("workspace too small: need %lld bytes, got %lld", need, (long long)a->workspace_bytes);
   float* img = reinterpret_cast<float*>(a->workspace);
   p.img = img;
+  p.trace = nullptr;
+  if (getenv("BNN_TC_TRACE")) {   // debug only: leaks one small buffer per call
+    unsigned long long* tb = nullptr;
+    if (cudaMalloc(&tb, 3 * 4096 * 16) == cudaSuccess) { cudaMemsetAsync(tb, 0, 3 * 4096 * 16, st); p.trace = tb; g_tc_trace = tb; }
+  }
   const bool want_moments = a->mean || a->var || a->part_mean || a->part_m2;
   p.part = want_moments ? reinterpret_cast<double*>(reinterpret_cast<char*>(a->workspace) + plan.img_bytes) : nullptr;
   {
@@ -663,6 +787,15 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
 }  // namespace bnn
 
 using namespace bnn;
+
+namespace bnn { unsigned long long* tc_trace_buffer(); }
+// debug: copy the last BNN_TC_TRACE timeline (3 x 4096 x {tag<<32|it, clock}) to host
+extern "C" int32_t bnn_tc_trace_dump(unsigned long long* host_out) {
+  unsigned long long* t = bnn::tc_trace_buffer();
+  if (!t || !host_out) BNN_FAIL("no trace recorded (set BNN_TC_TRACE=1)");
+  BNN_CUDA(cudaMemcpy(host_out, t, 3 * 4096 * 16, cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 // D[128, N] = A[128, K] * B[N, K]^T on tcgen05 (device pointers; K % 8 == 0, K <= 64; N % 16 == 0, N <= 256)
 extern "C" int32_t bnn_tc_selftest(const float* A, const float* B, float* D, int32_t K, int32_t N, int32_t passes, void* stream) {

@@ -121,6 +121,16 @@ def forward(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=False, 
     return out
 
 
+def tc_supported(arch: Arch, S=2, masked=False):
+    """True if the tensor-core forward takes this architecture (see bnn_forward_tc_supported)."""
+    a = _lib.ForwardArgs()
+    a.desc = arch.desc()
+    a.N, a.S, a.w_stride = 1, S, arch.stride
+    a.mask.mode = _lib.MASK_EXTERNAL if masked else _lib.MASK_NONE
+    a.precision = _lib.PREC_TF32X3
+    return bool(_lib.lib().bnn_forward_tc_supported(C.byref(a)))
+
+
 def forward_host(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=False, want_moments=True, precision="fp32"):
     """End-to-end variant: X / W / mask / outputs are HOST tensors (pin them); the library does the
     H2D copies, the launch, the D2H copies and synchronises."""

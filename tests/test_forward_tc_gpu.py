@@ -1,0 +1,96 @@
+"""GPU parity of the tensor-core (tcgen05) forward.  Stated tolerances (DESIGN.md "Precision"):
+  tf32x3 (3-pass error-compensated, FP32-grade): 1e-5 relative, same as the FP32 SIMT path;
+  tf32   (single pass, 10-bit mantissa operands) : 5e-3 relative (looser bound, never the default)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from helpers import golden, flat_to_nets, random_nets, max_rel, var_bound
+from oracle import bnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def run(dims, act, nets, X, prec, **kw):
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    arch = Arch(dims, act)
+    out = ops.forward(arch, X.cuda().contiguous(), arch.pack(nets).cuda(), want_pred=True, want_moments=True, precision=prec, **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu() for k, v in out.items() if not k.startswith("_")}
+
+
+@pytest.mark.parametrize("K,N,passes,tol", [(8, 16, 1, 2e-3), (16, 64, 3, 2e-6), (64, 208, 3, 2e-6), (64, 256, 1, 2e-3)])
+def test_tcgen05_selftest_gemm(K, N, passes, tol):
+    """The kernels' operand layout / descriptors / TMEM read-back on a bare GEMM tile vs float64."""
+    from bnn_b200 import _lib
+    g = torch.Generator().manual_seed(K * 1000 + N)
+    A, B = torch.randn(128, K, generator=g), torch.randn(N, K, generator=g)
+    Ad, Bd, D = A.cuda(), B.cuda(), torch.zeros(128, N, device="cuda")
+    _lib.check(_lib.lib().bnn_tc_selftest(Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), K, N, passes, None), "selftest")
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t()
+    assert float((D.cpu().double() - ref).abs().max() / ref.abs().max()) < tol
+
+
+@pytest.mark.parametrize("dims,act,S,N", [
+    ([16, 200, 200, 1], "relu", 5, 1000),      # cfg 4 shape: CTA pair (cta_group::2), ragged last tile
+    ([16, 200, 200, 1], "tanh", 9, 70000),     # several tiles per CTA pair, several samples
+    ([9, 100, 100, 1], "tanh", 40, 4573),      # cfg 3 shape: single CTA, sample groups
+    ([1, 50, 50, 1], "tanh", 33, 1000),        # cfg 2 shape (D = 1)
+    ([13, 50, 64, 3], "sigmoid", 7, 129),      # nout = 3, uneven widths
+    ([64, 256, 256, 4], "relu", 2, 300),       # largest supported: D = 64, H = 256, nout = 4
+    ([5, 8, 24, 2], "identity", 3, 50),        # tiny
+    ([16, 128, 128, 1], "relu", 1, 200),       # S = 1 -> var NaN
+])
+def test_tf32x3_matches_oracle(dims, act, S, N):
+    nets = random_nets(dims, S, seed=sum(dims) + S)
+    X = torch.randn(N, dims[0], generator=torch.Generator().manual_seed(N))
+    ref = O.sample_predict(nets, X, act, nout=dims[-1])
+    out = run(dims, act, nets, X, "tf32x3")
+    assert max_rel(out["pred"], ref) <= 1e-5
+    mean_ref, var_ref = O.predict_mv(ref, N)
+    assert max_rel(out["mean"], mean_ref) <= 1e-5
+    if S > 1:
+        dv = (out["var"].double() - var_ref.double()).abs()
+        vb = var_bound(ref, c=256.0, depth=3)      # 3xTF32 products carry ~2^-21 relative error each (vs 2^-24 FP32)
+        assert bool((dv <= vb).all()), float((dv / vb).max())
+    else:
+        assert bool(torch.isnan(out["var"]).all())
+
+
+def test_tf32_single_pass_looser_bound():
+    dims, S, N = [16, 200, 200, 1], 4, 600
+    nets = random_nets(dims, S, seed=1)
+    X = torch.randn(N, 16, generator=torch.Generator().manual_seed(2))
+    ref = O.sample_predict(nets, X, "relu", nout=1)
+    out = run(dims, "relu", nets, X, "tf32")
+    assert 1e-6 < max_rel(out["pred"], ref) <= 5e-3
+
+
+def test_tc_equals_simt_on_moments_partials():
+    """tensor-core and SIMT paths agree with each other (and expose the same shard moments for the multi-GPU merge)."""
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    dims, S, N = [16, 200, 200, 1], 12, 3000
+    arch = Arch(dims, "relu")
+    bank = arch.pack(random_nets(dims, S, seed=9)).cuda()
+    X = torch.randn(N, 16, generator=torch.Generator().manual_seed(4)).cuda()
+    a = ops.forward(arch, X, bank, want_partials=True, precision="fp32")
+    b = ops.forward(arch, X, bank, want_partials=True, precision="tf32x3")
+    assert max_rel(b["mean"].cpu(), a["mean"].cpu()) <= 1e-5
+    assert max_rel(b["part_mean"].cpu(), a["part_mean"].cpu()) <= 1e-5
+    assert max_rel(b["part_m2"].cpu(), a["part_m2"].cpu()) <= 1e-4
+
+
+def test_unsupported_shapes_are_refused_loudly():
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    for dims in ([13, 50, 1], [90, 512, 512, 512, 1], [16, 300, 300, 1]):
+        arch = Arch(dims, "relu")
+        bank = arch.pack(random_nets(dims, 2, seed=1)).cuda()
+        X = torch.randn(10, dims[0]).cuda()
+        with pytest.raises(ValueError, match="tensor-core"):
+            ops.forward(arch, X, bank, precision="tf32x3")          # no silent fallback to the SIMT kernel
+        assert ops.forward(arch, X, bank, precision="fp32")["mean"].shape == (10, 1)

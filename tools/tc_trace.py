@@ -1,0 +1,43 @@
+"""Dump the in-kernel timeline of the tensor-core forward (BNN_TC_TRACE=1): per K-step timestamps of the MMA issuer
+and of one producer warp of each WG-A set."""
+import os, sys
+os.environ["BNN_TC_TRACE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from bnn_b200 import ops, _lib
+from bnn_b200.layout import Arch
+dims = [int(v) for v in os.environ.get("DIMS", "16,200,200,1").split(",")]
+arch = Arch(dims, "relu")
+S, N = 4, 75776
+g = torch.Generator(device="cuda").manual_seed(0)
+X = torch.randn(N, dims[0], generator=g, device="cuda")
+bank = (0.1 * torch.randn(S, arch.stride, generator=g, device="cuda")) * arch.valid_mask().cuda()
+prec = sys.argv[1] if len(sys.argv) > 1 else "tf32x3"
+ops.forward(arch, X, bank, precision=prec)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+ops.forward(arch, X, bank, precision=prec)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1)
+buf = np.zeros(3 * 4096 * 2, dtype=np.uint64)
+_lib.check(_lib.lib().bnn_tc_trace_dump(buf.ctypes.data), "dump")
+buf = buf.reshape(3, 4096, 2)
+names = {20: "start", 21: "tile_end", 1: "mma:wait_full", 2: "mma:got_full", 3: "mma:committed", 10: "ld_start", 11: "ld_done", 12: "wait_empty", 13: "got_empty", 14: "signalled"}
+t0 = min(int(buf[w, 0, 1]) for w in range(3) if buf[w, 0, 1])
+lo, hi = int(os.environ.get("IT0", 30)), int(os.environ.get("IT1", 42))
+ev = []
+for w in range(3):
+    for tag_it, clk in buf[w]:
+        if clk == 0: break
+        tag, it = int(tag_it) >> 32, int(tag_it) & 0xffffffff
+        if lo <= it < hi: ev.append((int(clk) - t0, ["MMA", "A0", "A1"][w], names[tag], it))
+for e in sorted(ev): print(f"{e[0]:8d}  {e[1]:4s} {e[2]:14s} it={e[3]}")
+# per K-step period of the MMA thread
+m = [(int(t) & 0xffffffff, int(c)) for t, c in buf[0] if c and (int(t) >> 32) == 3]
+d = np.diff([c for _, c in m])
+tiles = [int(c) for t, c in buf[0] if c and (int(t) >> 32) == 21]
+start = [int(c) for t, c in buf[0] if c and (int(t) >> 32) == 20][0]
+print("tile periods (clk):", np.diff(tiles)[:12], " total clk %d over %.3f ms (incl. prep+finalize) -> >= %.0f MHz" % (tiles[-1] - start, ms, (tiles[-1] - start) / ms / 1e3))
+print("MMA commit-to-commit period: median %.0f  p10 %.0f  p90 %.0f  (n=%d)" % (np.median(d), np.percentile(d, 10), np.percentile(d, 90), len(d)))
