@@ -121,7 +121,8 @@ int64_t bnn_forward_workspace_bytes(const BnnForwardArgs* a);
  * launch; pred[S,N,nout] is only written when asked for.                   */
 int32_t bnn_forward(const BnnForwardArgs* a, void* stream);
 /* 1 if the tensor-core (tcgen05) forward takes this shape (2 hidden layers, D <= 64, H <= 256, nout <= 4,
- * per-sample bank, no masks), else 0 with the reason in bnn_last_error(); BNN_PREC_FP32 takes every shape */
+ * per-sample bank, no masks, and the hi/lo operand images of one network fit the shared memory of one CTA or
+ * of a CTA pair -- e.g. 16-200-200-1 does, 64-256-256-4 does not), else 0 with the reason in bnn_last_error(); BNN_PREC_FP32 takes every shape */
 int32_t bnn_forward_tc_supported(const BnnForwardArgs* a);
 /* tcgen05 self-test: D[128, N] = A[128, K] * B[N, K]^T (row-major device buffers, K % 8 == 0, K <= 64,
  * N % 16 == 0, N <= 256, passes = 1 (TF32) or 3 (3xTF32)) through the kernels' own operand layout */

@@ -40,7 +40,8 @@ def test_tcgen05_selftest_gemm(K, N, passes, tol):
     ([9, 100, 100, 1], "tanh", 40, 4573),      # cfg 3 shape: single CTA, sample groups
     ([1, 50, 50, 1], "tanh", 33, 1000),        # cfg 2 shape (D = 1)
     ([13, 50, 64, 3], "sigmoid", 7, 129),      # nout = 3, uneven widths
-    ([64, 256, 256, 4], "relu", 2, 300),       # largest supported: D = 64, H = 256, nout = 4
+    ([32, 128, 160, 4], "relu", 2, 300),       # wide input, nout = 4, CTA pair because of shared-memory footprint
+    ([64, 96, 64, 2], "relu", 3, 260),         # D = 64
     ([5, 8, 24, 2], "identity", 3, 50),        # tiny
     ([16, 128, 128, 1], "relu", 1, 200),       # S = 1 -> var NaN
 ])
@@ -87,7 +88,7 @@ def test_tc_equals_simt_on_moments_partials():
 def test_unsupported_shapes_are_refused_loudly():
     from bnn_b200 import ops
     from bnn_b200.layout import Arch
-    for dims in ([13, 50, 1], [90, 512, 512, 512, 1], [16, 300, 300, 1]):
+    for dims in ([13, 50, 1], [90, 512, 512, 512, 1], [16, 300, 300, 1], [64, 256, 256, 4]):
         arch = Arch(dims, "relu")
         bank = arch.pack(random_nets(dims, 2, seed=1)).cuda()
         X = torch.randn(10, dims[0]).cuda()
