@@ -94,4 +94,4 @@ def test_unsupported_shapes_are_refused_loudly():
         X = torch.randn(10, dims[0]).cuda()
         with pytest.raises(ValueError, match="tensor-core"):
             ops.forward(arch, X, bank, precision="tf32x3")          # no silent fallback to the SIMT kernel
-        assert ops.forward(arch, X, bank, precision="fp32")["mean"].shape == (10, 1)
+        assert ops.forward(arch, X, bank, precision="fp32")["mean"].shape == (10, dims[-1])
