@@ -27,13 +27,13 @@ namespace bnn {
 constexpr int kTcThreads = 416;       // WG-A (8 warps) + WG-B (4 warps) + 1 MMA/loader warp
 constexpr int kTcMmaWarp = 12;
 constexpr int kTcEpiThreads = 128;
-constexpr int kTcRing = 8;            // max A2 ring stages (one K = 8 step each)
-constexpr int kTcStageBytes = 2 * 2 * 128 * 16;  // hi + lo, 2 granule columns x 128 rows x 16 B = 8 KB
+constexpr int kTcRing = 4;            // max A2 ring stages
+constexpr int kTcStageBytes = 2 * 4 * 128 * 16;  // one stage = 16 K-columns (two K = 8 MMA steps): hi + lo, 4 granule columns x 128 rows x 16 B = 16 KB
 
 struct TcParams {
   int D, H1, H2, O, act;
   int Dp, N1, N2, K2;      // padded: K of layer 1 (mult of 8), N of layers 1/2 (mult of 16), K of layer 2 (mult of 8, <= N1)
-  int ring;                // A2 ring depth (3..kTcRing)
+  int ring;                // A2 ring depth (2..kTcRing) in 16-column stages
   int passes;              // 3 (tf32x3) or 1 (tf32)
   long long part_stride;   // floats per (sample, part) of the operand image
   long long img_stride;    // floats per sample of the operand image
@@ -174,7 +174,8 @@ __device__ __forceinline__ void trace_ev(unsigned long long* tr, int who, uint32
 }
 
 // barrier slots in shared memory
-enum { BAR_W_FULL = 0, BAR_A1_FULL, BAR_D1_FULL, BAR_D2_FULL, BAR_D2_EMPTY, BAR_A2_FULL, BAR_A2_EMPTY = BAR_A2_FULL + kTcRing,
+enum { BAR_W_FULL = 0, BAR_A1_FULL, BAR_D1_FULL, BAR_D2_FULL, BAR_D2_EMPTY, BAR_SAMPLE_DONE, BAR_VEC_FREE, BAR_A2_FULL,
+       BAR_A2_EMPTY = BAR_A2_FULL + kTcRing,
        BAR_COUNT = BAR_A2_EMPTY + kTcRing };
 
 // one warp signals "my part is done" to the MMA issuer (leader CTA): writers fence their generic-proxy
@@ -200,8 +201,19 @@ __device__ __forceinline__ float act_ct(float v) {
 
 // Roles: warps 0-7 (WG-A) run epilogue-1, two warps per TMEM lane quarter taking alternate 16-column batches
 // (warps 0-3 also build A1); warps 8-11 (WG-B) run epilogue-2 + the Welford update, so that epilogue-2 of tile t
-// overlaps layer 1 / epilogue-1 of tile t+1; warp 12 = MMA issuer + weight loader.
+// overlaps layer 1 / epilogue-1 of tile t+1; warp 12 = weight loader + MMA issuer.
 // A warp may only touch TMEM lanes [32 * (warp % 4), +32).
+//
+// Hand-off protocol (all mbarriers; "leader" = CTA 0 of the pair, the only one that issues MMAs):
+//   W_FULL       tx barrier: this sample's operand images + bias vector have landed in THIS CTA
+//   A1_FULL      4 x kPair warp arrivals on the leader: A1 of the tile is written (and W_FULL was seen in that CTA)
+//   D1_FULL      commit (multicast): layer-1 MMAs done -> epilogue-1 may read D1, A1 may be rebuilt
+//   A2_FULL[st]  4 x kPair warp arrivals on the leader: stage st (16 K-columns of the layer-2 A operand) is written
+//   A2_EMPTY[st] commit (multicast): the MMAs reading stage st are done
+//   D2_FULL      commit (multicast): layer-2 MMAs of the tile done -> epilogue-2 may read D2
+//   D2_EMPTY     4 x kPair warp arrivals on the leader: epilogue-2 drained D2
+//   SAMPLE_DONE  commit (multicast) after the last tile of a sample: B1/B2 may be overwritten
+//   VEC_FREE     4 local warp arrivals: epilogue-2 is done with this sample's bias vector (single-buffered)
 template <int kPair, int kAct>
 __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -209,7 +221,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   const uint32_t s_b1 = smem_u32(smem + p.sm_b1), s_b2 = smem_u32(smem + p.sm_b2);
   const uint32_t s_a1 = smem_u32(smem + p.sm_a1), s_ring = smem_u32(smem + p.sm_ring);
-  const uint32_t s_vec = smem_u32(smem + p.sm_vec);   // double buffered by sample parity
+  const uint32_t s_vec = smem_u32(smem + p.sm_vec);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = kPair == 1 ? 0u : cluster_ctarank();
@@ -220,6 +232,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
   const int pt0 = slot * p.tiles_per_slot, pt1 = min(p.n_tiles, pt0 + p.tiles_per_slot);
   const int N1h = p.N1 / kPair, N2h = p.N2 / kPair;
   const int n_k1 = p.Dp >> 3, n_k2 = p.K2 >> 3;
+  const int n_b2 = (n_k2 + 1) >> 1;   // 16-column batches (= ring stages) per tile; the last may hold one K-step
   const uint32_t b1_hl_bytes = (uint32_t)p.Dp * N1h * 4, b2_hl_bytes = (uint32_t)p.K2 * N2h * 4;
   const uint32_t a1_hl_bytes = (uint32_t)p.Dp * 128 * 4;
   const int vec_pad = (p.vec_len + 3) & ~3;
@@ -230,6 +243,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     mbar_init(&bars[BAR_D1_FULL], 1);
     mbar_init(&bars[BAR_D2_FULL], 1);
     mbar_init(&bars[BAR_D2_EMPTY], 4 * kPair);
+    mbar_init(&bars[BAR_SAMPLE_DONE], 1);
+    mbar_init(&bars[BAR_VEC_FREE], 4);
     for (int i = 0; i < kTcRing; ++i) {
       mbar_init(&bars[BAR_A2_FULL + i], 4 * kPair);
       mbar_init(&bars[BAR_A2_EMPTY + i], 1);
@@ -251,88 +266,99 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     // and wrap every uniform-datapath instruction -- UTCHMMA, UTCBAR -- in an ELECT/BRA.U.ANY loop with R2UR
     // transfers: ~90 instructions and ~700 cycles per K-step, which starved the tensor pipe.)
     const uint32_t idesc1 = tc::make_idesc_tf32(128 * kPair, p.N1), idesc2 = tc::make_idesc_tf32(128 * kPair, p.N2);
-    uint32_t tile_cnt = 0, ring_it = 0, tn = 0, ring_st = 0, ring_par = 0;
+    uint32_t tile_cnt = 0, tn = 0, ring_st = 0, ring_par = 0;
     unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? p.trace : nullptr;
     const uint64_t a1_desc0 = tc::make_smem_desc(s_a1, 2048u, 128u);
     const uint64_t b1_desc0 = tc::make_smem_desc(s_b1, (uint32_t)N1h * 16u, 128u);
     const uint64_t a2_desc0 = tc::make_smem_desc(s_ring, 2048u, 128u);
     const uint64_t b2_desc0 = tc::make_smem_desc(s_b2, (uint32_t)N2h * 16u, 128u);
     const uint64_t b1_step = (uint64_t)(2 * N1h), b2_step = (uint64_t)(2 * N2h);   // 16-byte units per K = 8 step
-    const uint64_t a1_step = (uint64_t)(2 * 128);
+    const uint64_t a_step = (uint64_t)(2 * 128);
     const bool three = p.passes == 3;
     trace_ev(tr, 0, tn, 20, 0);
     for (int s = s0; s < s1; ++s) {
-      // previous sample's MMAs have all completed (its last d2_full was observed below): reload the operands
+      const uint32_t spar = (uint32_t)(s - s0) & 1u;
+      // all MMAs of the previous sample are complete in both CTAs -> B1 / B2 may be overwritten
+      if (s > s0) mbar_wait(&bars[BAR_SAMPLE_DONE], spar ^ 1u);
+      const float* src = p.img + (long long)s * p.img_stride + (long long)rank * p.part_stride;
+      const uint32_t b1_bytes = three ? 2 * b1_hl_bytes : b1_hl_bytes;
+      const uint32_t b2_bytes = three ? 2 * b2_hl_bytes : b2_hl_bytes;
       if (tc::elect_one()) {
-        const float* src = p.img + (long long)s * p.img_stride + (long long)rank * p.part_stride;
-        const uint32_t b1_bytes = three ? 2 * b1_hl_bytes : b1_hl_bytes;
-        const uint32_t b2_bytes = three ? 2 * b2_hl_bytes : b2_hl_bytes;
         mbar_arrive_expect_tx(&bars[BAR_W_FULL], b1_bytes + b2_bytes + (uint32_t)vec_pad * 4);
         bulk_g2s(smem + p.sm_b1, src, b1_bytes, &bars[BAR_W_FULL]);
         bulk_g2s(smem + p.sm_b2, src + 2 * (long long)(b1_hl_bytes / 4), b2_bytes, &bars[BAR_W_FULL]);
-        bulk_g2s(smem + p.sm_vec + ((s - s0) & 1) * vec_pad * 4, p.img + (long long)s * p.img_stride + p.part_stride * kPair,
-                 (uint32_t)vec_pad * 4, &bars[BAR_W_FULL]);
       }
       __syncwarp();
-      if (leader) mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
+      // the bias vector is single-buffered: epilogue-2 of the previous sample must be done with it
+      if (s > s0) mbar_wait(&bars[BAR_VEC_FREE], spar ^ 1u);
+      if (tc::elect_one())
+        bulk_g2s(smem + p.sm_vec, p.img + (long long)s * p.img_stride + p.part_stride * kPair, (uint32_t)vec_pad * 4,
+                 &bars[BAR_W_FULL]);
+      __syncwarp();
+      if (!leader) continue;   // the peer CTA only loads; its tensor-core work is issued by the leader
+      mbar_wait(&bars[BAR_W_FULL], spar);
       for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
         const uint32_t tpar = tile_cnt & 1u;
-        if (leader) {
-          // ---- layer 1: D1 = A1 * B1^T
-          mbar_wait(&bars[BAR_A1_FULL], tpar);
-          tc::fence_after_thread_sync();
-          if (tc::elect_one()) {
-            uint64_t a_hi = a1_desc0, b_hi = b1_desc0;
-            const uint64_t a_lo_off = (uint64_t)(a1_hl_bytes >> 4), b_lo_off = (uint64_t)(b1_hl_bytes >> 4);
-            for (int ks = 0; ks < n_k1; ++ks) {
-              mma_tf32<kPair>(tmem_d1, a_hi, b_hi, idesc1, ks > 0);
-              if (three) {
-                mma_tf32<kPair>(tmem_d1, a_hi + a_lo_off, b_hi, idesc1, 1);
-                mma_tf32<kPair>(tmem_d1, a_hi, b_hi + b_lo_off, idesc1, 1);
-              }
-              a_hi += a1_step;
-              b_hi += b1_step;
+        // ---- layer 1: D1 = A1 * B1^T
+        mbar_wait(&bars[BAR_A1_FULL], tpar);
+        tc::fence_after_thread_sync();
+        if (tc::elect_one()) {
+          uint64_t a_hi = a1_desc0, b_hi = b1_desc0;
+          const uint64_t a_lo_off = (uint64_t)(a1_hl_bytes >> 4), b_lo_off = (uint64_t)(b1_hl_bytes >> 4);
+          for (int ks = 0; ks < n_k1; ++ks) {
+            mma_tf32<kPair>(tmem_d1, a_hi, b_hi, idesc1, ks > 0);
+            if (three) {
+              mma_tf32<kPair>(tmem_d1, a_hi + a_lo_off, b_hi, idesc1, 1);
+              mma_tf32<kPair>(tmem_d1, a_hi, b_hi + b_lo_off, idesc1, 1);
             }
-            mma_commit_all<kPair>(&bars[BAR_D1_FULL]);
+            a_hi += a_step;
+            b_hi += b1_step;
           }
-          __syncwarp();
-          // ---- layer 2: D2 = A2 * B2^T, A2 produced K-step by K-step by epilogue-1.  Software pipelined: the
-          //      (100+ cycle) barrier probe for stage k+1 runs while the tensor pipe executes the MMAs of stage k;
-          //      the commit of stage k is issued after it (it still only covers MMAs <= k).
-          uint64_t b_hi = b2_desc0;
-          const uint64_t b_lo_off = (uint64_t)(b2_hl_bytes >> 4);
-          mbar_wait(&bars[BAR_A2_FULL + ring_st], ring_par);
-          mbar_wait(&bars[BAR_D2_EMPTY], tpar ^ 1u);   // epilogue-2 of the previous tile drained D2
-          tc::fence_after_thread_sync();
-          for (int ks = 0; ks < n_k2; ++ks, ++ring_it) {
-            trace_ev(tr, 0, tn, 2, ring_it);
-            const uint32_t cur_st = ring_st;
-            const uint64_t a_hi = a2_desc0 + (uint64_t)(cur_st * (kTcStageBytes >> 4));
-            if (tc::elect_one()) {
-              mma_tf32<kPair>(tmem_d2, a_hi, b_hi, idesc2, ks > 0);
-              if (three) {
-                mma_tf32<kPair>(tmem_d2, a_hi + (uint64_t)(kTcStageBytes >> 5), b_hi, idesc2, 1);
-                mma_tf32<kPair>(tmem_d2, a_hi, b_hi + b_lo_off, idesc2, 1);
-              }
-            }
-            __syncwarp();
-            b_hi += b2_step;
-            if (++ring_st == (uint32_t)p.ring) { ring_st = 0; ring_par ^= 1u; }
-            if (ks + 1 < n_k2) {
-              trace_ev(tr, 0, tn, 1, ring_it + 1);
-              mbar_wait(&bars[BAR_A2_FULL + ring_st], ring_par);
-              tc::fence_after_thread_sync();
-            }
-            if (tc::elect_one()) mma_commit_all<kPair>(&bars[BAR_A2_EMPTY + cur_st]);
-            __syncwarp();
-            trace_ev(tr, 0, tn, 3, ring_it);
-          }
-          if (tc::elect_one()) mma_commit_all<kPair>(&bars[BAR_D2_FULL]);
-          __syncwarp();
+          mma_commit_all<kPair>(&bars[BAR_D1_FULL]);
         }
-        // every CTA's loader observes the end of the tile (keeps its phase in step; the last one per
-        // sample also licenses the operand reload above)
-        mbar_wait(&bars[BAR_D2_FULL], tpar);
+        __syncwarp();
+        // ---- layer 2: D2 = A2 * B2^T, A2 produced stage by stage (16 K-columns = two MMA K-steps) by epilogue-1.
+        //      Software pipelined: the (100+ cycle) barrier probe for stage b+1 runs while the tensor pipe executes
+        //      the 6 MMAs of stage b; the commit of stage b is issued after it (it still only covers MMAs <= b).
+        uint64_t b_hi = b2_desc0;
+        const uint64_t b_lo_off = (uint64_t)(b2_hl_bytes >> 4);
+        mbar_wait(&bars[BAR_A2_FULL + ring_st], ring_par);
+        mbar_wait(&bars[BAR_D2_EMPTY], tpar ^ 1u);   // epilogue-2 of the previous tile drained D2
+        tc::fence_after_thread_sync();
+        for (int b = 0; b < n_b2; ++b) {
+          trace_ev(tr, 0, tn, 2, tile_cnt * n_b2 + b);
+          const uint32_t cur_st = ring_st;
+          const int nks = min(2, n_k2 - 2 * b);
+          if (tc::elect_one()) {
+            uint64_t a_hi = a2_desc0 + (uint64_t)(cur_st * (kTcStageBytes >> 4));
+            uint64_t bj = b_hi;
+            for (int j = 0; j < nks; ++j) {
+              mma_tf32<kPair>(tmem_d2, a_hi, bj, idesc2, (b | j) > 0);
+              if (three) {
+                mma_tf32<kPair>(tmem_d2, a_hi + (uint64_t)(kTcStageBytes >> 5), bj, idesc2, 1);
+                mma_tf32<kPair>(tmem_d2, a_hi, bj + b_lo_off, idesc2, 1);
+              }
+              a_hi += a_step;
+              bj += b2_step;
+            }
+          }
+          __syncwarp();
+          b_hi += b2_step * (uint64_t)nks;
+          if (++ring_st == (uint32_t)p.ring) { ring_st = 0; ring_par ^= 1u; }
+          if (b + 1 < n_b2) {
+            trace_ev(tr, 0, tn, 1, tile_cnt * n_b2 + b + 1);
+            mbar_wait(&bars[BAR_A2_FULL + ring_st], ring_par);
+            tc::fence_after_thread_sync();
+          }
+          if (tc::elect_one()) mma_commit_all<kPair>(&bars[BAR_A2_EMPTY + cur_st]);
+          __syncwarp();
+          trace_ev(tr, 0, tn, 3, tile_cnt * n_b2 + b);
+        }
+        if (tc::elect_one()) {
+          mma_commit_all<kPair>(&bars[BAR_D2_FULL]);
+          if (pt + 1 == pt1) mma_commit_all<kPair>(&bars[BAR_SAMPLE_DONE]);
+        }
+        __syncwarp();
         trace_ev(tr, 0, tn, 21, tile_cnt);
       }
     }
@@ -342,13 +368,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     const int row = quarter * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     uint32_t tile_cnt = 0, tn = 0;
-    // ring position of this warp's next K-step (K-step index it -> stage it % ring, phase (it / ring) & 1), kept
-    // incrementally: the two sets leapfrog each other in 16-column batches
-    uint32_t my_st = 0, my_par = 0;
-    auto ring_advance = [&](uint32_t k) {
-      my_st += k;
-      while (my_st >= (uint32_t)p.ring) { my_st -= (uint32_t)p.ring; my_par ^= 1u; }
-    };
     unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quarter == 0) ? p.trace : nullptr;
     const int who = 1 + set;
     // A1 granule kc of point n: hi/lo split of X[n][4kc .. 4kc+3] (zero beyond D / N)
@@ -371,10 +390,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     constexpr int kPre = 4;   // granules of the next tile's input row prefetched into registers (D <= 16 fully)
     const int n_kc = p.Dp >> 2;
     for (int s = s0; s < s1; ++s) {
-      const uint32_t b1v = s_vec + (uint32_t)(((s - s0) & 1) * vec_pad) * 4u;
       for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
         const uint32_t tpar = tile_cnt & 1u;
-        const uint32_t it_base = tile_cnt * (uint32_t)n_k2;
         float xn[kPre][4];
         const bool have_next = (pt + 1 < pt1);
         const long long n_next = ((long long)(pt + 1) * kPair + rank) * 128 + row;
@@ -416,62 +433,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
           warp_signal_leader<kPair>(&bars[BAR_A1_FULL], lane);
         }
 
-        // ---- epilogue 1: D1 -> h1 = act(d + b1) -> hi/lo -> A2 ring, one K = 8 step per stage; this warp takes
-        //      the 16-column batches whose index parity equals `set`
-        // K-steps of this tile before this warp's first batch belong to the other set
-        {
-          const int first = set * 2 < n_k2 ? set * 2 : n_k2;
-          ring_advance((uint32_t)first);
-        }
-        int ks_done = set * 2 < n_k2 ? set * 2 : n_k2;   // K-steps of this tile accounted for in (my_st, my_par)
-        for (int c0 = set * 16; c0 < p.K2; c0 += 32) {
+        // ---- epilogue 1: D1 -> h1 = act(d + b1) -> hi/lo -> A2 ring; one 16-column batch = one ring stage; this warp
+        //      takes the batches whose index parity equals `set`
+        for (int b = set; b < n_b2; b += 2) {
+          const int c0 = b * 16;
           float d[16];
-          trace_ev(tr, who, tn, 10, it_base + (uint32_t)(c0 >> 3));
+          const uint32_t gb = tile_cnt * (uint32_t)n_b2 + (uint32_t)b;   // global stage-use index
+          trace_ev(tr, who, tn, 10, gb);
           tc::tmem_ld16(tmem_d1 + lane_sel + (uint32_t)c0, d);
-          trace_ev(tr, who, tn, 11, it_base + (uint32_t)(c0 >> 3));
-          float bb[16];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 t = lds128(b1v + (uint32_t)(c0 + q4 * 4) * 4u);
-            bb[q4 * 4 + 0] = t.x; bb[q4 * 4 + 1] = t.y; bb[q4 * 4 + 2] = t.z; bb[q4 * 4 + 3] = t.w;
-          }
-          // hi/lo of all 16 activations first, so that after a stage frees up only stores + the hand-off remain
+          trace_ev(tr, who, tn, 11, gb);
           float4 hi4[4], lo4[4];
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 bq = lds128(s_vec + (uint32_t)(c0 + q4 * 4) * 4u);
             float h[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = act_ct<kAct>(d[q4 * 4 + e] + bb[q4 * 4 + e]);
+            h[0] = act_ct<kAct>(d[q4 * 4 + 0] + bq.x);
+            h[1] = act_ct<kAct>(d[q4 * 4 + 1] + bq.y);
+            h[2] = act_ct<kAct>(d[q4 * 4 + 2] + bq.z);
+            h[3] = act_ct<kAct>(d[q4 * 4 + 3] + bq.w);
             hi4[q4] = make_float4(tc::tf32_hi(h[0]), tc::tf32_hi(h[1]), tc::tf32_hi(h[2]), tc::tf32_hi(h[3]));
             lo4[q4] = make_float4(h[0] - hi4[q4].x, h[1] - hi4[q4].y, h[2] - hi4[q4].z, h[3] - hi4[q4].w);
           }
+          const uint32_t st = gb % (uint32_t)p.ring, use = gb / (uint32_t)p.ring;
+          trace_ev(tr, who, tn, 12, gb);
+          mbar_wait(&bars[BAR_A2_EMPTY + st], (use & 1u) ^ 1u);
+          trace_ev(tr, who, tn, 13, gb);
+          const uint32_t sa = s_ring + st * kTcStageBytes + (uint32_t)row * 16u;
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (c0 + half * 8 >= p.K2) break;      // K2 is a multiple of 8, not necessarily of 16
-            const uint32_t it = it_base + (uint32_t)(c0 >> 3) + (uint32_t)half;
-            const uint32_t st = my_st, rpar = my_par;
-            trace_ev(tr, who, tn, 12, it);
-            mbar_wait(&bars[BAR_A2_EMPTY + st], rpar ^ 1u);
-            trace_ev(tr, who, tn, 13, it);
-            const uint32_t sa = s_ring + st * kTcStageBytes + (uint32_t)row * 16u;
-#pragma unroll
-            for (int q4 = 0; q4 < 2; ++q4) {
-              sts128(sa + (uint32_t)q4 * 2048u, hi4[half * 2 + q4]);
-              sts128(sa + kTcStageBytes / 2 + (uint32_t)q4 * 2048u, lo4[half * 2 + q4]);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            if (c0 + q4 * 4 < p.K2) {      // the last batch may hold a single K-step
+              sts128(sa + (uint32_t)q4 * 2048u, hi4[q4]);
+              sts128(sa + kTcStageBytes / 2 + (uint32_t)q4 * 2048u, lo4[q4]);
             }
-            warp_signal_leader<kPair>(&bars[BAR_A2_FULL + st], lane);
-            trace_ev(tr, who, tn, 14, it);
-            ring_advance(1);
-            ++ks_done;
           }
-          // skip the other set's batch (up to 2 K-steps), staying inside this tile
-          {
-            const int skip = n_k2 - ks_done < 2 ? n_k2 - ks_done : 2;
-            ring_advance((uint32_t)skip);
-            ks_done += skip;
-          }
+          warp_signal_leader<kPair>(&bars[BAR_A2_FULL + st], lane);
+          trace_ev(tr, who, tn, 14, gb);
         }
-        if (ks_done < n_k2) ring_advance((uint32_t)(n_k2 - ks_done));   // (only when this warp had no batch at all)
       }
     }
   } else {
@@ -483,12 +480,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     const long long M = p.N * p.O;
     double* st_mean = p.part ? p.part + (long long)g * 2 * M : nullptr;
     double* st_m2 = p.part ? st_mean + M : nullptr;
+    const uint32_t b2v = s_vec + (uint32_t)p.N1 * 4u, w3v = b2v + (uint32_t)p.N2 * 4u;
+    const float* b3 = reinterpret_cast<const float*>(smem + p.sm_vec) + p.N1 + p.N2 + p.O * p.N2;
     for (int s = s0; s < s1; ++s) {
-      const uint32_t vb = s_vec + (uint32_t)(((s - s0) & 1) * vec_pad) * 4u;
-      const uint32_t b2v = vb + (uint32_t)p.N1 * 4u, w3v = b2v + (uint32_t)p.N2 * 4u;
-      const float* b3 = reinterpret_cast<const float*>(smem + p.sm_vec) + ((s - s0) & 1) * vec_pad + p.N1 + p.N2 + p.O * p.N2;
       const double inv_cnt = 1.0 / (double)(s - s0 + 1);
       mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
+      float y0[4] = {b3[0], p.O > 1 ? b3[1] : 0.f, p.O > 2 ? b3[2] : 0.f, p.O > 3 ? b3[3] : 0.f};
       for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
         const uint32_t tpar = tile_cnt & 1u;
         const long long n = ((long long)pt * kPair + rank) * 128 + row;
@@ -501,21 +498,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             q0[o] = st_m2[n * p.O + o];
           }
         }
-        // ---- epilogue 2: D2 -> y[o] = b3[o] + sum_j w3[o][j] * act(d + b2[j])
+        // ---- epilogue 2: D2 -> y[o] = b3[o] + sum_j w3[o][j] * act(d + b2[j]); the TMEM load of batch i+1 is in
+        //      flight while batch i is reduced
         mbar_wait(&bars[BAR_D2_FULL], tpar);
         tc::fence_after_thread_sync();
-        float y[4] = {b3[0], p.O > 1 ? b3[1] : 0.f, p.O > 2 ? b3[2] : 0.f, p.O > 3 ? b3[3] : 0.f};
-        for (int c0 = 0; c0 < p.N2; c0 += 16) {
-          float d[16];
-          tc::tmem_ld16(tmem_d2 + lane_sel + (uint32_t)c0, d);
+        float y[4] = {y0[0], y0[1], y0[2], y0[3]};
+        auto reduce16 = [&](const uint32_t (&d)[16], int c0) {
           float t[16];
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             const float4 bq = lds128(b2v + (uint32_t)(c0 + q4 * 4) * 4u);
-            t[q4 * 4 + 0] = act_ct<kAct>(d[q4 * 4 + 0] + bq.x);
-            t[q4 * 4 + 1] = act_ct<kAct>(d[q4 * 4 + 1] + bq.y);
-            t[q4 * 4 + 2] = act_ct<kAct>(d[q4 * 4 + 2] + bq.z);
-            t[q4 * 4 + 3] = act_ct<kAct>(d[q4 * 4 + 3] + bq.w);
+            t[q4 * 4 + 0] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 0]) + bq.x);
+            t[q4 * 4 + 1] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 1]) + bq.y);
+            t[q4 * 4 + 2] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 2]) + bq.z);
+            t[q4 * 4 + 3] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 3]) + bq.w);
           }
           for (int o = 0; o < p.O; ++o) {
             float acc = y[o];
@@ -529,13 +525,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             }
             y[o] = acc;
           }
+        };
+        uint32_t da[16], db[16];
+        tc::tmem_ld16_issue(tmem_d2 + lane_sel, da);
+        for (int c0 = 0; c0 < p.N2; c0 += 32) {
+          tc::tmem_ld_wait(da);
+          const bool more = c0 + 16 < p.N2;
+          if (more) tc::tmem_ld16_issue(tmem_d2 + lane_sel + (uint32_t)(c0 + 16), db);
+          reduce16(da, c0);
+          if (more) {
+            tc::tmem_ld_wait(db);
+            if (c0 + 32 < p.N2) tc::tmem_ld16_issue(tmem_d2 + lane_sel + (uint32_t)(c0 + 32), da);
+            reduce16(db, c0 + 16);
+          }
         }
-        // D2 is drained: let the next tile's layer-2 MMAs overwrite it
+        // D2 is drained: let the next tile's layer-2 MMAs overwrite it; after the last tile of the sample the bias
+        // vector is free as well
         tc::fence_before_thread_sync();
         __syncwarp();
         if (lane == 0) {
           if constexpr (kPair == 1) mbar_arrive(&bars[BAR_D2_EMPTY]);
           else mbar_arrive_cluster(&bars[BAR_D2_EMPTY], 0);
+          if (pt + 1 == pt1) mbar_arrive(&bars[BAR_VEC_FREE]);
         }
         // ---- predictive reduction: FP64 Welford state of this point (only this thread ever touches it)
         if (in_range) {
@@ -661,14 +672,14 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
     const int N1h = p.N1 / kp, N2h = p.N2 / kp;
     if ((N1h & 7) || (N2h & 7)) continue;
     int ring_max = kTcRing;
-    if (const char* e = getenv("BNN_TC_RING")) { const int v = atoi(e); if (v >= 3 && v <= kTcRing) ring_max = v; }  // tuning knob
-    for (int ring = ring_max; ring >= 3 && !kpair; --ring) {   // ring = 2 hung in testing: not used
+    if (const char* e = getenv("BNN_TC_RING")) { const int v = atoi(e); if (v >= 2 && v <= kTcRing) ring_max = v; }  // tuning knob
+    for (int ring = ring_max; ring >= 2 && !kpair; --ring) {
       size_t o = 0;
       p.sm_b1 = (int)o; o += (size_t)2 * p.Dp * N1h * 4;
       p.sm_b2 = (int)o; o += (size_t)2 * p.K2 * N2h * 4;
       p.sm_a1 = (int)o; o += (size_t)2 * p.Dp * 128 * 4;
       p.sm_ring = (int)o; o += (size_t)ring * kTcStageBytes;
-      p.sm_vec = (int)o; o += (size_t)2 * vec_pad * 4;
+      p.sm_vec = (int)o; o += (size_t)vec_pad * 4;
       o = (o + 15) & ~(size_t)15;
       p.sm_bar = (int)o; o += (size_t)BAR_COUNT * 8 + 16;
       if (o <= (size_t)227 * 1024) { kpair = kp; plan->smem = o; p.ring = ring; }
