@@ -24,8 +24,8 @@
 
 namespace bnn {
 
-constexpr int kTcThreads = 416;       // WG-A (8 warps) + WG-B (4 warps) + 1 MMA/loader warp
-constexpr int kTcMmaWarp = 12;
+constexpr int kTcThreads = 544;       // WG-A (8 warps) + WG-B (8 warps) + 1 MMA/loader warp
+constexpr int kTcMmaWarp = 16;
 constexpr int kTcEpiThreads = 128;
 constexpr int kTcRing = 4;            // max A2 ring stages
 constexpr int kTcStageBytes = 2 * 4 * 128 * 16;  // one stage = 16 K-columns (two K = 8 MMA steps): hi + lo, 4 granule columns x 128 rows x 16 B = 16 KB
@@ -48,7 +48,7 @@ struct TcParams {
   int tmem_cols;
   unsigned long long* trace;   // debug timeline (BNN_TC_TRACE), null in production
   // shared memory offsets (bytes)
-  int sm_b1, sm_b2, sm_vec, sm_a1, sm_ring, sm_bar;
+  int sm_b1, sm_b2, sm_vec, sm_a1, sm_ring, sm_bar, sm_ypart;
 };
 
 // ---- operand image builder -------------------------------------------------------------------------
@@ -200,8 +200,9 @@ __device__ __forceinline__ float act_ct(float v) {
 }
 
 // Roles: warps 0-7 (WG-A) run epilogue-1, two warps per TMEM lane quarter taking alternate 16-column batches
-// (warps 0-3 also build A1); warps 8-11 (WG-B) run epilogue-2 + the Welford update, so that epilogue-2 of tile t
-// overlaps layer 1 / epilogue-1 of tile t+1; warp 12 = weight loader + MMA issuer.
+// (warps 0-3 also build A1); warps 8-15 (WG-B) run epilogue-2 (two per lane quarter, each reducing half of the D2
+// columns; partial outputs meet in shared memory) + the Welford update, overlapping layer 1 / epilogue-1 of tile t+1;
+// warp 16 = weight loader + MMA issuer.
 // A warp may only touch TMEM lanes [32 * (warp % 4), +32).
 //
 // Hand-off protocol (all mbarriers; "leader" = CTA 0 of the pair, the only one that issues MMAs):
@@ -211,9 +212,9 @@ __device__ __forceinline__ float act_ct(float v) {
 //   A2_FULL[st]  4 x kPair warp arrivals on the leader: stage st (16 K-columns of the layer-2 A operand) is written
 //   A2_EMPTY[st] commit (multicast): the MMAs reading stage st are done
 //   D2_FULL      commit (multicast): layer-2 MMAs of the tile done -> epilogue-2 may read D2
-//   D2_EMPTY     4 x kPair warp arrivals on the leader: epilogue-2 drained D2
+//   D2_EMPTY     8 x kPair warp arrivals on the leader: epilogue-2 drained D2
 //   SAMPLE_DONE  commit (multicast) after the last tile of a sample: B1/B2 may be overwritten
-//   VEC_FREE     4 local warp arrivals: epilogue-2 is done with this sample's bias vector (single-buffered)
+//   VEC_FREE     8 local warp arrivals: epilogue-2 is done with this sample's bias vector (single-buffered)
 template <int kPair, int kAct>
 __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -242,9 +243,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     mbar_init(&bars[BAR_A1_FULL], 4 * kPair);
     mbar_init(&bars[BAR_D1_FULL], 1);
     mbar_init(&bars[BAR_D2_FULL], 1);
-    mbar_init(&bars[BAR_D2_EMPTY], 4 * kPair);
+    mbar_init(&bars[BAR_D2_EMPTY], 8 * kPair);
     mbar_init(&bars[BAR_SAMPLE_DONE], 1);
-    mbar_init(&bars[BAR_VEC_FREE], 4);
+    mbar_init(&bars[BAR_VEC_FREE], 8);
     for (int i = 0; i < kTcRing; ++i) {
       mbar_init(&bars[BAR_A2_FULL + i], 4 * kPair);
       mbar_init(&bars[BAR_A2_EMPTY + i], 1);
@@ -473,33 +474,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     }
   } else {
     // ===================== WG-B: epilogue 2 + predictive reduction; thread = one point ===============================
-    const int wq = warp - 8;
-    const int row = wq * 32 + lane;
-    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
+    const int quarter = warp & 3, half = (warp - 8) >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     uint32_t tile_cnt = 0;
     const long long M = p.N * p.O;
     double* st_mean = p.part ? p.part + (long long)g * 2 * M : nullptr;
     double* st_m2 = p.part ? st_mean + M : nullptr;
     const uint32_t b2v = s_vec + (uint32_t)p.N1 * 4u, w3v = b2v + (uint32_t)p.N2 * 4u;
     const float* b3 = reinterpret_cast<const float*>(smem + p.sm_vec) + p.N1 + p.N2 + p.O * p.N2;
+    float* ypart = reinterpret_cast<float*>(smem + p.sm_ypart);   // [128][O] partial outputs of the half-1 warps
+    const int nb16 = p.N2 >> 4;
+    const int c_lo = half == 0 ? 0 : ((nb16 + 1) >> 1) * 16, c_hi = half == 0 ? ((nb16 + 1) >> 1) * 16 : p.N2;
     for (int s = s0; s < s1; ++s) {
       const double inv_cnt = 1.0 / (double)(s - s0 + 1);
       mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
-      float y0[4] = {b3[0], p.O > 1 ? b3[1] : 0.f, p.O > 2 ? b3[2] : 0.f, p.O > 3 ? b3[3] : 0.f};
+      float y0[4] = {0.f, 0.f, 0.f, 0.f};
+      if (half == 0) { y0[0] = b3[0]; if (p.O > 1) y0[1] = b3[1]; if (p.O > 2) y0[2] = b3[2]; if (p.O > 3) y0[3] = b3[3]; }
       for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
         const uint32_t tpar = tile_cnt & 1u;
         const long long n = ((long long)pt * kPair + rank) * 128 + row;
         const bool in_range = n < p.N;
         // this point's Welford state, fetched before the wait so that its latency hides behind the MMAs
         double mu0[4] = {0.0, 0.0, 0.0, 0.0}, q0[4] = {0.0, 0.0, 0.0, 0.0};
-        if (in_range && st_mean && s != s0) {
+        if (half == 0 && in_range && st_mean && s != s0) {
           for (int o = 0; o < p.O; ++o) {
             mu0[o] = st_mean[n * p.O + o];
             q0[o] = st_m2[n * p.O + o];
           }
         }
-        // ---- epilogue 2: D2 -> y[o] = b3[o] + sum_j w3[o][j] * act(d + b2[j]); the TMEM load of batch i+1 is in
-        //      flight while batch i is reduced
+        // ---- epilogue 2: D2 -> y[o] = b3[o] + sum_j w3[o][j] * act(d + b2[j]) over this warp's column half; the TMEM
+        //      load of batch i+1 is in flight while batch i is reduced (4 independent partial sums per output)
         mbar_wait(&bars[BAR_D2_FULL], tpar);
         tc::fence_after_thread_sync();
         float y[4] = {y0[0], y0[1], y0[2], y0[3]};
@@ -514,33 +519,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             t[q4 * 4 + 3] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 3]) + bq.w);
           }
           for (int o = 0; o < p.O; ++o) {
-            float acc = y[o];
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               const float4 wq4 = lds128(w3v + (uint32_t)(o * p.N2 + c0 + q4 * 4) * 4u);
-              acc = fmaf(wq4.x, t[q4 * 4 + 0], acc);
-              acc = fmaf(wq4.y, t[q4 * 4 + 1], acc);
-              acc = fmaf(wq4.z, t[q4 * 4 + 2], acc);
-              acc = fmaf(wq4.w, t[q4 * 4 + 3], acc);
+              a0 = fmaf(wq4.x, t[q4 * 4 + 0], a0);
+              a1 = fmaf(wq4.y, t[q4 * 4 + 1], a1);
+              a2 = fmaf(wq4.z, t[q4 * 4 + 2], a2);
+              a3 = fmaf(wq4.w, t[q4 * 4 + 3], a3);
             }
-            y[o] = acc;
+            y[o] += (a0 + a1) + (a2 + a3);
           }
         };
         uint32_t da[16], db[16];
-        tc::tmem_ld16_issue(tmem_d2 + lane_sel, da);
-        for (int c0 = 0; c0 < p.N2; c0 += 32) {
+        if (c_lo < c_hi) tc::tmem_ld16_issue(tmem_d2 + lane_sel + (uint32_t)c_lo, da);
+        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
           tc::tmem_ld_wait(da);
-          const bool more = c0 + 16 < p.N2;
+          const bool more = c0 + 16 < c_hi;
           if (more) tc::tmem_ld16_issue(tmem_d2 + lane_sel + (uint32_t)(c0 + 16), db);
           reduce16(da, c0);
           if (more) {
             tc::tmem_ld_wait(db);
-            if (c0 + 32 < p.N2) tc::tmem_ld16_issue(tmem_d2 + lane_sel + (uint32_t)(c0 + 32), da);
+            if (c0 + 32 < c_hi) tc::tmem_ld16_issue(tmem_d2 + lane_sel + (uint32_t)(c0 + 32), da);
             reduce16(db, c0 + 16);
           }
         }
-        // D2 is drained: let the next tile's layer-2 MMAs overwrite it; after the last tile of the sample the bias
-        // vector is free as well
+        // D2 is drained by this warp: let the next tile's layer-2 MMAs overwrite it; after the last tile of the sample
+        // the bias vector is free as well
         tc::fence_before_thread_sync();
         __syncwarp();
         if (lane == 0) {
@@ -548,8 +553,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
           else mbar_arrive_cluster(&bars[BAR_D2_EMPTY], 0);
           if (pt + 1 == pt1) mbar_arrive(&bars[BAR_VEC_FREE]);
         }
+        // the two column halves of a lane quarter meet in shared memory (named barrier 1 + quarter, 64 threads)
+        if (half == 1) {
+          for (int o = 0; o < p.O; ++o) ypart[row * p.O + o] = y[o];
+        }
+        named_bar_sync(1 + quarter, 64);
+        if (half == 0) {
+          for (int o = 0; o < p.O; ++o) y[o] += ypart[row * p.O + o];
+        }
+        named_bar_sync(1 + quarter, 64);   // ypart may be overwritten by the next tile
         // ---- predictive reduction: FP64 Welford state of this point (only this thread ever touches it)
-        if (in_range) {
+        if (half == 0 && in_range) {
           for (int o = 0; o < p.O; ++o) {
             const long long m = n * p.O + o;
             if (p.pred) p.pred[((long long)s * p.N + n) * p.O + o] = y[o];
@@ -680,6 +694,7 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
       p.sm_a1 = (int)o; o += (size_t)2 * p.Dp * 128 * 4;
       p.sm_ring = (int)o; o += (size_t)ring * kTcStageBytes;
       p.sm_vec = (int)o; o += (size_t)vec_pad * 4;
+      p.sm_ypart = (int)o; o += (size_t)128 * O * 4;
       o = (o + 15) & ~(size_t)15;
       p.sm_bar = (int)o; o += (size_t)BAR_COUNT * 8 + 16;
       if (o <= (size_t)227 * 1024) { kpair = kp; plan->smem = o; p.ring = ring; }

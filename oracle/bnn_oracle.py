@@ -24,6 +24,24 @@ F32_EPS = float(torch.finfo(torch.float32).eps)    # 2**-23
 F32_TINY = float(torch.finfo(torch.float32).tiny)  # 2**-126
 
 
+def warmup():
+    """Run torch's CPU kernels once before the oracle is used as a checker.
+
+    Observed on the GPU boxes (16-core Xeon, torch 2.11 CPU): the FIRST multi-threaded tanh/addmm call of a fresh
+    process occasionally returns values that differ by up to ~7e-5 on one thread's row chunk from every later
+    call with the same inputs (the device results agree with the later, stable values to 9e-7).  Tests, smoke() and
+    bench call this once so that the checker is deterministic."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4096, 64, generator=g)
+    w = torch.randn(128, 64, generator=g)
+    b = torch.zeros(128)
+    for _ in range(3):
+        for f in (torch.tanh, torch.relu, torch.sigmoid):
+            f(torch.addmm(b, x, w.t()))
+        F.softplus(x).sqrt().log1p()
+    return True
+
+
 # --------------------------------------------------------------------------- #
 # a1-a3: the MLP and the per-sample loop
 # --------------------------------------------------------------------------- #

@@ -20,3 +20,10 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _warm_cpu_oracle():
+    """See oracle.bnn_oracle.warmup(): torch's first CPU tanh/addmm call in a process is not reliable as a checker."""
+    from oracle import bnn_oracle
+    bnn_oracle.warmup()

@@ -25,6 +25,7 @@ def fused(dims, act, S, N, prec):
     import torch
     from helpers import random_nets, max_rel
     from oracle import bnn_oracle as O
+    O.warmup()
     from bnn_b200 import ops
     from bnn_b200.layout import Arch
     nets = random_nets(dims, S, seed=5)

@@ -8,7 +8,7 @@ from bnn_b200 import ops, _lib
 from bnn_b200.layout import Arch
 dims = [int(v) for v in os.environ.get("DIMS", "16,200,200,1").split(",")]
 arch = Arch(dims, "relu")
-S, N = 4, 75776
+S, N = 4, int(os.environ.get("NPTS", 75776))
 g = torch.Generator(device="cuda").manual_seed(0)
 X = torch.randn(N, dims[0], generator=g, device="cuda")
 bank = (0.1 * torch.randn(S, arch.stride, generator=g, device="cuda")) * arch.valid_mask().cuda()
