@@ -144,17 +144,20 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     __nanosleep(200);
   }
 }
+// Wait for the phase with the given parity.  try_wait takes a suspend-time hint: the hardware parks the thread until the
+// phase completes or the time limit expires, instead of returning after a short default limit -- with a dozen waiting
+// warps per SM, bare polling loops (TRYWAIT + BRA) took as many issue slots as the FFMAs of the working warps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(1000000u)
       : "memory");
 }
 // global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0, both 16B aligned)
