@@ -217,6 +217,20 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, 3))
     ms_e2e, _ = timed(step_e2e, e2e_steps, 1)
 
+    sgld = None
+    if not args.no_sgld:
+        try:
+            sgld = sgld_bench(dev, rank, args.sgld_steps)
+            if world > 1:
+                t = torch.tensor([sgld["steps_per_s_per_chain"]], device=dev, dtype=torch.float64)
+                dist.all_reduce(t)
+                sgld["steps_per_s_all_chains"] = float(t)
+            else:
+                sgld["steps_per_s_all_chains"] = sgld["steps_per_s_per_chain"]
+            sgld["chains"] = world
+        except Exception as e:      # the secondary metric must never take the headline down
+            sgld = {"error": repr(e)[:200]}
+
     evals_per_step = float(S) * n_gpus * N_POINTS
     value = evals_per_step * args.steps / (ms * 1e-3)
     e2e_value = evals_per_step * e2e_steps / (ms_e2e * 1e-3)
@@ -271,11 +285,79 @@ def run_ours(args):
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"S=16 samples x N=250000 points of the same workload, torch CPU loop, "
                                        f"{cores} threads, {cpu_t:.1f} s"},
-            "clocks": clk, "outputs_finite": finite,
+            "clocks": clk, "outputs_finite": finite, "sgld": sgld,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+SGLD_DIMS, SGLD_BATCH, SGLD_ROWS = [90, 512, 512, 512, 1], 128, 10_000_000     # BASELINE.json configs[4]
+
+
+def sgld_bench(dev, rank, steps, cpu=True):
+    """Secondary metric: SGLD steps/s of one pSGLD chain per GPU (cfg 5: synthetic 10M x 90 regression, 3x512 tanh MLP,
+    batch 128).  A step = minibatch gather + forward + backward (torch autograd captured in a CUDA graph: the stop-gap
+    SURVEY.md 8f ranks next) + the fused pSGLD update kernel + LR schedule."""
+    import torch
+    import torch.nn as nn
+    from bnn_b200.BNN_SGDMC import BNN_SGDMC
+    g = torch.Generator(device=dev).manual_seed(7)
+    X = torch.randn(SGLD_ROWS, SGLD_DIMS[0], generator=g, device=dev)
+    teacher = BNN_SGDMC(SGLD_DIMS[0], nn.Tanh(), SGLD_DIMS[1:-1], nout=1, conf={"device": str(dev), "seed": 7})
+    with torch.no_grad():
+        bank = teacher.arch.pack([teacher.nn.nn]).to(dev)
+        from bnn_b200 import ops
+        y = ops.forward(teacher.arch, X[:1_000_000].contiguous(), bank, want_pred=True, want_moments=False)["pred"].reshape(-1)
+        reps = SGLD_ROWS // y.shape[0]
+        y = y.repeat(reps) + 0.1 * torch.randn(SGLD_ROWS, generator=g, device=dev)   # teacher on a 1M slice, tiled (synthetic)
+    model = BNN_SGDMC(SGLD_DIMS[0], nn.Tanh(), SGLD_DIMS[1:-1], nout=1,
+                      conf={"device": str(dev), "seed": 100 + rank, "batch_size": SGLD_BATCH})
+    model._chain_init(dev)
+    model._perm, model._perm_pos = None, 0
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    yv = y.view(-1, 1)
+    model.sgld_steps(50, X, yv, gen)                    # warm-up (builds the graph)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    model.sgld_steps(steps, X, yv, gen)
+    e1.record()
+    torch.cuda.synchronize()
+    sps = steps / (e0.elapsed_time(e1) * 1e-3)
+    out = {"steps_per_s_per_chain": sps, "steps": steps, "batch": SGLD_BATCH, "params": model.arch.n_params + 1,
+           "workload": f"cfg5: one pSGLD chain per GPU, synthetic {SGLD_ROWS}x{SGLD_DIMS[0]} regression, "
+                       f"{'-'.join(map(str, SGLD_DIMS))} tanh MLP, batch {SGLD_BATCH}",
+           "gradient": "torch autograd in a CUDA graph (stop-gap)", "update": "bnn_psgld_step (fused, Philox in-kernel)",
+           "update_bytes_per_step": 20 * (model.arch.stride + 1)}
+    if cpu and rank == 0:
+        # CPU: the reference's sgld_steps body with the oracle's pSGLD restatement as the optimizer (pybnn is absent)
+        from oracle import bnn_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        Xc, yc = X[:100_000].cpu(), yv[:100_000].cpu()
+        net = [(W.clone(), b.clone()) for W, b in teacher.arch.unpack(bank[0].cpu())]
+        params = [t for pair in net for t in pair] + [torch.zeros(1)]
+        Vs = [torch.ones_like(t) for t in params]
+        def cpu_step(t):
+            idx = torch.randint(0, Xc.shape[0], (SGLD_BATCH,))
+            ps = [q.clone().requires_grad_(True) for q in params]
+            nn_ = [(ps[0], ps[1]), (ps[2], ps[3]), (ps[4], ps[5]), (ps[6], ps[7])]
+            U = O.sgdmc_neg_log_post(nn_, ps[8], Xc[idx], yc[idx], "tanh", SGLD_ROWS, 1e-2, 1e-1)
+            gs = torch.autograd.grad(U, ps)
+            f = float(O.lr_factor(t))
+            for k, (q, gq) in enumerate(zip(params, gs)):
+                params[k], Vs[k] = O.psgld_step(q, gq, Vs[k], (1e-1 if k == 8 else 2e-2) * f, torch.randn_like(q))
+        for t in range(5):
+            cpu_step(t)
+        t0 = time.perf_counter()
+        n_cpu = 100
+        for t in range(n_cpu):
+            cpu_step(5 + t)
+        out["cpu_steps_per_s"] = n_cpu / (time.perf_counter() - t0)
+        out["cpu_cores"] = os.cpu_count() or 1
+    del X, y
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -284,6 +366,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sgld", action="store_true", help="skip the secondary SGLD steps/s measurement")
+    ap.add_argument("--sgld-steps", type=int, default=2000)
     ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "fp32", "tf32"],
                     help="tf32x3: tcgen05 3-pass error-compensated (FP32-grade, default); fp32: SIMT FFMA; tf32: single pass (looser)")
     args = ap.parse_args()

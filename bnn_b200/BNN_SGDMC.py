@@ -11,6 +11,8 @@ What runs where:
     snapshots are row copies into the bank (BNN_SGDMC.py:124).
 pybnn is not needed.  The update rule is restated from Li et al. 2016 (UNPINNED).
 """
+import math
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -49,6 +51,7 @@ class BNN_SGDMC(nn.Module, BNN):
         self.psgld_alpha = conf.get('precondition_decay_rate', 0.99)
         self.psgld_lambda = conf.get('diagonal_bias', 1e-5)
         self.device = torch.device(conf['device']) if 'device' in conf else None
+        self.use_graph = bool(conf.get('cuda_graph', True))
 
         self.arch = Arch([dim] + list(num_hiddens) + [nout], act)
         self.log_precs = nn.Parameter(torch.zeros(self.nout))
@@ -65,76 +68,131 @@ class BNN_SGDMC(nn.Module, BNN):
 
     # ---- energy, evaluated on a packed parameter vector (BNN_SGDMC.py:61-74,83) ----------
     def _neg_log_post(self, theta, bx, by, num_train):
+        """U = -(loglik * N/|b| + logprior) on a packed parameter vector.  Written with Python-float constants only
+        (no host tensors are created), so that the whole forward + backward can be captured in a CUDA graph."""
         a = self.arch
         h = bx
         log_p = 0.
         for l in range(a.n_linear):
             blk = theta[a.offsets[l]: a.offsets[l] + a.outs[l] * a.lds[l]].view(a.outs[l], a.lds[l])
             W, b = blk[:, : a.ins[l]], blk[:, a.ins[l]]
-            std = self.gain * np.sqrt(2. / (a.outs[l] + a.ins[l]))
-            log_p = log_p + torch.distributions.Normal(0., std).log_prob(W).sum()
+            std = float(self.gain * np.sqrt(2. / (a.outs[l] + a.ins[l])))        # BNN_SGDMC.py:65
+            # sum of Normal(0, std).log_prob(W)                                    (:66)
+            log_p = log_p - (W * W).sum() / (2. * std * std) - W.numel() * (math.log(std) + 0.5 * math.log(2. * math.pi))
             h = torch.addmm(b, h, W.t())
             if l != a.n_linear - 1:
                 h = self._act_fn(h)
         log_precs = theta[a.stride: a.stride + self.nout]
         precs = log_precs.exp()
-        log_lik = (-0.5 * precs * (by - h) ** 2 + 0.5 * log_precs - 0.5 * np.log(2 * np.pi)).sum()
-        al, be = self.alpha_n.to(theta.device), self.beta_n.to(theta.device)
-        log_p = log_p + (torch.distributions.Gamma(al, be).log_prob(precs) + log_precs).sum()
+        log_lik = (-0.5 * precs * (by - h) ** 2 + 0.5 * log_precs - 0.5 * math.log(2. * math.pi)).sum()   # :72-74
+        al, be = float(self.alpha_n), float(self.beta_n)
+        # Gamma(al, be).log_prob(exp(l)) + l  (TransformedDistribution with ExpTransform().inv, :47,62)
+        log_p = log_p + (al * math.log(be) + (al - 1.) * log_precs - be * precs - math.lgamma(al) + log_precs).sum()
         return -1 * (log_lik * (num_train / bx.shape[0]) + log_p)
 
     @property
     def _act_fn(self):
         return {"relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "identity": lambda t: t}[self.arch.act]
 
+    # ---- the chain ----------------------------------------------------------------------------
+    def _chain_init(self, dev):
+        a = self.arch
+        n = (a.stride + self.nout + 3) // 4 * 4
+        self._theta = torch.zeros(n, device=dev)
+        self._theta[: a.stride] = a.pack([self.nn.nn])[0].to(dev)
+        self._theta[a.stride: a.stride + self.nout] = self.log_precs.data.to(dev)
+        self._V = torch.ones(n, device=dev)            # pybnn initialises the preconditioner state to ones
+        self._t = 0
+        self._valid = torch.zeros(n, device=dev)
+        self._valid[: a.stride] = a.valid_mask().to(dev).float()
+        self._valid[a.stride: a.stride + self.nout] = 1.
+        self._graph = None
+
+    def _grad_into(self, X, y, idx, num_train):
+        """loss and masked gradient of U at the current chain state for the minibatch idx (autograd stop-gap)."""
+        th = self._theta.detach().requires_grad_(True)
+        loss = self._neg_log_post(th, X[idx], y[idx], num_train)
+        grad, = torch.autograd.grad(loss, th)
+        return loss.detach(), grad * self._valid
+
+    def _build_graph(self, X, y, num_train):
+        """Capture forward + backward of one full-size minibatch in a CUDA graph (static index / gradient buffers):
+        at 1x50 .. 3x512 the step is launch-bound, so replaying one graph instead of ~60 eager launches is the
+        difference between ~2k and ~20k steps/s.  The pSGLD update stays a separate launch because its learning
+        rate changes every step."""
+        dev = self._theta.device
+        self._g_idx = torch.zeros(self.batch_size, dtype=torch.long, device=dev)
+        self._g_grad = torch.zeros_like(self._theta)
+        self._g_loss = torch.zeros((), device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                l, g = self._grad_into(X, y, self._g_idx, num_train)
+                self._g_grad.copy_(g); self._g_loss.copy_(l)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            l, g = self._grad_into(X, y, self._g_idx, num_train)
+            self._g_grad.copy_(g); self._g_loss.copy_(l)
+        self._graph = graph
+
+    def _sgld_step(self, X, y, idx, num_train):
+        """One SGLD step (BNN_SGDMC.py:81-87): gradient of U on the minibatch, fused pSGLD update, LR schedule."""
+        a = self.arch
+        if self.use_graph and idx.shape[0] == self.batch_size:
+            if self._graph is None:
+                self._build_graph(X, y, num_train)
+            self._g_idx.copy_(idx)
+            self._graph.replay()
+            loss, grad = self._g_loss, self._g_grad
+        else:                                                            # short last batch of an epoch: eager
+            loss, grad = self._grad_into(X, y, idx, num_train)
+            grad = grad.contiguous()
+        f = float(np.float32((1 + self._t) ** -0.33))                    # LambdaLR, BNN_SGDMC.py:101
+        ops.psgld_step(self._theta, grad, self._V, self.lr_weight * f, lr_tail=self.lr_noise * f, n_head=a.stride,
+                       alpha=self.psgld_alpha, lam=self.psgld_lambda, seed=self.seed, step=self._t)
+        self._t += 1
+        return loss
+
+    def sgld_steps(self, num_steps, X, y, gen):
+        """BNN_SGDMC.py:76-91: epochs of shuffled minibatches (last one may be short) until num_steps are done."""
+        num_train = X.shape[0]
+        step_cnt, loss = 0, torch.zeros(())
+        while step_cnt < num_steps:
+            if self._perm is None or self._perm_pos >= num_train:
+                self._perm = torch.randperm(num_train, generator=gen, device=X.device)   # DataLoader(shuffle=True), :110
+                self._perm_pos = 0
+            idx = self._perm[self._perm_pos: self._perm_pos + self.batch_size]
+            self._perm_pos += self.batch_size
+            loss = self._sgld_step(X, y, idx, num_train)
+            step_cnt += 1
+        return loss
+
     def train(self, X, y):
         dev = self._dev()
         a = self.arch
         X = self._to_dev(X)
         y = self._to_dev(y).view(-1, self.nout)
-        num_train = X.shape[0]
         if not self.warm_start or not hasattr(self, "_theta"):
             if not self.warm_start:
                 self.init_nn()
-            n = (a.stride + self.nout + 3) // 4 * 4
-            self._theta = torch.zeros(n, device=dev)
-            self._theta[: a.stride] = a.pack([self.nn.nn])[0].to(dev)
-            self._theta[a.stride: a.stride + self.nout] = self.log_precs.data.to(dev)
-            self._V = torch.ones(n, device=dev)            # pybnn initialises the preconditioner state to ones
-            self._t = 0
-        theta, V = self._theta, self._V
-        valid = torch.zeros_like(theta)
-        valid[: a.stride] = a.valid_mask().to(dev).float()
-        valid[a.stride: a.stride + self.nout] = 1.
-        gen = torch.Generator(device="cpu").manual_seed(self.seed)
-        bank_rows = []
-        step_cnt, total = 0, self.steps_burnin + self.steps
-        loss = torch.zeros(())
-        while step_cnt < total:
-            perm = torch.randperm(num_train, generator=gen).to(dev)      # DataLoader(shuffle=True), BNN_SGDMC.py:110
-            for i in range(0, num_train, self.batch_size):
-                idx = perm[i: i + self.batch_size]
-                th = theta.detach().requires_grad_(True)
-                loss = self._neg_log_post(th, X[idx], y[idx], num_train)
-                grad, = torch.autograd.grad(loss, th)
-                grad = (grad * valid).contiguous()
-                f = float(np.float32((1 + self._t) ** -0.33))                 # LambdaLR, BNN_SGDMC.py:101
-                ops.psgld_step(theta, grad, V, self.lr_weight * f, lr_tail=self.lr_noise * f, n_head=a.stride,
-                               alpha=self.psgld_alpha, lam=self.psgld_lambda, seed=self.seed, step=self._t)
-                theta.mul_(valid)                                            # padding stays zero
-                self._t += 1
-                step_cnt += 1
-                if step_cnt > self.steps_burnin and (step_cnt - self.steps_burnin) % self.keep_every == 0:
-                    bank_rows.append(theta[: a.stride].clone())
-                    prec = theta[a.stride: a.stride + self.nout].exp().mean()
-                    print('Step %4d, loss = %8.2f, precision = %g' % (step_cnt - self.steps_burnin, float(loss), float(prec)),
-                          flush=True)
-                if step_cnt >= total:
-                    break
-        self.nns = SampleBank(a, torch.stack(bank_rows).contiguous())
-        self.log_precs.data = theta[a.stride: a.stride + self.nout].detach().cpu()
-        last = a.to_module(theta[: a.stride])
-        self.nn.nn.load_state_dict(last.state_dict())
+            self._chain_init(dev)
+        self._graph = None
+        self._perm, self._perm_pos = None, 0
+        gen = torch.Generator(device=dev).manual_seed(self.seed)
+        self.sgld_steps(self.steps_burnin, X, y, gen)                     # burn-in
+        rows, step_cnt = [], 0
+        while step_cnt < self.steps:
+            loss = self.sgld_steps(self.keep_every, X, y, gen)
+            step_cnt += self.keep_every
+            self._theta.mul_(self._valid)                                 # Langevin noise also lands on layout padding: re-zero it
+            rows.append(self._theta[: a.stride].clone())                  # thinning snapshot = one bank row (:124)
+            prec = self._theta[a.stride: a.stride + self.nout].exp().mean()
+            print('Step %4d, loss = %8.2f, precision = %g' % (step_cnt, float(loss), float(prec)), flush=True)
+        self.nns = SampleBank(a, torch.stack(rows).contiguous())
+        self.log_precs.data = self._theta[a.stride: a.stride + self.nout].detach().cpu()
+        self.nn.nn.load_state_dict(a.to_module(self._theta[: a.stride]).state_dict())
         print('Number of samples: %d' % len(self.nns))
 
     # ---- the hot path (BNN_SGDMC.py:127-137) --------------------------------------------------
