@@ -116,41 +116,51 @@ class BNN_SGDMC(nn.Module, BNN):
         return loss.detach(), grad * self._valid
 
     def _build_graph(self, X, y, num_train):
-        """Capture forward + backward of one full-size minibatch in a CUDA graph (static index / gradient buffers):
-        at 1x50 .. 3x512 the step is launch-bound, so replaying one graph instead of ~60 eager launches is the
-        difference between ~2k and ~20k steps/s.  The pSGLD update stays a separate launch because its learning
-        rate changes every step."""
+        """Capture ONE WHOLE SGLD STEP in a CUDA graph: minibatch gather from the epoch permutation at a device-side
+        offset, forward + backward (torch autograd -- the stop-gap SURVEY.md 8f ranks next), the fused pSGLD update
+        with the LR-schedule factor computed in-kernel from a device step counter, and the counter increments.  At
+        1x50 .. 3x512 the step is launch-bound: one replay instead of ~60 eager launches + Python is the difference
+        between ~2k and >10k steps/s."""
         dev = self._theta.device
-        self._g_idx = torch.zeros(self.batch_size, dtype=torch.long, device=dev)
-        self._g_grad = torch.zeros_like(self._theta)
+        a = self.arch
+        self._g_off = torch.zeros((), dtype=torch.long, device=dev)           # position inside the epoch permutation
+        self._g_step = torch.full((), self._t, dtype=torch.long, device=dev)  # t of the LR schedule / Philox stream
         self._g_loss = torch.zeros((), device=dev)
+        self._g_perm = torch.zeros(num_train, dtype=torch.long, device=dev)
+        # every tensor the captured kernels read must outlive the graph: keep the index helper on self
+        self._g_ar = ar = torch.arange(self.batch_size, device=dev)
+
+        def one_step():
+            idx = self._g_perm[self._g_off + ar]
+            loss, grad = self._grad_into(X, y, idx, num_train)
+            ops.psgld_step_dev(self._theta, grad.contiguous(), self._V, self._g_step, self.lr_weight, lr_tail=self.lr_noise,
+                               n_head=a.stride, alpha=self.psgld_alpha, lam=self.psgld_lambda, seed=self.seed)
+            self._g_step.add_(1)
+            self._g_off.add_(self.batch_size)
+            self._g_loss.copy_(loss)
+
+        # warm-up on a side stream (autograd/cuBLAS workspaces), on scratch copies of the chain state
+        keep = (self._theta.clone(), self._V.clone())
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(3):
-                l, g = self._grad_into(X, y, self._g_idx, num_train)
-                self._g_grad.copy_(g); self._g_loss.copy_(l)
+                one_step()
         torch.cuda.current_stream(dev).wait_stream(side)
+        self._theta.copy_(keep[0]); self._V.copy_(keep[1])
+        self._g_step.fill_(self._t); self._g_off.zero_()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            l, g = self._grad_into(X, y, self._g_idx, num_train)
-            self._g_grad.copy_(g); self._g_loss.copy_(l)
+            one_step()
+        # the capture itself does not execute: state is untouched, counters still at (t, 0)
         self._graph = graph
 
     def _sgld_step(self, X, y, idx, num_train):
-        """One SGLD step (BNN_SGDMC.py:81-87): gradient of U on the minibatch, fused pSGLD update, LR schedule."""
+        """One eager SGLD step (BNN_SGDMC.py:81-87) -- used without CUDA graphs and for the short last batch of an epoch."""
         a = self.arch
-        if self.use_graph and idx.shape[0] == self.batch_size:
-            if self._graph is None:
-                self._build_graph(X, y, num_train)
-            self._g_idx.copy_(idx)
-            self._graph.replay()
-            loss, grad = self._g_loss, self._g_grad
-        else:                                                            # short last batch of an epoch: eager
-            loss, grad = self._grad_into(X, y, idx, num_train)
-            grad = grad.contiguous()
+        loss, grad = self._grad_into(X, y, idx, num_train)
         f = float(np.float32((1 + self._t) ** -0.33))                    # LambdaLR, BNN_SGDMC.py:101
-        ops.psgld_step(self._theta, grad, self._V, self.lr_weight * f, lr_tail=self.lr_noise * f, n_head=a.stride,
+        ops.psgld_step(self._theta, grad.contiguous(), self._V, self.lr_weight * f, lr_tail=self.lr_noise * f, n_head=a.stride,
                        alpha=self.psgld_alpha, lam=self.psgld_lambda, seed=self.seed, step=self._t)
         self._t += 1
         return loss
@@ -159,13 +169,26 @@ class BNN_SGDMC(nn.Module, BNN):
         """BNN_SGDMC.py:76-91: epochs of shuffled minibatches (last one may be short) until num_steps are done."""
         num_train = X.shape[0]
         step_cnt, loss = 0, torch.zeros(())
+        if self.use_graph and self._graph is None and num_train >= self.batch_size:
+            self._build_graph(X, y, num_train)
         while step_cnt < num_steps:
             if self._perm is None or self._perm_pos >= num_train:
                 self._perm = torch.randperm(num_train, generator=gen, device=X.device)   # DataLoader(shuffle=True), :110
                 self._perm_pos = 0
-            idx = self._perm[self._perm_pos: self._perm_pos + self.batch_size]
+                if self._graph is not None:
+                    self._g_perm.copy_(self._perm)
+                    self._g_off.zero_()
+            full = self._perm_pos + self.batch_size <= num_train
+            if self._graph is not None and full:
+                self._graph.replay()                                     # gather + fwd + bwd + update + counters
+                self._t += 1
+                loss = self._g_loss
+            else:
+                idx = self._perm[self._perm_pos: self._perm_pos + self.batch_size]
+                loss = self._sgld_step(X, y, idx, num_train)
+                if self._graph is not None:
+                    self._g_step.fill_(self._t)
             self._perm_pos += self.batch_size
-            loss = self._sgld_step(X, y, idx, num_train)
             step_cnt += 1
         return loss
 

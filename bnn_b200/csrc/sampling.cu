@@ -166,10 +166,19 @@ __global__ void __launch_bounds__(kEwBlock) apply_masks_kernel(const __grid_cons
 __global__ void __launch_bounds__(kEwBlock) psgld_kernel(float* __restrict__ theta, const float* __restrict__ grad,
                                                          float* __restrict__ V, long long n, long long n_head, float lr_head,
                                                          float lr_tail, float alpha, float lam, const float* __restrict__ noise,
-                                                         unsigned long long seed, long long step) {
+                                                         unsigned long long seed, long long step,
+                                                         const long long* __restrict__ step_dev) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long e = q << 2;
   if (e >= n) return;
+  if (step_dev) {
+    // graph-replay mode: the step counter lives on the device and the LambdaLR factor of BNN_SGDMC.py:101,
+    // np.float32((1 + it) ** -0.33), is applied here (double pow, rounded to float, exactly as numpy does)
+    step = *step_dev;
+    const float f = (float)pow((double)(1 + step), -0.33);
+    lr_head *= f;
+    lr_tail *= f;
+  }
   float z[4];
   if (!noise) philox_normal4(seed, (uint32_t)step, STREAM_SGLD, (uint64_t)q, z);
   const float om = 1.0f - alpha;
@@ -298,7 +307,19 @@ extern "C" int32_t bnn_psgld_step(float* theta, const float* grad, float* V, int
     BNN_FAIL("bnn_psgld_step: pointers must be 16-byte aligned");
   const long long quads = (n + 3) >> 2;
   psgld_kernel<<<(unsigned)((quads + kEwBlock - 1) / kEwBlock), kEwBlock, 0, (cudaStream_t)stream>>>(
-      theta, grad, V, n, n_head, lr_head, lr_tail, alpha, lam, noise, seed, step);
+      theta, grad, V, n, n_head, lr_head, lr_tail, alpha, lam, noise, seed, step, nullptr);
+  BNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t bnn_psgld_step_dev(float* theta, const float* grad, float* V, int64_t n, int64_t n_head, float lr_head,
+                                      float lr_tail, float alpha, float lam, uint64_t seed, const int64_t* step_dev,
+                                      void* stream) {
+  if (!theta || !grad || !V || !step_dev || n < 1) BNN_FAIL("bnn_psgld_step_dev: bad arguments");
+  if ((((uintptr_t)theta | (uintptr_t)grad | (uintptr_t)V) & 15) != 0) BNN_FAIL("bnn_psgld_step_dev: pointers must be 16-byte aligned");
+  const long long quads = (n + 3) >> 2;
+  psgld_kernel<<<(unsigned)((quads + kEwBlock - 1) / kEwBlock), kEwBlock, 0, (cudaStream_t)stream>>>(
+      theta, grad, V, n, n_head, lr_head, lr_tail, alpha, lam, nullptr, seed, 0, (const long long*)step_dev);
   BNN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -285,6 +285,17 @@ def psgld_step(theta, grad, V, lr_head, lr_tail=None, n_head=None, alpha=0.99, l
                                          seed & 0xFFFFFFFFFFFFFFFF, step, _stream(theta)), "bnn_psgld_step")
 
 
+def psgld_step_dev(theta, grad, V, step_dev, lr_head, lr_tail=None, n_head=None, alpha=0.99, lam=1e-5, seed=0):
+    """Graph-capturable pSGLD update: step index and LR-schedule factor come from the device counter `step_dev` (int64)."""
+    theta, grad, V = _dev(theta, "theta"), _dev(grad, "grad"), _dev(V, "V")
+    if step_dev.dtype != torch.int64 or not step_dev.is_cuda:
+        raise TypeError("step_dev must be an int64 CUDA tensor")
+    n = theta.numel()
+    _lib.check(_lib.lib().bnn_psgld_step_dev(_ptr(theta), _ptr(grad), _ptr(V), n, n if n_head is None else n_head, lr_head,
+                                             lr_head if lr_tail is None else lr_tail, alpha, lam, seed & 0xFFFFFFFFFFFFFFFF,
+                                             _ptr(step_dev), _stream(theta)), "bnn_psgld_step_dev")
+
+
 def philox_words(seed, subsequence, tag, n, device):
     out = torch.empty(n, dtype=torch.int32, device=device)
     _lib.check(_lib.lib().bnn_philox_words(seed, subsequence, tag, n, _ptr(out), _stream(out)), "bnn_philox_words")

@@ -185,6 +185,12 @@ int32_t bnn_psgld_step(float* theta, const float* grad, float* V, int64_t n, int
                        float lr_head, float lr_tail, float alpha, float lam, const float* noise,
                        uint64_t seed, int64_t step, void* stream);
 
+/* CUDA-graph friendly variant: the step index t is read from DEVICE memory (*step_dev), the base learning rates are
+ * multiplied in-kernel by the schedule factor float((1 + t) ** -0.33) of BNN_SGDMC.py:101, noise is always Philox
+ * (seed, t).  The caller increments *step_dev itself (stream-ordered) after the call.                          */
+int32_t bnn_psgld_step_dev(float* theta, const float* grad, float* V, int64_t n, int64_t n_head, float lr_head,
+                           float lr_tail, float alpha, float lam, uint64_t seed, const int64_t* step_dev, void* stream);
+
 /* raw Philox stream dump for tests: out[n] 32-bit words / normals */
 int32_t bnn_philox_words(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, uint32_t* out, void* stream);
 int32_t bnn_philox_normals(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, float* out, void* stream);

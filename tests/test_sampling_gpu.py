@@ -231,3 +231,17 @@ def test_psgld_stationary_variance():
             acc += float((theta.double() ** 2).mean()); cnt += 1
     assert abs(acc / cnt - s2) < 0.1 * s2
     assert bool((V == 1).all())
+
+
+def test_psgld_step_dev_equals_host_schedule():
+    """Graph-friendly variant: step index + LambdaLR factor from a device counter == host-side float32((1+t)**-0.33)."""
+    from bnn_b200 import ops
+    n, t = 4099, 37
+    g = torch.Generator().manual_seed(2)
+    theta, grad, V = torch.randn(n, generator=g), torch.randn(n, generator=g), torch.rand(n, generator=g) + 0.1
+    a_t, a_V = theta.cuda().clone(), V.cuda().clone()
+    b_t, b_V = theta.cuda().clone(), V.cuda().clone()
+    f = float(O.lr_factor(t))
+    ops.psgld_step(a_t, grad.cuda(), a_V, 2e-2 * f, lr_tail=1e-1 * f, n_head=n - 3, seed=9, step=t)
+    ops.psgld_step_dev(b_t, grad.cuda(), b_V, torch.tensor(t, dtype=torch.long, device="cuda"), 2e-2, lr_tail=1e-1, n_head=n - 3, seed=9)
+    assert torch.allclose(a_t, b_t, rtol=1e-6, atol=1e-7) and torch.equal(a_V, b_V)
