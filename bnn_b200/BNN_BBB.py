@@ -65,7 +65,7 @@ class BNN_BBB(BNN):
         self.weight_std = conf.get('weight_std', 0.1)
         self.kl_factor = conf.get('kl_factor', 1e-3)
         self.seed = int(conf.get('seed', 0))
-        self.precision = conf.get('precision', 'fp32')
+        self.precision = conf.get('precision', 'auto')   # tensor cores (3xTF32, FP32-grade) when the shape allows, else FP32 SIMT
         self.device = torch.device(conf['device']) if 'device' in conf else None
         self.arch = Arch([dim] + list(num_hiddens) + [1], act)
         self.nn = BayesianNN(dim, self.act, self.num_hiddens)

@@ -78,7 +78,7 @@ class BNN_CDropout(BNN):
         self.lscale = conf.get('lscale', 1e-1)
         self.dr = conf.get('dr', 2.)
         self.seed = int(conf.get('seed', 0))
-        self.precision = conf.get('precision', 'fp32')
+        self.precision = conf.get('precision', 'auto')   # tensor cores (3xTF32, FP32-grade) when the shape allows, else FP32 SIMT
         self.device = torch.device(conf['device']) if 'device' in conf else None
         self.arch = Arch([dim] + list(num_hiddens) + [1], act)
         self.layer_masked = [True] * self.arch.n_linear               # every layer, BNN_CDropout.py:59-65

@@ -44,7 +44,7 @@ class BNN_Dropout(BNN):
         self.l2_reg = conf.get('l2_reg', 1e-6)
         self.lr = conf.get('lr', 1e-2)
         self.seed = int(conf.get('seed', 0))
-        self.precision = conf.get('precision', 'fp32')
+        self.precision = conf.get('precision', 'auto')   # tensor cores (3xTF32, FP32-grade) when the shape allows, else FP32 SIMT
         self.device = torch.device(conf['device']) if 'device' in conf else None
         self.arch = Arch([dim] + list(num_hiddens) + [1], act)
         self.layer_masked = [i > 1 for i in self.arch.ins]             # BNN_Dropout.py:73

@@ -47,7 +47,7 @@ class BNN_SGDMC(nn.Module, BNN):
             print("Reset alpha_n = %g, beta_n = %g" % (self.alpha_n, self.beta_n))
         # ours
         self.seed = int(conf.get('seed', 0))
-        self.precision = conf.get('precision', 'fp32')
+        self.precision = conf.get('precision', 'auto')   # tensor cores (3xTF32, FP32-grade) when the shape allows, else FP32 SIMT
         self.psgld_alpha = conf.get('precondition_decay_rate', 0.99)
         self.psgld_lambda = conf.get('diagonal_bias', 1e-5)
         self.device = torch.device(conf['device']) if 'device' in conf else None

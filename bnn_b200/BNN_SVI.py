@@ -28,7 +28,7 @@ class BNN_SVI(BNN):
         self.weight_std = conf.get('weight_std', 1.0)
         self.noise_level = conf.get('noise_level', None)
         self.seed = int(conf.get('seed', 0))
-        self.precision = conf.get('precision', 'fp32')
+        self.precision = conf.get('precision', 'auto')   # tensor cores (3xTF32, FP32-grade) when the shape allows, else FP32 SIMT
         self.device = torch.device(conf['device']) if 'device' in conf else None
         self.arch = Arch([dim] + list(num_hiddens) + [1], act)
         self.nn = NN(dim, self.act, self.num_hiddens, nout=1)

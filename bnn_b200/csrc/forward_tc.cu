@@ -46,9 +46,17 @@ struct TcParams {
   float* pred;
   double* part;            // [G][2][M]  Welford state = shard moments
   int tmem_cols;
+  // per-sample input-unit masks (dropout family): m_off[l] = offset of Linear l's input mask in the mask vector, -1 = none
+  int mask_mode, mask_len, m_off[3];
+  const float* mask;
+  long long mask_stride;
+  float p_drop[3], temperature;
+  unsigned long long seed;
+  long long sample_offset;
+  int shared_w;            // 1: one network for all samples (w_stride == 0): operands are loaded once
   unsigned long long* trace;   // debug timeline (BNN_TC_TRACE), null in production
   // shared memory offsets (bytes)
-  int sm_b1, sm_b2, sm_vec, sm_a1, sm_ring, sm_bar, sm_ypart;
+  int sm_b1, sm_b2, sm_vec, sm_a1, sm_ring, sm_bar, sm_ypart, sm_mask;
 };
 
 // ---- operand image builder -------------------------------------------------------------------------
@@ -173,6 +181,16 @@ __device__ __forceinline__ void trace_ev(unsigned long long* tr, int who, uint32
   }
 }
 
+// keep-mask value of input unit j_global (index into the concatenated mask vector) of `layer` for global sample s:
+// identical streams to forward_simt.cu / bnn_dropout_masks, so all three agree bit for bit
+__device__ __forceinline__ float tc_mask_value(const TcParams& p, long long s_global, int s_local, int layer, int j_global) {
+  if (p.mask_mode == BNN_MASK_EXTERNAL) return __ldg(p.mask + (long long)s_local * p.mask_stride + j_global);
+  const uint32_t tag = p.mask_mode == BNN_MASK_BERNOULLI ? STREAM_BERNOULLI : STREAM_CONCRETE;
+  const u32x4 blk = philox_block(p.seed, (uint32_t)s_global, tag, (uint64_t)(j_global >> 2));
+  const float u = u24(pick_word(blk, j_global & 3));
+  return p.mask_mode == BNN_MASK_BERNOULLI ? bernoulli_keep(u, p.p_drop[layer]) : concrete_keep(u, p.p_drop[layer], p.temperature);
+}
+
 // barrier slots in shared memory
 enum { BAR_W_FULL = 0, BAR_A1_FULL, BAR_D1_FULL, BAR_D2_FULL, BAR_D2_EMPTY, BAR_SAMPLE_DONE, BAR_VEC_FREE, BAR_A2_FULL,
        BAR_A2_EMPTY = BAR_A2_FULL + kTcRing,
@@ -279,25 +297,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     trace_ev(tr, 0, tn, 20, 0);
     for (int s = s0; s < s1; ++s) {
       const uint32_t spar = (uint32_t)(s - s0) & 1u;
+      const bool reload = !p.shared_w || s == s0;   // a shared network is loaded once and stays resident
       // all MMAs of the previous sample are complete in both CTAs -> B1 / B2 may be overwritten
-      if (s > s0) mbar_wait(&bars[BAR_SAMPLE_DONE], spar ^ 1u);
-      const float* src = p.img + (long long)s * p.img_stride + (long long)rank * p.part_stride;
+      if (reload && s > s0) mbar_wait(&bars[BAR_SAMPLE_DONE], spar ^ 1u);
+      const long long s_img = p.shared_w ? 0 : s;
+      const float* src = p.img + s_img * p.img_stride + (long long)rank * p.part_stride;
       const uint32_t b1_bytes = three ? 2 * b1_hl_bytes : b1_hl_bytes;
       const uint32_t b2_bytes = three ? 2 * b2_hl_bytes : b2_hl_bytes;
-      if (tc::elect_one()) {
+      if (reload && tc::elect_one()) {
         mbar_arrive_expect_tx(&bars[BAR_W_FULL], b1_bytes + b2_bytes + (uint32_t)vec_pad * 4);
         bulk_g2s(smem + p.sm_b1, src, b1_bytes, &bars[BAR_W_FULL]);
         bulk_g2s(smem + p.sm_b2, src + 2 * (long long)(b1_hl_bytes / 4), b2_bytes, &bars[BAR_W_FULL]);
       }
       __syncwarp();
       // the bias vector is single-buffered: epilogue-2 of the previous sample must be done with it
-      if (s > s0) mbar_wait(&bars[BAR_VEC_FREE], spar ^ 1u);
-      if (tc::elect_one())
-        bulk_g2s(smem + p.sm_vec, p.img + (long long)s * p.img_stride + p.part_stride * kPair, (uint32_t)vec_pad * 4,
+      if (reload && s > s0) mbar_wait(&bars[BAR_VEC_FREE], spar ^ 1u);
+      if (reload && tc::elect_one())
+        bulk_g2s(smem + p.sm_vec, p.img + s_img * p.img_stride + p.part_stride * kPair, (uint32_t)vec_pad * 4,
                  &bars[BAR_W_FULL]);
       __syncwarp();
       if (!leader) continue;   // the peer CTA only loads; its tensor-core work is issued by the leader
-      mbar_wait(&bars[BAR_W_FULL], spar);
+      if (reload) mbar_wait(&bars[BAR_W_FULL], spar);
       for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
         const uint32_t tpar = tile_cnt & 1u;
         // ---- layer 1: D1 = A1 * B1^T
@@ -371,6 +391,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     uint32_t tile_cnt = 0, tn = 0;
     unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quarter == 0) ? p.trace : nullptr;
     const int who = 1 + set;
+    float* mk0 = reinterpret_cast<float*>(smem + p.sm_mask);   // this group's masks: m0[Dp] (inputs), m1[N1] (hidden 1)
+    float* mk1 = mk0 + p.Dp;
+    const bool has_m0 = p.mask_mode != BNN_MASK_NONE && p.m_off[0] >= 0;
+    const bool has_m1 = p.mask_mode != BNN_MASK_NONE && p.m_off[1] >= 0;
     // A1 granule kc of point n: hi/lo split of X[n][4kc .. 4kc+3] (zero beyond D / N)
     auto store_a1 = [&](int kc, const float (&x)[4]) {
       float4 hi, lo;
@@ -388,9 +412,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         x[e] = (n < p.N && k < p.D) ? __ldg(xr + k) : 0.0f;
       }
     };
+    auto mask_x = [&](int kc, float (&x)[4]) {   // dropout on the network inputs (BNN_Dropout.py:73-74 when dim > 1)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = kc * 4 + e;
+        if (k < p.D) x[e] *= mk0[k];
+      }
+    };
     constexpr int kPre = 4;   // granules of the next tile's input row prefetched into registers (D <= 16 fully)
     const int n_kc = p.Dp >> 2;
     for (int s = s0; s < s1; ++s) {
+      const bool reload = !p.shared_w || s == s0;
+      if (has_m0 || has_m1) {
+        // every WG-A warp is done with the previous sample's masks -> draw this sample's -> publish (named barrier 5)
+        named_bar_sync(5, 256);
+        const int t256 = warp * 32 + lane;
+        if (has_m0) for (int j = t256; j < p.D; j += 256) mk0[j] = tc_mask_value(p, p.sample_offset + s, s, 0, p.m_off[0] + j);
+        if (has_m1) for (int j = t256; j < p.N1; j += 256) mk1[j] = j < p.H1 ? tc_mask_value(p, p.sample_offset + s, s, 1, p.m_off[1] + j) : 0.0f;
+        named_bar_sync(5, 256);
+      }
       for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
         const uint32_t tpar = tile_cnt & 1u;
         float xn[kPre][4];
@@ -404,9 +444,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             for (int kc = 0; kc < n_kc; ++kc) {
               float x[4];
               load_x(n, kc, x);
+              if (has_m0) mask_x(kc, x);
               store_a1(kc, x);
             }
-            mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
+            if (reload) mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
             warp_signal_leader<kPair>(&bars[BAR_A1_FULL], lane);
           }
           if (have_next) {
@@ -414,7 +455,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             for (int kc = 0; kc < kPre; ++kc)
               if (kc < n_kc) load_x(n_next, kc, xn[kc]);
           }
-        } else if (pt == pt0) {
+        } else if (pt == pt0 && reload) {
           mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);   // b1 of this sample
         }
 
@@ -425,10 +466,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         if (set == 0 && have_next) {
 #pragma unroll
           for (int kc = 0; kc < kPre; ++kc)
-            if (kc < n_kc) store_a1(kc, xn[kc]);
+            if (kc < n_kc) {
+              if (has_m0) mask_x(kc, xn[kc]);
+              store_a1(kc, xn[kc]);
+            }
           for (int kc = kPre; kc < n_kc; ++kc) {
             float x[4];
             load_x(n_next, kc, x);
+            if (has_m0) mask_x(kc, x);
             store_a1(kc, x);
           }
           warp_signal_leader<kPair>(&bars[BAR_A1_FULL], lane);
@@ -452,6 +497,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             h[1] = act_ct<kAct>(d[q4 * 4 + 1] + bq.y);
             h[2] = act_ct<kAct>(d[q4 * 4 + 2] + bq.z);
             h[3] = act_ct<kAct>(d[q4 * 4 + 3] + bq.w);
+            if (has_m1) {   // dropout on the inputs of Linear 2
+              const float4 mq = *reinterpret_cast<const float4*>(mk1 + c0 + q4 * 4);
+              h[0] *= mq.x; h[1] *= mq.y; h[2] *= mq.z; h[3] *= mq.w;
+            }
             hi4[q4] = make_float4(tc::tf32_hi(h[0]), tc::tf32_hi(h[1]), tc::tf32_hi(h[2]), tc::tf32_hi(h[3]));
             lo4[q4] = make_float4(h[0] - hi4[q4].x, h[1] - hi4[q4].y, h[2] - hi4[q4].z, h[3] - hi4[q4].w);
           }
@@ -486,9 +535,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     float* ypart = reinterpret_cast<float*>(smem + p.sm_ypart);   // [128][O] partial outputs of the half-1 warps
     const int nb16 = p.N2 >> 4;
     const int c_lo = half == 0 ? 0 : ((nb16 + 1) >> 1) * 16, c_hi = half == 0 ? ((nb16 + 1) >> 1) * 16 : p.N2;
+    float* mk2 = reinterpret_cast<float*>(smem + p.sm_mask) + p.Dp + p.N1;   // this group's mask: m2[N2] (hidden 2)
+    const bool has_m2 = p.mask_mode != BNN_MASK_NONE && p.m_off[2] >= 0;
     for (int s = s0; s < s1; ++s) {
       const double inv_cnt = 1.0 / (double)(s - s0 + 1);
-      mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
+      if (!p.shared_w || s == s0) mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
+      if (has_m2) {
+        named_bar_sync(6, 256);
+        const int t256 = (warp - 8) * 32 + lane;
+        for (int j = t256; j < p.N2; j += 256) mk2[j] = j < p.H2 ? tc_mask_value(p, p.sample_offset + s, s, 2, p.m_off[2] + j) : 0.0f;
+        named_bar_sync(6, 256);
+      }
       float y0[4] = {0.f, 0.f, 0.f, 0.f};
       if (half == 0) { y0[0] = b3[0]; if (p.O > 1) y0[1] = b3[1]; if (p.O > 2) y0[2] = b3[2]; if (p.O > 3) y0[3] = b3[3]; }
       for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
@@ -517,6 +574,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             t[q4 * 4 + 1] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 1]) + bq.y);
             t[q4 * 4 + 2] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 2]) + bq.z);
             t[q4 * 4 + 3] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 3]) + bq.w);
+            if (has_m2) {   // dropout on the inputs of the last Linear
+              const float4 mq = *reinterpret_cast<const float4*>(mk2 + c0 + q4 * 4);
+              t[q4 * 4 + 0] *= mq.x; t[q4 * 4 + 1] *= mq.y; t[q4 * 4 + 2] *= mq.z; t[q4 * 4 + 3] *= mq.w;
+            }
           }
           for (int o = 0; o < p.O; ++o) {
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -669,8 +730,6 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   Layout L;
   if (make_layout(&a->desc, &L)) return -1;
   if (L.n_lin != 3) { set_error("tensor-core forward needs exactly 2 hidden layers (got %d Linear layers)", L.n_lin); return 1; }
-  if (a->mask.mode != BNN_MASK_NONE) { set_error("tensor-core forward does not take dropout masks yet"); return 1; }
-  if (a->w_stride == 0) { set_error("tensor-core forward needs a per-sample bank"); return 1; }
   const int D = L.in[0], H1 = L.out[0], H2 = L.out[1], O = L.out[2];
   if (D > 64 || H1 > 256 || H2 > 256 || O > 4) { set_error("tensor-core forward: shape outside D<=64, H<=256, O<=4"); return 1; }
   TcParams& p = plan->p;
@@ -696,6 +755,8 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
       p.sm_vec = (int)o; o += (size_t)vec_pad * 4;
       p.sm_ypart = (int)o; o += (size_t)128 * O * 4;
       o = (o + 15) & ~(size_t)15;
+      p.sm_mask = (int)o; if (a->mask.mode != BNN_MASK_NONE) o += (size_t)(p.Dp + p.N1 + p.N2) * 4;
+      o = (o + 15) & ~(size_t)15;
       p.sm_bar = (int)o; o += (size_t)BAR_COUNT * 8 + 16;
       if (o <= (size_t)227 * 1024) { kpair = kp; plan->smem = o; p.ring = ring; }
     }
@@ -710,6 +771,17 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   if (tc > 512) { set_error("tensor-core forward: accumulators exceed TMEM"); return 1; }
   p.tmem_cols = tc;
   p.X = a->X; p.N = a->N; p.S = (int)a->S; p.pred = a->pred;
+  p.shared_w = a->w_stride == 0;
+  p.mask_mode = a->mask.mode;
+  if (a->mask.mode != BNN_MASK_NONE) {
+    int mo[BNN_MAX_LINEAR];
+    p.mask_len = make_mask_offsets(L, a->mask.layer_masked, mo);
+    for (int l = 0; l < 3; ++l) { p.m_off[l] = mo[l]; p.p_drop[l] = a->mask.p_drop[l]; }
+    p.mask = a->mask.mask; p.mask_stride = a->mask.mask_stride; p.temperature = a->mask.temperature;
+    p.seed = a->mask.seed; p.sample_offset = a->mask.sample_offset;
+  } else {
+    p.m_off[0] = p.m_off[1] = p.m_off[2] = -1;
+  }
   // work split: slots over pair-tiles, sample groups when there are too few tiles
   const int tile_pts = 128 * kpair;
   p.n_tiles = (int)((a->N + tile_pts - 1) / tile_pts);
@@ -726,7 +798,7 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   const long long Sg = (a->S + G - 1) / G;
   G = (a->S + Sg - 1) / Sg;
   p.G = (int)G; p.Sg = (int)Sg;
-  plan->img_bytes = ((long long)a->S * p.img_stride * 4 + 255) & ~255LL;
+  plan->img_bytes = ((long long)(p.shared_w ? 1 : a->S) * p.img_stride * 4 + 255) & ~255LL;
   plan->part_bytes = (long long)G * 2 * a->N * O * (long long)sizeof(double);
   TcPrepParams& q = plan->q;
   q.D = D; q.H1 = H1; q.H2 = H2; q.O = O; q.Dp = p.Dp; q.N1 = p.N1; q.N2 = p.N2; q.K2 = p.K2; q.kpair = kpair;
@@ -771,7 +843,7 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
   {
     long long bx = (p.img_stride + 255) / 256;
     if (bx > 64) bx = 64;
-    dim3 grid((unsigned)bx, (unsigned)a->S);
+    dim3 grid((unsigned)bx, (unsigned)(p.shared_w ? 1 : a->S));
     tc_prep_kernel<<<grid, 256, 0, st>>>(plan.q, a->W, img);
     BNN_CUDA(cudaGetLastError());
   }

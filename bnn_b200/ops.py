@@ -92,7 +92,12 @@ def forward(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=False, 
         a.mask = mask.spec(arch)
         if mask.kind == "external" and mask.mask.shape[0] != a.S:
             raise ValueError("mask rows != S")
-    a.precision = _PREC[precision]
+    if precision == "auto":     # tensor cores (FP32-grade 3xTF32) when the shape is supported, else the FP32 SIMT kernel
+        a.precision = _lib.PREC_TF32X3
+        if not _lib.lib().bnn_forward_tc_supported(C.byref(a)):
+            a.precision = _lib.PREC_FP32
+    else:
+        a.precision = _PREC[precision]
     N, O, Sn = X.shape[0], arch.nout, int(a.S)
     if N < 1 or Sn < 1:
         raise ValueError("need at least one point and one sample")

@@ -95,3 +95,43 @@ def test_unsupported_shapes_are_refused_loudly():
         with pytest.raises(ValueError, match="tensor-core"):
             ops.forward(arch, X, bank, precision="tf32x3")          # no silent fallback to the SIMT kernel
         assert ops.forward(arch, X, bank, precision="fp32")["mean"].shape == (10, dims[-1])
+
+
+@pytest.mark.parametrize("fixture,kind", [("dropout_protein.npz", "external"), ("cdropout_protein.npz", "external")])
+def test_tc_masked_shared_weights_golden(fixture, kind):
+    """Dropout family on the tensor-core path: ONE base network + per-sample input-unit masks vs the reference's
+    recorded predictions of S column-scaled deep copies."""
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    g = golden(fixture)
+    dims = [int(d) for d in g["dims"]]
+    arch = Arch(dims, "tanh")
+    base = arch.pack(flat_to_nets(g["base"][None], dims))[0].cuda()
+    masks = torch.from_numpy(g["masks"]).cuda()
+    X = torch.from_numpy(g["X"]).cuda()
+    cfg = ops.MaskConfig("external", [True, True, True], mask=masks)
+    out = ops.forward(arch, X, base, S=masks.shape[0], mask=cfg, want_pred=True, precision="tf32x3")
+    assert max_rel(out["pred"].cpu().squeeze(-1), g["pred"]) <= 2e-5
+    assert max_rel(out["mean"].cpu().squeeze(-1), g["mean"].squeeze(-1)) <= 1e-5
+
+
+@pytest.mark.parametrize("kind", ["bernoulli", "concrete"])
+def test_tc_inkernel_masks_match_simt(kind):
+    """In-kernel Philox masks: tensor-core and SIMT forwards draw the same masks (same counters), so they agree to
+    FP32-grade accuracy for any sharding; per-sample bank + masks and several tiles/samples per CTA are exercised."""
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    dims = [9, 100, 100, 1]
+    arch = Arch(dims, "tanh")
+    base = arch.pack(random_nets(dims, 1, seed=8))[0].cuda()
+    X = torch.randn(20000, 9, generator=torch.Generator().manual_seed(3)).cuda()
+    S = 23
+    cfg = ops.MaskConfig(kind, [True, True, True], p_drop=[0.2, 0.4, 0.1], temperature=0.1, seed=123, sample_offset=50)
+    a = ops.forward(arch, X, base, S=S, mask=cfg, want_pred=True, precision="fp32")
+    b = ops.forward(arch, X, base, S=S, mask=cfg, want_pred=True, precision="tf32x3")
+    assert max_rel(b["pred"].cpu(), a["pred"].cpu()) <= 1e-5
+    assert max_rel(b["mean"].cpu(), a["mean"].cpu()) <= 1e-5
+    bank = arch.pack(random_nets(dims, S, seed=9)).cuda()          # per-sample weights AND masks
+    a = ops.forward(arch, X, bank, mask=cfg, want_pred=True, precision="fp32")
+    b = ops.forward(arch, X, bank, mask=cfg, want_pred=True, precision="tf32x3")
+    assert max_rel(b["pred"].cpu(), a["pred"].cpu()) <= 1e-5

@@ -60,7 +60,9 @@ def bbb_cpu():
         nets.append([O.bbb_split(O.bbb_rsample(l.mu.detach().cpu(), l.rho.detach().cpu(), torch.randn(l.mu.shape))) for l in gls])
     return O.predict_mv(O.sample_predict(nets, X, "tanh"), 1000)
 tg, tc = gpu_time(bbb_gpu), cpu_time(bbb_cpu, reps=1)
-rows.append(("cfg2 BBB 1-50-50-1 tanh, S=1000 draws + predict, N=1000", 1000 * 1000, tg, tc, float("nan"), "fp32"))
+rows.append(("cfg2 BBB 1-50-50-1 tanh, S=1000 draws + predict, N=1000 (fp32)", 1000 * 1000, tg, tc, float("nan"), "fp32"))
+m.precision = "tf32x3"
+rows.append(("cfg2 BBB, same (tf32x3)", 1000 * 1000, gpu_time(bbb_gpu), tc, float("nan"), "tf32x3"))
 
 # cfg 3: BNN_Dropout / BNN_CDropout, 9-100-100-1 tanh, 1000 MC-dropout passes, N = 4573 (protein test split size)
 from bnn_b200.BNN_Dropout import BNN_Dropout
@@ -75,7 +77,9 @@ for cls, name in ((BNN_Dropout, "Dropout p=0.05"), (BNN_CDropout, "CDropout")):
         nets = [m.arch.unpack(nns.packed(i).cpu()) for i in range(64)]
         return O.predict_mv(O.sample_predict(nets, X, "tanh"), 4573)
     tg, tc = gpu_time(do_gpu), cpu_time(do_cpu, reps=1) * (1000 / 64)
-    rows.append((f"cfg3 {name} 9-100-100-1 tanh, S=1000 masks + predict, N=4573", 1000 * 4573, tg, tc, float("nan"), "fp32"))
+    rows.append((f"cfg3 {name} 9-100-100-1 tanh, S=1000 masks + predict, N=4573 (fp32)", 1000 * 4573, tg, tc, float("nan"), "fp32"))
+    m.precision = "tf32x3"
+    rows.append((f"cfg3 {name}, same (tf32x3, tensor cores)", 1000 * 4573, gpu_time(do_gpu), tc, float("nan"), "tf32x3"))
 
 # cfg 4 slice: 16-200-200-1 relu, S = 1250 on one GPU, N = 100k slice (full N = 1M is bench.py); tensor-core path
 from bnn_b200 import ops
