@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "tc_common.cuh"
+#include <type_traits>
 
 namespace bnn {
 
@@ -526,7 +527,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     const int quarter = warp & 3, half = (warp - 8) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-    uint32_t tile_cnt = 0;
+    uint32_t tile_cnt = 0, tn = 0;
+    unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quarter == 0) ? p.trace : nullptr;
+    const int who = 3 + half;
     const long long M = p.N * p.O;
     double* st_mean = p.part ? p.part + (long long)g * 2 * M : nullptr;
     double* st_m2 = p.part ? st_mean + M : nullptr;
@@ -535,7 +538,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     float* ypart = reinterpret_cast<float*>(smem + p.sm_ypart);   // [128][O] partial outputs of the half-1 warps
     const int nb16 = p.N2 >> 4;
     const int c_lo = half == 0 ? 0 : ((nb16 + 1) >> 1) * 16, c_hi = half == 0 ? ((nb16 + 1) >> 1) * 16 : p.N2;
-    float* mk2 = reinterpret_cast<float*>(smem + p.sm_mask) + p.Dp + p.N1;   // this group's mask: m2[N2] (hidden 2)
+    // with dropout on the inputs of the last Linear, w3 is replaced by a per-sample copy with its columns scaled by the
+    // mask -- exactly what the reference does to the weight matrix (BNN_Dropout.py:70-75, BNN_CDropout.py:59-65)
+    float* w3m = reinterpret_cast<float*>(smem + p.sm_mask) + p.Dp + p.N1;   // [O][N2]
+    const float* b2s = reinterpret_cast<const float*>(smem + p.sm_vec) + p.N1;
+    const float* w3s = b2s + p.N2;
     const bool has_m2 = p.mask_mode != BNN_MASK_NONE && p.m_off[2] >= 0;
     for (int s = s0; s < s1; ++s) {
       const double inv_cnt = 1.0 / (double)(s - s0 + 1);
@@ -543,7 +550,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
       if (has_m2) {
         named_bar_sync(6, 256);
         const int t256 = (warp - 8) * 32 + lane;
-        for (int j = t256; j < p.N2; j += 256) mk2[j] = j < p.H2 ? tc_mask_value(p, p.sample_offset + s, s, 2, p.m_off[2] + j) : 0.0f;
+        for (int j = t256; j < p.N2; j += 256) {
+          const float m = j < p.H2 ? tc_mask_value(p, p.sample_offset + s, s, 2, p.m_off[2] + j) : 0.0f;
+          for (int o = 0; o < p.O; ++o) w3m[o * p.N2 + j] = w3s[o * p.N2 + j] * m;
+        }
         named_bar_sync(6, 256);
       }
       float y0[4] = {0.f, 0.f, 0.f, 0.f};
@@ -562,49 +572,75 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         }
         // ---- epilogue 2: D2 -> y[o] = b3[o] + sum_j w3[o][j] * act(d + b2[j]) over this warp's column half; the TMEM
         //      load of batch i+1 is in flight while batch i is reduced (4 independent partial sums per output)
+        trace_ev(tr, who, tn, 30, tile_cnt);
         mbar_wait(&bars[BAR_D2_FULL], tpar);
         tc::fence_after_thread_sync();
+        trace_ev(tr, who, tn, 31, tile_cnt);
         float y[4] = {y0[0], y0[1], y0[2], y0[3]};
-        auto reduce16 = [&](const uint32_t (&d)[16], int c0) {
-          float t[16];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 bq = lds128(b2v + (uint32_t)(c0 + q4 * 4) * 4u);
-            t[q4 * 4 + 0] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 0]) + bq.x);
-            t[q4 * 4 + 1] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 1]) + bq.y);
-            t[q4 * 4 + 2] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 2]) + bq.z);
-            t[q4 * 4 + 3] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 3]) + bq.w);
-            if (has_m2) {   // dropout on the inputs of the last Linear
-              const float4 mq = *reinterpret_cast<const float4*>(mk2 + c0 + q4 * 4);
-              t[q4 * 4 + 0] *= mq.x; t[q4 * 4 + 1] *= mq.y; t[q4 * 4 + 2] *= mq.z; t[q4 * 4 + 3] *= mq.w;
-            }
-          }
-          for (int o = 0; o < p.O; ++o) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        // Every tcgen05.ld / wait::ld round trip costs a few hundred cycles here regardless of its width (8 warps and the
+        // next tile's layer-1 MMAs share the TMEM ports), so D2 is drained with 32-column loads and the
+        // activations are consumed four columns at a time to keep the register count under the 120 the CTA allows.
+        // kSingle (one output: every configuration the reference ships but the multi-output toy) keeps four running
+        // partial sums in registers; the general case predicates an unrolled loop so y[] is never indexed at run time.
+        auto drain = [&](auto single_tag) {
+          constexpr bool kSingle = decltype(single_tag)::value;
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          const float* w3p = has_m2 ? w3m : w3s;
+          // the 16-column constants are plain shared-memory loads the compiler may schedule freely (the asm wrappers
+          // serialised one exposed LDS latency per four columns); the first set is fetched before the TMEM wait
+          float4 bq[4], wq[4];
+          auto fetch = [&](int c) {
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
-              const float4 wq4 = lds128(w3v + (uint32_t)(o * p.N2 + c0 + q4 * 4) * 4u);
-              a0 = fmaf(wq4.x, t[q4 * 4 + 0], a0);
-              a1 = fmaf(wq4.y, t[q4 * 4 + 1], a1);
-              a2 = fmaf(wq4.z, t[q4 * 4 + 2], a2);
-              a3 = fmaf(wq4.w, t[q4 * 4 + 3], a3);
+              bq[q4] = *reinterpret_cast<const float4*>(b2s + c + q4 * 4);
+              if constexpr (kSingle) wq[q4] = *reinterpret_cast<const float4*>(w3p + c + q4 * 4);
             }
-            y[o] += (a0 + a1) + (a2 + a3);
+          };
+          auto reduce16 = [&](const uint32_t* d, int c) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float t0 = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 0]) + bq[q4].x);
+              const float t1 = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 1]) + bq[q4].y);
+              const float t2 = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 2]) + bq[q4].z);
+              const float t3 = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 3]) + bq[q4].w);
+              if constexpr (kSingle) {
+                acc[0] = fmaf(wq[q4].x, t0, acc[0]);
+                acc[1] = fmaf(wq[q4].y, t1, acc[1]);
+                acc[2] = fmaf(wq[q4].z, t2, acc[2]);
+                acc[3] = fmaf(wq[q4].w, t3, acc[3]);
+              } else {
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                  if (o < p.O) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(w3p + o * p.N2 + c + q4 * 4);
+                    acc[o] += fmaf(w4.x, t0, w4.y * t1) + fmaf(w4.z, t2, w4.w * t3);
+                  }
+                }
+              }
+            }
+          };
+          uint32_t d[32];
+          for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+            const bool wide = c_hi - c0 >= 32;
+            if (wide) tc::tmem_ld32_issue(tmem_d2 + lane_sel + (uint32_t)c0, d);
+            else tc::tmem_ld16_issue_lo(tmem_d2 + lane_sel + (uint32_t)c0, d);
+            fetch(c0);
+            tc::tmem_ld_wait32(d);
+            reduce16(d, c0);
+            if (wide) {
+              fetch(c0 + 16);
+              reduce16(d + 16, c0 + 16);
+            }
+          }
+          if constexpr (kSingle) y[0] += (acc[0] + acc[1]) + (acc[2] + acc[3]);
+          else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) y[o] += acc[o];
           }
         };
-        uint32_t da[16], db[16];
-        if (c_lo < c_hi) tc::tmem_ld16_issue(tmem_d2 + lane_sel + (uint32_t)c_lo, da);
-        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-          tc::tmem_ld_wait(da);
-          const bool more = c0 + 16 < c_hi;
-          if (more) tc::tmem_ld16_issue(tmem_d2 + lane_sel + (uint32_t)(c0 + 16), db);
-          reduce16(da, c0);
-          if (more) {
-            tc::tmem_ld_wait(db);
-            if (c0 + 32 < c_hi) tc::tmem_ld16_issue(tmem_d2 + lane_sel + (uint32_t)(c0 + 32), da);
-            reduce16(db, c0 + 16);
-          }
-        }
+        if (p.O == 1) drain(std::true_type{});
+        else drain(std::false_type{});
+        trace_ev(tr, who, tn, 32, tile_cnt);
         // D2 is drained by this warp: let the next tile's layer-2 MMAs overwrite it; after the last tile of the sample
         // the bias vector is free as well
         tc::fence_before_thread_sync();
@@ -755,7 +791,7 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
       p.sm_vec = (int)o; o += (size_t)vec_pad * 4;
       p.sm_ypart = (int)o; o += (size_t)128 * O * 4;
       o = (o + 15) & ~(size_t)15;
-      p.sm_mask = (int)o; if (a->mask.mode != BNN_MASK_NONE) o += (size_t)(p.Dp + p.N1 + p.N2) * 4;
+      p.sm_mask = (int)o; if (a->mask.mode != BNN_MASK_NONE) o += (size_t)(p.Dp + p.N1 + p.O * p.N2) * 4;
       o = (o + 15) & ~(size_t)15;
       p.sm_bar = (int)o; o += (size_t)BAR_COUNT * 8 + 16;
       if (o <= (size_t)227 * 1024) { kpair = kp; plan->smem = o; p.ring = ring; }
@@ -836,7 +872,7 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
   p.trace = nullptr;
   if (getenv("BNN_TC_TRACE")) {   // debug only: leaks one small buffer per call
     unsigned long long* tb = nullptr;
-    if (cudaMalloc(&tb, 3 * 4096 * 16) == cudaSuccess) { cudaMemsetAsync(tb, 0, 3 * 4096 * 16, st); p.trace = tb; g_tc_trace = tb; }
+    if (cudaMalloc(&tb, 5 * 4096 * 16) == cudaSuccess) { cudaMemsetAsync(tb, 0, 5 * 4096 * 16, st); p.trace = tb; g_tc_trace = tb; }
   }
   const bool want_moments = a->mean || a->var || a->part_mean || a->part_m2;
   p.part = want_moments ? reinterpret_cast<double*>(reinterpret_cast<char*>(a->workspace) + plan.img_bytes) : nullptr;
@@ -891,7 +927,7 @@ namespace bnn { unsigned long long* tc_trace_buffer(); }
 extern "C" int32_t bnn_tc_trace_dump(unsigned long long* host_out) {
   unsigned long long* t = bnn::tc_trace_buffer();
   if (!t || !host_out) BNN_FAIL("no trace recorded (set BNN_TC_TRACE=1)");
-  BNN_CUDA(cudaMemcpy(host_out, t, 3 * 4096 * 16, cudaMemcpyDeviceToHost));
+  BNN_CUDA(cudaMemcpy(host_out, t, 5 * 4096 * 16, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -126,7 +126,7 @@ int32_t bnn_forward(const BnnForwardArgs* a, void* stream);
 int32_t bnn_forward_tc_supported(const BnnForwardArgs* a);
 /* tcgen05 self-test: D[128, N] = A[128, K] * B[N, K]^T (row-major device buffers, K % 8 == 0, K <= 64,
  * N % 16 == 0, N <= 256, passes = 1 (TF32) or 3 (3xTF32)) through the kernels' own operand layout */
-/* debug: timeline of the last tensor-core launch made with BNN_TC_TRACE=1 in the environment (3*4096*2 uint64) */
+/* debug: timeline of the last tensor-core launch made with BNN_TC_TRACE=1 in the environment (5*4096*2 uint64) */
 int32_t bnn_tc_trace_dump(unsigned long long* host_out);
 int32_t bnn_tc_selftest(const float* A, const float* B, float* D, int32_t K, int32_t N, int32_t passes, void* stream);
 

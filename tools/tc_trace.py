@@ -21,18 +21,26 @@ ops.forward(arch, X, bank, precision=prec)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
-buf = np.zeros(3 * 4096 * 2, dtype=np.uint64)
+buf = np.zeros(5 * 4096 * 2, dtype=np.uint64)
 _lib.check(_lib.lib().bnn_tc_trace_dump(buf.ctypes.data), "dump")
-buf = buf.reshape(3, 4096, 2)
-names = {20: "start", 21: "tile_end", 1: "mma:wait_full", 2: "mma:got_full", 3: "mma:committed", 10: "ld_start", 11: "ld_done", 12: "wait_empty", 13: "got_empty", 14: "signalled"}
-t0 = min(int(buf[w, 0, 1]) for w in range(3) if buf[w, 0, 1])
+buf = buf.reshape(5, 4096, 2)
+names = {36: "B:issued", 33: "B:ldwait", 34: "B:ldok", 35: "B:reduced", 30: "B:wait_d2full", 31: "B:got_d2full", 32: "B:drained", 20: "start", 21: "tile_end", 1: "mma:wait_full", 2: "mma:got_full", 3: "mma:committed", 10: "ld_start", 11: "ld_done", 12: "wait_empty", 13: "got_empty", 14: "signalled"}
+t0 = min(int(buf[w, 0, 1]) for w in range(5) if buf[w, 0, 1])
 lo, hi = int(os.environ.get("IT0", 30)), int(os.environ.get("IT1", 42))
 ev = []
-for w in range(3):
+tl, th = int(os.environ.get("T0", 0)), int(os.environ.get("T1", 0))
+n_epi = 0
+for w in range(5):
     for tag_it, clk in buf[w]:
         if clk == 0: break
         tag, it = int(tag_it) >> 32, int(tag_it) & 0xffffffff
-        if lo <= it < hi: ev.append((int(clk) - t0, ["MMA", "A0", "A1"][w], names[tag], it))
+        if tag in (33, 34, 35, 36):
+            if os.environ.get('EPI2') and w == 3 and tl <= it < th: ev.append((int(clk) - t0, 'B0', names[tag], it))
+        elif tag >= 30:
+            if tl <= it < th: ev.append((int(clk) - t0, ["MMA", "A0", "A1", "B0", "B1"][w], names[tag], it))
+        elif tag in (20, 21):
+            if tl <= it < th: ev.append((int(clk) - t0, "MMA", names[tag], it))
+        elif lo <= it < hi: ev.append((int(clk) - t0, ["MMA", "A0", "A1", "B0", "B1"][w], names[tag], it))
 for e in sorted(ev): print(f"{e[0]:8d}  {e[1]:4s} {e[2]:14s} it={e[3]}")
 # per K-step period of the MMA thread
 m = [(int(t) & 0xffffffff, int(c)) for t, c in buf[0] if c and (int(t) >> 32) == 3]
