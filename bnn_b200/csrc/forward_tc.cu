@@ -562,14 +562,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         const uint32_t tpar = tile_cnt & 1u;
         const long long n = ((long long)pt * kPair + rank) * 128 + row;
         const bool in_range = n < p.N;
-        // this point's Welford state, fetched before the wait so that its latency hides behind the MMAs
-        double mu0[4] = {0.0, 0.0, 0.0, 0.0}, q0[4] = {0.0, 0.0, 0.0, 0.0};
-        if (half == 0 && in_range && st_mean && s != s0) {
-          for (int o = 0; o < p.O; ++o) {
-            mu0[o] = st_mean[n * p.O + o];
-            q0[o] = st_m2[n * p.O + o];
-          }
-        }
         // ---- epilogue 2: D2 -> y[o] = b3[o] + sum_j w3[o][j] * act(d + b2[j]) over this warp's column half; the TMEM
         //      load of batch i+1 is in flight while batch i is reduced (4 independent partial sums per output)
         trace_ev(tr, who, tn, 30, tile_cnt);
@@ -650,25 +642,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
           else mbar_arrive_cluster(&bars[BAR_D2_EMPTY], 0);
           if (pt + 1 == pt1) mbar_arrive(&bars[BAR_VEC_FREE]);
         }
+        // this point's Welford state: fetched only now, off the critical path (D2 is already released and this warpgroup
+        // idles until the next tile's layer 2 is done), so that it holds no registers while D2 is drained
+        double mu0[4] = {0.0, 0.0, 0.0, 0.0}, q0[4] = {0.0, 0.0, 0.0, 0.0};
+        if (half == 0 && in_range && st_mean && s != s0) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {   // unrolled + predicated: mu0/q0/y stay in registers
+            if (o < p.O) {
+              mu0[o] = st_mean[n * p.O + o];
+              q0[o] = st_m2[n * p.O + o];
+            }
+          }
+        }
         // the two column halves of a lane quarter meet in shared memory (named barrier 1 + quarter, 64 threads)
         if (half == 1) {
-          for (int o = 0; o < p.O; ++o) ypart[row * p.O + o] = y[o];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) if (o < p.O) ypart[row * p.O + o] = y[o];
         }
         named_bar_sync(1 + quarter, 64);
         if (half == 0) {
-          for (int o = 0; o < p.O; ++o) y[o] += ypart[row * p.O + o];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) if (o < p.O) y[o] += ypart[row * p.O + o];
         }
         named_bar_sync(1 + quarter, 64);   // ypart may be overwritten by the next tile
         // ---- predictive reduction: FP64 Welford state of this point (only this thread ever touches it)
         if (half == 0 && in_range) {
-          for (int o = 0; o < p.O; ++o) {
-            const long long m = n * p.O + o;
-            if (p.pred) p.pred[((long long)s * p.N + n) * p.O + o] = y[o];
-            if (st_mean) {
-              const double dlt = (double)y[o] - mu0[o];
-              const double mu = mu0[o] + dlt * inv_cnt;
-              st_mean[m] = mu;
-              st_m2[m] = q0[o] + dlt * ((double)y[o] - mu);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            if (o < p.O) {
+              const long long m = n * p.O + o;
+              if (p.pred) p.pred[((long long)s * p.N + n) * p.O + o] = y[o];
+              if (st_mean) {
+                const double dlt = (double)y[o] - mu0[o];
+                const double mu = mu0[o] + dlt * inv_cnt;
+                st_mean[m] = mu;
+                st_m2[m] = q0[o] + dlt * ((double)y[o] - mu);
+              }
             }
           }
         }
@@ -693,7 +702,9 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(const float* __rest
   const uint32_t a_hl = (uint32_t)K * 128 * 4, b_hl = (uint32_t)K * N * 4;
   const uint32_t s_a = smem_u32(smem), s_b = s_a + 2 * a_hl;
   if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
-  if (warp == 4) tc::tmem_alloc(&tmem_slot, 256);
+  const bool a_in_tmem = (passes & 16) != 0;   // A operand staged in tensor memory (columns 256.. : hi[K], lo[K]; K <= 128)
+  passes &= 15;
+  if (warp == 4) tc::tmem_alloc(&tmem_slot, 512);
   // operands -> K-major granules, hi/lo
   for (int i = tid; i < (K / 4) * 128; i += blockDim.x) {
     const int kc = i / 128, r = i % 128;
@@ -716,7 +727,41 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(const float* __rest
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem = tmem_slot;
-  if (warp == 4 && lane == 0) {
+  if (a_in_tmem) {
+    if (warp < 4) {
+      const int r = warp * 32 + lane;
+      const uint32_t base = tmem + ((uint32_t)(warp * 32) << 16) + 256u;
+      for (int k0 = 0; k0 < K; k0 += 16) {
+        uint32_t hi[16], lo[16];
+        for (int j = 0; j < 16; ++j) {
+          const float x = k0 + j < K ? A[(size_t)r * K + k0 + j] : 0.0f;
+          const float h = tc::tf32_hi(x);
+          hi[j] = __float_as_uint(h);
+          lo[j] = __float_as_uint(x - h);
+        }
+        tc::tmem_st16(base + (uint32_t)k0, hi);
+        tc::tmem_st16(base + (uint32_t)(K + k0), lo);
+      }
+      tc::tmem_st_wait();
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+  }
+  if (warp == 4 && lane == 0 && a_in_tmem) {
+    const uint32_t idesc = tc::make_idesc_tf32(128, N);
+    for (int ks = 0; ks < K / 8; ++ks) {
+      const uint32_t a_hi = tmem + 256u + (uint32_t)(ks * 8), a_lo = a_hi + (uint32_t)K;
+      const uint64_t b_hi = tc::make_smem_desc(s_b + (uint32_t)(2 * ks) * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
+      const uint64_t b_lo = tc::make_smem_desc(s_b + b_hl + (uint32_t)(2 * ks) * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
+      tc::mma_tf32_ts(tmem, a_hi, b_hi, idesc, ks > 0);
+      if (passes == 3) {
+        tc::mma_tf32_ts(tmem, a_lo, b_hi, idesc, 1);
+        tc::mma_tf32_ts(tmem, a_hi, b_lo, idesc, 1);
+      }
+    }
+    tc::mma_commit(&bar);
+  } else if (warp == 4 && lane == 0) {
     const uint32_t idesc = tc::make_idesc_tf32(128, N);
     for (int ks = 0; ks < K / 8; ++ks) {
       const uint64_t a_hi = tc::make_smem_desc(s_a + (uint32_t)(2 * ks) * 2048u, 2048u, 128u);
@@ -743,7 +788,7 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(const float* __rest
   }
   tc::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem, 256);
+  if (warp == 4) tc::tmem_dealloc(tmem, 512);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
@@ -933,7 +978,7 @@ extern "C" int32_t bnn_tc_trace_dump(unsigned long long* host_out) {
 
 // D[128, N] = A[128, K] * B[N, K]^T on tcgen05 (device pointers; K % 8 == 0, K <= 64; N % 16 == 0, N <= 256)
 extern "C" int32_t bnn_tc_selftest(const float* A, const float* B, float* D, int32_t K, int32_t N, int32_t passes, void* stream) {
-  if (!A || !B || !D || K < 8 || K > 64 || (K & 7) || N < 16 || N > 256 || (N & 15) || (passes != 1 && passes != 3))
+  if (!A || !B || !D || K < 8 || K > 64 || (K & 7) || N < 16 || N > 256 || (N & 15) || ((passes & 15) != 1 && (passes & 15) != 3) || (passes & ~31))
     BNN_FAIL("bnn_tc_selftest: bad arguments");
   const size_t smem = (size_t)2 * K * 128 * 4 + (size_t)2 * K * N * 4;
   BNN_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

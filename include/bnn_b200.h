@@ -124,10 +124,11 @@ int32_t bnn_forward(const BnnForwardArgs* a, void* stream);
  * per-sample bank, no masks, and the hi/lo operand images of one network fit the shared memory of one CTA or
  * of a CTA pair -- e.g. 16-200-200-1 does, 64-256-256-4 does not), else 0 with the reason in bnn_last_error(); BNN_PREC_FP32 takes every shape */
 int32_t bnn_forward_tc_supported(const BnnForwardArgs* a);
-/* tcgen05 self-test: D[128, N] = A[128, K] * B[N, K]^T (row-major device buffers, K % 8 == 0, K <= 64,
- * N % 16 == 0, N <= 256, passes = 1 (TF32) or 3 (3xTF32)) through the kernels' own operand layout */
 /* debug: timeline of the last tensor-core launch made with BNN_TC_TRACE=1 in the environment (5*4096*2 uint64) */
 int32_t bnn_tc_trace_dump(unsigned long long* host_out);
+/* tcgen05 self-test: D[128, N] = A[128, K] * B[N, K]^T (row-major device buffers, K % 8 == 0, K <= 64,
+ * N % 16 == 0, N <= 256, passes = 1 (TF32) or 3 (3xTF32), + 16 to stage the A operand in tensor memory instead of
+ * shared memory) through the kernels' own operand layout */
 int32_t bnn_tc_selftest(const float* A, const float* B, float* D, int32_t K, int32_t N, int32_t passes, void* stream);
 
 /* ---- (e) standalone reduction and metrics ------------------------------- */
