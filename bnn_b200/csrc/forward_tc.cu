@@ -28,13 +28,13 @@ namespace bnn {
 constexpr int kTcThreads = 544;       // WG-A (8 warps) + WG-B (8 warps) + 1 MMA/loader warp
 constexpr int kTcMmaWarp = 16;
 constexpr int kTcEpiThreads = 128;
-constexpr int kTcRing = 4;            // max A2 ring stages
-constexpr int kTcStageBytes = 2 * 4 * 128 * 16;  // one stage = 16 K-columns (two K = 8 MMA steps): hi + lo, 4 granule columns x 128 rows x 16 B = 16 KB
+constexpr int kTcRing = 6;            // max A2 ring stages
+constexpr int kTcStageCols = 32;       // one A2 stage = 16 K-columns (two K = 8 MMA steps) in tensor memory: hi[16] then lo[16]
 
 struct TcParams {
   int D, H1, H2, O, act;
   int Dp, N1, N2, K2;      // padded: K of layer 1 (mult of 8), N of layers 1/2 (mult of 16), K of layer 2 (mult of 8, <= N1)
-  int ring;                // A2 ring depth (2..kTcRing) in 16-column stages
+  int ring;                // A2 ring depth (2..kTcRing) in 16-column stages (tensor memory, after D1 and D2)
   int passes;              // 3 (tf32x3) or 1 (tf32)
   long long part_stride;   // floats per (sample, part) of the operand image
   long long img_stride;    // floats per sample of the operand image
@@ -57,7 +57,7 @@ struct TcParams {
   int shared_w;            // 1: one network for all samples (w_stride == 0): operands are loaded once
   unsigned long long* trace;   // debug timeline (BNN_TC_TRACE), null in production
   // shared memory offsets (bytes)
-  int sm_b1, sm_b2, sm_vec, sm_a1, sm_ring, sm_bar, sm_ypart, sm_mask;
+  int sm_b1, sm_b2, sm_vec, sm_a1, sm_bar, sm_ypart, sm_mask;
 };
 
 // ---- operand image builder -------------------------------------------------------------------------
@@ -146,6 +146,22 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
         : "memory");
   }
 }
+// same with the A operand in tensor memory (each CTA of a pair supplies its own 128 rows at the same TMEM address)
+template <int kPair>
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kPair == 1) {
+    tc::mma_tf32_ts(tmem_d, tmem_a, bdesc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
 // MMA completion -> arrival on the barrier at this offset in every CTA of the pair
 template <int kPair>
 __device__ __forceinline__ void mma_commit_all(uint64_t* bar) {
@@ -210,6 +226,17 @@ __device__ __forceinline__ void warp_signal_leader(uint64_t* bar, int lane) {
   }
 }
 
+// same for data handed over in tensor memory (tcgen05.st completed by the caller): no async-proxy fence needed
+template <int kPair>
+__device__ __forceinline__ void warp_signal_tmem(uint64_t* bar, int lane) {
+  tc::fence_before_thread_sync();
+  __syncwarp();
+  if (lane == 0) {
+    if constexpr (kPair == 1) mbar_arrive(bar);
+    else mbar_arrive_cluster(bar, 0);
+  }
+}
+
 template <int kAct>
 __device__ __forceinline__ float act_ct(float v) {
   if constexpr (kAct == BNN_ACT_RELU) return fmaxf(v, 0.0f);
@@ -240,7 +267,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.sm_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   const uint32_t s_b1 = smem_u32(smem + p.sm_b1), s_b2 = smem_u32(smem + p.sm_b2);
-  const uint32_t s_a1 = smem_u32(smem + p.sm_a1), s_ring = smem_u32(smem + p.sm_ring);
+  const uint32_t s_a1 = smem_u32(smem + p.sm_a1);
   const uint32_t s_vec = smem_u32(smem + p.sm_vec);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -277,7 +304,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
   if constexpr (kPair == 2) cluster_sync_all();
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + (uint32_t)p.N1;
+  const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + (uint32_t)p.N1, tmem_a2 = tmem_d2 + (uint32_t)p.N2;
 
   if (warp == kTcMmaWarp) {
     // ===================== weight loader + MMA issuer =========================================================
@@ -290,7 +317,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? p.trace : nullptr;
     const uint64_t a1_desc0 = tc::make_smem_desc(s_a1, 2048u, 128u);
     const uint64_t b1_desc0 = tc::make_smem_desc(s_b1, (uint32_t)N1h * 16u, 128u);
-    const uint64_t a2_desc0 = tc::make_smem_desc(s_ring, 2048u, 128u);
     const uint64_t b2_desc0 = tc::make_smem_desc(s_b2, (uint32_t)N2h * 16u, 128u);
     const uint64_t b1_step = (uint64_t)(2 * N1h), b2_step = (uint64_t)(2 * N2h);   // 16-byte units per K = 8 step
     const uint64_t a_step = (uint64_t)(2 * 128);
@@ -339,7 +365,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
           mma_commit_all<kPair>(&bars[BAR_D1_FULL]);
         }
         __syncwarp();
-        // ---- layer 2: D2 = A2 * B2^T, A2 produced stage by stage (16 K-columns = two MMA K-steps) by epilogue-1.
+        // ---- layer 2: D2 = A2 * B2^T, A2 produced stage by stage (16 K-columns = two MMA K-steps) by epilogue-1 and
+        //      handed over in TENSOR MEMORY (the MMA reads its A operand from there), B2 from shared memory.
         //      Software pipelined: the (100+ cycle) barrier probe for stage b+1 runs while the tensor pipe executes
         //      the 6 MMAs of stage b; the commit of stage b is issued after it (it still only covers MMAs <= b).
         uint64_t b_hi = b2_desc0;
@@ -352,15 +379,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
           const uint32_t cur_st = ring_st;
           const int nks = min(2, n_k2 - 2 * b);
           if (tc::elect_one()) {
-            uint64_t a_hi = a2_desc0 + (uint64_t)(cur_st * (kTcStageBytes >> 4));
+            uint32_t a_hi = tmem_a2 + cur_st * (uint32_t)kTcStageCols;
             uint64_t bj = b_hi;
             for (int j = 0; j < nks; ++j) {
-              mma_tf32<kPair>(tmem_d2, a_hi, bj, idesc2, (b | j) > 0);
+              mma_tf32_ts<kPair>(tmem_d2, a_hi, bj, idesc2, (b | j) > 0);
               if (three) {
-                mma_tf32<kPair>(tmem_d2, a_hi + (uint64_t)(kTcStageBytes >> 5), bj, idesc2, 1);
-                mma_tf32<kPair>(tmem_d2, a_hi, bj + b_lo_off, idesc2, 1);
+                mma_tf32_ts<kPair>(tmem_d2, a_hi + 16u, bj, idesc2, 1);
+                mma_tf32_ts<kPair>(tmem_d2, a_hi, bj + b_lo_off, idesc2, 1);
               }
-              a_hi += a_step;
+              a_hi += 8u;
               bj += b2_step;
             }
           }
@@ -392,6 +419,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     uint32_t tile_cnt = 0, tn = 0;
     unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quarter == 0) ? p.trace : nullptr;
     const int who = 1 + set;
+    const bool three = p.passes == 3;
+    const float* b1s = reinterpret_cast<const float*>(smem + p.sm_vec);
     float* mk0 = reinterpret_cast<float*>(smem + p.sm_mask);   // this group's masks: m0[Dp] (inputs), m1[N1] (hidden 1)
     float* mk1 = mk0 + p.Dp;
     const bool has_m0 = p.mask_mode != BNN_MASK_NONE && p.m_off[0] >= 0;
@@ -489,10 +518,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
           trace_ev(tr, who, tn, 10, gb);
           tc::tmem_ld16(tmem_d1 + lane_sel + (uint32_t)c0, d);
           trace_ev(tr, who, tn, 11, gb);
-          float4 hi4[4], lo4[4];
+          uint32_t hi[16], lo[16];
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 bq = lds128(s_vec + (uint32_t)(c0 + q4 * 4) * 4u);
+            const float4 bq = *reinterpret_cast<const float4*>(b1s + c0 + q4 * 4);
             float h[4];
             h[0] = act_ct<kAct>(d[q4 * 4 + 0] + bq.x);
             h[1] = act_ct<kAct>(d[q4 * 4 + 1] + bq.y);
@@ -502,22 +531,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
               const float4 mq = *reinterpret_cast<const float4*>(mk1 + c0 + q4 * 4);
               h[0] *= mq.x; h[1] *= mq.y; h[2] *= mq.z; h[3] *= mq.w;
             }
-            hi4[q4] = make_float4(tc::tf32_hi(h[0]), tc::tf32_hi(h[1]), tc::tf32_hi(h[2]), tc::tf32_hi(h[3]));
-            lo4[q4] = make_float4(h[0] - hi4[q4].x, h[1] - hi4[q4].y, h[2] - hi4[q4].z, h[3] - hi4[q4].w);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float hh = tc::tf32_hi(h[e]);
+              hi[q4 * 4 + e] = __float_as_uint(hh);
+              lo[q4 * 4 + e] = __float_as_uint(h[e] - hh);
+            }
           }
           const uint32_t st = gb % (uint32_t)p.ring, use = gb / (uint32_t)p.ring;
           trace_ev(tr, who, tn, 12, gb);
-          mbar_wait(&bars[BAR_A2_EMPTY + st], (use & 1u) ^ 1u);
+          mbar_wait(&bars[BAR_A2_EMPTY + st], (use & 1u) ^ 1u);   // the MMAs that read this stage's previous contents are done
+          tc::fence_after_thread_sync();
           trace_ev(tr, who, tn, 13, gb);
-          const uint32_t sa = s_ring + st * kTcStageBytes + (uint32_t)row * 16u;
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            if (c0 + q4 * 4 < p.K2) {      // the last batch may hold a single K-step
-              sts128(sa + (uint32_t)q4 * 2048u, hi4[q4]);
-              sts128(sa + kTcStageBytes / 2 + (uint32_t)q4 * 2048u, lo4[q4]);
-            }
-          }
-          warp_signal_leader<kPair>(&bars[BAR_A2_FULL + st], lane);
+          const uint32_t ta = tmem_a2 + lane_sel + st * (uint32_t)kTcStageCols;
+          tc::tmem_st16(ta, hi);
+          if (three) tc::tmem_st16(ta + 16u, lo);
+          tc::tmem_st_wait();
+          warp_signal_tmem<kPair>(&bars[BAR_A2_FULL + st], lane);
           trace_ev(tr, who, tn, 14, gb);
         }
       }
@@ -825,21 +855,18 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   for (int kp = 1; kp <= 2 && !kpair; ++kp) {
     const int N1h = p.N1 / kp, N2h = p.N2 / kp;
     if ((N1h & 7) || (N2h & 7)) continue;
-    int ring_max = kTcRing;
-    if (const char* e = getenv("BNN_TC_RING")) { const int v = atoi(e); if (v >= 2 && v <= kTcRing) ring_max = v; }  // tuning knob
-    for (int ring = ring_max; ring >= 2 && !kpair; --ring) {
+    {
       size_t o = 0;
       p.sm_b1 = (int)o; o += (size_t)2 * p.Dp * N1h * 4;
       p.sm_b2 = (int)o; o += (size_t)2 * p.K2 * N2h * 4;
       p.sm_a1 = (int)o; o += (size_t)2 * p.Dp * 128 * 4;
-      p.sm_ring = (int)o; o += (size_t)ring * kTcStageBytes;
       p.sm_vec = (int)o; o += (size_t)vec_pad * 4;
       p.sm_ypart = (int)o; o += (size_t)128 * O * 4;
       o = (o + 15) & ~(size_t)15;
       p.sm_mask = (int)o; if (a->mask.mode != BNN_MASK_NONE) o += (size_t)(p.Dp + p.N1 + p.O * p.N2) * 4;
       o = (o + 15) & ~(size_t)15;
       p.sm_bar = (int)o; o += (size_t)BAR_COUNT * 8 + 16;
-      if (o <= (size_t)227 * 1024) { kpair = kp; plan->smem = o; p.ring = ring; }
+      if (o <= (size_t)227 * 1024) { kpair = kp; plan->smem = o; }
     }
   }
   if (!kpair) { set_error("tensor-core forward: weights do not fit shared memory even as a CTA pair"); return 1; }
@@ -847,9 +874,14 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   const int N1h = p.N1 / kpair, N2h = p.N2 / kpair;
   p.part_stride = 2LL * p.Dp * N1h + 2LL * p.K2 * N2h;
   p.img_stride = p.part_stride * kpair + vec_pad;
-  int cols = p.N1 + p.N2, tc = 32;
+  // tensor memory: D1 [N1] | D2 [N2] | A2 ring (as many 32-column stages as fit, 2..kTcRing)
+  int ring = (512 - p.N1 - p.N2) / kTcStageCols;
+  if (ring > kTcRing) ring = kTcRing;
+  if (const char* e = getenv("BNN_TC_RING")) { const int v = atoi(e); if (v >= 2 && v < ring) ring = v; }  // tuning knob
+  if (ring < 2) { set_error("tensor-core forward: accumulators and the activation ring exceed TMEM"); return 1; }
+  p.ring = ring;
+  int cols = p.N1 + p.N2 + ring * kTcStageCols, tc = 32;
   while (tc < cols) tc <<= 1;
-  if (tc > 512) { set_error("tensor-core forward: accumulators exceed TMEM"); return 1; }
   p.tmem_cols = tc;
   p.X = a->X; p.N = a->N; p.S = (int)a->S; p.pred = a->pred;
   p.shared_w = a->w_stride == 0;
