@@ -115,11 +115,12 @@ def forward(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=False, 
         out["part_m2"] = torch.empty(N, O, dtype=torch.float64, device=dev)
         a.part_mean, a.part_m2 = out["part_mean"].data_ptr(), out["part_m2"].data_ptr()
     L = _lib.lib()
-    if want_moments or want_partials:
-        nbytes = L.bnn_forward_workspace_bytes(C.byref(a))
-        if nbytes < 0:
-            _lib.check(-1, "bnn_forward_workspace_bytes")
-        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+    # scratch: Welford partials and, on the tensor-core path, the operand images (needed even for pred-only calls)
+    nbytes = L.bnn_forward_workspace_bytes(C.byref(a))
+    if nbytes < 0:
+        _lib.check(-1, "bnn_forward_workspace_bytes")
+    if nbytes > 0:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         out["_ws"] = ws   # keep alive until the caller drops the dict (stream-ordered use)
     _lib.check(L.bnn_forward(C.byref(a), _stream(X)), "bnn_forward")

@@ -137,3 +137,16 @@ def test_tc_inkernel_masks_match_simt(kind):
     a = ops.forward(arch, X, bank, mask=cfg, want_pred=True, precision="fp32")
     b = ops.forward(arch, X, bank, mask=cfg, want_pred=True, precision="tf32x3")
     assert max_rel(b["pred"].cpu(), a["pred"].cpu()) <= 1e-5
+
+
+def test_tc_pred_only_call():
+    """A pred-only call (no moments) still needs the operand-image scratch on the tensor-core path."""
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    dims, act = [16, 200, 200, 1], "relu"
+    nets, X = random_nets(dims, 3, seed=5), torch.randn(300, 16, generator=torch.Generator().manual_seed(6))
+    arch = Arch(dims, act)
+    out = ops.forward(arch, X.cuda(), arch.pack(nets).cuda(), want_pred=True, want_moments=False, precision="tf32x3")
+    torch.cuda.synchronize()
+    ref = O.sample_predict(nets, X, act, nout=1)
+    assert max_rel(out["pred"].cpu(), ref) < 1e-5
