@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbnn_b200.so")
+# BNN_B200_LIB selects another build of the same library (tools/tc_trace.py points it at the trace build)
+LIB_PATH = os.environ.get("BNN_B200_LIB") or os.path.join(HERE, "libbnn_b200.so")
 
 MAX_LINEAR = 8
 MAX_WIDTH = 1024
@@ -14,7 +15,7 @@ MAX_FUSED_NOUT = 64
 
 ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_IDENTITY = 0, 1, 2, 3
 MASK_NONE, MASK_EXTERNAL, MASK_BERNOULLI, MASK_CONCRETE = 0, 1, 2, 3
-PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
+PREC_FP32, PREC_TF32X3, PREC_TF32, PREC_TF32_BF16 = 0, 1, 2, 3
 SCALE_BBB, SCALE_SVI = 0, 1
 
 
@@ -49,6 +50,7 @@ PROTOTYPES = {
     "bnn_forward": (C.c_int32, [C.POINTER(ForwardArgs), C.c_void_p]),
     "bnn_forward_tc_supported": (C.c_int32, [C.POINTER(ForwardArgs)]),
     "bnn_tc_trace_dump": (C.c_int32, [C.c_void_p]),
+    "bnn_tc_mma_bench": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bnn_tc_selftest": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bnn_moments": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int64, C.c_void_p]),

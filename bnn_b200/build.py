@@ -25,9 +25,13 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, trace=False):
+    """trace=True builds libbnn_b200_trace.so: the same library with the in-kernel timeline probes of the tensor-core
+    forward compiled in (-DBNN_TC_TRACE_BUILD; debugging only, see tools/tc_trace.py)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_trace" if trace else "build")
+    lib = LIB.replace(".so", "_trace.so") if trace else LIB
+    flags = NVCC_FLAGS + (["-DBNN_TC_TRACE_BUILD"] if trace else [])
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "bnn_b200.h"))
@@ -37,13 +41,13 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             subprocess.run(cmd, check=True)
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs
+    if force or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-cudart", "static", "-o", lib] + objs
         subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

@@ -33,7 +33,9 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st);
 long long forward_tc_workspace_bytes(const BnnForwardArgs* a);
 int forward_tc_supported(const BnnForwardArgs* a);
 
-static bool use_tc(const BnnForwardArgs* a) { return a->precision == BNN_PREC_TF32X3 || a->precision == BNN_PREC_TF32; }
+static bool use_tc(const BnnForwardArgs* a) {
+  return a->precision == BNN_PREC_TF32X3 || a->precision == BNN_PREC_TF32 || a->precision == BNN_PREC_TF32_BF16;
+}
 
 static int check_forward_args(const BnnForwardArgs* a, bool host) {
   if (!a) BNN_FAIL("bnn_forward: null args");
@@ -48,7 +50,7 @@ static int check_forward_args(const BnnForwardArgs* a, bool host) {
   if (!host && (((uintptr_t)a->W) & 15)) BNN_FAIL("bnn_forward: W must be 16-byte aligned");
   if (a->mask.mode < BNN_MASK_NONE || a->mask.mode > BNN_MASK_CONCRETE) BNN_FAIL("bnn_forward: bad mask mode %d", a->mask.mode);
   if (a->mask.mode == BNN_MASK_EXTERNAL && !a->mask.mask) BNN_FAIL("bnn_forward: BNN_MASK_EXTERNAL without a mask tensor");
-  if (a->precision < BNN_PREC_FP32 || a->precision > BNN_PREC_TF32) BNN_FAIL("bnn_forward: unknown precision %d", a->precision);
+  if (a->precision < BNN_PREC_FP32 || a->precision > BNN_PREC_TF32_BF16) BNN_FAIL("bnn_forward: unknown precision %d", a->precision);
   if (!a->pred && !a->mean && !a->var && !a->part_mean && !a->part_m2) BNN_FAIL("bnn_forward: no output requested");
   return 0;
 }

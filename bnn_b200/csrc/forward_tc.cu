@@ -66,6 +66,7 @@ struct TcPrepParams {
   int ld0, ld1, ld2;
   long long off0, off1, off2, w_stride, part_stride, img_stride;
   int vec_len;
+  int mixed;   // second half of each operand region = two BF16 images (pairs per word) instead of the TF32 lo image
 };
 
 __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ TcPrepParams q, const float* __restrict__ W,
@@ -87,16 +88,32 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Tc
       if (r < 2 * b1_sz) { layer = 0; hl = r >= b1_sz; r -= hl * b1_sz; }
       else { r -= 2 * b1_sz; layer = 1; hl = r >= b2_sz; r -= hl * b2_sz; }
       const int rows = layer == 0 ? N1h : N2h;
-      const int e = (int)(r & 3);
-      const long long g = r >> 2;
-      const int kc = (int)(g / rows), n = (int)(g - (long long)kc * rows);
-      const int k = kc * 4 + e;
-      const int ng = part * rows + n;
-      float w = 0.0f;
-      if (layer == 0) { if (ng < q.H1 && k < q.D) w = Ws[q.off0 + (long long)ng * q.ld0 + k]; }
-      else            { if (ng < q.H2 && k < q.H1) w = Ws[q.off1 + (long long)ng * q.ld1 + k]; }
-      const float hi = tc::tf32_hi(w);
-      v = hl ? (w - hi) : hi;
+      auto weight = [&](int ng, int k) {
+        float w = 0.0f;
+        if (layer == 0) { if (ng < q.H1 && k < q.D) w = Ws[q.off0 + (long long)ng * q.ld0 + k]; }
+        else            { if (ng < q.H2 && k < q.H1) w = Ws[q.off1 + (long long)ng * q.ld1 + k]; }
+        return w;
+      };
+      if (hl && q.mixed) {
+        // BF16 images [kc8][n][8 x bf16]: bf16(w) in the first half of the region, bf16(w - tf32(w)) in the second
+        const long long half_sz = (layer == 0 ? b1_sz : b2_sz) >> 1;
+        const int lo_img = r >= half_sz;
+        r -= lo_img * half_sz;
+        const int e = (int)(r & 3);
+        const long long g = r >> 2;
+        const int kc8 = (int)(g / rows), n = (int)(g - (long long)kc8 * rows);
+        const int k = kc8 * 8 + 2 * e, ng = part * rows + n;
+        const float w0 = weight(ng, k), w1 = weight(ng, k + 1);
+        const uint32_t pk = lo_img ? tc::pack_bf16x2(w0 - tc::tf32_hi(w0), w1 - tc::tf32_hi(w1)) : tc::pack_bf16x2(w0, w1);
+        v = __uint_as_float(pk);
+      } else {
+        const int e = (int)(r & 3);
+        const long long g = r >> 2;
+        const int kc = (int)(g / rows), n = (int)(g - (long long)kc * rows);
+        const float w = weight(part * rows + n, kc * 4 + e);
+        const float hi = tc::tf32_hi(w);
+        v = hl ? (w - hi) : hi;
+      }
     } else {
       int j = (int)(r - q.part_stride * q.kpair);
       if (j < q.N1) { if (j < q.H1) v = Ws[q.off0 + (long long)j * q.ld0 + q.D]; }           // b1
@@ -162,6 +179,37 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         : "memory");
   }
 }
+// kind::f16 (BF16 operands, K = 16) variants for the correction terms of the mixed scheme
+template <int kPair>
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kPair == 1) {
+    tc::mma_bf16_ss(tmem_d, adesc, bdesc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+template <int kPair>
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kPair == 1) {
+    tc::mma_bf16_ts(tmem_d, tmem_a, bdesc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
 // MMA completion -> arrival on the barrier at this offset in every CTA of the pair
 template <int kPair>
 __device__ __forceinline__ void mma_commit_all(uint64_t* bar) {
@@ -190,6 +238,7 @@ __device__ __forceinline__ void tmem_dealloc_n(uint32_t addr, uint32_t ncols) {
 }
 
 // debug timeline: CTA (0,0) only; each traced warp owns 4096 (tag, clock) slots
+#ifdef BNN_TC_TRACE_BUILD
 __device__ __forceinline__ void trace_ev(unsigned long long* tr, int who, uint32_t& n, uint32_t tag, uint32_t it) {
   if (tr && n < 4096) {
     tr[((size_t)who * 4096 + n) * 2] = ((unsigned long long)tag << 32) | it;
@@ -197,6 +246,10 @@ __device__ __forceinline__ void trace_ev(unsigned long long* tr, int who, uint32
     ++n;
   }
 }
+#else
+// production build: the timeline probes compile to nothing (each one costs the single-threaded MMA issuer ~70 cycles)
+__device__ __forceinline__ void trace_ev(unsigned long long*, int, uint32_t&, uint32_t, uint32_t) {}
+#endif
 
 // keep-mask value of input unit j_global (index into the concatenated mask vector) of `layer` for global sample s:
 // identical streams to forward_simt.cu / bnn_dropout_masks, so all three agree bit for bit
@@ -320,7 +373,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     const uint64_t b2_desc0 = tc::make_smem_desc(s_b2, (uint32_t)N2h * 16u, 128u);
     const uint64_t b1_step = (uint64_t)(2 * N1h), b2_step = (uint64_t)(2 * N2h);   // 16-byte units per K = 8 step
     const uint64_t a_step = (uint64_t)(2 * 128);
-    const bool three = p.passes == 3;
+    const bool three = p.passes == 3, mixed = p.passes == 2;
+    const uint32_t idesc1h = tc::make_idesc_bf16(128 * kPair, p.N1), idesc2h = tc::make_idesc_bf16(128 * kPair, p.N2);
     trace_ev(tr, 0, tn, 20, 0);
     for (int s = s0; s < s1; ++s) {
       const uint32_t spar = (uint32_t)(s - s0) & 1u;
@@ -329,8 +383,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
       if (reload && s > s0) mbar_wait(&bars[BAR_SAMPLE_DONE], spar ^ 1u);
       const long long s_img = p.shared_w ? 0 : s;
       const float* src = p.img + s_img * p.img_stride + (long long)rank * p.part_stride;
-      const uint32_t b1_bytes = three ? 2 * b1_hl_bytes : b1_hl_bytes;
-      const uint32_t b2_bytes = three ? 2 * b2_hl_bytes : b2_hl_bytes;
+      const uint32_t b1_bytes = (three || mixed) ? 2 * b1_hl_bytes : b1_hl_bytes;
+      const uint32_t b2_bytes = (three || mixed) ? 2 * b2_hl_bytes : b2_hl_bytes;
       if (reload && tc::elect_one()) {
         mbar_arrive_expect_tx(&bars[BAR_W_FULL], b1_bytes + b2_bytes + (uint32_t)vec_pad * 4);
         bulk_g2s(smem + p.sm_b1, src, b1_bytes, &bars[BAR_W_FULL]);
@@ -359,6 +413,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
               mma_tf32<kPair>(tmem_d1, a_hi + a_lo_off, b_hi, idesc1, 1);
               mma_tf32<kPair>(tmem_d1, a_hi, b_hi + b_lo_off, idesc1, 1);
             }
+            if (mixed && (ks & 1)) {
+              // correction terms of this K = 16 block from the BF16 images (bf16(a) | bf16(a_lo) behind the TF32 image)
+              const uint64_t a16 = a1_desc0 + a_lo_off + (uint64_t)(ks >> 1) * a_step;
+              const uint64_t b16 = b1_desc0 + b_lo_off + (uint64_t)(ks >> 1) * b1_step;
+              mma_bf16<kPair>(tmem_d1, a16 + (a_lo_off >> 1), b16, idesc1h, 1);   // lo(a) . b
+              mma_bf16<kPair>(tmem_d1, a16, b16 + (b_lo_off >> 1), idesc1h, 1);   // a . lo(b)
+            }
             a_hi += a_step;
             b_hi += b1_step;
           }
@@ -369,7 +430,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         //      handed over in TENSOR MEMORY (the MMA reads its A operand from there), B2 from shared memory.
         //      Software pipelined: the (100+ cycle) barrier probe for stage b+1 runs while the tensor pipe executes
         //      the 6 MMAs of stage b; the commit of stage b is issued after it (it still only covers MMAs <= b).
-        uint64_t b_hi = b2_desc0;
         const uint64_t b_lo_off = (uint64_t)(b2_hl_bytes >> 4);
         mbar_wait(&bars[BAR_A2_FULL + ring_st], ring_par);
         mbar_wait(&bars[BAR_D2_EMPTY], tpar ^ 1u);   // epilogue-2 of the previous tile drained D2
@@ -377,31 +437,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         for (int b = 0; b < n_b2; ++b) {
           trace_ev(tr, 0, tn, 2, tile_cnt * n_b2 + b);
           const uint32_t cur_st = ring_st;
-          const int nks = min(2, n_k2 - 2 * b);
+          // Operands of this stage, computed HERE in convergent code so that they live in uniform registers: values
+          // produced inside the single-lane block below reach the UTCHMMA through one R2UR each, and that serial
+          // chain (not the tensor pipe) used to set the stage period.
+          const uint32_t a0 = tmem_a2 + cur_st * (uint32_t)kTcStageCols;
+          const uint64_t bd0 = b2_desc0 + (uint64_t)(2 * b) * b2_step, bd1 = bd0 + b2_step;
+          const uint32_t acc0 = b > 0 ? 1u : 0u;
+          const bool two = 2 * b + 1 < n_k2;   // the last stage of a 3xTF32 / TF32 tile may hold a single K-step
           if (tc::elect_one()) {
-            uint32_t a_hi = tmem_a2 + cur_st * (uint32_t)kTcStageCols;
-            uint64_t bj = b_hi;
-            for (int j = 0; j < nks; ++j) {
-              mma_tf32_ts<kPair>(tmem_d2, a_hi, bj, idesc2, (b | j) > 0);
-              if (three) {
-                mma_tf32_ts<kPair>(tmem_d2, a_hi + 16u, bj, idesc2, 1);
-                mma_tf32_ts<kPair>(tmem_d2, a_hi, bj + b_lo_off, idesc2, 1);
+            if (three) {
+              mma_tf32_ts<kPair>(tmem_d2, a0, bd0, idesc2, acc0);
+              mma_tf32_ts<kPair>(tmem_d2, a0 + 16u, bd0, idesc2, 1);
+              mma_tf32_ts<kPair>(tmem_d2, a0, bd0 + b_lo_off, idesc2, 1);
+              if (two) {
+                mma_tf32_ts<kPair>(tmem_d2, a0 + 8u, bd1, idesc2, 1);
+                mma_tf32_ts<kPair>(tmem_d2, a0 + 24u, bd1, idesc2, 1);
+                mma_tf32_ts<kPair>(tmem_d2, a0 + 8u, bd1 + b_lo_off, idesc2, 1);
               }
-              a_hi += 8u;
-              bj += b2_step;
+            } else if (mixed) {
+              // stage columns: tf32 hi [0,16) | bf16(a) pairs [16,24) | bf16(a_lo) pairs [24,32); the BF16 images of B2
+              // sit behind its TF32 image, one K = 16 block per stage
+              const uint64_t b16 = b2_desc0 + b_lo_off + (uint64_t)b * b2_step;
+              mma_tf32_ts<kPair>(tmem_d2, a0, bd0, idesc2, acc0);
+              mma_tf32_ts<kPair>(tmem_d2, a0 + 8u, bd1, idesc2, 1);
+              mma_bf16_ts<kPair>(tmem_d2, a0 + 24u, b16, idesc2h, 1);                     // lo(a) . b
+              mma_bf16_ts<kPair>(tmem_d2, a0 + 16u, b16 + (b_lo_off >> 1), idesc2h, 1);   // a . lo(b)
+            } else {
+              mma_tf32_ts<kPair>(tmem_d2, a0, bd0, idesc2, acc0);
+              if (two) mma_tf32_ts<kPair>(tmem_d2, a0 + 8u, bd1, idesc2, 1);
             }
+            // all MMAs issued so far complete -> the stage may be overwritten
+            mma_commit_all<kPair>(&bars[BAR_A2_EMPTY + cur_st]);
           }
           __syncwarp();
-          b_hi += b2_step * (uint64_t)nks;
+          trace_ev(tr, 0, tn, 3, tile_cnt * n_b2 + b);
           if (++ring_st == (uint32_t)p.ring) { ring_st = 0; ring_par ^= 1u; }
           if (b + 1 < n_b2) {
             trace_ev(tr, 0, tn, 1, tile_cnt * n_b2 + b + 1);
             mbar_wait(&bars[BAR_A2_FULL + ring_st], ring_par);
             tc::fence_after_thread_sync();
           }
-          if (tc::elect_one()) mma_commit_all<kPair>(&bars[BAR_A2_EMPTY + cur_st]);
-          __syncwarp();
-          trace_ev(tr, 0, tn, 3, tile_cnt * n_b2 + b);
         }
         if (tc::elect_one()) {
           mma_commit_all<kPair>(&bars[BAR_D2_FULL]);
@@ -419,7 +494,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     uint32_t tile_cnt = 0, tn = 0;
     unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quarter == 0) ? p.trace : nullptr;
     const int who = 1 + set;
-    const bool three = p.passes == 3;
+    const bool three = p.passes == 3, mixed = p.passes == 2;
     const float* b1s = reinterpret_cast<const float*>(smem + p.sm_vec);
     float* mk0 = reinterpret_cast<float*>(smem + p.sm_mask);   // this group's masks: m0[Dp] (inputs), m1[N1] (hidden 1)
     float* mk1 = mk0 + p.Dp;
@@ -432,7 +507,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
       lo.x = x[0] - hi.x; lo.y = x[1] - hi.y; lo.z = x[2] - hi.z; lo.w = x[3] - hi.w;
       const uint32_t a = s_a1 + (uint32_t)(kc * 128 + row) * 16u;
       sts128(a, hi);
-      sts128(a + a1_hl_bytes, lo);
+      if (mixed) {   // BF16 granule = 8 k: this 4-k granule fills half of one
+        const uint32_t a16 = s_a1 + a1_hl_bytes + (uint32_t)((kc >> 1) * 128 + row) * 16u + (uint32_t)(kc & 1) * 8u;
+        sts64(a16, make_float2(__uint_as_float(tc::pack_bf16x2(x[0], x[1])), __uint_as_float(tc::pack_bf16x2(x[2], x[3]))));
+        sts64(a16 + a1_hl_bytes / 2,
+              make_float2(__uint_as_float(tc::pack_bf16x2(lo.x, lo.y)), __uint_as_float(tc::pack_bf16x2(lo.z, lo.w))));
+      } else {
+        sts128(a + a1_hl_bytes, lo);
+      }
     };
     auto load_x = [&](long long n, int kc, float (&x)[4]) {
       const float* xr = p.X + n * p.D;
@@ -531,11 +613,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
               const float4 mq = *reinterpret_cast<const float4*>(mk1 + c0 + q4 * 4);
               h[0] *= mq.x; h[1] *= mq.y; h[2] *= mq.z; h[3] *= mq.w;
             }
+            float l[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float hh = tc::tf32_hi(h[e]);
               hi[q4 * 4 + e] = __float_as_uint(hh);
-              lo[q4 * 4 + e] = __float_as_uint(h[e] - hh);
+              l[e] = h[e] - hh;
+            }
+            if (mixed) {
+              lo[q4 * 2 + 0] = tc::pack_bf16x2(h[0], h[1]);
+              lo[q4 * 2 + 1] = tc::pack_bf16x2(h[2], h[3]);
+              lo[8 + q4 * 2 + 0] = tc::pack_bf16x2(l[0], l[1]);
+              lo[8 + q4 * 2 + 1] = tc::pack_bf16x2(l[2], l[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) lo[q4 * 4 + e] = __float_as_uint(l[e]);
             }
           }
           const uint32_t st = gb % (uint32_t)p.ring, use = gb / (uint32_t)p.ring;
@@ -545,7 +637,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
           trace_ev(tr, who, tn, 13, gb);
           const uint32_t ta = tmem_a2 + lane_sel + st * (uint32_t)kTcStageCols;
           tc::tmem_st16(ta, hi);
-          if (three) tc::tmem_st16(ta + 16u, lo);
+          if (three || mixed) tc::tmem_st16(ta + 16u, lo);   // tf32 lo [16,32)  or  bf16(h) pairs [16,24) | bf16(lo) pairs [24,32)
           tc::tmem_st_wait();
           warp_signal_tmem<kPair>(&bars[BAR_A2_FULL + st], lane);
           trace_ev(tr, who, tn, 14, gb);
@@ -735,6 +827,88 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(const float* __rest
   const bool a_in_tmem = (passes & 16) != 0;   // A operand staged in tensor memory (columns 256.. : hi[K], lo[K]; K <= 128)
   passes &= 15;
   if (warp == 4) tc::tmem_alloc(&tmem_slot, 512);
+  if (passes == 2) {
+    // ---- mixed scheme: a.b ~ tf32(a).tf32(b) [kind::tf32] + bf16(a - tf32(a)).bf16(b) + bf16(a).bf16(b - tf32(b)) [kind::f16];
+    //      per operand: tf32 image (16-byte granule = 4 k), then two bf16 images (16-byte granule = 8 k) in the second half
+    auto fill = [&](const float* src, int rows, uint32_t s_dst, uint32_t hl) {
+      for (int i = tid; i < (K / 8) * rows; i += blockDim.x) {
+        const int kc8 = i / rows, r = i % rows;
+        float x[8], h[8];
+        for (int e = 0; e < 8; ++e) { x[e] = src[(size_t)r * K + kc8 * 8 + e]; h[e] = tc::tf32_hi(x[e]); }
+        sts128(s_dst + (uint32_t)((2 * kc8) * rows + r) * 16u, make_float4(h[0], h[1], h[2], h[3]));
+        sts128(s_dst + (uint32_t)((2 * kc8 + 1) * rows + r) * 16u, make_float4(h[4], h[5], h[6], h[7]));
+        uint4 ph, pl;
+        ph.x = tc::pack_bf16x2(x[0], x[1]); ph.y = tc::pack_bf16x2(x[2], x[3]);
+        ph.z = tc::pack_bf16x2(x[4], x[5]); ph.w = tc::pack_bf16x2(x[6], x[7]);
+        pl.x = tc::pack_bf16x2(x[0] - h[0], x[1] - h[1]); pl.y = tc::pack_bf16x2(x[2] - h[2], x[3] - h[3]);
+        pl.z = tc::pack_bf16x2(x[4] - h[4], x[5] - h[5]); pl.w = tc::pack_bf16x2(x[6] - h[6], x[7] - h[7]);
+        *reinterpret_cast<uint4*>(smem + (s_dst - s_a) + hl + (size_t)i * 16) = ph;
+        *reinterpret_cast<uint4*>(smem + (s_dst - s_a) + hl + hl / 2 + (size_t)i * 16) = pl;
+      }
+    };
+    fill(A, 128, s_a, a_hl);
+    fill(B, N, s_b, b_hl);
+    fence_proxy_async();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem = tmem_slot;
+    if (a_in_tmem && warp < 4) {   // tensor memory: hi[K] | bf16 hi pairs [K/2] | bf16 lo pairs [K/2] from column 256
+      const int r = warp * 32 + lane;
+      const uint32_t base = tmem + ((uint32_t)(warp * 32) << 16) + 256u;
+      for (int k0 = 0; k0 < K; k0 += 16) {
+        uint32_t hi[16], ph[8], pl[8];
+        float x[16], h[16];
+        for (int j = 0; j < 16; ++j) { x[j] = A[(size_t)r * K + k0 + j]; h[j] = tc::tf32_hi(x[j]); hi[j] = __float_as_uint(h[j]); }
+        for (int j = 0; j < 8; ++j) {
+          ph[j] = tc::pack_bf16x2(x[2 * j], x[2 * j + 1]);
+          pl[j] = tc::pack_bf16x2(x[2 * j] - h[2 * j], x[2 * j + 1] - h[2 * j + 1]);
+        }
+        tc::tmem_st16(base + (uint32_t)k0, hi);
+        tc::tmem_st8(base + (uint32_t)(K + k0 / 2), ph);
+        tc::tmem_st8(base + (uint32_t)(K + K / 2 + k0 / 2), pl);
+      }
+      tc::tmem_st_wait();
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    if (warp == 4 && lane == 0) {
+      const uint32_t id32 = tc::make_idesc_tf32(128, N), id16 = tc::make_idesc_bf16(128, N);
+      for (int k16 = 0; k16 < K / 16; ++k16) {
+        const uint64_t b16h = tc::make_smem_desc(s_b + b_hl + (uint32_t)(2 * k16) * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
+        const uint64_t b16l = tc::make_smem_desc(s_b + b_hl + b_hl / 2 + (uint32_t)(2 * k16) * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
+        for (int j = 0; j < 2; ++j) {
+          const int ks = 2 * k16 + j;
+          const uint64_t bh = tc::make_smem_desc(s_b + (uint32_t)(2 * ks) * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
+          if (a_in_tmem) tc::mma_tf32_ts(tmem, tmem + 256u + (uint32_t)(ks * 8), bh, id32, ks > 0);
+          else tc::mma_tf32_ss(tmem, tc::make_smem_desc(s_a + (uint32_t)(2 * ks) * 2048u, 2048u, 128u), bh, id32, ks > 0);
+        }
+        if (a_in_tmem) {
+          tc::mma_bf16_ts(tmem, tmem + 256u + (uint32_t)(K + K / 2 + k16 * 8), b16h, id16, 1);   // lo(a) . b
+          tc::mma_bf16_ts(tmem, tmem + 256u + (uint32_t)(K + k16 * 8), b16l, id16, 1);           // a . lo(b)
+        } else {
+          tc::mma_bf16_ss(tmem, tc::make_smem_desc(s_a + a_hl + a_hl / 2 + (uint32_t)(2 * k16) * 2048u, 2048u, 128u), b16h, id16, 1);
+          tc::mma_bf16_ss(tmem, tc::make_smem_desc(s_a + a_hl + (uint32_t)(2 * k16) * 2048u, 2048u, 128u), b16l, id16, 1);
+        }
+      }
+      tc::mma_commit(&bar);
+    }
+    if (warp < 4) {
+      mbar_wait(&bar, 0);
+      tc::fence_after_thread_sync();
+      const int row = warp * 32 + lane;
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        float d[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, d);
+        for (int j = 0; j < 16; ++j) Dout[(size_t)row * N + c0 + j] = d[j];
+      }
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem, 512);
+    return;
+  }
   // operands -> K-major granules, hi/lo
   for (int i = tid; i < (K / 4) * 128; i += blockDim.x) {
     const int kc = i / 128, r = i % 128;
@@ -821,6 +995,65 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(const float* __rest
   if (warp == 4) tc::tmem_dealloc(tmem, 512);
 }
 
+// ---- MMA issue-rate probe (debug): `iters` back-to-back MMAs of one CTA (M = 128) into one accumulator, timed with
+//      clock64 from the first issue to the completion barrier.  mode: 0 tf32 SS, 1 tf32 TS, 2 bf16 SS, 3 bf16 TS,
+//      4 = the mixed stage pattern (tf32 TS x2 + bf16 TS x2), 5 = the 3xTF32 stage pattern (tf32 TS x6).
+//      Operand contents are whatever shared / tensor memory holds: only the timing is meaningful.
+__global__ void __launch_bounds__(160, 1) tc_mma_bench_kernel(int mode, int N, int iters, long long* out_clk) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 4) tc::tmem_alloc(&tmem_slot, 512);
+  fence_proxy_async();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 4) {   // converged warp, one elected lane issues (see the note in fwd_tc_kernel)
+    const uint32_t s0 = smem_u32(smem);
+    const uint64_t adesc = tc::make_smem_desc(s0, 2048u, 128u);
+    const uint64_t bdesc = tc::make_smem_desc(s0 + 8192u, (uint32_t)N * 16u, 128u);
+    const uint32_t id32 = tc::make_idesc_tf32(128, N), id16 = tc::make_idesc_bf16(128, N);
+    const uint32_t ta = tmem + 256u;
+    const long long t0 = clock64();
+    if (tc::elect_one()) {
+      if (mode == 0) for (int i = 0; i < iters; ++i) tc::mma_tf32_ss(tmem, adesc, bdesc, id32, 1);
+      else if (mode == 1) for (int i = 0; i < iters; ++i) tc::mma_tf32_ts(tmem, ta, bdesc, id32, 1);
+      else if (mode == 2) for (int i = 0; i < iters; ++i) tc::mma_bf16_ss(tmem, adesc, bdesc, id16, 1);
+      else if (mode == 3) for (int i = 0; i < iters; ++i) tc::mma_bf16_ts(tmem, ta, bdesc, id16, 1);
+      else if (mode == 4) {
+        for (int i = 0; i < iters; i += 4) {
+          tc::mma_tf32_ts(tmem, ta, bdesc, id32, 1);
+          tc::mma_tf32_ts(tmem, ta + 8u, bdesc, id32, 1);
+          tc::mma_bf16_ts(tmem, ta + 16u, bdesc, id16, 1);
+          tc::mma_bf16_ts(tmem, ta + 24u, bdesc, id16, 1);
+        }
+      } else {
+        for (int i = 0; i < iters; i += 3) {
+          tc::mma_tf32_ts(tmem, ta, bdesc, id32, 1);
+          tc::mma_tf32_ts(tmem, ta + 16u, bdesc, id32, 1);
+          tc::mma_tf32_ts(tmem, ta, bdesc, id32, 1);
+        }
+      }
+      tc::mma_commit(&bar);
+    }
+    __syncwarp();
+    const long long t1 = clock64();
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    if (lane == 0) {
+      out_clk[0] = t1 - t0;   // issue time
+      out_clk[1] = t2 - t0;   // until all MMAs completed
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem, 512);
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------
 static inline int roundup(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -846,8 +1079,9 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   TcParams& p = plan->p;
   memset(&p, 0, sizeof(p));
   p.D = D; p.H1 = H1; p.H2 = H2; p.O = O; p.act = L.act;
-  p.Dp = roundup(D, 8); p.N1 = roundup(H1, 16); p.N2 = roundup(H2, 16); p.K2 = roundup(H1, 8);
-  p.passes = a->precision == BNN_PREC_TF32 ? 1 : 3;
+  p.passes = a->precision == BNN_PREC_TF32 ? 1 : a->precision == BNN_PREC_TF32_BF16 ? 2 : 3;
+  const int kq = p.passes == 2 ? 16 : 8;   // the BF16 correction MMAs take K = 16 at a time
+  p.Dp = roundup(D, kq); p.N1 = roundup(H1, 16); p.N2 = roundup(H2, 16); p.K2 = roundup(H1, kq);
   p.vec_len = p.N1 + p.N2 + O * p.N2 + 4;
   const int vec_pad = (p.vec_len + 3) & ~3;
   // try one CTA per tile first (weights fully resident in one SM's shared memory), else a CTA pair
@@ -917,7 +1151,7 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   q.D = D; q.H1 = H1; q.H2 = H2; q.O = O; q.Dp = p.Dp; q.N1 = p.N1; q.N2 = p.N2; q.K2 = p.K2; q.kpair = kpair;
   q.ld0 = L.ld[0]; q.ld1 = L.ld[1]; q.ld2 = L.ld[2];
   q.off0 = L.off[0]; q.off1 = L.off[1]; q.off2 = L.off[2];
-  q.w_stride = a->w_stride; q.part_stride = p.part_stride; q.img_stride = p.img_stride; q.vec_len = p.vec_len;
+  q.w_stride = a->w_stride; q.part_stride = p.part_stride; q.img_stride = p.img_stride; q.vec_len = p.vec_len; q.mixed = p.passes == 2;
   return 0;
 }
 
@@ -947,10 +1181,12 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
   float* img = reinterpret_cast<float*>(a->workspace);
   p.img = img;
   p.trace = nullptr;
+#ifdef BNN_TC_TRACE_BUILD
   if (getenv("BNN_TC_TRACE")) {   // debug only: leaks one small buffer per call
     unsigned long long* tb = nullptr;
     if (cudaMalloc(&tb, 5 * 4096 * 16) == cudaSuccess) { cudaMemsetAsync(tb, 0, 5 * 4096 * 16, st); p.trace = tb; g_tc_trace = tb; }
   }
+#endif
   const bool want_moments = a->mean || a->var || a->part_mean || a->part_m2;
   p.part = want_moments ? reinterpret_cast<double*>(reinterpret_cast<char*>(a->workspace) + plan.img_bytes) : nullptr;
   {
@@ -1003,18 +1239,27 @@ namespace bnn { unsigned long long* tc_trace_buffer(); }
 // debug: copy the last BNN_TC_TRACE timeline (3 x 4096 x {tag<<32|it, clock}) to host
 extern "C" int32_t bnn_tc_trace_dump(unsigned long long* host_out) {
   unsigned long long* t = bnn::tc_trace_buffer();
-  if (!t || !host_out) BNN_FAIL("no trace recorded (set BNN_TC_TRACE=1)");
+  if (!t || !host_out) BNN_FAIL("no trace recorded (needs the trace build, tools/tc_trace.py, and BNN_TC_TRACE=1)");
   BNN_CUDA(cudaMemcpy(host_out, t, 5 * 4096 * 16, cudaMemcpyDeviceToHost));
   return 0;
 }
 
 // D[128, N] = A[128, K] * B[N, K]^T on tcgen05 (device pointers; K % 8 == 0, K <= 64; N % 16 == 0, N <= 256)
 extern "C" int32_t bnn_tc_selftest(const float* A, const float* B, float* D, int32_t K, int32_t N, int32_t passes, void* stream) {
-  if (!A || !B || !D || K < 8 || K > 64 || (K & 7) || N < 16 || N > 256 || (N & 15) || ((passes & 15) != 1 && (passes & 15) != 3) || (passes & ~31))
+  if (!A || !B || !D || K < 8 || K > 64 || (K & 7) || N < 16 || N > 256 || (N & 15) || ((passes & 15) < 1 || (passes & 15) > 3) || (passes & ~31) || ((passes & 15) == 2 && (K & 15)))
     BNN_FAIL("bnn_tc_selftest: bad arguments");
   const size_t smem = (size_t)2 * K * 128 * 4 + (size_t)2 * K * N * 4;
   BNN_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_selftest_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(A, B, D, K, N, passes);
+  BNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t bnn_tc_mma_bench(int32_t mode, int32_t N, int32_t iters, long long* dev_out_clk, void* stream) {
+  if (mode < 0 || mode > 5 || N < 16 || N > 256 || (N & 15) || iters < 1 || !dev_out_clk) BNN_FAIL("bnn_tc_mma_bench: bad arguments");
+  const size_t smem = 48 * 1024;
+  BNN_CUDA(cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_mma_bench_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(mode, N, iters, dev_out_clk);
   BNN_CUDA(cudaGetLastError());
   return 0;
 }

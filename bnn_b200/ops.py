@@ -8,7 +8,7 @@ import torch
 from . import _lib
 from .layout import Arch
 
-_PREC = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3, "tf32": _lib.PREC_TF32}
+_PREC = {"fp32": _lib.PREC_FP32, "tf32x3": _lib.PREC_TF32X3, "tf32": _lib.PREC_TF32, "tf32_bf16": _lib.PREC_TF32_BF16}
 
 
 def _dev(t, name):

@@ -75,7 +75,8 @@ typedef struct BnnMaskSpec {
 enum {
   BNN_PREC_FP32 = 0,    /* FP32 FFMA on the SIMT pipe: parity grade (1e-5) */
   BNN_PREC_TF32X3 = 1,  /* tcgen05 kind::tf32, 3-pass error-compensated (~FP32) */
-  BNN_PREC_TF32 = 2     /* tcgen05 kind::tf32 single pass (looser bound) */
+  BNN_PREC_TF32 = 2,    /* tcgen05 kind::tf32 single pass (looser bound) */
+  BNN_PREC_TF32_BF16 = 3 /* tcgen05: TF32 main term + two BF16 (kind::f16) correction terms, ~FP32 (2/3 of the tensor work of TF32X3) */
 };
 
 typedef struct BnnForwardArgs {
@@ -129,6 +130,9 @@ int32_t bnn_tc_trace_dump(unsigned long long* host_out);
 /* tcgen05 self-test: D[128, N] = A[128, K] * B[N, K]^T (row-major device buffers, K % 8 == 0, K <= 64,
  * N % 16 == 0, N <= 256, passes = 1 (TF32) or 3 (3xTF32), + 16 to stage the A operand in tensor memory instead of
  * shared memory) through the kernels' own operand layout */
+/* debug: issue-rate probe of the tensor pipe -- `iters` back-to-back M = 128 MMAs (mode 0 tf32 SS, 1 tf32 TS, 2 bf16 SS,
+ * 3 bf16 TS, 4 mixed stage pattern, 5 3xTF32 stage pattern); dev_out_clk[0] = issue cycles, [1] = cycles to completion */
+int32_t bnn_tc_mma_bench(int32_t mode, int32_t N, int32_t iters, long long* dev_out_clk, void* stream);
 int32_t bnn_tc_selftest(const float* A, const float* B, float* D, int32_t K, int32_t N, int32_t passes, void* stream);
 
 /* ---- (e) standalone reduction and metrics ------------------------------- */

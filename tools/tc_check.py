@@ -50,6 +50,12 @@ STAGES = {
     "p1": lambda: fused([16, 200, 200, 1], "relu", 3, 700, "tf32x3"),
     "p2": lambda: fused([16, 200, 200, 1], "tanh", 9, 70000, "tf32x3"),
     "p3": lambda: fused([16, 200, 200, 1], "relu", 2, 300, "tf32"),
+    "m1": lambda: fused([16, 100, 100, 1], "relu", 3, 300, "tf32_bf16"),
+    "m1b": lambda: fused([9, 100, 100, 1], "tanh", 40, 4573, "tf32_bf16"),
+    "m1c": lambda: fused([13, 50, 64, 3], "tanh", 7, 129, "tf32_bf16"),
+    "mp1": lambda: fused([16, 200, 200, 1], "relu", 3, 700, "tf32_bf16"),
+    "mp2": lambda: fused([16, 200, 200, 1], "tanh", 9, 70000, "tf32_bf16"),
+    "mp3": lambda: fused([16, 200, 200, 1], "relu", 64, 20000, "tf32_bf16"),
 }
 
 if __name__ == "__main__":

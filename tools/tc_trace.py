@@ -2,7 +2,10 @@
 and of one producer warp of each WG-A set."""
 import os, sys
 os.environ["BNN_TC_TRACE"] = "1"
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+# the probes are compiled in only in the trace build (python -m bnn_b200.build --trace)
+os.environ["BNN_B200_LIB"] = os.path.join(ROOT, "bnn_b200", "libbnn_b200_trace.so")
 import numpy as np, torch
 from bnn_b200 import ops, _lib
 from bnn_b200.layout import Arch
@@ -24,7 +27,7 @@ ms = e0.elapsed_time(e1)
 buf = np.zeros(5 * 4096 * 2, dtype=np.uint64)
 _lib.check(_lib.lib().bnn_tc_trace_dump(buf.ctypes.data), "dump")
 buf = buf.reshape(5, 4096, 2)
-names = {36: "B:issued", 33: "B:ldwait", 34: "B:ldok", 35: "B:reduced", 30: "B:wait_d2full", 31: "B:got_d2full", 32: "B:drained", 20: "start", 21: "tile_end", 1: "mma:wait_full", 2: "mma:got_full", 3: "mma:committed", 10: "ld_start", 11: "ld_done", 12: "wait_empty", 13: "got_empty", 14: "signalled"}
+names = {4: "mma:tf32_issued", 5: "mma:bf16_issued", 36: "B:issued", 33: "B:ldwait", 34: "B:ldok", 35: "B:reduced", 30: "B:wait_d2full", 31: "B:got_d2full", 32: "B:drained", 20: "start", 21: "tile_end", 1: "mma:wait_full", 2: "mma:got_full", 3: "mma:committed", 10: "ld_start", 11: "ld_done", 12: "wait_empty", 13: "got_empty", 14: "signalled"}
 t0 = min(int(buf[w, 0, 1]) for w in range(5) if buf[w, 0, 1])
 lo, hi = int(os.environ.get("IT0", 30)), int(os.environ.get("IT1", 42))
 ev = []
