@@ -27,7 +27,7 @@ class BNN(ABC):
 
     # ---- plumbing shared by the subclasses --------------------------------------
     device = None          # set by subclasses (torch.device("cuda", k))
-    precision = "auto"     # "auto" | "fp32" | "tf32x3" | "tf32" (see bnn_b200.ops.forward)
+    precision = "auto"     # "auto" | "fp32" | "tf32_bf16" | "tf32x3" | "tf32" (see bnn_b200.ops.forward)
 
     def _dev(self):
         if self.device is None:

@@ -92,8 +92,8 @@ def forward(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=False, 
         a.mask = mask.spec(arch)
         if mask.kind == "external" and mask.mask.shape[0] != a.S:
             raise ValueError("mask rows != S")
-    if precision == "auto":     # tensor cores (FP32-grade 3xTF32) when the shape is supported, else the FP32 SIMT kernel
-        a.precision = _lib.PREC_TF32X3
+    if precision == "auto":     # tensor cores (FP32-grade TF32 + BF16 corrections) when the shape is supported, else the FP32 SIMT kernel
+        a.precision = _lib.PREC_TF32_BF16
         if not _lib.lib().bnn_forward_tc_supported(C.byref(a)):
             a.precision = _lib.PREC_FP32
     else:

@@ -1,5 +1,6 @@
 """GPU parity of the tensor-core (tcgen05) forward.  Stated tolerances (DESIGN.md "Precision"):
   tf32x3 (3-pass error-compensated, FP32-grade): 1e-5 relative, same as the FP32 SIMT path;
+  tf32_bf16 (TF32 main term + two BF16 correction terms, FP32-grade): 1e-5 relative as well;
   tf32   (single pass, 10-bit mantissa operands) : 5e-3 relative (looser bound, never the default)."""
 import ctypes as C
 
@@ -49,17 +50,18 @@ def test_tcgen05_selftest_gemm(K, N, passes, tol):
     ([5, 8, 24, 2], "identity", 3, 50),        # tiny
     ([16, 128, 128, 1], "relu", 1, 200),       # S = 1 -> var NaN
 ])
-def test_tf32x3_matches_oracle(dims, act, S, N):
+@pytest.mark.parametrize("prec", ["tf32x3", "tf32_bf16"])
+def test_fp32_grade_tc_matches_oracle(dims, act, S, N, prec):
     nets = random_nets(dims, S, seed=sum(dims) + S)
     X = torch.randn(N, dims[0], generator=torch.Generator().manual_seed(N))
     ref = O.sample_predict(nets, X, act, nout=dims[-1])
-    out = run(dims, act, nets, X, "tf32x3")
+    out = run(dims, act, nets, X, prec)
     assert max_rel(out["pred"], ref) <= 1e-5
     mean_ref, var_ref = O.predict_mv(ref, N)
     assert max_rel(out["mean"], mean_ref) <= 1e-5
     if S > 1:
         dv = (out["var"].double() - var_ref.double()).abs()
-        vb = var_bound(ref, c=256.0, depth=3)      # 3xTF32 products carry ~2^-21 relative error each (vs 2^-24 FP32)
+        vb = var_bound(ref, c=256.0, depth=3)      # compensated products carry ~2^-21 relative error each (vs 2^-24 FP32)
         assert bool((dv <= vb).all()), float((dv / vb).max())
     else:
         assert bool(torch.isnan(out["var"]).all())
@@ -83,7 +85,7 @@ def test_tc_equals_simt_on_moments_partials():
     bank = arch.pack(random_nets(dims, S, seed=9)).cuda()
     X = torch.randn(N, 16, generator=torch.Generator().manual_seed(4)).cuda()
     a = ops.forward(arch, X, bank, want_partials=True, precision="fp32")
-    b = ops.forward(arch, X, bank, want_partials=True, precision="tf32x3")
+    b = ops.forward(arch, X, bank, want_partials=True, precision="tf32_bf16")
     assert max_rel(b["mean"].cpu(), a["mean"].cpu()) <= 1e-5
     assert max_rel(b["part_mean"].cpu(), a["part_mean"].cpu()) <= 1e-5
     assert max_rel(b["part_m2"].cpu(), a["part_m2"].cpu()) <= 1e-4
@@ -101,8 +103,9 @@ def test_unsupported_shapes_are_refused_loudly():
         assert ops.forward(arch, X, bank, precision="fp32")["mean"].shape == (10, dims[-1])
 
 
+@pytest.mark.parametrize("prec", ["tf32x3", "tf32_bf16"])
 @pytest.mark.parametrize("fixture,kind", [("dropout_protein.npz", "external"), ("cdropout_protein.npz", "external")])
-def test_tc_masked_shared_weights_golden(fixture, kind):
+def test_tc_masked_shared_weights_golden(fixture, kind, prec):
     """Dropout family on the tensor-core path: ONE base network + per-sample input-unit masks vs the reference's
     recorded predictions of S column-scaled deep copies."""
     from bnn_b200 import ops
@@ -114,13 +117,14 @@ def test_tc_masked_shared_weights_golden(fixture, kind):
     masks = torch.from_numpy(g["masks"]).cuda()
     X = torch.from_numpy(g["X"]).cuda()
     cfg = ops.MaskConfig("external", [True, True, True], mask=masks)
-    out = ops.forward(arch, X, base, S=masks.shape[0], mask=cfg, want_pred=True, precision="tf32x3")
+    out = ops.forward(arch, X, base, S=masks.shape[0], mask=cfg, want_pred=True, precision=prec)
     assert max_rel(out["pred"].cpu().squeeze(-1), g["pred"]) <= 2e-5
     assert max_rel(out["mean"].cpu().squeeze(-1), g["mean"].squeeze(-1)) <= 1e-5
 
 
+@pytest.mark.parametrize("prec", ["tf32x3", "tf32_bf16"])
 @pytest.mark.parametrize("kind", ["bernoulli", "concrete"])
-def test_tc_inkernel_masks_match_simt(kind):
+def test_tc_inkernel_masks_match_simt(kind, prec):
     """In-kernel Philox masks: tensor-core and SIMT forwards draw the same masks (same counters), so they agree to
     FP32-grade accuracy for any sharding; per-sample bank + masks and several tiles/samples per CTA are exercised."""
     from bnn_b200 import ops
@@ -132,12 +136,12 @@ def test_tc_inkernel_masks_match_simt(kind):
     S = 23
     cfg = ops.MaskConfig(kind, [True, True, True], p_drop=[0.2, 0.4, 0.1], temperature=0.1, seed=123, sample_offset=50)
     a = ops.forward(arch, X, base, S=S, mask=cfg, want_pred=True, precision="fp32")
-    b = ops.forward(arch, X, base, S=S, mask=cfg, want_pred=True, precision="tf32x3")
+    b = ops.forward(arch, X, base, S=S, mask=cfg, want_pred=True, precision=prec)
     assert max_rel(b["pred"].cpu(), a["pred"].cpu()) <= 1e-5
     assert max_rel(b["mean"].cpu(), a["mean"].cpu()) <= 1e-5
     bank = arch.pack(random_nets(dims, S, seed=9)).cuda()          # per-sample weights AND masks
     a = ops.forward(arch, X, bank, mask=cfg, want_pred=True, precision="fp32")
-    b = ops.forward(arch, X, bank, mask=cfg, want_pred=True, precision="tf32x3")
+    b = ops.forward(arch, X, bank, mask=cfg, want_pred=True, precision=prec)
     assert max_rel(b["pred"].cpu(), a["pred"].cpu()) <= 1e-5
 
 
