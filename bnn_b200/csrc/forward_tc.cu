@@ -56,6 +56,7 @@ struct TcParams {
   long long sample_offset;
   int shared_w;            // 1: one network for all samples (w_stride == 0): operands are loaded once
   unsigned long long* trace;   // debug timeline (BNN_TC_TRACE), null in production
+  int trace_mask;              // BNN_TC_TRACE value: bit 0 MMA per-stage events, bit 1 WG-A, bit 2 WG-B (tile ends always)
   // shared memory offsets (bytes)
   int sm_b1, sm_b2, sm_vec, sm_a1, sm_bar, sm_ypart, sm_mask;
 };
@@ -368,6 +369,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     const uint32_t idesc1 = tc::make_idesc_tf32(128 * kPair, p.N1), idesc2 = tc::make_idesc_tf32(128 * kPair, p.N2);
     uint32_t tile_cnt = 0, tn = 0, ring_st = 0, ring_par = 0;
     unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? p.trace : nullptr;
+    unsigned long long* trs = (p.trace_mask & 1) ? tr : nullptr;   // per-stage events (each costs this warp ~70 cycles)
     const uint64_t a1_desc0 = tc::make_smem_desc(s_a1, 2048u, 128u);
     const uint64_t b1_desc0 = tc::make_smem_desc(s_b1, (uint32_t)N1h * 16u, 128u);
     const uint64_t b2_desc0 = tc::make_smem_desc(s_b2, (uint32_t)N2h * 16u, 128u);
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         mbar_wait(&bars[BAR_D2_EMPTY], tpar ^ 1u);   // epilogue-2 of the previous tile drained D2
         tc::fence_after_thread_sync();
         for (int b = 0; b < n_b2; ++b) {
-          trace_ev(tr, 0, tn, 2, tile_cnt * n_b2 + b);
+          trace_ev(trs, 0, tn, 2, tile_cnt * n_b2 + b);
           const uint32_t cur_st = ring_st;
           // Operands of this stage, computed HERE in convergent code so that they live in uniform registers: values
           // produced inside the single-lane block below reach the UTCHMMA through one R2UR each, and that serial
@@ -444,6 +446,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
           const uint64_t bd0 = b2_desc0 + (uint64_t)(2 * b) * b2_step, bd1 = bd0 + b2_step;
           const uint32_t acc0 = b > 0 ? 1u : 0u;
           const bool two = 2 * b + 1 < n_k2;   // the last stage of a 3xTF32 / TF32 tile may hold a single K-step
+          // probe the next stage's barrier now: the probe's latency overlaps the MMA issue below, and in steady state
+          // (epilogue-1 runs a stage or two ahead) it already succeeds, so the blocking wait after the issue is skipped
+          uint32_t nxt_st = ring_st + 1, nxt_par = ring_par;
+          if (nxt_st == (uint32_t)p.ring) { nxt_st = 0; nxt_par ^= 1u; }
+          const bool nxt_ready = (b + 1 < n_b2) && mbar_test(&bars[BAR_A2_FULL + nxt_st], nxt_par);
           if (tc::elect_one()) {
             if (three) {
               mma_tf32_ts<kPair>(tmem_d2, a0, bd0, idesc2, acc0);
@@ -470,11 +477,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             mma_commit_all<kPair>(&bars[BAR_A2_EMPTY + cur_st]);
           }
           __syncwarp();
-          trace_ev(tr, 0, tn, 3, tile_cnt * n_b2 + b);
-          if (++ring_st == (uint32_t)p.ring) { ring_st = 0; ring_par ^= 1u; }
+          trace_ev(trs, 0, tn, 3, tile_cnt * n_b2 + b);
+          ring_st = nxt_st; ring_par = nxt_par;
           if (b + 1 < n_b2) {
-            trace_ev(tr, 0, tn, 1, tile_cnt * n_b2 + b + 1);
-            mbar_wait(&bars[BAR_A2_FULL + ring_st], ring_par);
+            trace_ev(trs, 0, tn, 1, tile_cnt * n_b2 + b + 1);
+            if (!nxt_ready) mbar_wait(&bars[BAR_A2_FULL + ring_st], ring_par);
             tc::fence_after_thread_sync();
           }
         }
@@ -492,8 +499,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     const int row = quarter * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     uint32_t tile_cnt = 0, tn = 0;
-    unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quarter == 0) ? p.trace : nullptr;
+    unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quarter == 0 && (p.trace_mask & 2)) ? p.trace : nullptr;
     const int who = 1 + set;
+    uint32_t ring_gb = 0, ring_st = 0, ring_use = 0;   // last stage index handled by this warp, its slot and use parity
     const bool three = p.passes == 3, mixed = p.passes == 2;
     const float* b1s = reinterpret_cast<const float*>(smem + p.sm_vec);
     float* mk0 = reinterpret_cast<float*>(smem + p.sm_mask);   // this group's masks: m0[Dp] (inputs), m1[N1] (hidden 1)
@@ -597,6 +605,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
           const int c0 = b * 16;
           float d[16];
           const uint32_t gb = tile_cnt * (uint32_t)n_b2 + (uint32_t)b;   // global stage-use index
+          // ring slot / use parity of stage gb, advanced incrementally (gb % ring and gb / ring cost ~25 instructions)
+          ring_st += gb - ring_gb;
+          ring_gb = gb;
+          while (ring_st >= (uint32_t)p.ring) { ring_st -= (uint32_t)p.ring; ring_use ^= 1u; }
           trace_ev(tr, who, tn, 10, gb);
           tc::tmem_ld16(tmem_d1 + lane_sel + (uint32_t)c0, d);
           trace_ev(tr, who, tn, 11, gb);
@@ -616,7 +628,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             float l[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float hh = tc::tf32_hi(h[e]);
+              const float hh = tc::tf32_hi_fast(h[e]);
               hi[q4 * 4 + e] = __float_as_uint(hh);
               l[e] = h[e] - hh;
             }
@@ -630,9 +642,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
               for (int e = 0; e < 4; ++e) lo[q4 * 4 + e] = __float_as_uint(l[e]);
             }
           }
-          const uint32_t st = gb % (uint32_t)p.ring, use = gb / (uint32_t)p.ring;
+          const uint32_t st = ring_st;
           trace_ev(tr, who, tn, 12, gb);
-          mbar_wait(&bars[BAR_A2_EMPTY + st], (use & 1u) ^ 1u);   // the MMAs that read this stage's previous contents are done
+          mbar_wait(&bars[BAR_A2_EMPTY + st], ring_use ^ 1u);   // the MMAs that read this stage's previous contents are done
           tc::fence_after_thread_sync();
           trace_ev(tr, who, tn, 13, gb);
           const uint32_t ta = tmem_a2 + lane_sel + st * (uint32_t)kTcStageCols;
@@ -650,7 +662,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     const int row = quarter * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     uint32_t tile_cnt = 0, tn = 0;
-    unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quarter == 0) ? p.trace : nullptr;
+    unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quarter == 0 && (p.trace_mask & 4)) ? p.trace : nullptr;
     const int who = 3 + half;
     const long long M = p.N * p.O;
     double* st_mean = p.part ? p.part + (long long)g * 2 * M : nullptr;
@@ -1184,7 +1196,7 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
 #ifdef BNN_TC_TRACE_BUILD
   if (getenv("BNN_TC_TRACE")) {   // debug only: leaks one small buffer per call
     unsigned long long* tb = nullptr;
-    if (cudaMalloc(&tb, 5 * 4096 * 16) == cudaSuccess) { cudaMemsetAsync(tb, 0, 5 * 4096 * 16, st); p.trace = tb; g_tc_trace = tb; }
+    if (cudaMalloc(&tb, 5 * 4096 * 16) == cudaSuccess) { cudaMemsetAsync(tb, 0, 5 * 4096 * 16, st); p.trace = tb; g_tc_trace = tb; p.trace_mask = atoi(getenv("BNN_TC_TRACE")); }
   }
 #endif
   const bool want_moments = a->mean || a->var || a->part_mean || a->part_m2;

@@ -1,7 +1,7 @@
 """Dump the in-kernel timeline of the tensor-core forward (BNN_TC_TRACE=1): per K-step timestamps of the MMA issuer
 and of one producer warp of each WG-A set."""
 import os, sys
-os.environ["BNN_TC_TRACE"] = "1"
+os.environ.setdefault("BNN_TC_TRACE", "7")   # bit 0 MMA per-stage events, bit 1 WG-A, bit 2 WG-B; tile ends always
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 # the probes are compiled in only in the trace build (python -m bnn_b200.build --trace)
@@ -51,4 +51,4 @@ d = np.diff([c for _, c in m])
 tiles = [int(c) for t, c in buf[0] if c and (int(t) >> 32) == 21]
 start = [int(c) for t, c in buf[0] if c and (int(t) >> 32) == 20][0]
 print("tile periods (clk):", np.diff(tiles)[:12], " total clk %d over %.3f ms (incl. prep+finalize) -> >= %.0f MHz" % (tiles[-1] - start, ms, (tiles[-1] - start) / ms / 1e3))
-print("MMA commit-to-commit period: median %.0f  p10 %.0f  p90 %.0f  (n=%d)" % (np.median(d), np.percentile(d, 10), np.percentile(d, 90), len(d)))
+if len(d): print("MMA commit-to-commit period: median %.0f  p10 %.0f  p90 %.0f  (n=%d)" % (np.median(d), np.percentile(d, 10), np.percentile(d, 90), len(d)))
