@@ -601,59 +601,68 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
 
         // ---- epilogue 1: D1 -> h1 = act(d + b1) -> hi/lo -> A2 ring; one 16-column batch = one ring stage; this warp
         //      takes the batches whose index parity equals `set`
-        for (int b = set; b < n_b2; b += 2) {
-          const int c0 = b * 16;
-          float d[16];
-          const uint32_t gb = tile_cnt * (uint32_t)n_b2 + (uint32_t)b;   // global stage-use index
-          // ring slot / use parity of stage gb, advanced incrementally (gb % ring and gb / ring cost ~25 instructions)
-          ring_st += gb - ring_gb;
-          ring_gb = gb;
-          while (ring_st >= (uint32_t)p.ring) { ring_st -= (uint32_t)p.ring; ring_use ^= 1u; }
-          trace_ev(tr, who, tn, 10, gb);
-          tc::tmem_ld16(tmem_d1 + lane_sel + (uint32_t)c0, d);
-          trace_ev(tr, who, tn, 11, gb);
-          uint32_t hi[16], lo[16];
+        // The D1 columns of this warp's NEXT stage are requested before the (long) wait for a free ring slot, so the
+        // TMEM load latency never sits on the stage's critical path; masked / unmasked versions are separate code.
+        auto epilogue1 = [&](auto masked_tag) {
+          constexpr bool kMasked = decltype(masked_tag)::value;
+          uint32_t d[16];
+          if (set < n_b2) tc::tmem_ld16_issue(tmem_d1 + lane_sel + (uint32_t)(set * 16), d);
+          for (int b = set; b < n_b2; b += 2) {
+            const int c0 = b * 16;
+            const uint32_t gb = tile_cnt * (uint32_t)n_b2 + (uint32_t)b;   // global stage-use index
+            // ring slot / use parity of stage gb, advanced incrementally (gb % ring and gb / ring cost ~25 instructions)
+            ring_st += gb - ring_gb;
+            ring_gb = gb;
+            while (ring_st >= (uint32_t)p.ring) { ring_st -= (uint32_t)p.ring; ring_use ^= 1u; }
+            trace_ev(tr, who, tn, 10, gb);
+            tc::tmem_ld_wait(d);
+            trace_ev(tr, who, tn, 11, gb);
+            uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 bq = *reinterpret_cast<const float4*>(b1s + c0 + q4 * 4);
-            float h[4];
-            h[0] = act_ct<kAct>(d[q4 * 4 + 0] + bq.x);
-            h[1] = act_ct<kAct>(d[q4 * 4 + 1] + bq.y);
-            h[2] = act_ct<kAct>(d[q4 * 4 + 2] + bq.z);
-            h[3] = act_ct<kAct>(d[q4 * 4 + 3] + bq.w);
-            if (has_m1) {   // dropout on the inputs of Linear 2
-              const float4 mq = *reinterpret_cast<const float4*>(mk1 + c0 + q4 * 4);
-              h[0] *= mq.x; h[1] *= mq.y; h[2] *= mq.z; h[3] *= mq.w;
-            }
-            float l[4];
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 bq = *reinterpret_cast<const float4*>(b1s + c0 + q4 * 4);
+              float h[4];
+              h[0] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 0]) + bq.x);
+              h[1] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 1]) + bq.y);
+              h[2] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 2]) + bq.z);
+              h[3] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 3]) + bq.w);
+              if constexpr (kMasked) {   // dropout on the inputs of Linear 2
+                const float4 mq = *reinterpret_cast<const float4*>(mk1 + c0 + q4 * 4);
+                h[0] *= mq.x; h[1] *= mq.y; h[2] *= mq.z; h[3] *= mq.w;
+              }
+              float l[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float hh = tc::tf32_hi_fast(h[e]);
-              hi[q4 * 4 + e] = __float_as_uint(hh);
-              l[e] = h[e] - hh;
-            }
-            if (mixed) {
-              lo[q4 * 2 + 0] = tc::pack_bf16x2(h[0], h[1]);
-              lo[q4 * 2 + 1] = tc::pack_bf16x2(h[2], h[3]);
-              lo[8 + q4 * 2 + 0] = tc::pack_bf16x2(l[0], l[1]);
-              lo[8 + q4 * 2 + 1] = tc::pack_bf16x2(l[2], l[3]);
-            } else {
+              for (int e = 0; e < 4; ++e) {
+                const float hh = tc::tf32_hi_fast(h[e]);
+                hi[q4 * 4 + e] = __float_as_uint(hh);
+                l[e] = h[e] - hh;
+              }
+              if (mixed) {
+                lo[q4 * 2 + 0] = tc::pack_bf16x2(h[0], h[1]);
+                lo[q4 * 2 + 1] = tc::pack_bf16x2(h[2], h[3]);
+                lo[8 + q4 * 2 + 0] = tc::pack_bf16x2(l[0], l[1]);
+                lo[8 + q4 * 2 + 1] = tc::pack_bf16x2(l[2], l[3]);
+              } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) lo[q4 * 4 + e] = __float_as_uint(l[e]);
+                for (int e = 0; e < 4; ++e) lo[q4 * 4 + e] = __float_as_uint(l[e]);
+              }
             }
+            if (b + 2 < n_b2) tc::tmem_ld16_issue(tmem_d1 + lane_sel + (uint32_t)(c0 + 32), d);   // next stage of this warp
+            const uint32_t st = ring_st;
+            trace_ev(tr, who, tn, 12, gb);
+            mbar_wait(&bars[BAR_A2_EMPTY + st], ring_use ^ 1u);   // the MMAs that read this stage's previous contents are done
+            tc::fence_after_thread_sync();
+            trace_ev(tr, who, tn, 13, gb);
+            const uint32_t ta = tmem_a2 + lane_sel + st * (uint32_t)kTcStageCols;
+            tc::tmem_st16(ta, hi);
+            if (three || mixed) tc::tmem_st16(ta + 16u, lo);   // tf32 lo [16,32)  or  bf16(h) pairs [16,24) | bf16(lo) pairs [24,32)
+            tc::tmem_st_wait();
+            warp_signal_tmem<kPair>(&bars[BAR_A2_FULL + st], lane);
+            trace_ev(tr, who, tn, 14, gb);
           }
-          const uint32_t st = ring_st;
-          trace_ev(tr, who, tn, 12, gb);
-          mbar_wait(&bars[BAR_A2_EMPTY + st], ring_use ^ 1u);   // the MMAs that read this stage's previous contents are done
-          tc::fence_after_thread_sync();
-          trace_ev(tr, who, tn, 13, gb);
-          const uint32_t ta = tmem_a2 + lane_sel + st * (uint32_t)kTcStageCols;
-          tc::tmem_st16(ta, hi);
-          if (three || mixed) tc::tmem_st16(ta + 16u, lo);   // tf32 lo [16,32)  or  bf16(h) pairs [16,24) | bf16(lo) pairs [24,32)
-          tc::tmem_st_wait();
-          warp_signal_tmem<kPair>(&bars[BAR_A2_FULL + st], lane);
-          trace_ev(tr, who, tn, 14, gb);
-        }
+        };
+        if (has_m1) epilogue1(std::true_type{});
+        else epilogue1(std::false_type{});
       }
     }
   } else {
