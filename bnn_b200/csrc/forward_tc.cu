@@ -27,7 +27,6 @@ namespace bnn {
 
 constexpr int kTcThreads = 544;       // WG-A (8 warps) + WG-B (8 warps) + 1 MMA/loader warp
 constexpr int kTcMmaWarp = 16;
-constexpr int kTcEpiThreads = 128;
 constexpr int kTcRing = 6;            // max A2 ring stages
 constexpr int kTcStageCols = 32;       // one A2 stage = 16 K-columns (two K = 8 MMA steps) in tensor memory: hi[16] then lo[16]
 
@@ -676,7 +675,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     const long long M = p.N * p.O;
     double* st_mean = p.part ? p.part + (long long)g * 2 * M : nullptr;
     double* st_m2 = p.part ? st_mean + M : nullptr;
-    const uint32_t b2v = s_vec + (uint32_t)p.N1 * 4u, w3v = b2v + (uint32_t)p.N2 * 4u;
     const float* b3 = reinterpret_cast<const float*>(smem + p.sm_vec) + p.N1 + p.N2 + p.O * p.N2;
     float* ypart = reinterpret_cast<float*>(smem + p.sm_ypart);   // [128][O] partial outputs of the half-1 warps
     const int nb16 = p.N2 >> 4;

@@ -144,28 +144,10 @@ extern "C" int32_t bnn_moments(const float* pred, int64_t S, int64_t M, float* m
   return finalize_moments((const double*)workspace, nullptr, G, Sg, S, M, mean, var, part_mean, part_m2, st);
 }
 
-// R shards laid out as part_mean[R][M], part_m2[R][M] (e.g. the all-gathered per-GPU moments)
-__global__ void merge_kernel(const double* __restrict__ pmean, const double* __restrict__ pm2, const long long* counts, int R,
-                             long long M, float* __restrict__ mean, float* __restrict__ var) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += stride) {
-    double n = 0.0, mu = 0.0, m2 = 0.0;
-    for (int r = 0; r < R; ++r) {
-      const double nb = (double)counts[r];
-      if (nb <= 0.0) continue;
-      const double d = pmean[(long long)r * M + m] - mu;
-      const double nn = n + nb;
-      mu += d * (nb / nn);
-      m2 += pm2[(long long)r * M + m] + d * d * (n * nb / nn);
-      n = nn;
-    }
-    if (mean) mean[m] = (float)mu;
-    if (var) var[m] = (float)(m2 / (n - 1.0));
-  }
-}
-
+// R shards laid out as part_mean[R][M], part_m2[R][M] (e.g. the all-gathered per-GPU moments); the shard sample counts
+// travel by value in the kernel arguments (no device buffer, graph-capturable)
 struct CountsArg { long long c[64]; };
-__global__ void merge_kernel_byval(const double* __restrict__ pmean, const double* __restrict__ pm2, CountsArg counts, int R,
+__global__ void merge_kernel(const double* __restrict__ pmean, const double* __restrict__ pm2, CountsArg counts, int R,
                                    long long M, float* __restrict__ mean, float* __restrict__ var) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += stride) {
@@ -189,7 +171,7 @@ extern "C" int32_t bnn_moments_merge(const double* part_mean, const double* part
   if (!part_mean || !part_m2 || !counts_host || R < 1 || R > 64 || M < 1) BNN_FAIL("bnn_moments_merge: bad arguments (R=%d)", R);
   CountsArg c;
   for (int r = 0; r < 64; ++r) c.c[r] = r < R ? counts_host[r] : 0;
-  merge_kernel_byval<<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>(part_mean, part_m2, c, R, M, mean, var);
+  merge_kernel<<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>(part_mean, part_m2, c, R, M, mean, var);
   BNN_CUDA(cudaGetLastError());
   return 0;
 }

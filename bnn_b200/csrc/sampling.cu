@@ -70,6 +70,9 @@ __global__ void __launch_bounds__(kEwBlock) reparam_kernel(const __grid_constant
 #pragma unroll
     for (int c = 0; c < 4; ++c) sg[c] = scale_of(r[c], mode);
     // samples handled by this thread: blockIdx.y, blockIdx.y + gridDim.y, ...
+    // two samples per trip: two independent Philox / Box-Muller chains in flight per thread (the kernel is bound by the
+    // ~200 instructions per quad of the counter RNG and the accurate logf / sincospif, not by its 16-byte store)
+#pragma unroll 2
     for (long long s = blockIdx.y; s < S; s += gridDim.y) {
       float z[4];
       if (eps) {
@@ -232,8 +235,10 @@ __global__ void philox_normals_kernel(unsigned long long seed, uint32_t subseq, 
 }
 
 static unsigned sample_rows(long long S, long long blocks_x) {
-  // y-dimension: enough CTAs for ~4 waves, each CTA looping over its samples
-  long long want = (4LL * sm_count() + blocks_x - 1) / blocks_x;
+  // y-dimension: ~32 CTAs per SM in total (several CTAs are resident per SM, so this is ~6-8 waves and the ragged last
+  // wave costs little -- 4 per SM came out as 1.04 waves on the cfg 4 bank and doubled the run time), each CTA looping
+  // over its samples
+  long long want = (32LL * sm_count() + blocks_x - 1) / blocks_x;
   if (want < 1) want = 1;
   if (want > S) want = S;
   if (want > 65535) want = 65535;

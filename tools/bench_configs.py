@@ -53,6 +53,7 @@ m = BNN_BBB(1, nn.Tanh(), [50, 50], conf={})
 X = torch.linspace(-3, 3, 1000).view(-1, 1); Xd = X.cuda()
 def bbb_gpu():
     nns = m.sample(1000); return m.predict_mv(Xd, nns)
+m.precision = "fp32"
 gls = m.nn.gaussian_layers()
 def bbb_cpu():
     nets = []
@@ -61,8 +62,8 @@ def bbb_cpu():
     return O.predict_mv(O.sample_predict(nets, X, "tanh"), 1000)
 tg, tc = gpu_time(bbb_gpu), cpu_time(bbb_cpu, reps=1)
 rows.append(("cfg2 BBB 1-50-50-1 tanh, S=1000 draws + predict, N=1000 (fp32)", 1000 * 1000, tg, tc, float("nan"), "fp32"))
-m.precision = "tf32x3"
-rows.append(("cfg2 BBB, same (tf32x3)", 1000 * 1000, gpu_time(bbb_gpu), tc, float("nan"), "tf32x3"))
+m.precision = "tf32_bf16"
+rows.append(("cfg2 BBB, same (tf32_bf16, tensor cores)", 1000 * 1000, gpu_time(bbb_gpu), tc, float("nan"), "tf32_bf16"))
 
 # cfg 3: BNN_Dropout / BNN_CDropout, 9-100-100-1 tanh, 1000 MC-dropout passes, N = 4573 (protein test split size)
 from bnn_b200.BNN_Dropout import BNN_Dropout
@@ -70,6 +71,7 @@ from bnn_b200.BNN_CDropout import BNN_CDropout
 X = torch.randn(4573, 9); Xd = X.cuda()
 for cls, name in ((BNN_Dropout, "Dropout p=0.05"), (BNN_CDropout, "CDropout")):
     m = cls(9, nn.Tanh(), [100, 100], conf={})
+    m.precision = "fp32"
     def do_gpu():
         nns = m.sample(1000); return m.predict_mv(Xd, nns)
     nns = m.sample(64)
@@ -78,8 +80,8 @@ for cls, name in ((BNN_Dropout, "Dropout p=0.05"), (BNN_CDropout, "CDropout")):
         return O.predict_mv(O.sample_predict(nets, X, "tanh"), 4573)
     tg, tc = gpu_time(do_gpu), cpu_time(do_cpu, reps=1) * (1000 / 64)
     rows.append((f"cfg3 {name} 9-100-100-1 tanh, S=1000 masks + predict, N=4573 (fp32)", 1000 * 4573, tg, tc, float("nan"), "fp32"))
-    m.precision = "tf32x3"
-    rows.append((f"cfg3 {name}, same (tf32x3, tensor cores)", 1000 * 4573, gpu_time(do_gpu), tc, float("nan"), "tf32x3"))
+    m.precision = "tf32_bf16"
+    rows.append((f"cfg3 {name}, same (tf32_bf16, tensor cores)", 1000 * 4573, gpu_time(do_gpu), tc, float("nan"), "tf32_bf16"))
 
 # cfg 4 slice: 16-200-200-1 relu, S = 1250 on one GPU, N = 100k slice (full N = 1M is bench.py); tensor-core path
 from bnn_b200 import ops
@@ -89,7 +91,7 @@ g = torch.Generator().manual_seed(0)
 bank = (0.1 * torch.randn(64, arch.stride, generator=g)) * arch.valid_mask()
 X = torch.randn(100_000, 16, generator=g); Xd, bd = X.cuda(), bank.cuda()
 nets = [arch.unpack(bank[s]) for s in range(8)]
-for prec in ("tf32x3", "fp32"):
+for prec in ("tf32_bf16", "tf32x3", "fp32"):
     tg = gpu_time(lambda: ops.forward(arch, Xd, bd, precision=prec), reps=10)
     tc = cpu_time(lambda: O.predict_mv(O.sample_predict(nets, X, "relu", nout=1), 100_000), reps=1) * (64 / 8)
     err = max_rel(ops.forward(arch, Xd, bd[:8].contiguous(), precision=prec)["mean"].cpu(),
