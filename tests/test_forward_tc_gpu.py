@@ -156,3 +156,40 @@ def test_tc_pred_only_call():
     torch.cuda.synchronize()
     ref = O.sample_predict(nets, X, act, nout=1)
     assert max_rel(out["pred"].cpu(), ref) < 1e-5
+
+
+def test_full_size_cfg4_properties():
+    """BASELINE cfg 4 at its full point count (N = 1,000,000; S reduced to 48 so the oracle spot-check stays in seconds):
+    size-independent properties of the tensor-core path --
+      * the moments of two sample shards, Chan-merged, equal the moments of the unsharded call (the multi-GPU path);
+      * permuting the samples does not change mean / var beyond FP32 rounding;
+      * a random subset of 1500 points agrees with the CPU oracle to the stated 1e-5."""
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    dims, act, S, N = [16, 200, 200, 1], "relu", 48, 1_000_000
+    arch = Arch(dims, act)
+    g = torch.Generator().manual_seed(11)
+    nets = random_nets(dims, S, seed=12)
+    bank = arch.pack(nets).cuda()
+    X = torch.randn(N, 16, generator=g)
+    Xd = X.cuda()
+    full = ops.forward(arch, Xd, bank, want_partials=True, precision="tf32_bf16")
+    a = ops.forward(arch, Xd, bank[:20].contiguous(), want_partials=True, precision="tf32_bf16")
+    b = ops.forward(arch, Xd, bank[20:].contiguous(), want_partials=True, precision="tf32_bf16")
+    pm = torch.stack([a["part_mean"].reshape(-1), b["part_mean"].reshape(-1)])
+    p2 = torch.stack([a["part_m2"].reshape(-1), b["part_m2"].reshape(-1)])
+    mean_m, var_m = ops.moments_merge(pm, p2, [20, 28])
+    torch.cuda.synchronize()
+    assert max_rel(mean_m.cpu(), full["mean"].cpu().reshape(-1)) <= 1e-6
+    assert max_rel(var_m.cpu(), full["var"].cpu().reshape(-1)) <= 1e-5
+    perm = torch.randperm(S, generator=g)
+    shuf = ops.forward(arch, Xd, bank[perm.cuda()].contiguous(), precision="tf32_bf16")
+    assert max_rel(shuf["mean"].cpu(), full["mean"].cpu()) <= 1e-6
+    assert max_rel(shuf["var"].cpu(), full["var"].cpu()) <= 1e-5
+    idx = torch.randperm(N, generator=g)[:1500]
+    ref = O.sample_predict(nets, X[idx], act, nout=1)
+    mean_ref, var_ref = O.predict_mv(ref, len(idx))
+    assert max_rel(full["mean"].cpu()[idx], mean_ref) <= 1e-5
+    dv = (full["var"].cpu()[idx].double() - var_ref.double()).abs()
+    assert bool((dv <= var_bound(ref, c=256.0, depth=3)).all())
+    assert bool(torch.isfinite(full["mean"]).all()) and bool(torch.isfinite(full["var"]).all())
