@@ -257,7 +257,12 @@ def run_ours(args):
                   "tf32": "one TF32 pass"}.get(args.precision, "")
         if tc:
             roof = {"bound": "tensor", "achieved": per_gpu_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
-                    "frac": per_gpu_tflops / bf16_peak, "traffic": None,
+                    "frac": per_gpu_tflops / bf16_peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this very launch (S=1250 x N=1M) from the committed
+                    # ncu --set full capture (profiles/r01_fwd_tc_ncu_full_summary.txt); algorithmic bytes are 0.297 GB -- the
+                    # sample-outer loop re-reads X and the float64 per-point state per sample out of L2 (8 % miss to DRAM,
+                    # 27 GB/s = 0.3 % of the HBM peak; the kernel is tensor bound)
+                    "traffic": 9.888e9 if args.precision == "tf32_bf16" else None, "traffic_unit": "bytes/launch",
                     "kernel": "fwd_tc_kernel<2,relu> (tcgen05 kind::tf32 + kind::f16, cta_group::2, A operand of layer 2 in TMEM)",
                     "flop_per_eval": FLOP_PER_EVAL,
                     "peak_source": peak_src + "; dense bf16",
