@@ -127,6 +127,61 @@ def forward(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=False, 
     return out
 
 
+def forward_streamed(arch: Arch, X_host, W_host, chunk=250, precision="auto", want_partials=False, device=None):
+    """predict_mv for inputs that live in (pinned) HOST memory: the bank is uploaded in chunks of `chunk` samples on a copy
+    stream while the previous chunk is being evaluated, each chunk is reduced to float64 per-point (mean, M2), and the
+    chunks are Chan-merged -- the same arithmetic as the multi-GPU shard merge, so the result equals one `forward` call
+    over the whole bank to FP64 rounding.  Returns {"mean", "var"} (float32) and, with want_partials, the merged float64
+    {"part_mean", "part_m2"} of the whole bank (for `distributed.merge_shards`)."""
+    if X_host.is_cuda or W_host.is_cuda:
+        raise TypeError("forward_streamed takes host tensors (use forward for device tensors)")
+    if W_host.dim() != 2 or W_host.shape[1] < arch.stride:
+        raise ValueError(f"W must be [S, >= {arch.stride}]")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    S, stride = W_host.shape
+    chunk = max(1, min(int(chunk), S))
+    comp = torch.cuda.current_stream(dev)
+    copy = torch.cuda.Stream(dev)
+    Xd = X_host.to(dev, non_blocking=True)
+    bufs = [torch.empty(chunk, stride, dtype=torch.float32, device=dev) for _ in range(2 if S > chunk else 1)]
+    freed = [None, None]
+    n_tot, mean, m2 = 0, None, None
+    keep = []
+    for i, lo in enumerate(range(0, S, chunk)):
+        n = min(chunk, S - lo)
+        buf = bufs[i % len(bufs)]
+        with torch.cuda.stream(copy):
+            if freed[i % 2] is not None:
+                copy.wait_event(freed[i % 2])              # the evaluation that last read this buffer is done
+            elif i == 0:
+                copy.wait_stream(comp)
+            buf[:n].copy_(W_host[lo:lo + n], non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(copy)
+        comp.wait_event(up)
+        out = forward(arch, Xd, buf[:n], want_moments=False, want_partials=True, precision=precision)
+        ev = torch.cuda.Event()
+        ev.record(comp)
+        freed[i % 2] = ev
+        keep.append(out)
+        pm, p2 = out["part_mean"], out["part_m2"]
+        if mean is None:
+            n_tot, mean, m2 = n, pm, p2
+        else:                                               # Chan et al. pairwise merge, float64 on the device
+            d = pm - mean
+            nn = n_tot + n
+            mean = mean + d * (n / nn)
+            m2 = m2 + p2 + d * d * (n_tot * n / nn)
+            n_tot = nn
+    res = {}
+    res["mean"], res["var"] = moments_merge(mean.unsqueeze(0), m2.unsqueeze(0), [n_tot])
+    if want_partials:
+        res["part_mean"], res["part_m2"] = mean, m2
+    for b in bufs:
+        b.record_stream(comp)
+    return res
+
+
 def tc_supported(arch: Arch, S=2, masked=False):
     """True if the tensor-core forward takes this architecture (see bnn_forward_tc_supported)."""
     a = _lib.ForwardArgs()

@@ -193,3 +193,21 @@ def test_full_size_cfg4_properties():
     dv = (full["var"].cpu()[idx].double() - var_ref.double()).abs()
     assert bool((dv <= var_bound(ref, c=256.0, depth=3)).all())
     assert bool(torch.isfinite(full["mean"]).all()) and bool(torch.isfinite(full["var"]).all())
+
+
+@pytest.mark.parametrize("prec", ["tf32_bf16", "fp32"])
+def test_forward_streamed_equals_forward(prec):
+    """Host-resident inputs, bank uploaded chunk by chunk behind the evaluation: same moments as one device call."""
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    dims, S, N = [16, 200, 200, 1], 23, 3000
+    arch = Arch(dims, "relu")
+    bank = arch.pack(random_nets(dims, S, seed=21))
+    X = torch.randn(N, 16, generator=torch.Generator().manual_seed(22))
+    ref = ops.forward(arch, X.cuda(), bank.cuda(), want_partials=True, precision=prec)
+    out = ops.forward_streamed(arch, X.pin_memory(), bank.pin_memory(), chunk=5, precision=prec, want_partials=True)
+    torch.cuda.synchronize()
+    assert max_rel(out["mean"].cpu(), ref["mean"].cpu()) <= 1e-6
+    assert max_rel(out["var"].cpu(), ref["var"].cpu()) <= 1e-5
+    assert max_rel(out["part_mean"].cpu(), ref["part_mean"].cpu()) <= 1e-9
+    assert max_rel(out["part_m2"].cpu(), ref["part_m2"].cpu()) <= 1e-8
