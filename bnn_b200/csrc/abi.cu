@@ -108,9 +108,10 @@ extern "C" int32_t bnn_forward(const BnnForwardArgs* a, void* stream) {
 // ---- host-buffer path ---------------------------------------------------------
 namespace {
 struct HostWs {
-  void* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  cudaStream_t st = nullptr;
+  void* buf[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  cudaStream_t st = nullptr, st_copy = nullptr;
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   int ensure(int i, size_t bytes) {
     if (bytes <= cap[i]) return 0;
     if (buf[i]) cudaFree(buf[i]);
@@ -121,13 +122,19 @@ struct HostWs {
     return 0;
   }
   void release() {
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 10; ++i) {
       if (buf[i]) cudaFree(buf[i]);
       buf[i] = nullptr;
       cap[i] = 0;
     }
+    for (int i = 0; i < 2; ++i) {
+      if (ev_up[i]) cudaEventDestroy(ev_up[i]);
+      if (ev_free[i]) cudaEventDestroy(ev_free[i]);
+      ev_up[i] = ev_free[i] = nullptr;
+    }
     if (st) cudaStreamDestroy(st);
-    st = nullptr;
+    if (st_copy) cudaStreamDestroy(st_copy);
+    st = st_copy = nullptr;
   }
 };
 HostWs g_ws;
@@ -153,18 +160,71 @@ extern "C" int32_t bnn_forward_host(const BnnForwardArgs* ah) {
   const long long nets = a.w_stride == 0 ? 1 : a.S;
   const long long wst = a.w_stride == 0 ? L.off[L.n_lin] : a.w_stride;
   const size_t w_bytes = (size_t)nets * wst * 4;
-  enum { BX = 0, BW, BMASK, BPRED, BMEAN, BVAR, BPART, BWS };
-  if (g_ws.ensure(BX, x_bytes) || g_ws.ensure(BW, w_bytes)) return -2;
+  enum { BX = 0, BW, BMASK, BPRED, BMEAN, BVAR, BPART, BWS, BW2, BCHUNK };
+  if (g_ws.ensure(BX, x_bytes)) return -2;
   BNN_CUDA(cudaMemcpyAsync(g_ws.buf[BX], ah->X, x_bytes, cudaMemcpyHostToDevice, st));
-  BNN_CUDA(cudaMemcpyAsync(g_ws.buf[BW], ah->W, w_bytes, cudaMemcpyHostToDevice, st));
   a.X = (const float*)g_ws.buf[BX];
-  a.W = (const float*)g_ws.buf[BW];
   if (a.mask.mode == BNN_MASK_EXTERNAL) {
     const size_t mb = (size_t)a.S * a.mask.mask_stride * 4;
     if (g_ws.ensure(BMASK, mb)) return -2;
     BNN_CUDA(cudaMemcpyAsync(g_ws.buf[BMASK], ah->mask.mask, mb, cudaMemcpyHostToDevice, st));
     a.mask.mask = (const float*)g_ws.buf[BMASK];
   }
+  // ---- large per-sample banks, moments only: upload the bank in chunks on a copy stream behind the evaluation of the
+  //      previous chunk; every chunk is reduced to float64 (mean, M2) per point and the chunks are Chan-merged
+  //      (bnn_moments_merge), which is the arithmetic of the multi-GPU shard merge
+  const long long kChunk = 256;
+  if (a.w_stride != 0 && a.S >= 3 * kChunk && !ah->pred && !ah->part_mean && !ah->part_m2 && (ah->mean || ah->var)) {
+    long long chunk = kChunk;
+    while ((a.S + chunk - 1) / chunk > 64) chunk *= 2;          // bnn_moments_merge takes at most 64 shards
+    const int R = (int)((a.S + chunk - 1) / chunk);
+    const size_t cb = (size_t)chunk * a.w_stride * 4;
+    if (!g_ws.st_copy) BNN_CUDA(cudaStreamCreateWithFlags(&g_ws.st_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      if (!g_ws.ev_up[i]) BNN_CUDA(cudaEventCreateWithFlags(&g_ws.ev_up[i], cudaEventDisableTiming));
+      if (!g_ws.ev_free[i]) BNN_CUDA(cudaEventCreateWithFlags(&g_ws.ev_free[i], cudaEventDisableTiming));
+    }
+    if (g_ws.ensure(BW, cb) || g_ws.ensure(BW2, cb) || g_ws.ensure(BCHUNK, (size_t)R * M * 16)) return -2;
+    if (g_ws.ensure(BMEAN, (size_t)M * 4) || g_ws.ensure(BVAR, (size_t)M * 4)) return -2;
+    double* parts = (double*)g_ws.buf[BCHUNK];                  // [R][M] means, then [R][M] M2s
+    int64_t counts[64];
+    BnnForwardArgs c = a;
+    c.mean = c.var = nullptr;
+    c.S = chunk;
+    const long long wsb = use_tc(&c) ? forward_tc_workspace_bytes(&c) : forward_simt_workspace_bytes(&c);
+    if (wsb < 0) return -1;
+    if (g_ws.ensure(BWS, (size_t)(wsb > 16 ? wsb : 16))) return -2;
+    c.workspace = g_ws.buf[BWS];
+    c.workspace_bytes = wsb;
+    for (int i = 0; i < R; ++i) {
+      const long long lo = (long long)i * chunk, n = (a.S - lo < chunk) ? a.S - lo : chunk;
+      void* wb = g_ws.buf[(i & 1) ? BW2 : BW];
+      if (i >= 2) BNN_CUDA(cudaStreamWaitEvent(g_ws.st_copy, g_ws.ev_free[i & 1], 0));   // chunk i-2 has been evaluated
+      BNN_CUDA(cudaMemcpyAsync(wb, ah->W + lo * a.w_stride, (size_t)n * a.w_stride * 4, cudaMemcpyHostToDevice, g_ws.st_copy));
+      BNN_CUDA(cudaEventRecord(g_ws.ev_up[i & 1], g_ws.st_copy));
+      BNN_CUDA(cudaStreamWaitEvent(st, g_ws.ev_up[i & 1], 0));
+      c.W = (const float*)wb;
+      c.S = n;
+      c.part_mean = parts + (long long)i * M;
+      c.part_m2 = parts + (long long)(R + i) * M;
+      if (a.mask.mode == BNN_MASK_EXTERNAL) c.mask.mask = a.mask.mask + lo * a.mask.mask_stride;
+      c.mask.sample_offset = a.mask.sample_offset + lo;          // in-kernel Philox streams are indexed by the global sample
+      counts[i] = n;
+      const int rc = use_tc(&c) ? forward_tc(&c, st) : forward_simt(&c, st);
+      if (rc) return rc;
+      BNN_CUDA(cudaEventRecord(g_ws.ev_free[i & 1], st));
+    }
+    if (bnn_moments_merge(parts, parts + (long long)R * M, counts, R, M, ah->mean ? (float*)g_ws.buf[BMEAN] : nullptr,
+                          ah->var ? (float*)g_ws.buf[BVAR] : nullptr, st))
+      return -2;
+    if (ah->mean) BNN_CUDA(cudaMemcpyAsync(ah->mean, g_ws.buf[BMEAN], (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+    if (ah->var) BNN_CUDA(cudaMemcpyAsync(ah->var, g_ws.buf[BVAR], (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+    BNN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
+  if (g_ws.ensure(BW, w_bytes)) return -2;
+  BNN_CUDA(cudaMemcpyAsync(g_ws.buf[BW], ah->W, w_bytes, cudaMemcpyHostToDevice, st));
+  a.W = (const float*)g_ws.buf[BW];
   if (ah->pred) {
     if (g_ws.ensure(BPRED, (size_t)a.S * M * 4)) return -2;
     a.pred = (float*)g_ws.buf[BPRED];

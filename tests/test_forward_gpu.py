@@ -103,3 +103,21 @@ def test_variance_stress():
     mean, var = ops.moments(pred.cuda())
     assert max_rel(var.cpu(), pred.var(dim=0)) <= 1e-5
     assert max_rel(mean.cpu(), pred.mean(dim=0)) <= 1e-6
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32_bf16"])
+def test_forward_host_pipelined_matches_device_call(precision):
+    """bnn_forward_host (host pointers in, host pointers out): banks of >= 768 samples are uploaded in chunks behind the
+    evaluation and Chan-merged; smaller ones go through in one piece.  Both must agree with the device-pointer call."""
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    dims = [16, 200, 200, 1] if precision != "fp32" else [6, 24, 1]
+    arch = Arch(dims, "tanh")
+    g = torch.Generator().manual_seed(5)
+    for S, N in ((900, 300), (40, 300)):
+        bank = ((0.3 * torch.randn(S, arch.stride, generator=g)) * arch.valid_mask()).contiguous()
+        X = torch.randn(N, dims[0], generator=g)
+        ref = ops.forward(arch, X.cuda(), bank.cuda(), precision=precision)
+        out = ops.forward_host(arch, X.pin_memory(), bank.pin_memory(), precision=precision)
+        assert max_rel(out["mean"], ref["mean"].cpu()) <= 1e-6
+        assert max_rel(out["var"], ref["var"].cpu()) <= 1e-5
