@@ -5,8 +5,8 @@ What runs where:
   * sample / sample_predict / predict_mv / validate: the fused CUDA forward over the [S, stride]
     bank of thinned chain states (no deepcopy'd nn.Modules);
   * train: the chain state theta = [packed network | log_precs] lives in ONE device vector; each
-    SGLD step is torch autograd for the minibatch gradient of U (BNN_SGDMC.py:61-83, the stop-gap
-    SURVEY.md 8f ranks next) followed by the fused bnn_psgld_step kernel (update + RMSprop
+    SGLD step is a hand-derived minibatch gradient of U (BNN_SGDMC.py:61-83: a few GEMMs on the packed
+    blocks; a fused step kernel is the row SURVEY.md 8f ranks next) followed by the fused bnn_psgld_step kernel (update + RMSprop
     preconditioner + in-kernel Philox noise + both LR groups, BNN_SGDMC.py:86-87,96-101); thinning
     snapshots are row copies into the bank (BNN_SGDMC.py:124).
 pybnn is not needed.  The update rule is restated from Li et al. 2016 (UNPINNED).
@@ -108,16 +108,114 @@ class BNN_SGDMC(nn.Module, BNN):
         self._valid[a.stride: a.stride + self.nout] = 1.
         self._graph = None
 
-    def _grad_into(self, X, y, idx, num_train):
-        """loss and masked gradient of U at the current chain state for the minibatch idx (autograd stop-gap)."""
+    def _grad_autograd(self, X, y, idx, num_train):
+        """loss and masked gradient of U by torch autograd (reference implementation of the gradient; ~150 tiny kernels
+        per step at 3x512 -- kept for the test that pins _grad_into against it and for activations without a closed-form
+        derivative here)."""
         th = self._theta.detach().requires_grad_(True)
         loss = self._neg_log_post(th, X[idx], y[idx], num_train)
         grad, = torch.autograd.grad(loss, th)
         return loss.detach(), grad * self._valid
 
+    def _grad_buffers(self, B, dev):
+        """Scratch of the hand-derived gradient for batch size B: augmented layer inputs [B, ld] = (h | 1 | 0-pad), so that
+        one GEMM against a packed block [out, ld] = (W | b | pad) gives W h + b, and dz^T @ (h | 1 | 0) gives (dW | db | 0)."""
+        # one set per batch size, never freed while the chain lives: a captured CUDA graph keeps pointing at its set
+        cache = self.__dict__.setdefault("_gb_cache", {})
+        key = (int(B), str(dev), int(self._theta.data_ptr()))
+        if key not in cache:
+            a = self.arch
+            hs = []
+            for l in range(a.n_linear):
+                h = torch.zeros(B, a.lds[l], device=dev)
+                h[:, a.ins[l]] = 1.
+                hs.append(h)
+            grad = torch.zeros_like(self._theta)
+            # d(-log prior)/dW = W / std_l^2 on weight entries only (BNN_SGDMC.py:65-66), 0 on biases / padding
+            ps = torch.zeros_like(self._theta)
+            logc = 0.
+            for l in range(a.n_linear):
+                std = float(self.gain * np.sqrt(2. / (a.outs[l] + a.ins[l])))
+                blk = ps[a.offsets[l]: a.offsets[l] + a.outs[l] * a.lds[l]].view(a.outs[l], a.lds[l])
+                blk[:, : a.ins[l]] = 1. / (std * std)
+                logc += a.outs[l] * a.ins[l] * (math.log(std) + 0.5 * math.log(2. * math.pi))
+            cache[key] = (hs, grad, ps, logc)
+        return cache[key]
+
+    def _grad_into(self, X, y, idx, num_train):
+        """loss U (BNN_SGDMC.py:61-74,83) and its gradient at the current chain state for the minibatch idx, derived by hand
+        on the packed parameter vector: L forward GEMMs, L + (L - 1) backward GEMMs and a handful of elementwise kernels
+        (~40 launches instead of autograd's ~150), graph-capturable (no host tensors, no allocation-dependent control flow).
+        tanh / relu / sigmoid / identity activations; pinned against autograd by tests/test_sampling_gpu.py."""
+        with torch.no_grad():
+            return self._grad_manual(X, y, idx, num_train)
+
+    def _grad_manual(self, X, y, idx, num_train):
+        a = self.arch
+        th = self._theta
+        bx, by = X[idx], y[idx]
+        B = bx.shape[0]
+        hs, grad, ps, logc = self._grad_buffers(B, th.device)
+        L = a.n_linear
+        blks = [th[a.offsets[l]: a.offsets[l] + a.outs[l] * a.lds[l]].view(a.outs[l], a.lds[l]) for l in range(L)]
+        hs[0][:, : a.ins[0]] = bx
+        for l in range(L):
+            z = torch.mm(hs[l], blks[l].t())                       # W h + b (bias column meets the ones column)
+            if l != L - 1:
+                dst = hs[l + 1][:, : a.outs[l]]
+                if a.act == "tanh":
+                    torch.tanh(z, out=dst)
+                elif a.act == "relu":
+                    torch.clamp(z, min=0., out=dst)
+                elif a.act == "sigmoid":
+                    torch.sigmoid(z, out=dst)
+                else:
+                    dst.copy_(z)
+        out = z                                                      # [B, nout]
+        lp = th[a.stride: a.stride + self.nout]
+        scale = float(num_train) / B
+        al, be = float(self.alpha_n), float(self.beta_n)
+        pw = ps * th                                                 # W / std^2 on weight entries
+        if th.is_cuda:
+            # residuals, loss U, dU/d(log_precs), dU/d(out) in one launch (bnn_sgld_head)
+            scr = self.__dict__.setdefault("_head_scr", {})
+            k = (B, self.nout, str(th.device))
+            if k not in scr:
+                scr[k] = (torch.empty(B, self.nout, device=th.device), torch.zeros((), device=th.device))
+            dz, loss = scr[k]
+            ops.sgld_head(out.contiguous(), by.contiguous(), lp, scale, al, be, torch.dot(pw, th), logc, dz,
+                          grad[a.stride: a.stride + self.nout], loss)
+        else:                                                        # same arithmetic in torch (CPU tensors: tests only)
+            precs = lp.exp()
+            r = out - by
+            rr = (r * r).sum(0)
+            # U = -(scale * loglik + logprior)
+            log_lik = (-0.5 * precs * rr + B * (0.5 * lp - 0.5 * math.log(2. * math.pi))).sum()
+            log_p = -0.5 * torch.dot(pw, th) - logc + \
+                (al * math.log(be) + (al - 1.) * lp - be * precs - math.lgamma(al) + lp).sum()
+            loss = -1 * (log_lik * scale + log_p)
+            grad[a.stride: a.stride + self.nout] = -scale * (-0.5 * precs * rr + 0.5 * B) - (al - be * precs)
+            dz = (scale * precs) * r                                 # dU/dout
+        for l in range(L - 1, -1, -1):
+            gb = grad[a.offsets[l]: a.offsets[l] + a.outs[l] * a.lds[l]].view(a.outs[l], a.lds[l])
+            pb = pw[a.offsets[l]: a.offsets[l] + a.outs[l] * a.lds[l]].view(a.outs[l], a.lds[l])
+            torch.addmm(pb, dz.t(), hs[l], out=gb)                   # (dW + W / std^2 | db | 0)
+            if l > 0:
+                dh = torch.mm(dz, blks[l])[:, : a.ins[l]]           # dU/dh_{l-1}
+                h = hs[l][:, : a.ins[l]]
+                if a.act == "tanh":
+                    dz = torch.ops.aten.tanh_backward(dh, h)
+                elif a.act == "relu":
+                    dz = dh * (h > 0)
+                elif a.act == "sigmoid":
+                    dz = torch.ops.aten.sigmoid_backward(dh, h)
+                else:
+                    dz = dh.contiguous()
+        return loss, grad
+
     def _build_graph(self, X, y, num_train):
         """Capture ONE WHOLE SGLD STEP in a CUDA graph: minibatch gather from the epoch permutation at a device-side
-        offset, forward + backward (torch autograd -- the stop-gap SURVEY.md 8f ranks next), the fused pSGLD update
+        offset, forward + backward (hand-derived, a few GEMMs; SURVEY.md 8f ranks a fused step kernel next), the fused pSGLD update
         with the LR-schedule factor computed in-kernel from a device step counter, and the counter increments.  At
         1x50 .. 3x512 the step is launch-bound: one replay instead of ~60 eager launches + Python is the difference
         between ~2k and >10k steps/s."""

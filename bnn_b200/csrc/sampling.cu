@@ -234,6 +234,49 @@ __global__ void philox_normals_kernel(unsigned long long seed, uint32_t subseq, 
   for (int c = 0; c < 4 && (q << 2) + c < n; ++c) out[(q << 2) + c] = z[c];
 }
 
+// ---- SGLD energy head (BNN_SGDMC.py:61-74,83): everything between the network output and the backward pass, in ONE
+// launch of one CTA -- residuals, per-output sum of squares, the loss U = -(scale * loglik + logprior), dU/d(log_prec) and
+// dU/d(out).  As torch ops these are ~25 launches on 1..nout-element tensors per SGLD step.
+//   loglik   = sum_b,o ( -0.5 * prec_o * r^2 + 0.5 * lp_o - 0.5 * log(2 pi) )                      (:72-74)
+//   logprior = -0.5 * prior_quad - log_const + sum_o ( a log b + (a - 1) lp_o - b prec_o - lgamma(a) + lp_o )   (:47,62-66)
+__global__ void __launch_bounds__(256) sgld_head_kernel(const float* __restrict__ out, const float* __restrict__ y,
+                                                        const float* __restrict__ log_precs, long long B, int nout, float scale,
+                                                        float al, float be, float lgamma_al, const float* __restrict__ prior_quad,
+                                                        float log_const, float* __restrict__ dz, float* __restrict__ grad_lp,
+                                                        float* __restrict__ loss) {
+  __shared__ float rr[64];
+  __shared__ float red[256];
+  const int tid = threadIdx.x;
+  float total_ll = 0.f, total_lp = 0.f;
+  for (int o = 0; o < nout; ++o) {
+    const float lp = log_precs[o], prec = expf(lp);
+    float acc = 0.f;
+    for (long long b = tid; b < B; b += blockDim.x) {
+      const float r = out[b * nout + o] - y[b * nout + o];
+      acc = fmaf(r, r, acc);
+      dz[b * nout + o] = scale * prec * r;
+    }
+    red[tid] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+      if (tid < w) red[tid] += red[tid + w];
+      __syncthreads();
+    }
+    if (tid == 0) rr[o] = red[0];
+    __syncthreads();
+    if (tid == 0) {
+      const float s2 = rr[o];
+      total_ll += -0.5f * prec * s2 + (float)B * (0.5f * lp - 0.91893853320467274178f);
+      total_lp += al * logf(be) + (al - 1.f) * lp - be * prec - lgamma_al + lp;
+      grad_lp[o] = -scale * (-0.5f * prec * s2 + 0.5f * (float)B) - (al - be * prec);
+    }
+  }
+  if (tid == 0 && loss) {
+    const float logp = -0.5f * (prior_quad ? prior_quad[0] : 0.f) - log_const + total_lp;
+    loss[0] = -(total_ll * scale + logp);
+  }
+}
+
 static unsigned sample_rows(long long S, long long blocks_x) {
   // y-dimension: ~32 CTAs per SM in total (several CTAs are resident per SM, so this is ~6-8 waves and the ragged last
   // wave costs little -- 4 per SM came out as 1.04 waves on the cfg 4 bank and doubled the run time), each CTA looping
@@ -325,6 +368,16 @@ extern "C" int32_t bnn_psgld_step_dev(float* theta, const float* grad, float* V,
   const long long quads = (n + 3) >> 2;
   psgld_kernel<<<(unsigned)((quads + kEwBlock - 1) / kEwBlock), kEwBlock, 0, (cudaStream_t)stream>>>(
       theta, grad, V, n, n_head, lr_head, lr_tail, alpha, lam, nullptr, seed, 0, (const long long*)step_dev);
+  BNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t bnn_sgld_head(const float* out, const float* y, const float* log_precs, int64_t B, int32_t nout, float scale,
+                                 float alpha_n, float beta_n, const float* prior_quad, float log_const, float* dz,
+                                 float* grad_log_precs, float* loss, void* stream) {
+  if (!out || !y || !log_precs || !dz || !grad_log_precs || B < 1 || nout < 1 || nout > 64) BNN_FAIL("bnn_sgld_head: bad arguments");
+  sgld_head_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(out, y, log_precs, B, nout, scale, alpha_n, beta_n, lgammaf(alpha_n),
+                                                       prior_quad, log_const, dz, grad_log_precs, loss);
   BNN_CUDA(cudaGetLastError());
   return 0;
 }

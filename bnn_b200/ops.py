@@ -357,6 +357,15 @@ def psgld_step_dev(theta, grad, V, step_dev, lr_head, lr_tail=None, n_head=None,
                                              _ptr(step_dev), _stream(theta)), "bnn_psgld_step_dev")
 
 
+def sgld_head(out, y, log_precs, scale, alpha_n, beta_n, prior_quad, log_const, dz, grad_log_precs, loss):
+    """Energy head of one SGLD step (see bnn_sgld_head): writes dz, grad_log_precs, loss in place."""
+    B, nout = out.shape
+    _lib.check(_lib.lib().bnn_sgld_head(_ptr(_dev(out, "out")), _ptr(_dev(y, "y")), _ptr(log_precs), B, nout, float(scale),
+                                        float(alpha_n), float(beta_n), _ptr(prior_quad) if prior_quad is not None else None,
+                                        float(log_const), _ptr(dz), _ptr(grad_log_precs), _ptr(loss), _stream(out)),
+               "bnn_sgld_head")
+
+
 def philox_words(seed, subsequence, tag, n, device):
     out = torch.empty(n, dtype=torch.int32, device=device)
     _lib.check(_lib.lib().bnn_philox_words(seed, subsequence, tag, n, _ptr(out), _stream(out)), "bnn_philox_words")

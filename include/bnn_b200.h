@@ -196,6 +196,14 @@ int32_t bnn_psgld_step(float* theta, const float* grad, float* V, int64_t n, int
 int32_t bnn_psgld_step_dev(float* theta, const float* grad, float* V, int64_t n, int64_t n_head, float lr_head,
                            float lr_tail, float alpha, float lam, uint64_t seed, const int64_t* step_dev, void* stream);
 
+/* SGLD energy head (replaces the scalar arithmetic of BNN_SGDMC.py:61-74,83 between the network output and the backward
+ * pass): out, y [B, nout]; log_precs [nout]; scale = N_train / B; prior_quad = device scalar sum_l sum W^2 / std_l^2 (or null);
+ * log_const = sum_l n_l * (log std_l + 0.5 log 2 pi).  Writes dz = dU/d(out) [B, nout], dU/d(log_precs) [nout] and the
+ * loss U = -(scale * loglik + logprior) [1] (loss may be null).  One launch, graph-capturable.                    */
+int32_t bnn_sgld_head(const float* out, const float* y, const float* log_precs, int64_t B, int32_t nout, float scale,
+                      float alpha_n, float beta_n, const float* prior_quad, float log_const, float* dz,
+                      float* grad_log_precs, float* loss, void* stream);
+
 /* raw Philox stream dump for tests: out[n] 32-bit words / normals */
 int32_t bnn_philox_words(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, uint32_t* out, void* stream);
 int32_t bnn_philox_normals(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, float* out, void* stream);

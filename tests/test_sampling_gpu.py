@@ -245,3 +245,23 @@ def test_psgld_step_dev_equals_host_schedule():
     ops.psgld_step(a_t, grad.cuda(), a_V, 2e-2 * f, lr_tail=1e-1 * f, n_head=n - 3, seed=9, step=t)
     ops.psgld_step_dev(b_t, grad.cuda(), b_V, torch.tensor(t, dtype=torch.long, device="cuda"), 2e-2, lr_tail=1e-1, n_head=n - 3, seed=9)
     assert torch.allclose(a_t, b_t, rtol=1e-6, atol=1e-7) and torch.equal(a_V, b_V)
+
+
+@pytest.mark.parametrize("act,hid,nout", [("tanh", [512, 512, 512], 1), ("relu", [50], 1), ("sigmoid", [7, 5], 3)])
+def test_sgld_hand_derived_gradient_matches_autograd(act, hid, nout):
+    """The minibatch gradient of U used by the SGLD step (a few GEMMs on the packed blocks) against torch autograd on the
+    same energy (BNN_SGDMC.py:61-83)."""
+    import torch.nn as nn
+    from bnn_b200.BNN_SGDMC import BNN_SGDMC
+    torch.manual_seed(3)
+    dev = torch.device("cuda")
+    m = BNN_SGDMC(9, {"tanh": nn.Tanh(), "relu": nn.ReLU(), "sigmoid": nn.Sigmoid()}[act], hid, nout=nout,
+                  conf={"batch_size": 32, "device": "cuda"})
+    m._chain_init(dev)
+    m._theta[: m.arch.stride] += 0.05 * torch.randn(m.arch.stride, device=dev) * m.arch.valid_mask().to(dev)
+    X, y = torch.randn(500, 9, device=dev), torch.randn(500, nout, device=dev)
+    idx = torch.randperm(500, device=dev)[:32]
+    l_ref, g_ref = m._grad_autograd(X, y, idx, 500)
+    l_new, g_new = m._grad_into(X, y, idx, 500)
+    assert abs(float(l_new) - float(l_ref)) <= 1e-5 * abs(float(l_ref))
+    assert float((g_new - g_ref).abs().max() / g_ref.abs().max()) <= 1e-5
