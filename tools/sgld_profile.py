@@ -27,5 +27,6 @@ import collections
 agg = collections.OrderedDict()
 for e in ev:
     k = e.name[:70]; a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += e.device_time
+print("per-launch us of our kernels:", [round(e.device_time, 1) for e in ev if "bnn::" in e.name])
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
     print(f"{t:8.1f} us  x{n:<3d} {k}")
