@@ -183,12 +183,13 @@ __global__ void __launch_bounds__(kEwBlock) psgld_kernel(float* __restrict__ the
     lr_tail *= f;
   }
   float z[4];
-  if (!noise) philox_normal4(seed, (uint32_t)step, STREAM_SGLD, (uint64_t)q, z);
   const float om = 1.0f - alpha;
   if (e + 4 <= n) {
-    const float4 t4 = *reinterpret_cast<const float4*>(theta + e);
-    const float4 g4 = *reinterpret_cast<const float4*>(grad + e);
-    const float4 v4 = *reinterpret_cast<const float4*>(V + e);
+    // the three streaming loads go out first; the ~200 instructions of Philox + Box-Muller run under their latency
+    const float4 t4 = __ldcs(reinterpret_cast<const float4*>(theta + e));
+    const float4 g4 = __ldcs(reinterpret_cast<const float4*>(grad + e));
+    const float4 v4 = __ldcs(reinterpret_cast<const float4*>(V + e));
+    if (!noise) philox_normal4(seed, (uint32_t)step, STREAM_SGLD, (uint64_t)q, z);
     if (noise) {
       const float4 n4 = *reinterpret_cast<const float4*>(noise + e);
       z[0] = n4.x; z[1] = n4.y; z[2] = n4.z; z[3] = n4.w;
@@ -203,9 +204,10 @@ __global__ void __launch_bounds__(kEwBlock) psgld_kernel(float* __restrict__ the
       const float G = 1.0f / (lam + sqrtf(v[c]));
       t[c] = t[c] - (0.5f * lr * G * g[c] + sqrtf(lr * G) * z[c]);
     }
-    *reinterpret_cast<float4*>(theta + e) = make_float4(t[0], t[1], t[2], t[3]);
-    *reinterpret_cast<float4*>(V + e) = make_float4(v[0], v[1], v[2], v[3]);
+    __stcs(reinterpret_cast<float4*>(theta + e), make_float4(t[0], t[1], t[2], t[3]));
+    __stcs(reinterpret_cast<float4*>(V + e), make_float4(v[0], v[1], v[2], v[3]));
   } else {
+    if (!noise) philox_normal4(seed, (uint32_t)step, STREAM_SGLD, (uint64_t)q, z);
     for (int c = 0; e + c < n; ++c) {
       const float lr = (e + c) < n_head ? lr_head : lr_tail;
       const float g = grad[e + c];
