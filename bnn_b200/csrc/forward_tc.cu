@@ -290,12 +290,24 @@ __device__ __forceinline__ void warp_signal_tmem(uint64_t* bar, int lane) {
   }
 }
 
+// Activations of the tensor-core path.  tanh / sigmoid go through MUFU.EX2 + MUFU.RCP (5 / 4 instructions; libdevice's
+// tanhf is ~18 with both of its branches predicated, and the epilogues are instruction-bound): absolute error <= 2e-7 on
+// values in [-1, 1], the same order as the 3xTF32 / TF32+BF16 products feeding them (parity tests: 1e-5 max-normalised).
+// The FP32 SIMT path keeps tanhf / expf.
 template <int kAct>
 __device__ __forceinline__ float act_ct(float v) {
   if constexpr (kAct == BNN_ACT_RELU) return fmaxf(v, 0.0f);
-  else if constexpr (kAct == BNN_ACT_TANH) return tanhf(v);
-  else if constexpr (kAct == BNN_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
-  else return v;
+  else if constexpr (kAct == BNN_ACT_TANH) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 2.8853900817779268f));   // exp(2 v)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);                                                   // 1 - 2 / (exp(2 v) + 1)
+  } else if constexpr (kAct == BNN_ACT_SIGMOID) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));  // exp(-v)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return r;
+  } else return v;
 }
 
 // Roles: warps 0-7 (WG-A) run epilogue-1, two warps per TMEM lane quarter taking alternate 16-column batches
@@ -503,7 +515,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     uint32_t ring_gb = 0, ring_st = 0, ring_use = 0;   // last stage index handled by this warp, its slot and use parity
     const bool three = p.passes == 3, mixed = p.passes == 2;
     const float* b1s = reinterpret_cast<const float*>(smem + p.sm_vec);
-    float* mk0 = reinterpret_cast<float*>(smem + p.sm_mask);   // this group's masks: m0[Dp] (inputs), m1[N1] (hidden 1)
+    // this group's masks m0[Dp] (inputs) | m1[N1] (hidden 1), double-buffered by sample parity: with a shared network the
+    // next sample's first tile is prepared while the current sample's last tile is still in flight
+    float* mk_base = reinterpret_cast<float*>(smem + p.sm_mask);
+    const int mk_sz = p.Dp + p.N1;
+    float* mk0 = mk_base;
     float* mk1 = mk0 + p.Dp;
     const bool has_m0 = p.mask_mode != BNN_MASK_NONE && p.m_off[0] >= 0;
     const bool has_m1 = p.mask_mode != BNN_MASK_NONE && p.m_off[1] >= 0;
@@ -531,39 +547,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         x[e] = (n < p.N && k < p.D) ? __ldg(xr + k) : 0.0f;
       }
     };
-    auto mask_x = [&](int kc, float (&x)[4]) {   // dropout on the network inputs (BNN_Dropout.py:73-74 when dim > 1)
+    auto mask_x = [&](const float* m0, int kc, float (&x)[4]) {   // dropout on the network inputs (BNN_Dropout.py:73-74 when dim > 1)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int k = kc * 4 + e;
-        if (k < p.D) x[e] *= mk0[k];
+        if (k < p.D) x[e] *= m0[k];
       }
     };
     constexpr int kPre = 4;   // granules of the next tile's input row prefetched into registers (D <= 16 fully)
     const int n_kc = p.Dp >> 2;
+    auto draw_masks = [&](int sm) {   // masks of sample sm into the buffer of its parity (all 256 WG-A threads)
+      float* m0 = mk_base + ((sm - s0) & 1) * mk_sz;
+      float* m1 = m0 + p.Dp;
+      const int t256 = warp * 32 + lane;
+      if (has_m0) for (int j = t256; j < p.D; j += 256) m0[j] = tc_mask_value(p, p.sample_offset + sm, sm, 0, p.m_off[0] + j);
+      if (has_m1) for (int j = t256; j < p.N1; j += 256) m1[j] = j < p.H1 ? tc_mask_value(p, p.sample_offset + sm, sm, 1, p.m_off[1] + j) : 0.0f;
+    };
     for (int s = s0; s < s1; ++s) {
       const bool reload = !p.shared_w || s == s0;
+      // With a shared network nothing is reloaded between samples, so (sample, tile) pairs form one continuous stream: the
+      // pair after the last tile of sample s is the first tile of sample s + 1, prepared like any next tile.
+      const bool chain = p.shared_w && s + 1 < s1;
       if (has_m0 || has_m1) {
-        // every WG-A warp is done with the previous sample's masks -> draw this sample's -> publish (named barrier 5)
+        // masks are drawn ONE SAMPLE AHEAD (the next sample's first A1 needs them during this sample's last tile): every
+        // WG-A warp has left sample s - 1, whose buffer is the one overwritten now (named barrier 5)
         named_bar_sync(5, 256);
-        const int t256 = warp * 32 + lane;
-        if (has_m0) for (int j = t256; j < p.D; j += 256) mk0[j] = tc_mask_value(p, p.sample_offset + s, s, 0, p.m_off[0] + j);
-        if (has_m1) for (int j = t256; j < p.N1; j += 256) mk1[j] = j < p.H1 ? tc_mask_value(p, p.sample_offset + s, s, 1, p.m_off[1] + j) : 0.0f;
+        if (s == s0) draw_masks(s0);
+        if (s + 1 < s1) draw_masks(s + 1);
         named_bar_sync(5, 256);
       }
+      mk0 = mk_base + ((s - s0) & 1) * mk_sz;
+      mk1 = mk0 + p.Dp;
+      const float* mk0_next = mk_base + ((s + 1 - s0) & 1) * mk_sz;
       for (int pt = pt0; pt < pt1; ++pt, ++tile_cnt) {
         const uint32_t tpar = tile_cnt & 1u;
         float xn[kPre][4];
-        const bool have_next = (pt + 1 < pt1);
-        const long long n_next = ((long long)(pt + 1) * kPair + rank) * 128 + row;
+        const bool last_pt = pt + 1 == pt1;
+        const bool have_next = !last_pt || chain;
+        const int pt_next = last_pt ? pt0 : pt + 1;
+        const float* m0_next = last_pt ? mk0_next : mk0;
+        const long long n_next = ((long long)pt_next * kPair + rank) * 128 + row;
+        const bool prepared = pt > pt0 || (p.shared_w && s > s0);   // A1 of this pair was built during the previous pair
         if (set == 0) {
-          if (pt == pt0) {
-            // first tile of a sample: build A1 on the critical path; the operands of this sample must have
-            // landed in THIS CTA before the leader may use them, so wait for them before signalling
+          if (!prepared) {
+            // first tile of the stream / of a freshly loaded sample: build A1 on the critical path; the operands of this
+            // sample must have landed in THIS CTA before the leader may use them, so wait for them before signalling
             const long long n = ((long long)pt * kPair + rank) * 128 + row;
             for (int kc = 0; kc < n_kc; ++kc) {
               float x[4];
               load_x(n, kc, x);
-              if (has_m0) mask_x(kc, x);
+              if (has_m0) mask_x(mk0, kc, x);
               store_a1(kc, x);
             }
             if (reload) mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
@@ -586,13 +619,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
 #pragma unroll
           for (int kc = 0; kc < kPre; ++kc)
             if (kc < n_kc) {
-              if (has_m0) mask_x(kc, xn[kc]);
+              if (has_m0) mask_x(m0_next, kc, xn[kc]);
               store_a1(kc, xn[kc]);
             }
           for (int kc = kPre; kc < n_kc; ++kc) {
             float x[4];
             load_x(n_next, kc, x);
-            if (has_m0) mask_x(kc, x);
+            if (has_m0) mask_x(m0_next, kc, x);
             store_a1(kc, x);
           }
           warp_signal_leader<kPair>(&bars[BAR_A1_FULL], lane);
@@ -681,7 +714,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     const int c_lo = half == 0 ? 0 : ((nb16 + 1) >> 1) * 16, c_hi = half == 0 ? ((nb16 + 1) >> 1) * 16 : p.N2;
     // with dropout on the inputs of the last Linear, w3 is replaced by a per-sample copy with its columns scaled by the
     // mask -- exactly what the reference does to the weight matrix (BNN_Dropout.py:70-75, BNN_CDropout.py:59-65)
-    float* w3m = reinterpret_cast<float*>(smem + p.sm_mask) + p.Dp + p.N1;   // [O][N2]
+    float* w3m = reinterpret_cast<float*>(smem + p.sm_mask) + 2 * (p.Dp + p.N1);   // [O][N2]
     const float* b2s = reinterpret_cast<const float*>(smem + p.sm_vec) + p.N1;
     const float* w3s = b2s + p.N2;
     const bool has_m2 = p.mask_mode != BNN_MASK_NONE && p.m_off[2] >= 0;
@@ -1116,7 +1149,7 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
       p.sm_vec = (int)o; o += (size_t)vec_pad * 4;
       p.sm_ypart = (int)o; o += (size_t)128 * O * 4;
       o = (o + 15) & ~(size_t)15;
-      p.sm_mask = (int)o; if (a->mask.mode != BNN_MASK_NONE) o += (size_t)(p.Dp + p.N1 + p.O * p.N2) * 4;
+      p.sm_mask = (int)o; if (a->mask.mode != BNN_MASK_NONE) o += (size_t)(2 * (p.Dp + p.N1) + p.O * p.N2) * 4;
       o = (o + 15) & ~(size_t)15;
       p.sm_bar = (int)o; o += (size_t)BAR_COUNT * 8 + 16;
       if (o <= (size_t)227 * 1024) { kpair = kp; plan->smem = o; }

@@ -22,3 +22,10 @@ n2 = m2.sample(1000)
 print("cfg2 sample(1000): %.3f ms" % t(lambda: m2.sample(1000)))
 print("cfg2 predict_mv : %.3f ms" % t(lambda: m2.predict_mv(X2, n2)))
 m2.predict_mv(X2,n2); torch.cuda.synchronize(); e0.record(); m2.predict_mv(X2,n2); e1.record(); torch.cuda.synchronize(); print("  device time of predict_mv: %.3f ms" % e0.elapsed_time(e1))
+from torch.profiler import profile, ProfilerActivity
+for name, fn in (("cfg3 predict_mv", lambda: m.predict_mv(X, nns)), ("cfg2 predict_mv", lambda: m2.predict_mv(X2, n2))):
+    fn(); torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn(); torch.cuda.synchronize()
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    print(name, "kernels:", [(e.name[:40], round(e.device_time, 1)) for e in ev])

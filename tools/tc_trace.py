@@ -16,11 +16,18 @@ g = torch.Generator(device="cuda").manual_seed(0)
 X = torch.randn(N, dims[0], generator=g, device="cuda")
 bank = (0.1 * torch.randn(S, arch.stride, generator=g, device="cuda")) * arch.valid_mask().cuda()
 prec = sys.argv[1] if len(sys.argv) > 1 else "tf32x3"
-ops.forward(arch, X, bank, precision=prec)
+if os.environ.get("MASKED"):     # dropout family: ONE shared network + per-sample external masks (cfg 3)
+    S = int(os.environ.get("NS", 64))
+    masks = (torch.rand(S, sum(dims[:-1]), generator=g, device="cuda") > 0.05).float()
+    cfg = ops.MaskConfig("external", [True] * (len(dims) - 1), mask=masks)
+    run = lambda: ops.forward(arch, X, bank[0].contiguous(), S=S, mask=cfg, precision=prec)
+else:
+    run = lambda: ops.forward(arch, X, bank, precision=prec)
+run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-ops.forward(arch, X, bank, precision=prec)
+run()
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
