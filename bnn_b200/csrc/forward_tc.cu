@@ -1,21 +1,26 @@
 // Kernel (a)+(e), tensor-core variant: fused S x N batched MLP forward on tcgen05 (5th-gen tensor cores),
-// accumulators in TMEM, FP32-grade accuracy through 3xTF32 error compensation
-//     A*B ~= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo          (hi = tf32(x) rounded to nearest, lo = x - hi exactly)
-// or a single TF32 pass (BNN_PREC_TF32, looser bound).  Replaces the same reference code as forward_simt.cu
-// (the `for i in range(S): pred[i] = nns[i](X)` loops + BNN.py:36-37) for the wide configs where the layers are
-// real contractions (M = 128/256 points, N = hidden width, K = previous width).
+// accumulators in TMEM, FP32-grade accuracy through error-compensated products.  With a = a_h + a_l, a_h = tf32(a):
+//     a*b ~= a_h*b_h + a_l*b + a*b_l
+//   BNN_PREC_TF32X3   : all three terms as TF32 MMAs (kind::tf32, K = 8)
+//   BNN_PREC_TF32_BF16: main term TF32, the two (2^-11 small) correction terms as BF16 MMAs (kind::f16, K = 16) on
+//                       bf16(a_l)*bf16(b) and bf16(a)*bf16(b_l) -- 4 instead of 6 bf16-equivalent passes per MAC
+//   BNN_PREC_TF32     : a single TF32 pass (looser bound, opt-in).
+// Replaces the same reference code as forward_simt.cu (the `for i in range(S): pred[i] = nns[i](X)` loops +
+// BNN.py:36-37) for the wide configs where the layers are real contractions (M = 128/256 points, N = hidden width,
+// K = previous width).
 //
 // Shape family: dims = [D, H1, H2, O] with D <= 64, H1, H2 <= 256, O <= 4 (the last Linear is a dot product in
 // the epilogue).  One CTA (kPair = 1) or one CTA pair on two SMs (kPair = 2, cta_group::2, M = 256) owns a range
 // of 128-point tiles and walks the posterior samples in the outer loop:
-//   per sample : the sample's weights, pre-split into hi/lo UMMA operand images by tc_prep_kernel, are bulk-copied
-//                (TMA bulk engine) into shared memory ONCE and stay resident for all tiles (pair mode: each CTA
-//                holds half of the N rows of every B operand, the tensor core reads both halves);
-//   per tile   : X tile -> A1 (hi/lo) -> MMA1 -> D1[TMEM] -> epilogue-1 (bias, activation, hi/lo split) writes the
-//                layer-2 A operand K-step by K-step into a shared-memory ring -> MMA2 consumes the ring into
-//                D2[TMEM] -> epilogue-2 (bias, activation, dot with w3) -> y -> FP64 Welford update of the
-//                per-point state (global, owned by this CTA; finalised by finalize_moments()).
-// Roles: warps 0-3 = epilogue/compute (TMEM lane quarter = warp id), warp 4 = MMA issuer + weight loader.
+//   per sample : the sample's weights, pre-split into UMMA operand images by tc_prep_kernel, are bulk-copied (TMA bulk
+//                engine) into shared memory ONCE and stay resident for all tiles (pair mode: each CTA holds half of
+//                the N rows of every B operand, the tensor core reads both halves);
+//   per tile   : X tile -> A1 images (smem) -> MMA1 -> D1[TMEM] -> epilogue-1 (bias, activation, split) writes the
+//                layer-2 A operand stage by stage BACK INTO TENSOR MEMORY (tcgen05.st; a ring of 32-column stages
+//                behind D1 and D2) -> MMA2 reads A from TMEM (TS form) and B2 from shared memory into D2[TMEM] ->
+//                epilogue-2 (bias, activation, dot with w3) -> y -> FP64 Welford update of the per-point state
+//                (global, owned by this CTA; finalised by finalize_moments()).
+// Roles (544 threads): warps 0-7 epilogue-1 (+ A1), warps 8-15 epilogue-2 + reduction, warp 16 weight loader + MMA issuer.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -32,9 +37,9 @@ constexpr int kTcStageCols = 32;       // one A2 stage = 16 K-columns (two K = 8
 
 struct TcParams {
   int D, H1, H2, O, act;
-  int Dp, N1, N2, K2;      // padded: K of layer 1 (mult of 8), N of layers 1/2 (mult of 16), K of layer 2 (mult of 8, <= N1)
+  int Dp, N1, N2, K2;      // padded: K of layer 1 (mult of 8; 16 in mixed mode), N of layers 1/2 (mult of 16), K of layer 2 (<= N1)
   int ring;                // A2 ring depth (2..kTcRing) in 16-column stages (tensor memory, after D1 and D2)
-  int passes;              // 3 (tf32x3) or 1 (tf32)
+  int passes;              // 3 (tf32x3), 2 (tf32 + two bf16 correction terms) or 1 (tf32)
   long long part_stride;   // floats per (sample, part) of the operand image
   long long img_stride;    // floats per sample of the operand image
   int vec_len;             // floats: b1[N1] b2[N2] w3[O*N2] b3[4]
