@@ -92,7 +92,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------
@@ -296,7 +296,7 @@ def run_ours(args):
                                        f"{cores} threads, {cpu_t:.1f} s"},
             "clocks": clk, "outputs_finite": finite, "sgld": sgld,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -369,6 +369,28 @@ def sgld_bench(dev, rank, steps, cpu=True):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner goes to fd 1 regardless of
+    NCCL_DEBUG_FILE), so fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -381,6 +403,7 @@ def main():
                     help="tf32_bf16: tcgen05 TF32 main term + two BF16 correction terms (FP32-grade, default); tf32x3: 3-pass "
                          "error-compensated TF32 (FP32-grade); fp32: SIMT FFMA; tf32: single pass (looser bound)")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
