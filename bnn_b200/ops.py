@@ -182,13 +182,14 @@ def forward_streamed(arch: Arch, X_host, W_host, chunk=250, precision="auto", wa
     return res
 
 
-def tc_supported(arch: Arch, S=2, masked=False):
-    """True if the tensor-core forward takes this architecture (see bnn_forward_tc_supported)."""
+def tc_supported(arch: Arch, S=2, masked=False, precision="tf32_bf16"):
+    """True if the tensor-core forward takes this architecture in this precision mode (see bnn_forward_tc_supported; the
+    modes pad K differently, so a shape at the shared-memory limit may fit one and not the other)."""
     a = _lib.ForwardArgs()
     a.desc = arch.desc()
     a.N, a.S, a.w_stride = 1, S, arch.stride
     a.mask.mode = _lib.MASK_EXTERNAL if masked else _lib.MASK_NONE
-    a.precision = _lib.PREC_TF32X3
+    a.precision = _PREC[precision]
     return bool(_lib.lib().bnn_forward_tc_supported(C.byref(a)))
 
 

@@ -211,3 +211,35 @@ def test_forward_streamed_equals_forward(prec):
     assert max_rel(out["var"].cpu(), ref["var"].cpu()) <= 1e-5
     assert max_rel(out["part_mean"].cpu(), ref["part_mean"].cpu()) <= 1e-9
     assert max_rel(out["part_m2"].cpu(), ref["part_m2"].cpu()) <= 1e-8
+
+
+def test_random_shape_sweep_tc_vs_simt():
+    """Seeded sweep over the supported shape family (D <= 64, H <= 256, O <= 4, any N / S, all activations, with and
+    without in-kernel masks): the tensor-core path against the FP32 SIMT path of the same library (which the other tests
+    pin to the oracle).  Shapes the tensor-core path refuses are skipped through bnn_forward_tc_supported."""
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    rng = torch.Generator().manual_seed(2024)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=rng))
+    done = 0
+    for trial in range(40):
+        dims = [ri(1, 64), ri(2, 256), ri(2, 256), ri(1, 4)]
+        act = ["relu", "tanh", "sigmoid", "identity"][ri(0, 3)]
+        S, N = ri(1, 9), ri(1, 700)
+        masked = trial % 3 == 0
+        arch = Arch(dims, act)
+        precs = [pr for pr in ("tf32_bf16", "tf32x3") if ops.tc_supported(arch, S=S, masked=masked, precision=pr)]
+        if not precs:
+            continue
+        bank = ((0.4 / (max(dims) ** 0.5) * 6) * torch.randn(S, arch.stride, generator=rng) * arch.valid_mask()).contiguous().cuda()
+        X = torch.randn(N, dims[0], generator=rng).cuda()
+        kw = {}
+        if masked:
+            kw["mask"] = ops.MaskConfig("bernoulli", [dims[0] > 1, True, True], p_drop=[0.1, 0.3, 0.2], seed=trial, sample_offset=7)
+        a = ops.forward(arch, X, bank, want_pred=True, precision="fp32", **kw)
+        for prec in precs:
+            b = ops.forward(arch, X, bank, want_pred=True, precision=prec, **kw)
+            assert max_rel(b["pred"].cpu(), a["pred"].cpu()) <= 1e-5, (dims, act, S, N, masked, prec)
+            assert max_rel(b["mean"].cpu(), a["mean"].cpu()) <= 1e-5, (dims, act, S, N, masked, prec)
+        done += 1
+    assert done >= 15
