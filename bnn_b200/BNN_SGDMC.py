@@ -66,6 +66,25 @@ class BNN_SGDMC(nn.Module, BNN):
             if type(l) == nn.Linear:
                 nn.init.xavier_uniform_(l.weight, gain=self.gain)
 
+    # ---- the reference's two energy terms on the module state (BNN_SGDMC.py:61-74), for callers that use them directly;
+    #      the chain itself evaluates them fused on the packed vector (_neg_log_post / _grad_into)
+    def log_prior(self):
+        al, be = float(self.alpha_n), float(self.beta_n)
+        lp = self.log_precs
+        # Gamma(al, be).log_prob(exp(l)) + l: TransformedDistribution with ExpTransform().inv (:47, :62)
+        log_p = (al * math.log(be) + (al - 1.) * lp - be * lp.exp() - math.lgamma(al) + lp).sum()
+        for n, p in self.nn.nn.named_parameters():
+            if "weight" in n:
+                std = float(self.gain * np.sqrt(2. / (p.shape[0] + p.shape[1])))                 # :65
+                log_p = log_p - (p * p).sum() / (2. * std * std) - p.numel() * (math.log(std) + 0.5 * math.log(2. * math.pi))
+        return log_p
+
+    def log_lik(self, X, y):
+        y = y.view(-1, self.nout)
+        out = self.nn(X).view(-1, self.nout)
+        precs = self.log_precs.exp()
+        return (-0.5 * precs * (y - out) ** 2 + 0.5 * self.log_precs - 0.5 * math.log(2. * math.pi)).sum()   # :72-74
+
     # ---- energy, evaluated on a packed parameter vector (BNN_SGDMC.py:61-74,83) ----------
     def _neg_log_post(self, theta, bx, by, num_train):
         """U = -(loglik * N/|b| + logprior) on a packed parameter vector.  Written with Python-float constants only

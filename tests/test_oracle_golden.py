@@ -104,3 +104,18 @@ def test_psgld_restatement_and_schedule():
     G = 1 / (1e-5 + Vexp.sqrt())
     assert torch.allclose(V2, Vexp) and torch.allclose(th2, th - (0.005 * G * g + (0.01 * G).sqrt() * xi))
     assert O.lr_factor(0) == np.float32(1.0) and abs(float(O.lr_factor(9)) - 10 ** -0.33) < 1e-7
+
+
+def test_sgdmc_energy_terms_match_oracle():
+    """BNN_SGDMC.log_prior / log_lik (kept for API parity with BNN_SGDMC.py:61-74) against the oracle's energy:
+    U = -(log_lik * N / |b| + log_prior)."""
+    import torch.nn as nn
+    from bnn_b200.BNN_SGDMC import BNN_SGDMC
+    torch.manual_seed(4)
+    m = BNN_SGDMC(5, nn.Tanh(), [7, 6], nout=2, conf={})
+    m.log_precs.data = torch.tensor([0.3, -0.4])
+    X, y = torch.randn(11, 5), torch.randn(11, 2)
+    net = [(l.weight.detach(), l.bias.detach()) for l in m.nn.nn if isinstance(l, nn.Linear)]
+    u_ref = O.sgdmc_neg_log_post(net, m.log_precs.detach(), X, y, "tanh", num_train=40, alpha_n=m.alpha_n, beta_n=m.beta_n)
+    u = -(m.log_lik(X, y) * (40 / 11) + m.log_prior())
+    assert abs(float(u) - float(u_ref)) <= 1e-5 * abs(float(u_ref))
