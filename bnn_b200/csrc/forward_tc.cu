@@ -79,15 +79,17 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Tc
   const long long s = blockIdx.y;
   const float* Ws = W + s * q.w_stride;
   float* out = img + s * q.img_stride;
+  // all per-sample indices fit 32 bits (one image is < 2^20 floats): 32-bit divisions, the 64-bit ones dominated this kernel
   const int N1h = q.N1 / q.kpair, N2h = q.N2 / q.kpair;
-  const long long b1_sz = (long long)q.Dp * N1h, b2_sz = (long long)q.K2 * N2h;
-  const long long total = q.img_stride;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const int b1_sz = q.Dp * N1h, b2_sz = q.K2 * N2h;
+  const int total = (int)q.img_stride, part_stride = (int)q.part_stride;
+  const int off0 = (int)q.off0, off1 = (int)q.off1, off2 = (int)q.off2;
+  for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < total; i += (int)(gridDim.x * blockDim.x)) {
     float v = 0.0f;
-    long long r = i;
-    if (r < q.part_stride * q.kpair) {
-      const int part = (int)(r / q.part_stride);
-      r -= part * q.part_stride;
+    int r = i;
+    if (r < part_stride * q.kpair) {
+      const int part = r >= part_stride ? 1 : 0;      // kpair <= 2
+      r -= part * part_stride;
       // regions: [B1 hi][B1 lo][B2 hi][B2 lo], each [kc][n][4]
       int layer, hl;
       if (r < 2 * b1_sz) { layer = 0; hl = r >= b1_sz; r -= hl * b1_sz; }
@@ -95,38 +97,38 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Tc
       const int rows = layer == 0 ? N1h : N2h;
       auto weight = [&](int ng, int k) {
         float w = 0.0f;
-        if (layer == 0) { if (ng < q.H1 && k < q.D) w = Ws[q.off0 + (long long)ng * q.ld0 + k]; }
-        else            { if (ng < q.H2 && k < q.H1) w = Ws[q.off1 + (long long)ng * q.ld1 + k]; }
+        if (layer == 0) { if (ng < q.H1 && k < q.D) w = Ws[off0 + ng * q.ld0 + k]; }
+        else            { if (ng < q.H2 && k < q.H1) w = Ws[off1 + ng * q.ld1 + k]; }
         return w;
       };
       if (hl && q.mixed) {
         // BF16 images [kc8][n][8 x bf16]: bf16(w) in the first half of the region, bf16(w - tf32(w)) in the second
-        const long long half_sz = (layer == 0 ? b1_sz : b2_sz) >> 1;
+        const int half_sz = (layer == 0 ? b1_sz : b2_sz) >> 1;
         const int lo_img = r >= half_sz;
         r -= lo_img * half_sz;
-        const int e = (int)(r & 3);
-        const long long g = r >> 2;
-        const int kc8 = (int)(g / rows), n = (int)(g - (long long)kc8 * rows);
+        const int e = r & 3;
+        const int g = r >> 2;
+        const int kc8 = g / rows, n = g - kc8 * rows;
         const int k = kc8 * 8 + 2 * e, ng = part * rows + n;
         const float w0 = weight(ng, k), w1 = weight(ng, k + 1);
         const uint32_t pk = lo_img ? tc::pack_bf16x2(w0 - tc::tf32_hi(w0), w1 - tc::tf32_hi(w1)) : tc::pack_bf16x2(w0, w1);
         v = __uint_as_float(pk);
       } else {
-        const int e = (int)(r & 3);
-        const long long g = r >> 2;
-        const int kc = (int)(g / rows), n = (int)(g - (long long)kc * rows);
+        const int e = r & 3;
+        const int g = r >> 2;
+        const int kc = g / rows, n = g - kc * rows;
         const float w = weight(part * rows + n, kc * 4 + e);
         const float hi = tc::tf32_hi(w);
         v = hl ? (w - hi) : hi;
       }
     } else {
-      int j = (int)(r - q.part_stride * q.kpair);
-      if (j < q.N1) { if (j < q.H1) v = Ws[q.off0 + (long long)j * q.ld0 + q.D]; }           // b1
-      else if ((j -= q.N1) < q.N2) { if (j < q.H2) v = Ws[q.off1 + (long long)j * q.ld1 + q.H1]; }  // b2
-      else if ((j -= q.N2) < q.O * q.N2) {                                                          // w3[o][j]
+      int j = r - part_stride * q.kpair;
+      if (j < q.N1) { if (j < q.H1) v = Ws[off0 + j * q.ld0 + q.D]; }                      // b1
+      else if ((j -= q.N1) < q.N2) { if (j < q.H2) v = Ws[off1 + j * q.ld1 + q.H1]; }      // b2
+      else if ((j -= q.N2) < q.O * q.N2) {                                                 // w3[o][j]
         const int o = j / q.N2, c = j - o * q.N2;
-        if (c < q.H2) v = Ws[q.off2 + (long long)o * q.ld2 + c];
-      } else if ((j -= q.O * q.N2) < q.O) v = Ws[q.off2 + (long long)j * q.ld2 + q.H2];            // b3
+        if (c < q.H2) v = Ws[off2 + o * q.ld2 + c];
+      } else if ((j -= q.O * q.N2) < q.O) v = Ws[off2 + j * q.ld2 + q.H2];                 // b3
     }
     out[i] = v;
   }
