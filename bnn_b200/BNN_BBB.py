@@ -72,10 +72,16 @@ class BNN_BBB(BNN):
         self._draws = 0                                        # Philox subsequence counter: every draw is fresh
 
     def _packed_mu_rho(self):
+        """(mu, rho) packed bias-last on the device; cached until a parameter is modified in place or replaced (tensor
+        version counters), so that repeated sample() calls do not re-upload and re-pack the variational parameters."""
         gls = self.nn.gaussian_layers()
         dev = self._dev()
-        return (self.arch.pack_bias_last([l.mu.detach().to(dev) for l in gls]),
-                self.arch.pack_bias_last([l.rho.detach().to(dev) for l in gls]))
+        key = (str(dev),) + tuple((id(p), p._version, p.data_ptr()) for l in gls for p in (l.mu, l.rho))
+        if getattr(self, "_mr_key", None) != key:
+            self._mr = (self.arch.pack_bias_last([l.mu.detach().to(dev) for l in gls]),
+                        self.arch.pack_bias_last([l.rho.detach().to(dev) for l in gls]))
+            self._mr_key = key
+        return self._mr
 
     def kl(self):
         """KL(q || N(0, weight_std)) of BNN_BBB.loss (BNN_BBB.py:107-110), by the fused kernel."""
