@@ -29,6 +29,15 @@ class BNN(ABC):
     device = None          # set by subclasses (torch.device("cuda", k))
     precision = "auto"     # "auto" | "fp32" | "tf32_bf16" | "tf32x3" | "tf32" (see bnn_b200.ops.forward)
 
+    def _cached_pack(self, name, params, build):
+        """build() -> device tensor(s) derived from `params`; reused until one of them is modified in place, re-pointed
+        (.data = ...) or replaced.  Keeps repeated sample() calls from re-packing / re-uploading unchanged networks."""
+        key = (str(self._dev()),) + tuple((id(p), p._version, p.data_ptr()) for p in params)
+        cache = self.__dict__.setdefault("_pack_cache", {})
+        if name not in cache or cache[name][0] != key:
+            cache[name] = (key, build())
+        return cache[name][1]
+
     def _dev(self):
         if self.device is None:
             if not torch.cuda.is_available():

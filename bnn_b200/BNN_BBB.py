@@ -76,12 +76,9 @@ class BNN_BBB(BNN):
         version counters), so that repeated sample() calls do not re-upload and re-pack the variational parameters."""
         gls = self.nn.gaussian_layers()
         dev = self._dev()
-        key = (str(dev),) + tuple((id(p), p._version, p.data_ptr()) for l in gls for p in (l.mu, l.rho))
-        if getattr(self, "_mr_key", None) != key:
-            self._mr = (self.arch.pack_bias_last([l.mu.detach().to(dev) for l in gls]),
-                        self.arch.pack_bias_last([l.rho.detach().to(dev) for l in gls]))
-            self._mr_key = key
-        return self._mr
+        return self._cached_pack("mu_rho", [p for l in gls for p in (l.mu, l.rho)],
+                                 lambda: (self.arch.pack_bias_last([l.mu.detach().to(dev) for l in gls]),
+                                          self.arch.pack_bias_last([l.rho.detach().to(dev) for l in gls])))
 
     def kl(self):
         """KL(q || N(0, weight_std)) of BNN_BBB.loss (BNN_BBB.py:107-110), by the fused kernel."""

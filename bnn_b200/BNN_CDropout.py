@@ -128,7 +128,7 @@ class BNN_CDropout(BNN):
         """uniforms (optional, [S, mask_len]) injects the reference's torch.rand draws for exact parity."""
         dev = self._dev()
         lin = [(l.layer[1].weight, l.layer[1].bias) for l in self.nn.cd_layers()]
-        base = self.arch.pack([lin])[0].to(dev)
+        base = self._cached_pack("base", [t for wb in lin for t in wb], lambda: self.arch.pack([lin])[0].to(dev))
         cfg = ops.MaskConfig("concrete", self.layer_masked, p_drop=self.drop_probs(), temperature=0.1, seed=self.seed,
                              sample_offset=self._draws)
         if uniforms is not None:

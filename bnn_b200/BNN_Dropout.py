@@ -87,7 +87,7 @@ class BNN_Dropout(BNN):
     def sample(self, num_samples=1, masks=None):
         """masks (optional, [S, mask_len]) injects the reference's own draws for exact parity."""
         dev = self._dev()
-        base = self.arch.pack([self.nn.nn])[0].to(dev)
+        base = self._cached_pack("base", list(self.nn.nn.parameters()), lambda: self.arch.pack([self.nn.nn])[0].to(dev))
         if masks is None:
             masks = ops.dropout_masks(self.arch, self.mask_config(), num_samples, dev)
             self._draws += num_samples
