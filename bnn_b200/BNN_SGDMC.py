@@ -169,15 +169,21 @@ class BNN_SGDMC(nn.Module, BNN):
         with torch.no_grad():
             return self._grad_manual(X, y, idx, num_train)
 
-    def _grad_manual(self, X, y, idx, num_train):
+    def _grad_manual(self, X, y, idx, num_train, gathered=None):
+        """gathered = (B, y_batch): the minibatch is already in the augmented first-layer input of the B-row buffer set
+        (bnn_sgld_gather, CUDA-graph path); otherwise it is gathered here from idx."""
         a = self.arch
         th = self._theta
-        bx, by = X[idx], y[idx]
-        B = bx.shape[0]
+        if gathered is None:
+            bx, by = X[idx], y[idx]
+            B = bx.shape[0]
+        else:
+            B, by = gathered
         hs, grad, ps, logc = self._grad_buffers(B, th.device)
         L = a.n_linear
         blks = [th[a.offsets[l]: a.offsets[l] + a.outs[l] * a.lds[l]].view(a.outs[l], a.lds[l]) for l in range(L)]
-        hs[0][:, : a.ins[0]] = bx
+        if gathered is None:
+            hs[0][:, : a.ins[0]] = bx
         for l in range(L):
             z = torch.mm(hs[l], blks[l].t())                       # W h + b (bias column meets the ones column)
             if l != L - 1:
@@ -244,16 +250,18 @@ class BNN_SGDMC(nn.Module, BNN):
         self._g_step = torch.full((), self._t, dtype=torch.long, device=dev)  # t of the LR schedule / Philox stream
         self._g_loss = torch.zeros((), device=dev)
         self._g_perm = torch.zeros(num_train, dtype=torch.long, device=dev)
-        # every tensor the captured kernels read must outlive the graph: keep the index helper on self
-        self._g_ar = ar = torch.arange(self.batch_size, device=dev)
+
+        B = self.batch_size
+        self._g_yb = torch.empty(B, self.nout, device=dev)
+        h0 = self._grad_buffers(B, dev)[0][0]                               # augmented first-layer input of the B-row set
 
         def one_step():
-            idx = self._g_perm[self._g_off + ar]
-            loss, grad = self._grad_into(X, y, idx, num_train)
-            ops.psgld_step_dev(self._theta, grad.contiguous(), self._V, self._g_step, self.lr_weight, lr_tail=self.lr_noise,
+            ops.sgld_gather(X, y, self._g_perm, self._g_off, h0, self._g_yb)      # DataLoader batch at the device-side offset
+            with torch.no_grad():
+                loss, grad = self._grad_manual(X, y, None, num_train, gathered=(B, self._g_yb))
+            ops.psgld_step_dev(self._theta, grad, self._V, self._g_step, self.lr_weight, lr_tail=self.lr_noise,
                                n_head=a.stride, alpha=self.psgld_alpha, lam=self.psgld_lambda, seed=self.seed)
-            self._g_step.add_(1)
-            self._g_off.add_(self.batch_size)
+            ops.sgld_advance(self._g_step, self._g_off, B)
             self._g_loss.copy_(loss)
 
         # warm-up on a side stream (autograd/cuBLAS workspaces), on scratch copies of the chain state

@@ -279,6 +279,25 @@ __global__ void __launch_bounds__(256) sgld_head_kernel(const float* __restrict_
   }
 }
 
+// ---- SGLD minibatch gather (the DataLoader(shuffle=True) batch of BNN_SGDMC.py:80,110): rows perm[*off .. *off + B) of X
+// and y go straight into the augmented first-layer input (h0 | 1 | 0-pad), row pitch ldh, and the target block.  The epoch
+// position lives on the device so that the launch can be replayed from a CUDA graph (one launch instead of an index add,
+// three index kernels and a strided copy).
+__global__ void __launch_bounds__(128) sgld_gather_kernel(const float* __restrict__ X, const float* __restrict__ y,
+                                                          const long long* __restrict__ perm, const long long* __restrict__ off,
+                                                          int D, int nout, int ldh, float* __restrict__ h0,
+                                                          float* __restrict__ yb) {
+  const long long b = blockIdx.x;
+  const long long row = perm[*off + b];
+  for (int k = threadIdx.x; k < D; k += blockDim.x) h0[b * ldh + k] = X[row * D + k];
+  for (int o = threadIdx.x; o < nout; o += blockDim.x) yb[b * nout + o] = y[row * nout + o];
+}
+// step and epoch-position counters of the captured SGLD step (after the update of the step has been enqueued)
+__global__ void sgld_advance_kernel(long long* step, long long* off, long long batch) {
+  *step += 1;
+  *off += batch;
+}
+
 static unsigned sample_rows(long long S, long long blocks_x) {
   // y-dimension: ~32 CTAs per SM in total (several CTAs are resident per SM, so this is ~6-8 waves and the ragged last
   // wave costs little -- 4 per SM came out as 1.04 waves on the cfg 4 bank and doubled the run time), each CTA looping
@@ -380,6 +399,22 @@ extern "C" int32_t bnn_sgld_head(const float* out, const float* y, const float* 
   if (!out || !y || !log_precs || !dz || !grad_log_precs || B < 1 || nout < 1 || nout > 64) BNN_FAIL("bnn_sgld_head: bad arguments");
   sgld_head_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(out, y, log_precs, B, nout, scale, alpha_n, beta_n, lgammaf(alpha_n),
                                                        prior_quad, log_const, dz, grad_log_precs, loss);
+  BNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t bnn_sgld_gather(const float* X, const float* y, const int64_t* perm, const int64_t* off_dev, int64_t B, int32_t D,
+                                   int32_t nout, int32_t ldh, float* h0, float* y_batch, void* stream) {
+  if (!X || !y || !perm || !off_dev || !h0 || !y_batch || B < 1 || D < 1 || nout < 1 || ldh < D) BNN_FAIL("bnn_sgld_gather: bad arguments");
+  sgld_gather_kernel<<<(unsigned)B, 128, 0, (cudaStream_t)stream>>>(X, y, (const long long*)perm, (const long long*)off_dev, D, nout, ldh,
+                                                                  h0, y_batch);
+  BNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t bnn_sgld_advance(int64_t* step_dev, int64_t* off_dev, int64_t batch, void* stream) {
+  if (!step_dev || !off_dev) BNN_FAIL("bnn_sgld_advance: bad arguments");
+  sgld_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)step_dev, (long long*)off_dev, batch);
   BNN_CUDA(cudaGetLastError());
   return 0;
 }

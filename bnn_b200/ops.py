@@ -367,6 +367,17 @@ def sgld_head(out, y, log_precs, scale, alpha_n, beta_n, prior_quad, log_const, 
                "bnn_sgld_head")
 
 
+def sgld_gather(X, y, perm, off_dev, h0, y_batch):
+    """Minibatch rows perm[off .. off + B) of X, y into the augmented first-layer input h0 [B, ld] and y_batch [B, nout]."""
+    B, ldh = h0.shape
+    _lib.check(_lib.lib().bnn_sgld_gather(_ptr(_dev(X, "X")), _ptr(_dev(y, "y")), _ptr(perm), _ptr(off_dev), B, X.shape[1],
+                                          y_batch.shape[1], ldh, _ptr(h0), _ptr(y_batch), _stream(X)), "bnn_sgld_gather")
+
+
+def sgld_advance(step_dev, off_dev, batch):
+    _lib.check(_lib.lib().bnn_sgld_advance(_ptr(step_dev), _ptr(off_dev), int(batch), _stream(step_dev)), "bnn_sgld_advance")
+
+
 def philox_words(seed, subsequence, tag, n, device):
     out = torch.empty(n, dtype=torch.int32, device=device)
     _lib.check(_lib.lib().bnn_philox_words(seed, subsequence, tag, n, _ptr(out), _stream(out)), "bnn_philox_words")

@@ -204,6 +204,14 @@ int32_t bnn_sgld_head(const float* out, const float* y, const float* log_precs, 
                       float alpha_n, float beta_n, const float* prior_quad, float log_const, float* dz,
                       float* grad_log_precs, float* loss, void* stream);
 
+/* SGLD minibatch gather for a CUDA-graph-replayed step (the shuffled DataLoader batch of BNN_SGDMC.py:80,110): rows
+ * perm[*off_dev .. *off_dev + B) of X [N, D] and y [N, nout] -> h0 [B, ldh] columns [0, D) (the caller keeps column D = 1 and
+ * the padding = 0: the augmented first-layer input) and y_batch [B, nout].  bnn_sgld_advance adds 1 to *step_dev and
+ * `batch` to *off_dev (stream-ordered, after the update of the step).                                              */
+int32_t bnn_sgld_gather(const float* X, const float* y, const int64_t* perm, const int64_t* off_dev, int64_t B, int32_t D,
+                        int32_t nout, int32_t ldh, float* h0, float* y_batch, void* stream);
+int32_t bnn_sgld_advance(int64_t* step_dev, int64_t* off_dev, int64_t batch, void* stream);
+
 /* raw Philox stream dump for tests: out[n] 32-bit words / normals */
 int32_t bnn_philox_words(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, uint32_t* out, void* stream);
 int32_t bnn_philox_normals(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, float* out, void* stream);

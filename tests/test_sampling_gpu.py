@@ -265,3 +265,25 @@ def test_sgld_hand_derived_gradient_matches_autograd(act, hid, nout):
     l_new, g_new = m._grad_into(X, y, idx, 500)
     assert abs(float(l_new) - float(l_ref)) <= 1e-5 * abs(float(l_ref))
     assert float((g_new - g_ref).abs().max() / g_ref.abs().max()) <= 1e-5
+
+
+def test_sgld_gather_and_advance():
+    """The minibatch gather of the captured SGLD step equals torch indexing at the device-side epoch offset; the counter
+    kernel advances step and offset."""
+    from bnn_b200 import ops
+    dev = "cuda"
+    g = torch.Generator().manual_seed(0)
+    N, D, nout, B, ld = 1000, 9, 2, 32, 12
+    X, y = torch.randn(N, D, generator=g).to(dev), torch.randn(N, nout, generator=g).to(dev)
+    perm = torch.randperm(N, generator=g).to(dev)
+    off = torch.tensor(64, dtype=torch.long, device=dev)
+    step = torch.tensor(5, dtype=torch.long, device=dev)
+    h0 = torch.zeros(B, ld, device=dev)
+    h0[:, D] = 1.0
+    yb = torch.empty(B, nout, device=dev)
+    ops.sgld_gather(X, y, perm, off, h0, yb)
+    idx = perm[64:64 + B]
+    assert torch.equal(h0[:, :D], X[idx]) and torch.equal(yb, y[idx])
+    assert bool((h0[:, D] == 1).all()) and bool((h0[:, D + 1:] == 0).all())
+    ops.sgld_advance(step, off, B)
+    assert int(step) == 6 and int(off) == 96
