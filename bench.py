@@ -337,7 +337,7 @@ def sgld_bench(dev, rank, steps, cpu=True):
     out = {"steps_per_s_per_chain": sps, "steps": steps, "batch": SGLD_BATCH, "params": model.arch.n_params + 1,
            "workload": f"cfg5: one pSGLD chain per GPU, synthetic {SGLD_ROWS}x{SGLD_DIMS[0]} regression, "
                        f"{'-'.join(map(str, SGLD_DIMS))} tanh MLP, batch {SGLD_BATCH}",
-           "gradient": "hand-derived on the packed vector: bnn_sgld_gather + 10 cuBLAS SGEMMs + bnn_sgld_head + 7 elementwise launches, whole step = one CUDA-graph replay of 24 launches", "update": "bnn_psgld_step (fused, Philox in-kernel)",
+           "gradient": "hand-derived on the packed vector: bnn_sgld_gather + 10 cuBLAS SGEMMs + 6 activation kernels + bnn_sgld_prior + bnn_sgld_head, whole step = one CUDA-graph replay of 21 launches", "update": "bnn_psgld_step (fused, Philox in-kernel)",
            "update_bytes_per_step": 20 * (model.arch.stride + 1)}
     if cpu and rank == 0:
         # CPU: the reference's sgld_steps body with the oracle's pSGLD restatement as the optimizer (pybnn is absent)

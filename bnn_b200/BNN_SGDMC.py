@@ -200,17 +200,19 @@ class BNN_SGDMC(nn.Module, BNN):
         lp = th[a.stride: a.stride + self.nout]
         scale = float(num_train) / B
         al, be = float(self.alpha_n), float(self.beta_n)
-        pw = ps * th                                                 # W / std^2 on weight entries
         if th.is_cuda:
-            # residuals, loss U, dU/d(log_precs), dU/d(out) in one launch (bnn_sgld_head)
+            # prior gradient + energy (bnn_sgld_prior), then residuals, loss U, dU/d(log_precs), dU/d(out) (bnn_sgld_head)
             scr = self.__dict__.setdefault("_head_scr", {})
-            k = (B, self.nout, str(th.device))
+            k = (B, self.nout, str(th.device), int(th.data_ptr()))
             if k not in scr:
-                scr[k] = (torch.empty(B, self.nout, device=th.device), torch.zeros((), device=th.device))
-            dz, loss = scr[k]
-            ops.sgld_head(out.contiguous(), by.contiguous(), lp, scale, al, be, torch.dot(pw, th), logc, dz,
+                scr[k] = (torch.empty(B, self.nout, device=th.device), torch.zeros((), device=th.device),
+                          torch.empty_like(th), torch.zeros(65, device=th.device), torch.zeros((), device=th.device))
+            dz, loss, pw, pscr, quad = scr[k]
+            ops.sgld_prior(ps, th, pw, pscr, quad)
+            ops.sgld_head(out.contiguous(), by.contiguous(), lp, scale, al, be, quad, logc, dz,
                           grad[a.stride: a.stride + self.nout], loss)
         else:                                                        # same arithmetic in torch (CPU tensors: tests only)
+            pw = ps * th                                             # W / std^2 on weight entries
             precs = lp.exp()
             r = out - by
             rr = (r * r).sum(0)
@@ -262,7 +264,7 @@ class BNN_SGDMC(nn.Module, BNN):
             ops.psgld_step_dev(self._theta, grad, self._V, self._g_step, self.lr_weight, lr_tail=self.lr_noise,
                                n_head=a.stride, alpha=self.psgld_alpha, lam=self.psgld_lambda, seed=self.seed)
             ops.sgld_advance(self._g_step, self._g_off, B)
-            self._g_loss.copy_(loss)
+            self._g_loss = loss                                             # the head kernel's own output buffer (no copy)
 
         # warm-up on a side stream (autograd/cuBLAS workspaces), on scratch copies of the chain state
         keep = (self._theta.clone(), self._V.clone())

@@ -71,6 +71,7 @@ PROTOTYPES = {
                                        C.c_float, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p]),
     "bnn_sgld_head": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float,
                                   C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bnn_sgld_prior": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bnn_sgld_gather": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "bnn_sgld_advance": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

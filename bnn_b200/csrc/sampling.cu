@@ -279,6 +279,41 @@ __global__ void __launch_bounds__(256) sgld_head_kernel(const float* __restrict_
   }
 }
 
+// ---- SGLD prior term: pw = ps * theta (the gradient of -log prior: W / std_l^2 on weight entries, 0 elsewhere) and its
+// energy sum_i pw_i * theta_i in one launch.  Per-CTA partial sums are combined by the last CTA to finish, in CTA order, so
+// the result does not depend on scheduling (no floating-point atomics).
+__global__ void __launch_bounds__(256) sgld_prior_kernel(const float* __restrict__ ps, const float* __restrict__ theta, long long n,
+                                                         float* __restrict__ pw, float* __restrict__ partial,
+                                                         unsigned int* __restrict__ ticket, float* __restrict__ quad) {
+  __shared__ float red[256];
+  __shared__ bool last;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float t = theta[i], v = ps[i] * t;
+    pw[i] = v;
+    acc = fmaf(v, t, acc);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = red[0];
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float s = 0.f;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += ((volatile float*)partial)[b];
+    quad[0] = s;
+    *ticket = 0u;   // ready for the next launch (graph replay)
+  }
+}
+
 // ---- SGLD minibatch gather (the DataLoader(shuffle=True) batch of BNN_SGDMC.py:80,110): rows perm[*off .. *off + B) of X
 // and y go straight into the augmented first-layer input (h0 | 1 | 0-pad), row pitch ldh, and the target block.  The epoch
 // position lives on the device so that the launch can be replayed from a CUDA graph (one launch instead of an index add,
@@ -399,6 +434,16 @@ extern "C" int32_t bnn_sgld_head(const float* out, const float* y, const float* 
   if (!out || !y || !log_precs || !dz || !grad_log_precs || B < 1 || nout < 1 || nout > 64) BNN_FAIL("bnn_sgld_head: bad arguments");
   sgld_head_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(out, y, log_precs, B, nout, scale, alpha_n, beta_n, lgammaf(alpha_n),
                                                        prior_quad, log_const, dz, grad_log_precs, loss);
+  BNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t bnn_sgld_prior(const float* prior_scale, const float* theta, int64_t n, float* pw, float* scratch, float* quad,
+                                  void* stream) {
+  if (!prior_scale || !theta || !pw || !scratch || !quad || n < 1) BNN_FAIL("bnn_sgld_prior: bad arguments");
+  // scratch: 64 floats of per-CTA partial sums followed by one zero-initialised 32-bit ticket (65 x 4 bytes)
+  const int blocks = 64;
+  sgld_prior_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(prior_scale, theta, n, pw, scratch, (unsigned int*)(scratch + 64), quad);
   BNN_CUDA(cudaGetLastError());
   return 0;
 }

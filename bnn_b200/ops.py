@@ -367,6 +367,12 @@ def sgld_head(out, y, log_precs, scale, alpha_n, beta_n, prior_quad, log_const, 
                "bnn_sgld_head")
 
 
+def sgld_prior(prior_scale, theta, pw, scratch, quad):
+    """pw = prior_scale * theta and quad = sum(pw * theta) in one launch (scratch: 65 floats, last one zero initially)."""
+    _lib.check(_lib.lib().bnn_sgld_prior(_ptr(prior_scale), _ptr(_dev(theta, "theta")), theta.numel(), _ptr(pw), _ptr(scratch),
+                                         _ptr(quad), _stream(theta)), "bnn_sgld_prior")
+
+
 def sgld_gather(X, y, perm, off_dev, h0, y_batch):
     """Minibatch rows perm[off .. off + B) of X, y into the augmented first-layer input h0 [B, ld] and y_batch [B, nout]."""
     B, ldh = h0.shape

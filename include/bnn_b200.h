@@ -204,6 +204,12 @@ int32_t bnn_sgld_head(const float* out, const float* y, const float* log_precs, 
                       float alpha_n, float beta_n, const float* prior_quad, float log_const, float* dz,
                       float* grad_log_precs, float* loss, void* stream);
 
+/* SGLD prior term (BNN_SGDMC.py:63-66): pw[i] = prior_scale[i] * theta[i] (prior_scale = 1 / std_l^2 on weight entries, 0 on
+ * biases / padding) and quad[0] = sum_i pw[i] * theta[i], deterministic.  scratch: 65 floats, the last one zero before the
+ * first call (the kernel re-zeroes it).                                                                             */
+int32_t bnn_sgld_prior(const float* prior_scale, const float* theta, int64_t n, float* pw, float* scratch, float* quad,
+                       void* stream);
+
 /* SGLD minibatch gather for a CUDA-graph-replayed step (the shuffled DataLoader batch of BNN_SGDMC.py:80,110): rows
  * perm[*off_dev .. *off_dev + B) of X [N, D] and y [N, nout] -> h0 [B, ldh] columns [0, D) (the caller keeps column D = 1 and
  * the padding = 0: the augmented first-layer input) and y_batch [B, nout].  bnn_sgld_advance adds 1 to *step_dev and

@@ -287,3 +287,23 @@ def test_sgld_gather_and_advance():
     assert bool((h0[:, D] == 1).all()) and bool((h0[:, D + 1:] == 0).all())
     ops.sgld_advance(step, off, B)
     assert int(step) == 6 and int(off) == 96
+
+
+def test_sgld_prior_kernel():
+    """pw = prior_scale * theta and its energy sum(pw * theta): exact elementwise, deterministic reduction (replayable:
+    the ticket re-zeroes itself)."""
+    from bnn_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    n = 572_420
+    ps = (torch.rand(n, generator=g) > 0.1).float().cuda() * 3.7
+    th = torch.randn(n, generator=g).cuda()
+    pw, scr, quad = torch.empty_like(th), torch.zeros(65, device="cuda"), torch.zeros((), device="cuda")
+    vals = []
+    for _ in range(3):
+        ops.sgld_prior(ps, th, pw, scr, quad)
+        torch.cuda.synchronize()
+        vals.append(float(quad))
+    assert torch.equal(pw, ps * th)
+    ref = float((ps.double() * th.double() * th.double()).sum())
+    assert abs(vals[0] - ref) <= 1e-5 * abs(ref)
+    assert vals[0] == vals[1] == vals[2]
