@@ -58,7 +58,7 @@ PROTOTYPES = {
     "bnn_moments_merge": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_int64, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "bnn_metrics": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
-                                C.c_void_p]),
+                                C.c_void_p, C.c_void_p]),
     "bnn_reparam_kl": (C.c_int32, [C.POINTER(MlpDesc), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                    C.c_int64, C.c_int64, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "bnn_dropout_masks": (C.c_int32, [C.POINTER(MlpDesc), C.POINTER(MaskSpec), C.c_void_p, C.c_int64, C.c_void_p,
@@ -98,7 +98,7 @@ def lib():
             fn = getattr(handle, name)   # AttributeError if the .so does not export what the header declares
             fn.restype = res
             fn.argtypes = args
-        if handle.bnn_abi_version() != 1:
+        if handle.bnn_abi_version() != 2:
             raise RuntimeError("libbnn_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -18,13 +18,16 @@ void set_error(const char* fmt, ...) {
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;  // B200
+  // cached per device: conf['device'] lets models sit on different GPUs of one process
+  static int n[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;  // B200
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
 }
 
 int forward_simt(const BnnForwardArgs* a, cudaStream_t st);
@@ -137,13 +140,24 @@ struct HostWs {
     st = st_copy = nullptr;
   }
 };
-HostWs g_ws;
+// one workspace (buffers, streams, events) per device: the buffers of device 0 must never be handed to a launch on device 1
+constexpr int kMaxDevices = 64;
+HostWs g_ws_dev[kMaxDevices];
 std::mutex g_ws_mu;
 }  // namespace
 
 extern "C" void bnn_release_workspace(void) {
   std::lock_guard<std::mutex> lk(g_ws_mu);
-  g_ws.release();
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < kMaxDevices; ++d) {
+    bool used = g_ws_dev[d].st || g_ws_dev[d].st_copy;
+    for (int i = 0; i < 10; ++i) used = used || g_ws_dev[d].buf[i];
+    if (!used) continue;
+    cudaSetDevice(d);
+    g_ws_dev[d].release();
+  }
+  cudaSetDevice(cur);
 }
 
 extern "C" int32_t bnn_forward_host(const BnnForwardArgs* ah) {
@@ -151,6 +165,10 @@ extern "C" int32_t bnn_forward_host(const BnnForwardArgs* ah) {
   std::lock_guard<std::mutex> lk(g_ws_mu);
   Layout L;
   if (make_layout(&ah->desc, &L)) return -1;
+  int cur_dev = 0;
+  BNN_CUDA(cudaGetDevice(&cur_dev));
+  if (cur_dev < 0 || cur_dev >= kMaxDevices) BNN_FAIL("bnn_forward_host: device index %d out of range", cur_dev);
+  HostWs& g_ws = g_ws_dev[cur_dev];
   if (!g_ws.st) BNN_CUDA(cudaStreamCreateWithFlags(&g_ws.st, cudaStreamNonBlocking));
   cudaStream_t st = g_ws.st;
   BnnForwardArgs a = *ah;

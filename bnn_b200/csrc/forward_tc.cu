@@ -72,11 +72,12 @@ struct TcPrepParams {
   long long off0, off1, off2, w_stride, part_stride, img_stride;
   int vec_len;
   int mixed;   // second half of each operand region = two BF16 images (pairs per word) instead of the TF32 lo image
+  long long S; // networks to convert (1 for a shared network)
 };
 
 __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ TcPrepParams q, const float* __restrict__ W,
                                                       float* __restrict__ img) {
-  const long long s = blockIdx.y;
+  for (long long s = blockIdx.y; s < q.S; s += gridDim.y) {   // grid.y is clamped to 65535: stride over the samples
   const float* Ws = W + s * q.w_stride;
   float* out = img + s * q.img_stride;
   // all per-sample indices fit 32 bits (one image is < 2^20 floats): 32-bit divisions, the 64-bit ones dominated this kernel
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Tc
       } else if ((j -= q.O * q.N2) < q.O) v = Ws[off2 + j * q.ld2 + q.H2];                 // b3
     }
     out[i] = v;
+  }
   }
 }
 
@@ -1251,7 +1253,8 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
   {
     long long bx = (p.img_stride + 255) / 256;
     if (bx > 64) bx = 64;
-    dim3 grid((unsigned)bx, (unsigned)(p.shared_w ? 1 : a->S));
+    plan.q.S = p.shared_w ? 1 : a->S;
+    dim3 grid((unsigned)bx, (unsigned)(plan.q.S > 65535 ? 65535 : plan.q.S));
     tc_prep_kernel<<<grid, 256, 0, st>>>(plan.q, a->W, img);
     BNN_CUDA(cudaGetLastError());
   }

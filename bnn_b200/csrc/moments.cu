@@ -223,13 +223,13 @@ __global__ void metrics_final_kernel(const double* acc, long long N, int nout, f
 }  // namespace bnn
 
 extern "C" int32_t bnn_metrics(const float* mean, const float* var, const float* y, const float* noise_var, int64_t N,
-                               int32_t nout, float* out, void* stream) {
-  if (!mean || !var || !y || !out || N < 1 || nout < 1 || nout > kMetMaxOut)
+                               int32_t nout, float* out, double* scratch, void* stream) {
+  if (!mean || !var || !y || !out || !scratch || N < 1 || nout < 1 || nout > kMetMaxOut)
     BNN_FAIL("bnn_metrics: bad arguments (N=%lld, nout=%d, max nout %d)", (long long)N, nout, kMetMaxOut);
   cudaStream_t st = (cudaStream_t)stream;
-  // FP64 accumulators live in a small per-process device scratch (stream-ordered use)
-  static double* acc = nullptr;
-  if (!acc) BNN_CUDA(cudaMalloc(&acc, sizeof(double) * (2 * kMetMaxOut + 1)));
+  // FP64 accumulators: caller-provided device scratch (no process-wide state: models on different GPUs / streams in one
+  // process must not share accumulators)
+  double* acc = scratch;
   metrics_zero_kernel<<<1, 2 * kMetMaxOut + 1, 0, st>>>(acc, 2 * nout + 1);
   metrics_kernel<<<grid_for(N * nout, kMetBlock * 4), kMetBlock, 0, st>>>(mean, var, y, noise_var, N, nout, acc);
   metrics_final_kernel<<<1, kMetMaxOut, 0, st>>>(acc, N, nout, out);

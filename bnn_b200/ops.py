@@ -283,8 +283,9 @@ def metrics(mean, var, y, noise_var=None):
         if nv.numel() != nout:
             raise ValueError("noise_var needs one value per output")
     out = torch.empty(2 * nout + 1, dtype=torch.float32, device=mean.device)
-    _lib.check(_lib.lib().bnn_metrics(_ptr(mean), _ptr(var), _ptr(y), _ptr(nv), N, nout, _ptr(out), _stream(mean)),
-               "bnn_metrics")
+    acc = torch.empty(2 * nout + 1, dtype=torch.float64, device=mean.device)     # the kernel's FP64 accumulators
+    _lib.check(_lib.lib().bnn_metrics(_ptr(mean), _ptr(var), _ptr(y), _ptr(nv), N, nout, _ptr(out), _ptr(acc),
+                                      _stream(mean)), "bnn_metrics")
     host = out.cpu()
     if host[2 * nout] > 0:
         raise ValueError("predictive variance is not positive (the reference's Normal(scale) raises here too)")

@@ -10,8 +10,8 @@
  * Conventions
  *   - every pointer is a raw DEVICE pointer unless the name ends in _host;
  *     the caller owns all memory; nothing is allocated behind the caller's
- *     back except inside the *_host convenience calls (workspace cached per
- *     thread and freed by bnn_release_workspace());
+ *     back except inside the *_host convenience calls (one workspace per
+ *     device, cached for the process and freed by bnn_release_workspace());
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
  *     device entry points are asynchronous and never synchronise;
  *   - return value: 0 = ok, <0 = error; bnn_last_error() gives the message;
@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BNN_ABI_VERSION 1
+#define BNN_ABI_VERSION 2
 #define BNN_MAX_LINEAR 8       /* Linear layers per network (hidden + output) */
 #define BNN_MAX_WIDTH 1024     /* widest layer / input the forward kernels take */
 #define BNN_MAX_FUSED_NOUT 64  /* nout limit of the fused forward+moments kernel */
@@ -121,9 +121,9 @@ int64_t bnn_forward_workspace_bytes(const BnnForwardArgs* a);
  * `preds.mean(0), preds.var(0)` of BNN.predict_mv (BNN.py:34-37), in one
  * launch; pred[S,N,nout] is only written when asked for.                   */
 int32_t bnn_forward(const BnnForwardArgs* a, void* stream);
-/* 1 if the tensor-core (tcgen05) forward takes this shape (2 hidden layers, D <= 64, H <= 256, nout <= 4,
- * per-sample bank, no masks, and the hi/lo operand images of one network fit the shared memory of one CTA or
- * of a CTA pair -- e.g. 16-200-200-1 does, 64-256-256-4 does not), else 0 with the reason in bnn_last_error(); BNN_PREC_FP32 takes every shape */
+/* 1 if the tensor-core (tcgen05) forward takes this shape in this precision mode, else 0 with the reason in
+ * bnn_last_error().  Per-sample banks and the dropout family (one shared network + per-sample masks, external or
+ * in-kernel) are both supported.  BNN_PREC_FP32 takes every shape. */
 int32_t bnn_forward_tc_supported(const BnnForwardArgs* a);
 /* debug: timeline of the last tensor-core launch made with BNN_TC_TRACE=1 in the environment (5*4096*2 uint64) */
 int32_t bnn_tc_trace_dump(unsigned long long* host_out);
@@ -152,9 +152,11 @@ int32_t bnn_moments_merge(const double* part_mean, const double* part_m2, const 
 /* replaces: BNN.validate's rmse / nll lines (BNN.py:30-31) and, with
  * noise_var != NULL (per output, device), experiments/SGDMC.py:83-93.
  * out = {rmse[nout], nll[nout]} floats followed by one float holding the count
- * of non-positive variances (the reference raises there: Normal(scale<=0)).  */
+ * of non-positive variances (the reference raises there: Normal(scale<=0)).
+ * scratch: 2*nout+1 doubles of device memory owned by the caller (the FP64 accumulators).  */
 int32_t bnn_metrics(const float* mean, const float* var, const float* y, const float* noise_var,
-                    int64_t N, int32_t nout, float* out /* [2*nout+1] */, void* stream);
+                    int64_t N, int32_t nout, float* out /* [2*nout+1] */, double* scratch /* [2*nout+1], device */,
+                    void* stream);
 
 /* ---- (b) reparameterised weight draws + KL ------------------------------ */
 enum { BNN_SCALE_BBB = 0 /* sqrt(softplus(max(rho,-35))) BNN_BBB.py:24-27 */,

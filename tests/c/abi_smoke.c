@@ -13,7 +13,7 @@ int main(void) {
   d.n_linear = 3;
   d.dims[0] = 16; d.dims[1] = 200; d.dims[2] = 200; d.dims[3] = 1;
   d.act = BNN_ACT_RELU;
-  if (bnn_abi_version() != 1) { printf("abi %d\n", (int)bnn_abi_version()); return 1; }
+  if (bnn_abi_version() != BNN_ABI_VERSION) { printf("abi %d\n", (int)bnn_abi_version()); return 1; }
   /* cfg 4: rows of roundup4(in + 1) floats: 200 x 20 + 200 x 204 + 1 x 204 = 45004 */
   if (bnn_param_stride(&d) != 45004) { printf("stride %lld\n", (long long)bnn_param_stride(&d)); return 2; }
   if (bnn_layer_ld(&d, 0) != 20 || bnn_layer_ld(&d, 1) != 204 || bnn_layer_ld(&d, 2) != 204) return 3;

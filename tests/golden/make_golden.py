@@ -47,6 +47,8 @@ import BNN_CDropout as ref_cdo     # noqa: E402
 from util import normalize         # noqa: E402
 
 from oracle import bnn_oracle as O  # noqa: E402
+sys.path.insert(0, os.path.dirname(HERE))
+from helpers import energy_inputs   # noqa: E402  (shared with the tests, which rebuild the same inputs)
 
 
 def seq_to_net(seq):
@@ -274,9 +276,70 @@ def gen_cdropout_protein():
          pred=pred, mean=py, var=pv)
 
 
+# --------------------------------------------------------------------------- #
+ENERGY_CASES = [
+    # name, dims, act, B, num_train, conf
+    ("relu_1x50", [13, 50, 1], "relu", 32, 455, {}),
+    ("relu_1x50_uci", [13, 50, 1], "relu", 128, 455, {"alpha_n": 0.5, "beta_n": 0.4}),       # experiments/SGDMC.py:63-72
+    ("tanh_3x512", [90, 512, 512, 512, 1], "tanh", 128, 10_000_000, {}),
+    ("tanh_2x30_mo3", [10, 30, 30, 3], "tanh", 37, 2000, {"alpha_n": 0.5, "beta_n": 0.4}),  # nout = 3, ragged batch
+    ("tanh_3x512_mo3", [90, 512, 512, 512, 3], "tanh", 128, 10_000_000, {}),
+    ("tanh_1x50_noise", [1, 50, 1], "tanh", 20, 20, {"noise_level": 0.01}),                 # BNN_SGDMC.py:39-45
+]
+GRAD_STRIDE = 61      # big gradients are stored as every 61st element + their sum and L2 norm
+
+
+def gen_sgdmc_energy():
+    """a12 energy: the reference's own log_prior(), log_lik(bx, by), loss and autograd gradient
+    (BNN_SGDMC.py:61-74, :83-85) on deterministic inputs -- pins oracle.sgdmc_neg_log_post and, on the GPU, the fused
+    SGLD step's gradient."""
+    out = {"names": np.array([c[0] for c in ENERGY_CASES]), "grad_stride": GRAD_STRIDE}
+    for ci, (name, dims, act, B, num_train, conf) in enumerate(ENERGY_CASES):
+        nout = dims[-1]
+        model = ref_sgdmc.BNN_SGDMC(dims[0], {"relu": nn.ReLU(), "tanh": nn.Tanh()}[act], dims[1:-1], nout=nout, conf=conf)
+        net, log_precs, X, y = energy_inputs(dims, nout, B, 1000 + ci)
+        lins = [l for l in model.nn.nn if isinstance(l, nn.Linear)]
+        for lin, (W, b) in zip(lins, net):
+            lin.weight.data, lin.bias.data = W.clone(), b.clone()
+        model.log_precs.data = log_precs.clone()
+        log_prior = model.log_prior()                                    # BNN_SGDMC.py:61-67
+        log_lik = model.log_lik(X, y)                                    # :69-74
+        loss = -1 * (log_lik * (num_train / X.shape[0]) + log_prior)     # :83
+        model.zero_grad()
+        loss.backward()                                                  # :85
+        # pin the oracle restatement: value and gradient
+        ps = [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in net]
+        lp = log_precs.clone().requires_grad_(True)
+        U = O.sgdmc_neg_log_post(ps, lp, X, y, act, num_train, float(model.alpha_n), float(model.beta_n))
+        assert torch.allclose(U.detach(), loss.detach(), rtol=2e-6), (name, float(U), float(loss))
+        gs = torch.autograd.grad(U, [t for pr in ps for t in pr] + [lp])
+        ref_gs = [t.grad for lin in lins for t in (lin.weight, lin.bias)] + [model.log_precs.grad]
+        for a, b_ in zip(gs, ref_gs):
+            assert float((a - b_).abs().max()) <= 2e-5 * float(b_.abs().max() + 1e-30), name
+        out[f"{name}.dims"] = np.array(dims)
+        out[f"{name}.act"] = np.array(act)
+        out[f"{name}.B"] = B
+        out[f"{name}.num_train"] = num_train
+        out[f"{name}.seed"] = 1000 + ci
+        out[f"{name}.alpha_n"] = float(model.alpha_n)
+        out[f"{name}.beta_n"] = float(model.beta_n)
+        out[f"{name}.log_prior"] = log_prior.detach()
+        out[f"{name}.log_lik"] = log_lik.detach()
+        out[f"{name}.loss"] = loss.detach()
+        out[f"{name}.grad_log_precs"] = model.log_precs.grad
+        for li, lin in enumerate(lins):
+            for tag, t in (("W", lin.weight.grad), ("b", lin.bias.grad)):
+                v = t.detach().reshape(-1)
+                out[f"{name}.g{tag}{li}.sub"] = v[::GRAD_STRIDE] if v.numel() > 4096 else v
+                out[f"{name}.g{tag}{li}.sum"] = v.double().sum()
+                out[f"{name}.g{tag}{li}.norm"] = v.double().norm()
+    save("sgdmc_energy.npz", **out)
+
+
 if __name__ == "__main__":
     gen_sgdmc_boston()
     gen_sgdmc_multiout()
     gen_bbb_sinc()
     gen_dropout_protein()
     gen_cdropout_protein()
+    gen_sgdmc_energy()

@@ -57,3 +57,55 @@ def var_bound(pred_ref, rel=1e-5, c=32.0, depth=2):
     scale = p.abs().amax(dim=0)
     c = c * max(1.0, depth / 2.0)      # forward rounding accumulates layer by layer
     return rel * var + c * eps * (scale * var.sqrt() + var) + 1e-30
+
+
+def energy_inputs(dims, nout, B, seed):
+    """Deterministic inputs of the SGDMC energy fixture, from numpy's frozen legacy stream (RandomState), so that the
+    tests can rebuild them bit for bit on any box without storing megabytes of weights:
+    per Linear W[out,in] ~ 0.5 * xavier-uniform(gain 5/3), b ~ U(-0.1, 0.1); log_precs ~ N(0.3, 0.2); X ~ N(0,1); y ~ N(0,1)."""
+    rs = np.random.RandomState(seed)
+    net = []
+    for i, o in zip(dims[:-1], dims[1:]):
+        bound = 0.5 * (5. / 3) * np.sqrt(6. / (i + o))
+        W = rs.uniform(-bound, bound, size=(o, i)).astype(np.float32)
+        b = rs.uniform(-0.1, 0.1, size=(o,)).astype(np.float32)
+        net.append((torch.from_numpy(W), torch.from_numpy(b)))
+    log_precs = torch.from_numpy((0.3 + 0.2 * rs.standard_normal(nout)).astype(np.float32))
+    X = torch.from_numpy(rs.standard_normal((B, dims[0])).astype(np.float32))
+    y = torch.from_numpy(rs.standard_normal((B, nout)).astype(np.float32))
+    return net, log_precs, X, y
+
+
+def energy_cases():
+    """The reference-recorded SGDMC energy / gradient fixture (tests/golden/sgdmc_energy.npz) as a list of dicts with the
+    inputs rebuilt from their seed."""
+    g = golden("sgdmc_energy.npz")
+    cases = []
+    for name in [str(n) for n in g["names"]]:
+        c = {k[len(name) + 1:]: g[k] for k in g if k.startswith(name + ".")}
+        c["name"] = name
+        c["dims"] = [int(d) for d in c["dims"]]
+        c["act"] = str(c["act"])
+        c["B"], c["num_train"], c["seed"] = int(c["B"]), int(c["num_train"]), int(c["seed"])
+        c["grad_stride"] = int(g["grad_stride"])
+        c["net"], c["log_precs"], c["X"], c["y"] = energy_inputs(c["dims"], c["dims"][-1], c["B"], c["seed"])
+        cases.append(c)
+    return cases
+
+
+def check_energy_grads(case, grads, grad_log_precs, rtol=2e-5):
+    """grads: [(gW, gb), ...] per Linear (any float tensors); compares with the reference's autograd gradient recorded in
+    the fixture (every grad_stride-th element of the big tensors, plus sum and L2 norm of each)."""
+    stride = case["grad_stride"]
+    for li, pair in enumerate(grads):
+        for tag, t in zip(("W", "b"), pair):
+            v = torch.as_tensor(t).detach().cpu().double().reshape(-1)
+            sub = torch.from_numpy(case[f"g{tag}{li}.sub"]).double()
+            got = v[::stride] if v.numel() > 4096 else v
+            scale = float(sub.abs().max()) + 1e-30
+            assert float((got - sub).abs().max()) <= rtol * scale, (case["name"], tag, li, float((got - sub).abs().max()) / scale)
+            norm = float(case[f"g{tag}{li}.norm"])
+            assert abs(float(v.norm()) - norm) <= rtol * (norm + 1e-30), (case["name"], tag, li, "norm")
+    glp = torch.as_tensor(grad_log_precs).detach().cpu().double().reshape(-1)
+    ref = torch.from_numpy(case["grad_log_precs"]).double().reshape(-1)
+    assert float((glp - ref).abs().max()) <= rtol * float(ref.abs().max() + 1e-30), (case["name"], "log_precs")

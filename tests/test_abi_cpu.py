@@ -26,7 +26,7 @@ def test_library_exports_everything_the_header_declares():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/bnn_b200.h but not exported"
     assert sorted(_lib.PROTOTYPES) == names          # the ctypes table mirrors the header one to one
-    assert _lib.lib().bnn_abi_version() == 1
+    assert _lib.lib().bnn_abi_version() == 2
 
 
 @pytest.mark.parametrize("dims", [[13, 50, 1], [1, 50, 50, 1], [9, 100, 100, 1], [16, 200, 200, 1], [90, 512, 512, 512, 1], [7, 3, 5]])

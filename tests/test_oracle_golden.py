@@ -119,3 +119,16 @@ def test_sgdmc_energy_terms_match_oracle():
     u_ref = O.sgdmc_neg_log_post(net, m.log_precs.detach(), X, y, "tanh", num_train=40, alpha_n=m.alpha_n, beta_n=m.beta_n)
     u = -(m.log_lik(X, y) * (40 / 11) + m.log_prior())
     assert abs(float(u) - float(u_ref)) <= 1e-5 * abs(float(u_ref))
+
+
+def test_sgdmc_energy_golden():
+    """oracle.sgdmc_neg_log_post and its autograd gradient against the reference's own log_prior / log_lik / loss /
+    loss.backward() (BNN_SGDMC.py:61-74,83-85) recorded in sgdmc_energy.npz -- pins the energy half of row a12."""
+    from helpers import energy_cases, check_energy_grads
+    for c in energy_cases():
+        ps = [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in c["net"]]
+        lp = c["log_precs"].clone().requires_grad_(True)
+        U = O.sgdmc_neg_log_post(ps, lp, c["X"], c["y"], c["act"], c["num_train"], float(c["alpha_n"]), float(c["beta_n"]))
+        assert abs(float(U) - float(c["loss"])) <= 2e-6 * abs(float(c["loss"])), c["name"]
+        gs = torch.autograd.grad(U, [q for pr in ps for q in pr] + [lp])
+        check_energy_grads(c, [(gs[2 * i], gs[2 * i + 1]) for i in range(len(ps))], gs[-1])

@@ -54,6 +54,14 @@ for S, M in ((1000, 4573), (1000, 1_000_000)):
     rows.append(("moments_kernel + finalize", f"S={S} M={M}", 4.0 * S * M + 8.0 * M, ms))
     del pred
 
+# (d) dropout masks: 4 * S * mask_len bytes written
+a3 = Arch([9, 100, 100, 1], "tanh")
+for kind, pd in (("bernoulli", [0.05] * 3), ("concrete", [0.1, 0.5, 0.7])):
+    for S in (1000, 200_000):
+        cfg = ops.MaskConfig(kind, [True, True, True], p_drop=pd, seed=3)
+        ms = timeit(lambda: ops.dropout_masks(a3, cfg, S, dev))
+        rows.append((f"masks_kernel ({kind})", f"S={S} mask_len=209", 4.0 * S * 209, ms))
+
 out = []
 print(f"{'kernel':28s} {'size':26s} {'MB':>10s} {'ms':>9s} {'GB/s':>9s} {'frac of %.0f GB/s' % PEAK:>18s}")
 for k, sz, b, ms in rows:
