@@ -4,11 +4,10 @@ learned log-precision per output.
 What runs where:
   * sample / sample_predict / predict_mv / validate: the fused CUDA forward over the [S, stride]
     bank of thinned chain states (no deepcopy'd nn.Modules);
-  * train: the chain state theta = [packed network | log_precs] lives in ONE device vector; each
-    SGLD step is a hand-derived minibatch gradient of U (BNN_SGDMC.py:61-83: a few GEMMs on the packed
-    blocks; a fused step kernel is the row SURVEY.md 8f ranks next) followed by the fused bnn_psgld_step kernel (update + RMSprop
-    preconditioner + in-kernel Philox noise + both LR groups, BNN_SGDMC.py:86-87,96-101); thinning
-    snapshots are row copies into the bank (BNN_SGDMC.py:124).
+  * train: the chain state theta = [packed network | log_precs] lives in ONE device vector; every run of
+    SGLD steps (BNN_SGDMC.py:76-91: shuffled minibatch, log_prior / log_lik, backward, pSGLD update with
+    in-kernel Philox noise, both LR groups, LambdaLR factor) is ONE launch of the persistent fused step
+    kernel (bnn_sgld_run, csrc/sgld_step.cu); thinning snapshots are row copies into the bank (:124).
 pybnn is not needed.  The update rule is restated from Li et al. 2016 (UNPINNED).
 """
 import math
@@ -50,8 +49,8 @@ class BNN_SGDMC(nn.Module, BNN):
         self.precision = conf.get('precision', 'auto')   # tensor cores (3xTF32, FP32-grade) when the shape allows, else FP32 SIMT
         self.psgld_alpha = conf.get('precondition_decay_rate', 0.99)
         self.psgld_lambda = conf.get('diagonal_bias', 1e-5)
+        self.psgld_mode = int(conf.get('precond_mode', 0))     # 0: G = 1/(lam + sqrt(V)) (Li et al. 2016); 1: G = 1/sqrt(V + lam)
         self.device = torch.device(conf['device']) if 'device' in conf else None
-        self.use_graph = bool(conf.get('cuda_graph', True))
 
         self.arch = Arch([dim] + list(num_hiddens) + [nout], act)
         self.log_precs = nn.Parameter(torch.zeros(self.nout))
@@ -67,7 +66,7 @@ class BNN_SGDMC(nn.Module, BNN):
                 nn.init.xavier_uniform_(l.weight, gain=self.gain)
 
     # ---- the reference's two energy terms on the module state (BNN_SGDMC.py:61-74), for callers that use them directly;
-    #      the chain itself evaluates them fused on the packed vector (_neg_log_post / _grad_into)
+    #      the chain itself evaluates them (and their gradient) inside the fused step kernel
     def log_prior(self):
         al, be = float(self.alpha_n), float(self.beta_n)
         lp = self.log_precs
@@ -85,238 +84,30 @@ class BNN_SGDMC(nn.Module, BNN):
         precs = self.log_precs.exp()
         return (-0.5 * precs * (y - out) ** 2 + 0.5 * self.log_precs - 0.5 * math.log(2. * math.pi)).sum()   # :72-74
 
-    # ---- energy, evaluated on a packed parameter vector (BNN_SGDMC.py:61-74,83) ----------
-    def _neg_log_post(self, theta, bx, by, num_train):
-        """U = -(loglik * N/|b| + logprior) on a packed parameter vector.  Written with Python-float constants only
-        (no host tensors are created), so that the whole forward + backward can be captured in a CUDA graph."""
-        a = self.arch
-        h = bx
-        log_p = 0.
-        for l in range(a.n_linear):
-            blk = theta[a.offsets[l]: a.offsets[l] + a.outs[l] * a.lds[l]].view(a.outs[l], a.lds[l])
-            W, b = blk[:, : a.ins[l]], blk[:, a.ins[l]]
-            std = float(self.gain * np.sqrt(2. / (a.outs[l] + a.ins[l])))        # BNN_SGDMC.py:65
-            # sum of Normal(0, std).log_prob(W)                                    (:66)
-            log_p = log_p - (W * W).sum() / (2. * std * std) - W.numel() * (math.log(std) + 0.5 * math.log(2. * math.pi))
-            h = torch.addmm(b, h, W.t())
-            if l != a.n_linear - 1:
-                h = self._act_fn(h)
-        log_precs = theta[a.stride: a.stride + self.nout]
-        precs = log_precs.exp()
-        log_lik = (-0.5 * precs * (by - h) ** 2 + 0.5 * log_precs - 0.5 * math.log(2. * math.pi)).sum()   # :72-74
-        al, be = float(self.alpha_n), float(self.beta_n)
-        # Gamma(al, be).log_prob(exp(l)) + l  (TransformedDistribution with ExpTransform().inv, :47,62)
-        log_p = log_p + (al * math.log(be) + (al - 1.) * log_precs - be * precs - math.lgamma(al) + log_precs).sum()
-        return -1 * (log_lik * (num_train / bx.shape[0]) + log_p)
-
-    @property
-    def _act_fn(self):
-        return {"relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "identity": lambda t: t}[self.arch.act]
-
     # ---- the chain ----------------------------------------------------------------------------
-    def _chain_init(self, dev):
+    def _new_chain(self, dev):
+        """What the reference's train() builds at BNN_SGDMC.py:96-101: a FRESH optimizer (V = 1) and scheduler (t = 0) over
+        the CURRENT self.nn / self.log_precs -- also on a warm start, which only skips init_nn() (:114-115)."""
         a = self.arch
-        n = (a.stride + self.nout + 3) // 4 * 4
-        self._theta = torch.zeros(n, device=dev)
-        self._theta[: a.stride] = a.pack([self.nn.nn])[0].to(dev)
-        self._theta[a.stride: a.stride + self.nout] = self.log_precs.data.to(dev)
-        self._V = torch.ones(n, device=dev)            # pybnn initialises the preconditioner state to ones
-        self._t = 0
-        self._valid = torch.zeros(n, device=dev)
-        self._valid[: a.stride] = a.valid_mask().to(dev).float()
-        self._valid[a.stride: a.stride + self.nout] = 1.
-        self._graph = None
+        chain = ops.SgldChain(a, self.batch_size, dev, self.lr_weight, self.lr_noise, float(self.alpha_n), float(self.beta_n),
+                              seed=self.seed, precond_decay=self.psgld_alpha, diagonal_bias=self.psgld_lambda, gain=self.gain,
+                              precond_mode=self.psgld_mode)
+        chain.set_state(a.pack([self.nn.nn])[0], self.log_precs.data)
+        return chain
 
-    def _grad_autograd(self, X, y, idx, num_train):
-        """loss and masked gradient of U by torch autograd (reference implementation of the gradient; ~150 tiny kernels
-        per step at 3x512 -- kept for the test that pins _grad_into against it and for activations without a closed-form
-        derivative here)."""
-        th = self._theta.detach().requires_grad_(True)
-        loss = self._neg_log_post(th, X[idx], y[idx], num_train)
-        grad, = torch.autograd.grad(loss, th)
-        return loss.detach(), grad * self._valid
-
-    def _grad_buffers(self, B, dev):
-        """Scratch of the hand-derived gradient for batch size B: augmented layer inputs [B, ld] = (h | 1 | 0-pad), so that
-        one GEMM against a packed block [out, ld] = (W | b | pad) gives W h + b, and dz^T @ (h | 1 | 0) gives (dW | db | 0)."""
-        # one set per batch size, never freed while the chain lives: a captured CUDA graph keeps pointing at its set
-        cache = self.__dict__.setdefault("_gb_cache", {})
-        key = (int(B), str(dev), int(self._theta.data_ptr()))
-        if key not in cache:
-            a = self.arch
-            hs = []
-            for l in range(a.n_linear):
-                h = torch.zeros(B, a.lds[l], device=dev)
-                h[:, a.ins[l]] = 1.
-                hs.append(h)
-            grad = torch.zeros_like(self._theta)
-            # d(-log prior)/dW = W / std_l^2 on weight entries only (BNN_SGDMC.py:65-66), 0 on biases / padding
-            ps = torch.zeros_like(self._theta)
-            logc = 0.
-            for l in range(a.n_linear):
-                std = float(self.gain * np.sqrt(2. / (a.outs[l] + a.ins[l])))
-                blk = ps[a.offsets[l]: a.offsets[l] + a.outs[l] * a.lds[l]].view(a.outs[l], a.lds[l])
-                blk[:, : a.ins[l]] = 1. / (std * std)
-                logc += a.outs[l] * a.ins[l] * (math.log(std) + 0.5 * math.log(2. * math.pi))
-            cache[key] = (hs, grad, ps, logc)
-        return cache[key]
-
-    def _grad_into(self, X, y, idx, num_train):
-        """loss U (BNN_SGDMC.py:61-74,83) and its gradient at the current chain state for the minibatch idx, derived by hand
-        on the packed parameter vector: L forward GEMMs, L + (L - 1) backward GEMMs and a handful of elementwise kernels
-        (~40 launches instead of autograd's ~150), graph-capturable (no host tensors, no allocation-dependent control flow).
-        tanh / relu / sigmoid / identity activations; pinned against autograd by tests/test_sampling_gpu.py."""
-        with torch.no_grad():
-            return self._grad_manual(X, y, idx, num_train)
-
-    def _grad_manual(self, X, y, idx, num_train, gathered=None):
-        """gathered = (B, y_batch): the minibatch is already in the augmented first-layer input of the B-row buffer set
-        (bnn_sgld_gather, CUDA-graph path); otherwise it is gathered here from idx."""
-        a = self.arch
-        th = self._theta
-        if gathered is None:
-            bx, by = X[idx], y[idx]
-            B = bx.shape[0]
-        else:
-            B, by = gathered
-        hs, grad, ps, logc = self._grad_buffers(B, th.device)
-        L = a.n_linear
-        blks = [th[a.offsets[l]: a.offsets[l] + a.outs[l] * a.lds[l]].view(a.outs[l], a.lds[l]) for l in range(L)]
-        if gathered is None:
-            hs[0][:, : a.ins[0]] = bx
-        for l in range(L):
-            z = torch.mm(hs[l], blks[l].t())                       # W h + b (bias column meets the ones column)
-            if l != L - 1:
-                dst = hs[l + 1][:, : a.outs[l]]
-                if a.act == "tanh":
-                    torch.tanh(z, out=dst)
-                elif a.act == "relu":
-                    torch.clamp(z, min=0., out=dst)
-                elif a.act == "sigmoid":
-                    torch.sigmoid(z, out=dst)
-                else:
-                    dst.copy_(z)
-        out = z                                                      # [B, nout]
-        lp = th[a.stride: a.stride + self.nout]
-        scale = float(num_train) / B
-        al, be = float(self.alpha_n), float(self.beta_n)
-        if th.is_cuda:
-            # prior gradient + energy (bnn_sgld_prior), then residuals, loss U, dU/d(log_precs), dU/d(out) (bnn_sgld_head)
-            scr = self.__dict__.setdefault("_head_scr", {})
-            k = (B, self.nout, str(th.device), int(th.data_ptr()))
-            if k not in scr:
-                scr[k] = (torch.empty(B, self.nout, device=th.device), torch.zeros((), device=th.device),
-                          torch.empty_like(th), torch.zeros(65, device=th.device), torch.zeros((), device=th.device))
-            dz, loss, pw, pscr, quad = scr[k]
-            ops.sgld_prior(ps, th, pw, pscr, quad)
-            ops.sgld_head(out.contiguous(), by.contiguous(), lp, scale, al, be, quad, logc, dz,
-                          grad[a.stride: a.stride + self.nout], loss)
-        else:                                                        # same arithmetic in torch (CPU tensors: tests only)
-            pw = ps * th                                             # W / std^2 on weight entries
-            precs = lp.exp()
-            r = out - by
-            rr = (r * r).sum(0)
-            # U = -(scale * loglik + logprior)
-            log_lik = (-0.5 * precs * rr + B * (0.5 * lp - 0.5 * math.log(2. * math.pi))).sum()
-            log_p = -0.5 * torch.dot(pw, th) - logc + \
-                (al * math.log(be) + (al - 1.) * lp - be * precs - math.lgamma(al) + lp).sum()
-            loss = -1 * (log_lik * scale + log_p)
-            grad[a.stride: a.stride + self.nout] = -scale * (-0.5 * precs * rr + 0.5 * B) - (al - be * precs)
-            dz = (scale * precs) * r                                 # dU/dout
-        for l in range(L - 1, -1, -1):
-            gb = grad[a.offsets[l]: a.offsets[l] + a.outs[l] * a.lds[l]].view(a.outs[l], a.lds[l])
-            pb = pw[a.offsets[l]: a.offsets[l] + a.outs[l] * a.lds[l]].view(a.outs[l], a.lds[l])
-            torch.addmm(pb, dz.t(), hs[l], out=gb)                   # (dW + W / std^2 | db | 0)
-            if l > 0:
-                dh = torch.mm(dz, blks[l])[:, : a.ins[l]]           # dU/dh_{l-1}
-                h = hs[l][:, : a.ins[l]]
-                if a.act == "tanh":
-                    dz = torch.ops.aten.tanh_backward(dh, h)
-                elif a.act == "relu":
-                    dz = dh * (h > 0)
-                elif a.act == "sigmoid":
-                    dz = torch.ops.aten.sigmoid_backward(dh, h)
-                else:
-                    dz = dh.contiguous()
-        return loss, grad
-
-    def _build_graph(self, X, y, num_train):
-        """Capture ONE WHOLE SGLD STEP in a CUDA graph: minibatch gather from the epoch permutation at a device-side
-        offset, forward + backward (hand-derived, a few GEMMs; SURVEY.md 8f ranks a fused step kernel next), the fused pSGLD update
-        with the LR-schedule factor computed in-kernel from a device step counter, and the counter increments.  At
-        1x50 .. 3x512 the step is launch-bound: one replay instead of ~60 eager launches + Python is the difference
-        between ~2k and >10k steps/s."""
-        dev = self._theta.device
-        a = self.arch
-        self._g_off = torch.zeros((), dtype=torch.long, device=dev)           # position inside the epoch permutation
-        self._g_step = torch.full((), self._t, dtype=torch.long, device=dev)  # t of the LR schedule / Philox stream
-        self._g_loss = torch.zeros((), device=dev)
-        self._g_perm = torch.zeros(num_train, dtype=torch.long, device=dev)
-
-        B = self.batch_size
-        self._g_yb = torch.empty(B, self.nout, device=dev)
-        h0 = self._grad_buffers(B, dev)[0][0]                               # augmented first-layer input of the B-row set
-
-        def one_step():
-            ops.sgld_gather(X, y, self._g_perm, self._g_off, h0, self._g_yb)      # DataLoader batch at the device-side offset
-            with torch.no_grad():
-                loss, grad = self._grad_manual(X, y, None, num_train, gathered=(B, self._g_yb))
-            ops.psgld_step_dev(self._theta, grad, self._V, self._g_step, self.lr_weight, lr_tail=self.lr_noise,
-                               n_head=a.stride, alpha=self.psgld_alpha, lam=self.psgld_lambda, seed=self.seed)
-            ops.sgld_advance(self._g_step, self._g_off, B)
-            self._g_loss = loss                                             # the head kernel's own output buffer (no copy)
-
-        # warm-up on a side stream (autograd/cuBLAS workspaces), on scratch copies of the chain state
-        keep = (self._theta.clone(), self._V.clone())
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                one_step()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        self._theta.copy_(keep[0]); self._V.copy_(keep[1])
-        self._g_step.fill_(self._t); self._g_off.zero_()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            one_step()
-        # the capture itself does not execute: state is untouched, counters still at (t, 0)
-        self._graph = graph
-
-    def _sgld_step(self, X, y, idx, num_train):
-        """One eager SGLD step (BNN_SGDMC.py:81-87) -- used without CUDA graphs and for the short last batch of an epoch."""
-        a = self.arch
-        loss, grad = self._grad_into(X, y, idx, num_train)
-        f = float(np.float32((1 + self._t) ** -0.33))                    # LambdaLR, BNN_SGDMC.py:101
-        ops.psgld_step(self._theta, grad.contiguous(), self._V, self.lr_weight * f, lr_tail=self.lr_noise * f, n_head=a.stride,
-                       alpha=self.psgld_alpha, lam=self.psgld_lambda, seed=self.seed, step=self._t)
-        self._t += 1
-        return loss
-
-    def sgld_steps(self, num_steps, X, y, gen):
-        """BNN_SGDMC.py:76-91: epochs of shuffled minibatches (last one may be short) until num_steps are done."""
-        num_train = X.shape[0]
-        step_cnt, loss = 0, torch.zeros(())
-        if self.use_graph and self._graph is None and num_train >= self.batch_size:
-            self._build_graph(X, y, num_train)
+    def sgld_steps(self, num_steps, num_train):
+        """BNN_SGDMC.py:76-91: iterate the shuffled loader (a NEW permutation every time the loader is re-entered, i.e. at
+        every call and after every exhausted epoch; the last batch of an epoch may be short) until num_steps are done.
+        Each run of consecutive steps inside one epoch is ONE launch of the fused step kernel."""
+        chain, B = self._chain, self.batch_size
+        per_epoch = (num_train + B - 1) // B
+        step_cnt, loss = 0, None
         while step_cnt < num_steps:
-            if self._perm is None or self._perm_pos >= num_train:
-                self._perm = torch.randperm(num_train, generator=gen, device=X.device)   # DataLoader(shuffle=True), :110
-                self._perm_pos = 0
-                if self._graph is not None:
-                    self._g_perm.copy_(self._perm)
-                    self._g_off.zero_()
-            full = self._perm_pos + self.batch_size <= num_train
-            if self._graph is not None and full:
-                self._graph.replay()                                     # gather + fwd + bwd + update + counters
-                self._t += 1
-                loss = self._g_loss
-            else:
-                idx = self._perm[self._perm_pos: self._perm_pos + self.batch_size]
-                loss = self._sgld_step(X, y, idx, num_train)
-                if self._graph is not None:
-                    self._g_step.fill_(self._t)
-            self._perm_pos += self.batch_size
-            step_cnt += 1
+            n = min(num_steps - step_cnt, per_epoch)
+            perm = ops.sgld_perm(self.seed, self._epoch, num_train, min(num_train, n * B), chain.device)
+            self._epoch += 1
+            loss = chain.run(perm, 0, n, want_loss=(step_cnt + n >= num_steps))
+            step_cnt += n
         return loss
 
     def train(self, X, y):
@@ -324,25 +115,27 @@ class BNN_SGDMC(nn.Module, BNN):
         a = self.arch
         X = self._to_dev(X)
         y = self._to_dev(y).view(-1, self.nout)
-        if not self.warm_start or not hasattr(self, "_theta"):
-            if not self.warm_start:
-                self.init_nn()
-            self._chain_init(dev)
-        self._graph = None
-        self._perm, self._perm_pos = None, 0
-        gen = torch.Generator(device=dev).manual_seed(self.seed)
-        self.sgld_steps(self.steps_burnin, X, y, gen)                     # burn-in
-        rows, step_cnt = [], 0
+        num_train = X.shape[0]
+        if not self.warm_start:
+            self.init_nn()
+        self._chain = self._new_chain(dev)
+        self._chain.bind(X, y)
+        self._epoch = 0
+        self.sgld_steps(self.steps_burnin, num_train)                     # burn-in
+        n_keep = (self.steps + self.keep_every - 1) // self.keep_every
+        bank = torch.empty(n_keep, a.stride, device=dev)
+        step_cnt, k = 0, 0
         while step_cnt < self.steps:
-            loss = self.sgld_steps(self.keep_every, X, y, gen)
+            loss = self.sgld_steps(self.keep_every, num_train)
             step_cnt += self.keep_every
-            self._theta.mul_(self._valid)                                 # Langevin noise also lands on layout padding: re-zero it
-            rows.append(self._theta[: a.stride].clone())                  # thinning snapshot = one bank row (:124)
-            prec = self._theta[a.stride: a.stride + self.nout].exp().mean()
+            bank[k].copy_(self._chain.state[: a.stride])                  # thinning snapshot = one bank row (:124)
+            k += 1
+            prec = self._chain.state[a.stride: a.stride + self.nout].exp().mean()
             print('Step %4d, loss = %8.2f, precision = %g' % (step_cnt, float(loss), float(prec)), flush=True)
-        self.nns = SampleBank(a, torch.stack(rows).contiguous())
-        self.log_precs.data = self._theta[a.stride: a.stride + self.nout].detach().cpu()
-        self.nn.nn.load_state_dict(a.to_module(self._theta[: a.stride]).state_dict())
+        self._chain.check()
+        self.nns = SampleBank(a, bank[:k].contiguous())
+        self.log_precs.data = self._chain.state[a.stride: a.stride + self.nout].detach().cpu()
+        self.nn.nn.load_state_dict(a.to_module(self._chain.state[: a.stride]).state_dict())
         print('Number of samples: %d' % len(self.nns))
 
     # ---- the hot path (BNN_SGDMC.py:127-137) --------------------------------------------------

@@ -36,6 +36,14 @@ class ForwardArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
+class SgldChain(C.Structure):
+    _fields_ = [("desc", MlpDesc), ("batch", C.c_int32), ("theta", C.c_void_p), ("thetaT", C.c_void_p), ("V", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("X", C.c_void_p), ("y", C.c_void_p),
+                ("perm", C.c_void_p), ("num_train", C.c_int64), ("lr_weight", C.c_float), ("lr_noise", C.c_float),
+                ("precond_decay", C.c_float), ("diagonal_bias", C.c_float), ("alpha_n", C.c_float), ("beta_n", C.c_float),
+                ("gain", C.c_float), ("precond_mode", C.c_int32), ("seed", C.c_uint64)]
+
+
 # name -> (restype, argtypes); mirrors include/bnn_b200.h one to one
 PROTOTYPES = {
     "bnn_abi_version": (C.c_int32, []),
@@ -67,14 +75,14 @@ PROTOTYPES = {
                                     C.c_int64, C.c_void_p, C.c_void_p]),
     "bnn_psgld_step": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_float,
                                    C.c_float, C.c_float, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p]),
-    "bnn_psgld_step_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_float,
-                                       C.c_float, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p]),
-    "bnn_sgld_head": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_float,
-                                  C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "bnn_sgld_prior": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "bnn_sgld_gather": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
-                                    C.c_void_p, C.c_void_p, C.c_void_p]),
-    "bnn_sgld_advance": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "bnn_sgld_theta_len": (C.c_int64, [C.POINTER(MlpDesc)]),
+    "bnn_sgld_theta_t_len": (C.c_int64, [C.POINTER(MlpDesc)]),
+    "bnn_sgld_workspace_bytes": (C.c_int64, [C.POINTER(MlpDesc), C.c_int32]),
+    "bnn_sgld_init": (C.c_int32, [C.POINTER(SgldChain), C.c_int32, C.c_void_p]),
+    "bnn_sgld_run": (C.c_int32, [C.POINTER(SgldChain), C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
+    "bnn_sgld_perm": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "bnn_sgld_status": (C.c_int32, [C.POINTER(SgldChain), C.POINTER(C.c_int32), C.c_void_p]),
     "bnn_philox_words": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]),
     "bnn_philox_normals": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]),
     "bnn_measure_fp32_tflops": (C.c_double, []),

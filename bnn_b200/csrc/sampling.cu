@@ -4,7 +4,9 @@
 //   (b) bnn_reparam_kl   : W[s] = mu + sigma(rho) * eps   + KL(q || N(0, weight_std))
 //                          BNN_BBB.py:24-27, :107-110; BNN_SVI.py:42-46
 //   (c) bnn_psgld_step   : preconditioned SGLD update (pybnn's pSGLD.step at
-//                          BNN_SGDMC.py:86; arithmetic restated from Li et al. 2016)
+//                          BNN_SGDMC.py:86; arithmetic restated from Li et al. 2016) on a caller-supplied
+//                          gradient; the chain itself runs the fused step of sgld_step.cu, whose update
+//                          epilogue is the same arithmetic
 //   (d) bnn_dropout_masks / bnn_apply_masks : BNN_Dropout.py:70-75, BNN_CDropout.py:59-65
 #include "common.cuh"
 #include "philox.cuh"
@@ -169,19 +171,10 @@ __global__ void __launch_bounds__(kEwBlock) apply_masks_kernel(const __grid_cons
 __global__ void __launch_bounds__(kEwBlock) psgld_kernel(float* __restrict__ theta, const float* __restrict__ grad,
                                                          float* __restrict__ V, long long n, long long n_head, float lr_head,
                                                          float lr_tail, float alpha, float lam, const float* __restrict__ noise,
-                                                         unsigned long long seed, long long step,
-                                                         const long long* __restrict__ step_dev) {
+                                                         unsigned long long seed, long long step) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long e = q << 2;
   if (e >= n) return;
-  if (step_dev) {
-    // graph-replay mode: the step counter lives on the device and the LambdaLR factor of BNN_SGDMC.py:101,
-    // np.float32((1 + it) ** -0.33), is applied here (double pow, rounded to float, exactly as numpy does)
-    step = *step_dev;
-    const float f = (float)pow((double)(1 + step), -0.33);
-    lr_head *= f;
-    lr_tail *= f;
-  }
   float z[4];
   const float om = 1.0f - alpha;
   if (e + 4 <= n) {
@@ -234,103 +227,6 @@ __global__ void philox_normals_kernel(unsigned long long seed, uint32_t subseq, 
   float z[4];
   philox_normal4(seed, subseq, tag, (uint64_t)q, z);
   for (int c = 0; c < 4 && (q << 2) + c < n; ++c) out[(q << 2) + c] = z[c];
-}
-
-// ---- SGLD energy head (BNN_SGDMC.py:61-74,83): everything between the network output and the backward pass, in ONE
-// launch of one CTA -- residuals, per-output sum of squares, the loss U = -(scale * loglik + logprior), dU/d(log_prec) and
-// dU/d(out).  As torch ops these are ~25 launches on 1..nout-element tensors per SGLD step.
-//   loglik   = sum_b,o ( -0.5 * prec_o * r^2 + 0.5 * lp_o - 0.5 * log(2 pi) )                      (:72-74)
-//   logprior = -0.5 * prior_quad - log_const + sum_o ( a log b + (a - 1) lp_o - b prec_o - lgamma(a) + lp_o )   (:47,62-66)
-__global__ void __launch_bounds__(256) sgld_head_kernel(const float* __restrict__ out, const float* __restrict__ y,
-                                                        const float* __restrict__ log_precs, long long B, int nout, float scale,
-                                                        float al, float be, float lgamma_al, const float* __restrict__ prior_quad,
-                                                        float log_const, float* __restrict__ dz, float* __restrict__ grad_lp,
-                                                        float* __restrict__ loss) {
-  __shared__ float rr[64];
-  __shared__ float red[256];
-  const int tid = threadIdx.x;
-  float total_ll = 0.f, total_lp = 0.f;
-  for (int o = 0; o < nout; ++o) {
-    const float lp = log_precs[o], prec = expf(lp);
-    float acc = 0.f;
-    for (long long b = tid; b < B; b += blockDim.x) {
-      const float r = out[b * nout + o] - y[b * nout + o];
-      acc = fmaf(r, r, acc);
-      dz[b * nout + o] = scale * prec * r;
-    }
-    red[tid] = acc;
-    __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
-      if (tid < w) red[tid] += red[tid + w];
-      __syncthreads();
-    }
-    if (tid == 0) rr[o] = red[0];
-    __syncthreads();
-    if (tid == 0) {
-      const float s2 = rr[o];
-      total_ll += -0.5f * prec * s2 + (float)B * (0.5f * lp - 0.91893853320467274178f);
-      total_lp += al * logf(be) + (al - 1.f) * lp - be * prec - lgamma_al + lp;
-      grad_lp[o] = -scale * (-0.5f * prec * s2 + 0.5f * (float)B) - (al - be * prec);
-    }
-  }
-  if (tid == 0 && loss) {
-    const float logp = -0.5f * (prior_quad ? prior_quad[0] : 0.f) - log_const + total_lp;
-    loss[0] = -(total_ll * scale + logp);
-  }
-}
-
-// ---- SGLD prior term: pw = ps * theta (the gradient of -log prior: W / std_l^2 on weight entries, 0 elsewhere) and its
-// energy sum_i pw_i * theta_i in one launch.  Per-CTA partial sums are combined by the last CTA to finish, in CTA order, so
-// the result does not depend on scheduling (no floating-point atomics).
-__global__ void __launch_bounds__(256) sgld_prior_kernel(const float* __restrict__ ps, const float* __restrict__ theta, long long n,
-                                                         float* __restrict__ pw, float* __restrict__ partial,
-                                                         unsigned int* __restrict__ ticket, float* __restrict__ quad) {
-  __shared__ float red[256];
-  __shared__ bool last;
-  float acc = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float t = theta[i], v = ps[i] * t;
-    pw[i] = v;
-    acc = fmaf(v, t, acc);
-  }
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
-    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    partial[blockIdx.x] = red[0];
-    __threadfence();
-    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
-    float s = 0.f;
-    for (unsigned b = 0; b < gridDim.x; ++b) s += ((volatile float*)partial)[b];
-    quad[0] = s;
-    *ticket = 0u;   // ready for the next launch (graph replay)
-  }
-}
-
-// ---- SGLD minibatch gather (the DataLoader(shuffle=True) batch of BNN_SGDMC.py:80,110): rows perm[*off .. *off + B) of X
-// and y go straight into the augmented first-layer input (h0 | 1 | 0-pad), row pitch ldh, and the target block.  The epoch
-// position lives on the device so that the launch can be replayed from a CUDA graph (one launch instead of an index add,
-// three index kernels and a strided copy).
-__global__ void __launch_bounds__(128) sgld_gather_kernel(const float* __restrict__ X, const float* __restrict__ y,
-                                                          const long long* __restrict__ perm, const long long* __restrict__ off,
-                                                          int D, int nout, int ldh, float* __restrict__ h0,
-                                                          float* __restrict__ yb) {
-  const long long b = blockIdx.x;
-  const long long row = perm[*off + b];
-  for (int k = threadIdx.x; k < D; k += blockDim.x) h0[b * ldh + k] = X[row * D + k];
-  for (int o = threadIdx.x; o < nout; o += blockDim.x) yb[b * nout + o] = y[row * nout + o];
-}
-// step and epoch-position counters of the captured SGLD step (after the update of the step has been enqueued)
-__global__ void sgld_advance_kernel(long long* step, long long* off, long long batch) {
-  *step += 1;
-  *off += batch;
 }
 
 static unsigned sample_rows(long long S, long long blocks_x) {
@@ -411,55 +307,7 @@ extern "C" int32_t bnn_psgld_step(float* theta, const float* grad, float* V, int
     BNN_FAIL("bnn_psgld_step: pointers must be 16-byte aligned");
   const long long quads = (n + 3) >> 2;
   psgld_kernel<<<(unsigned)((quads + kEwBlock - 1) / kEwBlock), kEwBlock, 0, (cudaStream_t)stream>>>(
-      theta, grad, V, n, n_head, lr_head, lr_tail, alpha, lam, noise, seed, step, nullptr);
-  BNN_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int32_t bnn_psgld_step_dev(float* theta, const float* grad, float* V, int64_t n, int64_t n_head, float lr_head,
-                                      float lr_tail, float alpha, float lam, uint64_t seed, const int64_t* step_dev,
-                                      void* stream) {
-  if (!theta || !grad || !V || !step_dev || n < 1) BNN_FAIL("bnn_psgld_step_dev: bad arguments");
-  if ((((uintptr_t)theta | (uintptr_t)grad | (uintptr_t)V) & 15) != 0) BNN_FAIL("bnn_psgld_step_dev: pointers must be 16-byte aligned");
-  const long long quads = (n + 3) >> 2;
-  psgld_kernel<<<(unsigned)((quads + kEwBlock - 1) / kEwBlock), kEwBlock, 0, (cudaStream_t)stream>>>(
-      theta, grad, V, n, n_head, lr_head, lr_tail, alpha, lam, nullptr, seed, 0, (const long long*)step_dev);
-  BNN_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int32_t bnn_sgld_head(const float* out, const float* y, const float* log_precs, int64_t B, int32_t nout, float scale,
-                                 float alpha_n, float beta_n, const float* prior_quad, float log_const, float* dz,
-                                 float* grad_log_precs, float* loss, void* stream) {
-  if (!out || !y || !log_precs || !dz || !grad_log_precs || B < 1 || nout < 1 || nout > 64) BNN_FAIL("bnn_sgld_head: bad arguments");
-  sgld_head_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(out, y, log_precs, B, nout, scale, alpha_n, beta_n, lgammaf(alpha_n),
-                                                       prior_quad, log_const, dz, grad_log_precs, loss);
-  BNN_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int32_t bnn_sgld_prior(const float* prior_scale, const float* theta, int64_t n, float* pw, float* scratch, float* quad,
-                                  void* stream) {
-  if (!prior_scale || !theta || !pw || !scratch || !quad || n < 1) BNN_FAIL("bnn_sgld_prior: bad arguments");
-  // scratch: 64 floats of per-CTA partial sums followed by one zero-initialised 32-bit ticket (65 x 4 bytes)
-  const int blocks = 64;
-  sgld_prior_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(prior_scale, theta, n, pw, scratch, (unsigned int*)(scratch + 64), quad);
-  BNN_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int32_t bnn_sgld_gather(const float* X, const float* y, const int64_t* perm, const int64_t* off_dev, int64_t B, int32_t D,
-                                   int32_t nout, int32_t ldh, float* h0, float* y_batch, void* stream) {
-  if (!X || !y || !perm || !off_dev || !h0 || !y_batch || B < 1 || D < 1 || nout < 1 || ldh < D) BNN_FAIL("bnn_sgld_gather: bad arguments");
-  sgld_gather_kernel<<<(unsigned)B, 128, 0, (cudaStream_t)stream>>>(X, y, (const long long*)perm, (const long long*)off_dev, D, nout, ldh,
-                                                                  h0, y_batch);
-  BNN_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int32_t bnn_sgld_advance(int64_t* step_dev, int64_t* off_dev, int64_t batch, void* stream) {
-  if (!step_dev || !off_dev) BNN_FAIL("bnn_sgld_advance: bad arguments");
-  sgld_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)step_dev, (long long*)off_dev, batch);
+      theta, grad, V, n, n_head, lr_head, lr_tail, alpha, lam, noise, seed, step);
   BNN_CUDA(cudaGetLastError());
   return 0;
 }

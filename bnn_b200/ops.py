@@ -348,41 +348,102 @@ def psgld_step(theta, grad, V, lr_head, lr_tail=None, n_head=None, alpha=0.99, l
                                          seed & 0xFFFFFFFFFFFFFFFF, step, _stream(theta)), "bnn_psgld_step")
 
 
-def psgld_step_dev(theta, grad, V, step_dev, lr_head, lr_tail=None, n_head=None, alpha=0.99, lam=1e-5, seed=0):
-    """Graph-capturable pSGLD update: step index and LR-schedule factor come from the device counter `step_dev` (int64)."""
-    theta, grad, V = _dev(theta, "theta"), _dev(grad, "grad"), _dev(V, "V")
-    if step_dev.dtype != torch.int64 or not step_dev.is_cuda:
-        raise TypeError("step_dev must be an int64 CUDA tensor")
-    n = theta.numel()
-    _lib.check(_lib.lib().bnn_psgld_step_dev(_ptr(theta), _ptr(grad), _ptr(V), n, n if n_head is None else n_head, lr_head,
-                                             lr_head if lr_tail is None else lr_tail, alpha, lam, seed & 0xFFFFFFFFFFFFFFFF,
-                                             _ptr(step_dev), _stream(theta)), "bnn_psgld_step_dev")
+def sgld_perm(seed, epoch, N, count, device, offset=0):
+    """Entries [offset, offset + count) of the epoch's shuffled order (bnn_sgld_perm): int64 device tensor."""
+    out = torch.empty(int(count), dtype=torch.int64, device=device)
+    _lib.check(_lib.lib().bnn_sgld_perm(seed & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, int(N), int(offset), int(count),
+                                        _ptr(out), _stream(out)), "bnn_sgld_perm")
+    return out
 
 
-def sgld_head(out, y, log_precs, scale, alpha_n, beta_n, prior_quad, log_const, dz, grad_log_precs, loss):
-    """Energy head of one SGLD step (see bnn_sgld_head): writes dz, grad_log_precs, loss in place."""
-    B, nout = out.shape
-    _lib.check(_lib.lib().bnn_sgld_head(_ptr(_dev(out, "out")), _ptr(_dev(y, "y")), _ptr(log_precs), B, nout, float(scale),
-                                        float(alpha_n), float(beta_n), _ptr(prior_quad) if prior_quad is not None else None,
-                                        float(log_const), _ptr(dz), _ptr(grad_log_precs), _ptr(loss), _stream(out)),
-               "bnn_sgld_head")
+class SgldChain:
+    """Device-resident state of one pSGLD chain + the fused step kernel (bnn_sgld_run, csrc/sgld_step.cu).
 
+    theta = [packed network | log_precs | pad] (double-buffered), V (preconditioner, ones at start), t (steps taken: LR
+    schedule + Philox subsequence).  Mirrors what BNN_SGDMC.train sets up at BNN_SGDMC.py:96-101."""
 
-def sgld_prior(prior_scale, theta, pw, scratch, quad):
-    """pw = prior_scale * theta and quad = sum(pw * theta) in one launch (scratch: 65 floats, last one zero initially)."""
-    _lib.check(_lib.lib().bnn_sgld_prior(_ptr(prior_scale), _ptr(_dev(theta, "theta")), theta.numel(), _ptr(pw), _ptr(scratch),
-                                         _ptr(quad), _stream(theta)), "bnn_sgld_prior")
+    def __init__(self, arch: Arch, batch, device, lr_weight, lr_noise, alpha_n, beta_n, seed=0, precond_decay=0.99,
+                 diagonal_bias=1e-5, gain=5. / 3, precond_mode=0):
+        L = _lib.lib()
+        self.arch, self.batch, self.device = arch, int(batch), torch.device(device)
+        d = arch.desc()
+        self.n_theta = int(L.bnn_sgld_theta_len(C.byref(d)))
+        self.n_thetaT = int(L.bnn_sgld_theta_t_len(C.byref(d)))
+        ws = int(L.bnn_sgld_workspace_bytes(C.byref(d), self.batch))
+        if min(self.n_theta, self.n_thetaT, ws) < 0:
+            _lib.check(-1, "bnn_sgld_workspace_bytes")
+        self.theta = torch.zeros(2, self.n_theta, device=self.device)
+        self.thetaT = torch.zeros(2, self.n_thetaT, device=self.device)
+        self.V = torch.ones(self.n_theta, device=self.device)
+        self.ws = torch.zeros(ws, dtype=torch.uint8, device=self.device)
+        self.loss = torch.zeros(1, device=self.device)
+        self.cur, self.t = 0, 0
+        c = _lib.SgldChain()
+        c.desc, c.batch = d, self.batch
+        c.theta, c.thetaT, c.V = self.theta.data_ptr(), self.thetaT.data_ptr(), self.V.data_ptr()
+        c.workspace, c.workspace_bytes = self.ws.data_ptr(), ws
+        c.lr_weight, c.lr_noise = float(lr_weight), float(lr_noise)
+        c.precond_decay, c.diagonal_bias = float(precond_decay), float(diagonal_bias)
+        c.alpha_n, c.beta_n, c.gain = float(alpha_n), float(beta_n), float(gain)
+        c.precond_mode, c.seed = int(precond_mode), int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._c = c
+        self._keep = None
 
+    def set_state(self, packed_net, log_precs):
+        """Start (or restart) the chain at this network / these log-precisions: V = 1, t = 0 (a fresh optimizer and scheduler,
+        as every BNN_SGDMC.train call builds, BNN_SGDMC.py:100-101)."""
+        a = self.arch
+        self.cur, self.t = 0, 0
+        self.theta.zero_()
+        self.theta[0, : a.stride] = packed_net.to(self.device, torch.float32) * a.valid_mask().to(self.device)
+        self.theta[0, a.stride: a.stride + a.nout] = log_precs.to(self.device, torch.float32)
+        self.V.fill_(1.)
+        _lib.check(_lib.lib().bnn_sgld_init(C.byref(self._c), self.cur, _stream(self.theta)), "bnn_sgld_init")
 
-def sgld_gather(X, y, perm, off_dev, h0, y_batch):
-    """Minibatch rows perm[off .. off + B) of X, y into the augmented first-layer input h0 [B, ld] and y_batch [B, nout]."""
-    B, ldh = h0.shape
-    _lib.check(_lib.lib().bnn_sgld_gather(_ptr(_dev(X, "X")), _ptr(_dev(y, "y")), _ptr(perm), _ptr(off_dev), B, X.shape[1],
-                                          y_batch.shape[1], ldh, _ptr(h0), _ptr(y_batch), _stream(X)), "bnn_sgld_gather")
+    def bind(self, X, y, num_train=None):
+        """Training set of the chain.  num_train (default: rows of X) is the N of the N/|b| likelihood scale and the
+        length of an epoch; a caller may bind a buffer holding only the rows its permutations will ever index."""
+        X, y = _dev(X, "X"), _dev(y, "y")
+        if X.dim() != 2 or X.shape[1] != self.arch.dims[0] or y.numel() != X.shape[0] * self.arch.nout:
+            raise ValueError("X must be [N, dim] and y [N, nout]")
+        self._keep = (X, y)
+        self._c.X, self._c.y = X.data_ptr(), y.data_ptr()
+        self._c.num_train = int(num_train) if num_train is not None else X.shape[0]
 
+    def _perm(self, perm):
+        if perm.dtype != torch.int64 or not perm.is_cuda or not perm.is_contiguous():
+            raise TypeError("perm must be a contiguous int64 CUDA tensor")
+        self._c.perm = perm.data_ptr()
 
-def sgld_advance(step_dev, off_dev, batch):
-    _lib.check(_lib.lib().bnn_sgld_advance(_ptr(step_dev), _ptr(off_dev), int(batch), _stream(step_dev)), "bnn_sgld_advance")
+    def run(self, perm, perm_off, n_steps, want_loss=True):
+        """n_steps fused SGLD steps on the batches perm[perm_off + i * batch ...]; returns the device scalar holding the
+        loss of the last step (valid after the launch completes)."""
+        self._perm(perm)
+        if perm_off + (n_steps - 1) * self.batch >= min(perm.numel(), self._c.num_train):
+            raise ValueError("the launch would run past the permutation")
+        _lib.check(_lib.lib().bnn_sgld_run(C.byref(self._c), self.cur, self.t, int(perm_off), int(n_steps),
+                                           _ptr(self.loss) if want_loss else None, None, _stream(self.theta)), "bnn_sgld_run")
+        self.t += n_steps
+        self.cur ^= n_steps & 1
+        return self.loss
+
+    def grad(self, perm, perm_off=0):
+        """(dU/dtheta [n_theta], loss U) at the current state for the batch at perm_off -- no update (tests)."""
+        self._perm(perm)
+        g = torch.zeros(self.n_theta, device=self.device)
+        _lib.check(_lib.lib().bnn_sgld_run(C.byref(self._c), self.cur, self.t, int(perm_off), 1, _ptr(self.loss), _ptr(g),
+                                           _stream(self.theta)), "bnn_sgld_run")
+        return g, self.loss.clone()
+
+    def check(self):
+        st = C.c_int32(0)
+        _lib.check(_lib.lib().bnn_sgld_status(C.byref(self._c), C.byref(st), _stream(self.theta)), "bnn_sgld_status")
+        if st.value != 0:
+            raise RuntimeError("fused SGLD step: a grid barrier timed out; the chain state is undefined")
+
+    @property
+    def state(self):
+        return self.theta[self.cur]
 
 
 def philox_words(seed, subsequence, tag, n, device):

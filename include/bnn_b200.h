@@ -192,33 +192,54 @@ int32_t bnn_psgld_step(float* theta, const float* grad, float* V, int64_t n, int
                        float lr_head, float lr_tail, float alpha, float lam, const float* noise,
                        uint64_t seed, int64_t step, void* stream);
 
-/* CUDA-graph friendly variant: the step index t is read from DEVICE memory (*step_dev), the base learning rates are
- * multiplied in-kernel by the schedule factor float((1 + t) ** -0.33) of BNN_SGDMC.py:101, noise is always Philox
- * (seed, t).  The caller increments *step_dev itself (stream-ordered) after the call.                          */
-int32_t bnn_psgld_step_dev(float* theta, const float* grad, float* V, int64_t n, int64_t n_head, float lr_head,
-                           float lr_tail, float alpha, float lam, uint64_t seed, const int64_t* step_dev, void* stream);
-
-/* SGLD energy head (replaces the scalar arithmetic of BNN_SGDMC.py:61-74,83 between the network output and the backward
- * pass): out, y [B, nout]; log_precs [nout]; scale = N_train / B; prior_quad = device scalar sum_l sum W^2 / std_l^2 (or null);
- * log_const = sum_l n_l * (log std_l + 0.5 log 2 pi).  Writes dz = dU/d(out) [B, nout], dU/d(log_precs) [nout] and the
- * loss U = -(scale * loglik + logprior) [1] (loss may be null).  One launch, graph-capturable.                    */
-int32_t bnn_sgld_head(const float* out, const float* y, const float* log_precs, int64_t B, int32_t nout, float scale,
-                      float alpha_n, float beta_n, const float* prior_quad, float log_const, float* dz,
-                      float* grad_log_precs, float* loss, void* stream);
-
-/* SGLD prior term (BNN_SGDMC.py:63-66): pw[i] = prior_scale[i] * theta[i] (prior_scale = 1 / std_l^2 on weight entries, 0 on
- * biases / padding) and quad[0] = sum_i pw[i] * theta[i], deterministic.  scratch: 65 floats, the last one zero before the
- * first call (the kernel re-zeroes it).                                                                             */
-int32_t bnn_sgld_prior(const float* prior_scale, const float* theta, int64_t n, float* pw, float* scratch, float* quad,
-                       void* stream);
-
-/* SGLD minibatch gather for a CUDA-graph-replayed step (the shuffled DataLoader batch of BNN_SGDMC.py:80,110): rows
- * perm[*off_dev .. *off_dev + B) of X [N, D] and y [N, nout] -> h0 [B, ldh] columns [0, D) (the caller keeps column D = 1 and
- * the padding = 0: the augmented first-layer input) and y_batch [B, nout].  bnn_sgld_advance adds 1 to *step_dev and
- * `batch` to *off_dev (stream-ordered, after the update of the step).                                              */
-int32_t bnn_sgld_gather(const float* X, const float* y, const int64_t* perm, const int64_t* off_dev, int64_t B, int32_t D,
-                        int32_t nout, int32_t ldh, float* h0, float* y_batch, void* stream);
-int32_t bnn_sgld_advance(int64_t* step_dev, int64_t* off_dev, int64_t batch, void* stream);
+/* ---- (f1) fused SGLD step ---------------------------------------------------- */
+/* replaces: the body of BNN_SGDMC.sgld_steps (BNN_SGDMC.py:76-91) -- shuffled minibatch (:80,110), log_prior / log_lik /
+ * loss (:61-74,83), loss.backward() (:85), pSGLD.step() and the LambdaLR factor (:86-87,96-101) -- for n_steps
+ * consecutive steps in ONE persistent cooperative kernel launch (no library GEMM, no elementwise launches; see
+ * csrc/sgld_step.cu).  The chain state is owned by the caller:
+ *   theta  [2][bnn_sgld_theta_len]  packed network | log_precs[nout] | pad, double-buffered by step parity;
+ *   thetaT [2][bnn_sgld_theta_t_len] transposed weight copies of Linear 1.. (maintained by the kernel);
+ *   V      [bnn_sgld_theta_len]     RMSprop preconditioner state (pybnn initialises it to ones);
+ *   workspace                       bnn_sgld_workspace_bytes() bytes of activations / output gradients / counters.
+ * bnn_sgld_init: after writing the initial state into theta[cur] (and V), zeroes the workspace and builds thetaT[cur].
+ * bnn_sgld_run : steps t0 .. t0+n_steps-1 on the batches perm[perm_off + i*batch ..] (the last batch of an epoch may be
+ *   short; a launch must not run past num_train).  Reads theta[cur]; after the call the current buffer is
+ *   cur ^ (n_steps & 1).  loss_out (device, may be NULL) receives U = -(loglik * N/|b| + logprior) of the last step.
+ *   grad_out (device [theta_len], may be NULL): gradient-only mode for tests -- ONE step, writes dU/dtheta, no update.
+ * Update rule (UNPINNED, pybnn absent): V <- a V + (1-a) g^2; G = 1/(lam + sqrt(V)) (precond_mode 0) or 1/sqrt(V + lam)
+ *   (precond_mode 1); theta <- theta - (0.5 lr_t G g + sqrt(lr_t G) xi), lr_t = lr * float32((1+t)^-0.33), xi = Philox
+ *   (seed, t); layout padding is never touched.                                                                        */
+typedef struct BnnSgldChain {
+  BnnMlpDesc desc;
+  int32_t batch;             /* rows per minibatch (BNN_SGDMC.py:30) */
+  float* theta;
+  float* thetaT;
+  float* V;
+  void* workspace;
+  int64_t workspace_bytes;
+  const float* X;            /* [num_train, dims[0]] */
+  const float* y;            /* [num_train, nout]    */
+  const int64_t* perm;       /* epoch permutation [num_train] (DataLoader(shuffle=True), :110) */
+  int64_t num_train;
+  float lr_weight, lr_noise; /* the two param groups of :96-98 */
+  float precond_decay;       /* a   (pybnn default 0.99) */
+  float diagonal_bias;       /* lam (pybnn default 1e-5) */
+  float alpha_n, beta_n;     /* Gamma prior of the precisions (:35-36, :47) */
+  float gain;                /* weight-prior gain (5/3, :51) */
+  int32_t precond_mode;
+  uint64_t seed;
+} BnnSgldChain;
+int64_t bnn_sgld_theta_len(const BnnMlpDesc* d);
+int64_t bnn_sgld_theta_t_len(const BnnMlpDesc* d);
+int64_t bnn_sgld_workspace_bytes(const BnnMlpDesc* d, int32_t batch);
+int32_t bnn_sgld_init(const BnnSgldChain* c, int32_t cur, void* stream);
+int32_t bnn_sgld_run(const BnnSgldChain* c, int32_t cur, int64_t t0, int64_t perm_off, int32_t n_steps, float* loss_out,
+                     float* grad_out, void* stream);
+/* entries [offset, offset + count) of the pseudo-random permutation of [0, N) keyed by (seed, epoch): the shuffled order of
+ * DataLoader(shuffle=True) (BNN_SGDMC.py:110) without materialising all N entries -- a chain only consumes a prefix */
+int32_t bnn_sgld_perm(uint64_t seed, uint32_t epoch, int64_t N, int64_t offset, int64_t count, int64_t* out, void* stream);
+/* synchronises; *status_host = 0 ok, 1 = a grid barrier of the last launch timed out (chain state undefined) */
+int32_t bnn_sgld_status(const BnnSgldChain* c, int32_t* status_host, void* stream);
 
 /* raw Philox stream dump for tests: out[n] 32-bit words / normals */
 int32_t bnn_philox_words(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, uint32_t* out, void* stream);

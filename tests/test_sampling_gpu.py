@@ -231,79 +231,3 @@ def test_psgld_stationary_variance():
             acc += float((theta.double() ** 2).mean()); cnt += 1
     assert abs(acc / cnt - s2) < 0.1 * s2
     assert bool((V == 1).all())
-
-
-def test_psgld_step_dev_equals_host_schedule():
-    """Graph-friendly variant: step index + LambdaLR factor from a device counter == host-side float32((1+t)**-0.33)."""
-    from bnn_b200 import ops
-    n, t = 4099, 37
-    g = torch.Generator().manual_seed(2)
-    theta, grad, V = torch.randn(n, generator=g), torch.randn(n, generator=g), torch.rand(n, generator=g) + 0.1
-    a_t, a_V = theta.cuda().clone(), V.cuda().clone()
-    b_t, b_V = theta.cuda().clone(), V.cuda().clone()
-    f = float(O.lr_factor(t))
-    ops.psgld_step(a_t, grad.cuda(), a_V, 2e-2 * f, lr_tail=1e-1 * f, n_head=n - 3, seed=9, step=t)
-    ops.psgld_step_dev(b_t, grad.cuda(), b_V, torch.tensor(t, dtype=torch.long, device="cuda"), 2e-2, lr_tail=1e-1, n_head=n - 3, seed=9)
-    assert torch.allclose(a_t, b_t, rtol=1e-6, atol=1e-7) and torch.equal(a_V, b_V)
-
-
-@pytest.mark.parametrize("act,hid,nout", [("tanh", [512, 512, 512], 1), ("relu", [50], 1), ("sigmoid", [7, 5], 3)])
-def test_sgld_hand_derived_gradient_matches_autograd(act, hid, nout):
-    """The minibatch gradient of U used by the SGLD step (a few GEMMs on the packed blocks) against torch autograd on the
-    same energy (BNN_SGDMC.py:61-83)."""
-    import torch.nn as nn
-    from bnn_b200.BNN_SGDMC import BNN_SGDMC
-    torch.manual_seed(3)
-    dev = torch.device("cuda")
-    m = BNN_SGDMC(9, {"tanh": nn.Tanh(), "relu": nn.ReLU(), "sigmoid": nn.Sigmoid()}[act], hid, nout=nout,
-                  conf={"batch_size": 32, "device": "cuda"})
-    m._chain_init(dev)
-    m._theta[: m.arch.stride] += 0.05 * torch.randn(m.arch.stride, device=dev) * m.arch.valid_mask().to(dev)
-    X, y = torch.randn(500, 9, device=dev), torch.randn(500, nout, device=dev)
-    idx = torch.randperm(500, device=dev)[:32]
-    l_ref, g_ref = m._grad_autograd(X, y, idx, 500)
-    l_new, g_new = m._grad_into(X, y, idx, 500)
-    assert abs(float(l_new) - float(l_ref)) <= 1e-5 * abs(float(l_ref))
-    assert float((g_new - g_ref).abs().max() / g_ref.abs().max()) <= 1e-5
-
-
-def test_sgld_gather_and_advance():
-    """The minibatch gather of the captured SGLD step equals torch indexing at the device-side epoch offset; the counter
-    kernel advances step and offset."""
-    from bnn_b200 import ops
-    dev = "cuda"
-    g = torch.Generator().manual_seed(0)
-    N, D, nout, B, ld = 1000, 9, 2, 32, 12
-    X, y = torch.randn(N, D, generator=g).to(dev), torch.randn(N, nout, generator=g).to(dev)
-    perm = torch.randperm(N, generator=g).to(dev)
-    off = torch.tensor(64, dtype=torch.long, device=dev)
-    step = torch.tensor(5, dtype=torch.long, device=dev)
-    h0 = torch.zeros(B, ld, device=dev)
-    h0[:, D] = 1.0
-    yb = torch.empty(B, nout, device=dev)
-    ops.sgld_gather(X, y, perm, off, h0, yb)
-    idx = perm[64:64 + B]
-    assert torch.equal(h0[:, :D], X[idx]) and torch.equal(yb, y[idx])
-    assert bool((h0[:, D] == 1).all()) and bool((h0[:, D + 1:] == 0).all())
-    ops.sgld_advance(step, off, B)
-    assert int(step) == 6 and int(off) == 96
-
-
-def test_sgld_prior_kernel():
-    """pw = prior_scale * theta and its energy sum(pw * theta): exact elementwise, deterministic reduction (replayable:
-    the ticket re-zeroes itself)."""
-    from bnn_b200 import ops
-    g = torch.Generator().manual_seed(1)
-    n = 572_420
-    ps = (torch.rand(n, generator=g) > 0.1).float().cuda() * 3.7
-    th = torch.randn(n, generator=g).cuda()
-    pw, scr, quad = torch.empty_like(th), torch.zeros(65, device="cuda"), torch.zeros((), device="cuda")
-    vals = []
-    for _ in range(3):
-        ops.sgld_prior(ps, th, pw, scr, quad)
-        torch.cuda.synchronize()
-        vals.append(float(quad))
-    assert torch.equal(pw, ps * th)
-    ref = float((ps.double() * th.double() * th.double()).sum())
-    assert abs(vals[0] - ref) <= 1e-5 * abs(ref)
-    assert vals[0] == vals[1] == vals[2]
