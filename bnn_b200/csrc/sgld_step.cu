@@ -21,6 +21,7 @@
 // weights of layers >= 1 carry a transposed copy maintained by the update epilogue.  theta / thetaT are double-buffered by
 // step parity: all reads of a step see theta_cur, all updates write theta_next -- no intra-step hazards, no extra barrier.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "philox.cuh"
@@ -30,7 +31,12 @@ namespace bnn {
 constexpr int kSgThreads = 256;
 constexpr int kSgKC = 64;            // K chunk (floats)
 constexpr int kSgLds = kSgKC + 4;    // smem row pitch: 68 words = 4 (mod 32) -> 8 consecutive rows hit 32 distinct banks
-constexpr int kSgStages = 3;
+// Stage counts per tile family.  A tile's operands are tiny (<= 110 KB) but every access is an L2 round trip of ~450
+// cycles (DRAM ~1000), so the ring is deep enough to put the WHOLE K extent of a tile in flight at once (K <= 768 resp.
+// 384): tile time = one latency + transfer, instead of one latency per two chunks.
+constexpr int kSgStagesF = 12;   // 32 x 16 tiles: 12 x 13,056 B
+constexpr int kSgStagesW = 6;    // 64 x 32 tiles:  6 x 26,112 B
+constexpr int kSgMaxStages = 12;
 
 struct SgLayer {
   int in, out, ld, ldz, ldT;
@@ -63,6 +69,8 @@ struct SgParams {
   int* err;
   float* loss_out;                     // U of the LAST step of the launch (may be null)
   float* grad_out;                     // debug: when non-null the step writes dU/dtheta here and does NOT update
+  int dbg;                             // debug (BNN_SGLD_DBG): 1 skip the FMA loop, 2 skip the dense loads, 4 skip the epilogues
+  long long* trace;                    // debug: [grid][2 * L phases][2] clock64 (work done, barrier passed) of the LAST step
 };
 
 // ---- small helpers ---------------------------------------------------------------------------------------------------
@@ -85,8 +93,9 @@ __device__ __forceinline__ bool grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
   if (threadIdx.x == 0) {
     target += gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // release at gpu scope: the CTA's writes (ordered before this by the bar.sync above) are visible to whoever acquires
+    // the counter; cheaper than __threadfence() (= fence.sc.gpu) followed by a relaxed add
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     unsigned long long spins = 0;
     int bad = 0;
     while ((int)(ld_acquire_u32(counter) - target) < 0) {
@@ -111,68 +120,68 @@ __device__ __forceinline__ float act_bwd(float h, int act) {
 }
 
 // ---- operands ----------------------------------------------------------------------------------------------------------
+// The kernel is kept SMALL on purpose (rolled loops, ONE inlined copy of the tile core per tile shape, one job loop for all
+// phases): a step executes every phase's code exactly once per tile, so straight-line code is instruction-fetch bound -- the
+// first version (fully unrolled prefetch prologues, three inlined copies of the core, ~130 KB of SASS) spent 3.5k of a tile's
+// 12.9k cycles with the FMAs, the loads and the epilogue all switched off.
 enum { OP_DENSE = 0, OP_GATHER_X = 1, OP_GATHER_XT = 2 };
 struct SgOperand {
   int kind;
   const float* p;      // DENSE: [rows, ld]
   int ld;
   int rows_valid;      // rows >= rows_valid read as zero
-  int k_valid;         // k >= k_valid reads as zero (multiple of 4 for DENSE)
-  // gather kinds: X[perm[b] * D + k]; batch rows >= rows_live are zero (short last batch of an epoch)
-  const float* X;
-  const long long* perm;   // already offset to this step's batch
+  int k_valid;         // k >= k_valid reads as zero (multiple of 4)
+};
+// what the gather kinds need (X[perm[b] * D + k]; batch rows >= rows_live are zero: short last batch of an epoch)
+struct SgGather {
+  const float* __restrict__ X;
+  const long long* perm;   // this step's batch rows (shared-memory copy of perm[off .. off + B))
   int D, B, rows_live;
 };
 
-// one K chunk of ROWS operand rows -> smem [ROWS][kSgLds]
-template <int ROWS>
-__device__ __forceinline__ void load_chunk(const SgOperand& op, int row0, int k0, float* dst) {
-  const int tid = threadIdx.x;
-  if (op.kind == OP_DENSE) {
-    const uint32_t d0 = smem_u32(dst);
+// gathered operands (synchronous): rows = batch index b, K = input feature (forward of Linear 0: kT = false) or rows = input
+// feature, K = batch index (dW of Linear 0: kT = true); augmented with the ones column / row at feature == D.  Four
+// independent loads are in flight per thread before the first store.
+template <int ROWS, bool kT>
+__device__ __forceinline__ void load_gather(const SgGather& gq, int row0, int k0, float* dst) {
+#pragma unroll 1
+  for (int base = threadIdx.x; base < ROWS * kSgKC; base += 4 * kSgThreads) {
+    float v[4];
 #pragma unroll
-    for (int idx = tid; idx < ROWS * (kSgKC / 4); idx += kSgThreads) {
-      const int r = idx >> 4, c = idx & 15;
-      const int row = row0 + r, k = k0 + c * 4;
-      const bool ok = row < op.rows_valid && k < op.k_valid;
-      const float* src = ok ? op.p + (long long)row * op.ld + k : op.p;
-      cp_async16(d0 + (uint32_t)(r * kSgLds + c * 4) * 4u, src, ok ? 16 : 0);
-    }
-  } else if (op.kind == OP_GATHER_X) {
-    // rows = batch index b, K index = input feature k; augmented with the ones column at k == D
-    for (int idx = tid; idx < ROWS * kSgKC; idx += kSgThreads) {
-      const int r = idx >> 6, kk = idx & 63;
-      const int b = row0 + r, k = k0 + kk;
-      float v = 0.0f;
-      if (b < op.B) {
-        if (k < op.D) { if (b < op.rows_live) v = __ldg(op.X + op.perm[b] * op.D + k); }
-        else if (k == op.D) v = 1.0f;
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + u * kSgThreads;
+      const int r = kT ? idx % ROWS : idx >> 6, kk = kT ? idx / ROWS : idx & 63;
+      const int b = kT ? k0 + kk : row0 + r, f = kT ? row0 + r : k0 + kk;
+      v[u] = 0.0f;
+      if (idx < ROWS * kSgKC && b < gq.rows_live) {
+        if (f < gq.D) v[u] = __ldg(gq.X + gq.perm[b] * gq.D + f);
+        else if (f == gq.D) v[u] = 1.0f;
       }
-      dst[r * kSgLds + kk] = v;
     }
-  } else {
-    // rows = input feature kf (row D = ones), K index = batch index b
-    for (int idx = tid; idx < ROWS * kSgKC; idx += kSgThreads) {
-      const int r = idx % ROWS, kk = idx / ROWS;
-      const int kf = row0 + r, b = k0 + kk;
-      float v = 0.0f;
-      if (b < op.rows_live) {
-        if (kf < op.D) v = __ldg(op.X + op.perm[b] * op.D + kf);
-        else if (kf == op.D) v = 1.0f;
-      }
-      dst[r * kSgLds + kk] = v;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + u * kSgThreads;
+      if (idx < ROWS * kSgKC) dst[(kT ? idx % ROWS : idx >> 6) * kSgLds + (kT ? idx / ROWS : idx & 63)] = v[u];
     }
   }
 }
 
-// ---- one tile: acc[TM x TN] over K, reduced over the K-slices, handed quad by quad to the epilogue -----------------------
-// Thread tile 4 x 4 (rows ty + TY * i, columns tx + TX * j); the 256 threads form KS = 256 / (TY * TX) K-slices, slice ks
-// takes the float4 groups g = ks, ks + KS, ... of every chunk.
-template <int TM, int TN, typename Epi>
-__device__ __forceinline__ void run_tile(const SgOperand& A, const SgOperand& Bop, int m0, int n0, int K, float* smem, Epi&& epi) {
+// ---- tile core: red[TM x TN] = sum_k A[m0 + ., k] B[n0 + ., k], left in shared memory (row-major, after the K-slices are summed)
+// Operands: 16-byte cp.async into padded shared-memory rows, completion per ring stage on an mbarrier (every thread posts a
+// deferred arrival that fires when its own copies of the stage have landed: no per-chunk __syncthreads).  Rows beyond the
+// operand are not copied (garbage rows only feed output rows / columns the epilogues discard); the K tail is skipped.
+// Compute: FP32 FFMA, thread tile 4 x 4 (rows ty + TY * i, columns tx + TX * j); the 256 threads form KS = 256 / (TY * TX)
+// K-slices, slice ks takes the float4 groups g = ks, ks + KS, ... of every chunk.
+// Measured alternatives (profiles/r02_sgld_step_notes.md): mma.sync m16n8k8 TF32 with 3xTF32 compensation is NOT faster --
+// the legacy warp-level tensor path of this chip issues one TF32 mma per ~32 cycles per SM sub-partition, i.e. the FFMA
+// rate, and the compensation needs three of them; one cp.async.bulk per 256-byte operand row was slower than 16-byte
+// cp.async (432 small bulk copies per tile); 16 warps instead of 8 did not change the K loop.
+template <int TM, int TN, int NS>
+__device__ __forceinline__ void tile_core(const SgOperand& A, const SgOperand& Bop, const SgGather& gq, int m0, int n0, int K,
+                                          float* smem, uint64_t* bars, uint32_t& phase_bits, int dbg, long long* probe) {
   constexpr int TY = TM / 4, TX = TN / 4, THR = TY * TX, KS = kSgThreads / THR;
   constexpr int STAGE = (TM + TN) * kSgLds;
-  static_assert(KS >= 1 && KS * THR == kSgThreads, "tile shape");
+  static_assert(KS >= 1 && KS * THR == kSgThreads && NS <= kSgMaxStages, "tile shape");
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = (tid / TX) % TY, ks = tid / THR;
   float acc[4][4];
@@ -181,32 +190,61 @@ __device__ __forceinline__ void run_tile(const SgOperand& A, const SgOperand& Bo
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
+  if (probe && tid == 0) probe[0] = clock64();
   const int nchunks = (K + kSgKC - 1) / kSgKC;
-  auto issue = [&](int c) {
-    float* st = smem + (c % kSgStages) * STAGE;
-    load_chunk<TM>(A, m0, c * kSgKC, st);
-    load_chunk<TN>(Bop, n0, c * kSgKC, st + TM * kSgLds);
-  };
+  const bool a_dense = A.kind == OP_DENSE, b_dense = Bop.kind == OP_DENSE;
+  const int va = min(TM, A.rows_valid - m0), vb = min(TN, Bop.rows_valid - n0);   // valid rows of the tile (>= 1)
+  auto issue_dense = [&](int c) {
+    if (dbg & 2) return;
+    const int k0 = c * kSgKC;
+    const int kq = (min(kSgKC, K - k0) + 3) >> 2;                  // float4s per row in this chunk
+    float* st = smem + (c % NS) * STAGE;
+    const uint32_t d0 = smem_u32(st);
 #pragma unroll
-  for (int s = 0; s < kSgStages - 1; ++s) {
-    if (s < nchunks) issue(s);
-    cp_async_commit();
+    for (int idx = tid; idx < (TM + TN) * (kSgKC / 4); idx += kSgThreads) {
+      const int r = idx >> 4, c4 = idx & 15;
+      const bool isA = r < TM;
+      const int rr = isA ? r : r - TM;
+      const SgOperand& op = isA ? A : Bop;
+      if (c4 < kq && rr < (isA ? va : vb) && (isA ? a_dense : b_dense))
+        cp_async16(d0 + (uint32_t)(r * kSgLds + c4 * 4) * 4u, op.p + (long long)((isA ? m0 : n0) + rr) * op.ld + k0 + c4 * 4, 16);
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[c % NS])) : "memory");
+  };
+  auto issue_gather = [&](int c) {
+    if (dbg & 2) return;
+    float* st = smem + (c % NS) * STAGE;
+    if (!a_dense) load_gather<TM, false>(gq, m0, c * kSgKC, st);
+    if (!b_dense) load_gather<TN, true>(gq, n0, c * kSgKC, st + TM * kSgLds);
+  };
+  // prologue: everything the ring holds
+  {
+    const int npre = min(nchunks, NS);
+#pragma unroll 1
+    for (int c = 0; c < npre; ++c) issue_dense(c);
+    if (!a_dense || !b_dense) {
+#pragma unroll 1
+      for (int c = 0; c < npre; ++c) issue_gather(c);
+      __syncthreads();                     // gathered rows are plain shared-memory stores
+    }
   }
+  if (probe && tid == 0) probe[1] = clock64();
+#pragma unroll 1
   for (int c = 0; c < nchunks; ++c) {
-    cp_async_wait<kSgStages - 2>();
-    __syncthreads();                       // chunk c visible to all; everyone is done with chunk c - 1 (its stage is refilled now)
-    if (c + kSgStages - 1 < nchunks) issue(c + kSgStages - 1);
-    cp_async_commit();
-    const float* As = smem + (c % kSgStages) * STAGE;
-    const float* Bs = As + TM * kSgLds;
+    const int s = c % NS;
+    if (!(dbg & 2)) mbar_wait_spin(&bars[s], (phase_bits >> s) & 1u);
+    phase_bits ^= 1u << s;
+    const float* As = smem + s * STAGE + ty * kSgLds;
+    const float* Bs = smem + s * STAGE + (TM + tx) * kSgLds;
     const int rem = K - c * kSgKC;
-    const int gmax = rem >= kSgKC ? kSgKC / 4 : (rem + 3) >> 2;
+    const int gmax = (dbg & 1) ? 0 : (rem >= kSgKC ? kSgKC / 4 : (rem + 3) >> 2);
+#pragma unroll 1
     for (int g = ks; g < gmax; g += KS) {
       float4 a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty + TY * i) * kSgLds + g * 4);
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(As + TY * i * kSgLds + g * 4);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + (tx + TX * j) * kSgLds + g * 4);
+      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + TX * j * kSgLds + g * 4);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -217,29 +255,35 @@ __device__ __forceinline__ void run_tile(const SgOperand& A, const SgOperand& Bo
           acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
         }
     }
+    if (c + NS < nchunks) {                // refill this stage (only for K beyond the ring: layers wider than 768 / 384)
+      __syncthreads();                     // every warp is done with chunk c
+      issue_dense(c + NS);
+      if (!a_dense || !b_dense) { issue_gather(c + NS); __syncthreads(); }
+    }
   }
-  cp_async_wait<0>();
   __syncthreads();                         // all slices done with the stages: reuse them for the cross-slice reduction
-  float* red = smem;                       // [KS][TM * TN]
+  if (probe && tid == 0) probe[2] = clock64();
+  float* red = smem + TM * TN;             // [KS][TM * TN] partials behind the [TM * TN] result
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) red[ks * (TM * TN) + (ty + TY * i) * TN + tx + TX * j] = acc[i][j];
   __syncthreads();
+#pragma unroll 1
   for (int q = tid; q < TM * TN / 4; q += kSgThreads) {
     float4 v = *reinterpret_cast<const float4*>(red + q * 4);
 #pragma unroll
-    for (int s = 1; s < KS; ++s) {
-      const float4 w = *reinterpret_cast<const float4*>(red + s * (TM * TN) + q * 4);
+    for (int s2 = 1; s2 < KS; ++s2) {
+      const float4 w = *reinterpret_cast<const float4*>(red + s2 * (TM * TN) + q * 4);
       v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
     }
-    const int e = q * 4;
-    epi(m0 + e / TN, n0 + e % TN, v);      // row, first of 4 consecutive columns
+    *reinterpret_cast<float4*>(smem + q * 4) = v;
   }
-  __syncthreads();                         // red is free again before the next tile's loads
+  __syncthreads();
+  if (probe && tid == 0) probe[3] = clock64();
 }
 
-// ---- update of one quad of parameters (shared by the dW epilogue and the log-precision job) -------------------------------
+// ---- update of one parameter (shared by the dW epilogue and the log-precision job) ----------------------------------------
 __device__ __forceinline__ void psgld_update1(float& t, float& v, float g, float z, float lr, float alpha, float lam, int mode) {
   v = alpha * v + (1.0f - alpha) * g * g;
   const float G = mode == 0 ? 1.0f / (lam + sqrtf(v)) : rsqrtf(v + lam);
@@ -252,11 +296,20 @@ constexpr int WT_M = 64, WT_N = 32;   // dW tiles over [out, ld]
 __global__ void __launch_bounds__(kSgThreads, 1) sgld_step_kernel(const __grid_constant__ SgParams p) {
   extern __shared__ __align__(16) float sg_smem[];
   __shared__ int s_flag;
+  __shared__ long long s_perm[1024];   // this step's batch rows
+  __shared__ __align__(8) uint64_t s_bars[kSgMaxStages];   // one per ring stage: "the chunk's bytes have landed"
   unsigned int bar_target = 0;
+  uint32_t phase_bits = 0;             // parity to wait for next, per stage (uniform across the CTA)
   const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < kSgMaxStages; ++i) mbar_init(&s_bars[i], kSgThreads);   // every thread posts one (deferred) arrival per use
+    fence_barrier_init();
+  }
+  __syncthreads();
   const int L = p.L;
   const bool debug = p.grad_out != nullptr;
 
+#pragma unroll 1
   for (int it = 0; it < p.n_steps; ++it) {
     const long long t = p.t0 + it;
     const int cur = (p.cur + it) & 1;
@@ -267,141 +320,158 @@ __global__ void __launch_bounds__(kSgThreads, 1) sgld_step_kernel(const __grid_c
     const long long boff = p.perm_off + (long long)it * p.B;
     const long long left = p.num_train - boff;
     const int rows = left < p.B ? (int)left : p.B;                 // the last batch of an epoch may be short (:80)
-    const long long* perm = p.perm + boff;
+    // the batch's rows, read once per step per CTA (the gathers and the head index X / y through it); the previous step's
+    // readers are behind that step's last grid barrier
+    for (int b = tid; b < rows; b += kSgThreads) s_perm[b] = p.perm[boff + b];
+    __syncthreads();
+    SgGather gq;
+    gq.X = p.X; gq.perm = s_perm; gq.D = p.D; gq.B = p.B; gq.rows_live = rows;
     const float scale = (float)((double)p.num_train / (double)rows);   // N / |b|  (:83)
     const float f = (float)pow((double)(1 + t), -0.33);            // LambdaLR: np.float32((1 + it) ** -0.33)  (:101)
     const float lr_w = p.lr_w * f, lr_n = p.lr_n * f;
+    const bool want_loss = p.loss_out != nullptr && it == p.n_steps - 1;
+    const int bm = (p.B + FT_M - 1) / FT_M;                         // batch-row tiles
 
-    // ================= forward =================
-    for (int l = 0; l < L; ++l) {
+    // phases 0 .. L-1: forward of Linear ph; phases L .. 2L-1: backward + update of Linear 2L-1-ph
+#pragma unroll 1
+    for (int ph = 0; ph < 2 * L; ++ph) {
+      const bool fwd = ph < L;
+      const int l = fwd ? ph : 2 * L - 1 - ph;
       const SgLayer& Y = p.ly[l];
-      SgOperand A, Bo;
-      if (l == 0) { A.kind = OP_GATHER_X; A.X = p.X; A.perm = perm; A.D = p.D; A.B = p.B; A.rows_live = rows; A.p = nullptr; A.ld = 0; A.rows_valid = p.B; A.k_valid = Y.ld; }
-      else { A.kind = OP_DENSE; A.p = Y.h; A.ld = Y.ld; A.rows_valid = p.B; A.k_valid = Y.ld; }
-      Bo.kind = OP_DENSE; Bo.p = th + Y.off; Bo.ld = Y.ld; Bo.rows_valid = Y.out; Bo.k_valid = Y.ld;
-      const int tm = (p.B + FT_M - 1) / FT_M, tn = (Y.out + FT_N - 1) / FT_N;
-      const bool last = l == L - 1;
-      for (int job = blockIdx.x; job < tm * tn; job += gridDim.x) {
-        const int m0 = (job % tm) * FT_M, n0 = (job / tm) * FT_N;
-        run_tile<FT_M, FT_N>(A, Bo, m0, n0, Y.ld, sg_smem, [&](int b, int j0, float4 v) {
-          if (b >= p.B) return;
-          const float vv[4] = {v.x, v.y, v.z, v.w};
-          if (!last) {
-            const SgLayer& Nx = p.ly[l + 1];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int j = j0 + c;
-              if (j < Y.out) {
-                const float a = act_fwd(vv[c], p.act);
-                Nx.h[(long long)b * Nx.ld + j] = a;
-                Nx.hT[(long long)j * p.Bp + b] = a;
-              }
-            }
-          } else {
-            // head: residual, dU/d(out) and the per-output sum of squares (BNN_SGDMC.py:69-74, :83)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int o = j0 + c;
-              if (o < Y.out) {
-                float dzv = 0.0f;
-                if (b < rows) {
-                  const float r = vv[c] - __ldg(p.y + perm[b] * p.nout + o);
-                  dzv = scale * expf(th[p.n_head + o]) * r;
-                  atomicAdd(&p.acc[o], (double)r * (double)r);
-                }
-                Y.dz[(long long)b * Y.ldz + o] = dzv;
-                Y.dzT[(long long)o * p.Bp + b] = dzv;
-              }
-            }
-          }
-        });
-      }
-      if (!grid_barrier(p.bar, bar_target, p.err, &s_flag)) return;
-    }
-
-    // ================= backward + update =================
-    for (int l = L - 1; l >= 0; --l) {
-      const SgLayer& Y = p.ly[l];
-      const int wm = (Y.out + WT_M - 1) / WT_M, wn = (Y.ld + WT_N - 1) / WT_N;
-      const int n_dw = wm * wn;
-      const int hm = (p.B + FT_M - 1) / FT_M, hn = l > 0 ? (Y.in + FT_N - 1) / FT_N : 0;
-      const int n_dh = hm * hn;
-      const int n_jobs = n_dw + n_dh + (l == L - 1 ? 1 : 0);
+      const int wm = (Y.out + WT_M - 1) / WT_M;
+      const int n_dw = fwd ? 0 : wm * ((Y.ld + WT_N - 1) / WT_N);
+      const int n_ft = bm * (fwd ? (Y.out + FT_N - 1) / FT_N : (l > 0 ? (Y.in + FT_N - 1) / FT_N : 0));
+      const int n_jobs = n_dw + n_ft + ((!fwd && l == L - 1) ? 1 : 0);
+      long long* probe = (p.trace && it == p.n_steps - 1 && blockIdx.x == 1) ? p.trace + 1024 * 2 * BNN_MAX_LINEAR * 2 + ph * 8 : nullptr;
+      if (probe && tid == 0) probe[5] = clock64();
+#pragma unroll 1
       for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
         if (job < n_dw) {
-          // ---- dW_l tile + pSGLD update of that tile of theta / V
+          // ---- dW_l tile [64 x 32] over K = batch, then the pSGLD update of that tile of theta / V
           SgOperand A, Bo;
           A.kind = OP_DENSE; A.p = Y.dzT; A.ld = p.Bp; A.rows_valid = Y.out; A.k_valid = p.Bp;
-          if (l == 0) { Bo.kind = OP_GATHER_XT; Bo.X = p.X; Bo.perm = perm; Bo.D = p.D; Bo.B = p.B; Bo.rows_live = rows; Bo.p = nullptr; Bo.ld = 0; Bo.rows_valid = Y.ld; Bo.k_valid = p.Bp; }
-          else { Bo.kind = OP_DENSE; Bo.p = Y.hT; Bo.ld = p.Bp; Bo.rows_valid = Y.ld; Bo.k_valid = p.Bp; }
+          Bo.kind = l == 0 ? OP_GATHER_XT : OP_DENSE; Bo.p = Y.hT; Bo.ld = p.Bp; Bo.rows_valid = Y.ld; Bo.k_valid = p.Bp;
           const int m0 = (job % wm) * WT_M, n0 = (job / wm) * WT_N;
+          tile_core<WT_M, WT_N, kSgStagesW>(A, Bo, gq, m0, n0, p.Bp, sg_smem, s_bars, phase_bits, p.dbg, job == blockIdx.x ? probe : nullptr);
           double quad_local = 0.0;
-          run_tile<WT_M, WT_N>(A, Bo, m0, n0, p.Bp, sg_smem, [&](int j, int k0, float4 v) {
-            if (j >= Y.out || k0 >= Y.ld) return;
-            const long long e = Y.off + (long long)j * Y.ld + k0;          // multiple of 4: one Philox block per quad
-            const float4 t4 = *reinterpret_cast<const float4*>(th + e);
-            float tt[4] = {t4.x, t4.y, t4.z, t4.w};
-            float g[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int k = k0 + c;
-              if (k < Y.in) {                                                // weight entry: + d(-log prior)/dW = W / std^2  (:65-66)
-                g[c] = fmaf(Y.inv_var, tt[c], g[c]);
-                quad_local += (double)(Y.inv_var * tt[c]) * (double)tt[c];
-              } else if (k > Y.in) g[c] = 0.0f;                              // layout padding: no gradient, no noise, stays zero
-            }
-            if (debug) {
-              *reinterpret_cast<float4*>(p.grad_out + e) = make_float4(g[0], g[1], g[2], g[3]);
-              return;
-            }
-            const float4 v4 = *reinterpret_cast<const float4*>(p.V + e);
-            float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-            float z[4];
-            philox_normal4(p.seed, (uint32_t)t, STREAM_SGLD, (uint64_t)(e >> 2), z);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int k = k0 + c;
-              if (k <= Y.in) psgld_update1(tt[c], vv[c], g[c], z[c], lr_w, p.alpha, p.lam, p.precond_mode);
-              else tt[c] = 0.0f;
-            }
-            *reinterpret_cast<float4*>(th_next + e) = make_float4(tt[0], tt[1], tt[2], tt[3]);
-            *reinterpret_cast<float4*>(p.V + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-            if (l > 0) {
+          if (!(p.dbg & 4)) {
+#pragma unroll 1
+            for (int q = tid; q < WT_M * WT_N / 4; q += kSgThreads) {
+              const int j = m0 + (q * 4) / WT_N, k0 = n0 + (q * 4) % WT_N;
+              if (j >= Y.out || k0 >= Y.ld) continue;
+              const float4 v = *reinterpret_cast<const float4*>(sg_smem + q * 4);
+              const long long e = Y.off + (long long)j * Y.ld + k0;          // multiple of 4: one Philox block per quad
+              const float4 t4 = *reinterpret_cast<const float4*>(th + e);
+              float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+              float g[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const int k = k0 + c;
-                if (k < Y.in) thT_next[Y.offT + (long long)k * Y.ldT + j] = tt[c];
+                if (k < Y.in) {                                                // weight entry: + d(-log prior)/dW = W / std^2  (:65-66)
+                  g[c] = fmaf(Y.inv_var, tt[c], g[c]);
+                  quad_local += (double)(Y.inv_var * tt[c]) * (double)tt[c];
+                } else if (k > Y.in) g[c] = 0.0f;                              // layout padding: no gradient, no noise, stays zero
+              }
+              if (debug) {
+                *reinterpret_cast<float4*>(p.grad_out + e) = make_float4(g[0], g[1], g[2], g[3]);
+                continue;
+              }
+              const float4 v4 = *reinterpret_cast<const float4*>(p.V + e);
+              float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+              float z[4];
+              philox_normal4(p.seed, (uint32_t)t, STREAM_SGLD, (uint64_t)(e >> 2), z);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int k = k0 + c;
+                if (k <= Y.in) psgld_update1(tt[c], vv[c], g[c], z[c], lr_w, p.alpha, p.lam, p.precond_mode);
+                else tt[c] = 0.0f;
+              }
+              *reinterpret_cast<float4*>(th_next + e) = make_float4(tt[0], tt[1], tt[2], tt[3]);
+              *reinterpret_cast<float4*>(p.V + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+              if (l > 0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const int k = k0 + c;
+                  if (k < Y.in) thT_next[Y.offT + (long long)k * Y.ldT + j] = tt[c];
+                }
               }
             }
-          });
-          if (p.loss_out != nullptr && it == p.n_steps - 1) {
+          }
+          __syncthreads();                 // the result tile in shared memory is free for the next job's loads
+          if (want_loss) {
             // prior energy sum W^2 / std^2 of the step's INPUT parameters (the loss is evaluated before the update, :81-83)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) quad_local += __shfl_xor_sync(0xffffffffu, quad_local, o);
             if ((tid & 31) == 0 && quad_local != 0.0) atomicAdd(&p.acc[p.nout], quad_local);
           }
-        } else if (job < n_dw + n_dh) {
-          // ---- dh tile -> dz_{l-1} = dh * act'(h_l)
+        } else if (job < n_dw + n_ft) {
+          // ---- [32 x 16] tile over [batch, features]: forward of Linear l, or dh of Linear l (-> dz of Linear l - 1)
           const int jj = job - n_dw;
-          const SgLayer& Pv = p.ly[l - 1];
+          const int m0 = (jj % bm) * FT_M, n0 = (jj / bm) * FT_N;
           SgOperand A, Bo;
-          A.kind = OP_DENSE; A.p = Y.dz; A.ld = Y.ldz; A.rows_valid = p.B; A.k_valid = Y.ldz;
-          Bo.kind = OP_DENSE; Bo.p = thT + Y.offT; Bo.ld = Y.ldT; Bo.rows_valid = Y.in; Bo.k_valid = Y.ldT;
-          const int m0 = (jj % hm) * FT_M, n0 = (jj / hm) * FT_N;
-          run_tile<FT_M, FT_N>(A, Bo, m0, n0, Y.ldz, sg_smem, [&](int b, int k0, float4 v) {
-            if (b >= p.B) return;
+          A.kind = OP_DENSE; Bo.kind = OP_DENSE;
+          int K;
+          if (fwd) {
+            if (l == 0) A.kind = OP_GATHER_X;
+            A.p = Y.h; A.ld = Y.ld; A.rows_valid = p.B; A.k_valid = Y.ld;
+            Bo.p = th + Y.off; Bo.ld = Y.ld; Bo.rows_valid = Y.out; Bo.k_valid = Y.ld;
+            K = Y.ld;
+          } else {
+            A.p = Y.dz; A.ld = Y.ldz; A.rows_valid = p.B; A.k_valid = Y.ldz;
+            Bo.p = thT + Y.offT; Bo.ld = Y.ldT; Bo.rows_valid = Y.in; Bo.k_valid = Y.ldT;
+            K = Y.ldz;
+          }
+          tile_core<FT_M, FT_N, kSgStagesF>(A, Bo, gq, m0, n0, K, sg_smem, s_bars, phase_bits, p.dbg, job == blockIdx.x ? probe : nullptr);
+          if (!(p.dbg & 4) && tid < FT_M * FT_N / 4) {
+            const int b = m0 + (tid * 4) / FT_N, c0 = n0 + (tid * 4) % FT_N;
+            const float4 v = *reinterpret_cast<const float4*>(sg_smem + tid * 4);
             const float vv[4] = {v.x, v.y, v.z, v.w};
+            if (b < p.B) {
+              if (fwd && l < L - 1) {
+                // hidden layer: h_{l+1} = act(z), stored row-major and transposed
+                const SgLayer& Nx = p.ly[l + 1];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int k = k0 + c;
-              if (k < Y.in) {
-                const float hv = __ldcg(Y.h + (long long)b * Y.ld + k);
-                const float d = vv[c] * act_bwd(hv, p.act);
-                Pv.dz[(long long)b * Pv.ldz + k] = d;
-                Pv.dzT[(long long)k * p.Bp + b] = d;
+                for (int c = 0; c < 4; ++c) {
+                  const int j = c0 + c;
+                  if (j < Y.out) {
+                    const float a = act_fwd(vv[c], p.act);
+                    Nx.h[(long long)b * Nx.ld + j] = a;
+                    Nx.hT[(long long)j * p.Bp + b] = a;
+                  }
+                }
+              } else if (fwd) {
+                // head: residual, dU/d(out) and the per-output sum of squares (BNN_SGDMC.py:69-74, :83)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const int o = c0 + c;
+                  if (o < Y.out) {
+                    float dzv = 0.0f;
+                    if (b < rows) {
+                      const float r = vv[c] - __ldg(p.y + s_perm[b] * p.nout + o);
+                      dzv = scale * expf(th[p.n_head + o]) * r;
+                      atomicAdd(&p.acc[o], (double)r * (double)r);
+                    }
+                    Y.dz[(long long)b * Y.ldz + o] = dzv;
+                    Y.dzT[(long long)o * p.Bp + b] = dzv;
+                  }
+                }
+              } else {
+                // dz_{l-1} = dh * act'(h_l)
+                const SgLayer& Pv = p.ly[l - 1];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const int k = c0 + c;
+                  if (k < Y.in) {
+                    const float hv = __ldcg(Y.h + (long long)b * Y.ld + k);
+                    const float d = vv[c] * act_bwd(hv, p.act);
+                    Pv.dz[(long long)b * Pv.ldz + k] = d;
+                    Pv.dzT[(long long)k * p.Bp + b] = d;
+                  }
+                }
               }
             }
-          });
+          }
+          __syncthreads();                 // the result tile in shared memory is free for the next job's loads
         } else {
           // ---- log-precision group (BNN_SGDMC.py:62, :96-98): closed-form gradient, same update rule, lr_noise
           if (tid < ((p.n_theta - p.n_head) >> 2)) {
@@ -435,12 +505,15 @@ __global__ void __launch_bounds__(kSgThreads, 1) sgld_step_kernel(const __grid_c
           }
         }
       }
+      if (probe && tid == 0) probe[4] = clock64();
+      if (p.trace && it == p.n_steps - 1 && tid == 0) p.trace[((long long)blockIdx.x * 2 * L + ph) * 2] = clock64();
       if (!grid_barrier(p.bar, bar_target, p.err, &s_flag)) return;
+      if (p.trace && it == p.n_steps - 1 && tid == 0) p.trace[((long long)blockIdx.x * 2 * L + ph) * 2 + 1] = clock64();
     }
 
     // ================= end of step: loss of the last step, reset of the accumulators =================
     if (blockIdx.x == 0 && tid == 0) {
-      if (p.loss_out != nullptr && it == p.n_steps - 1) {
+      if (want_loss) {
         float total_ll = 0.0f, total_lp = 0.0f;
         for (int o = 0; o < p.nout; ++o) {
           const float lp = th[p.n_head + o], prec = expf(lp);
@@ -565,7 +638,8 @@ static int sg_plan(const BnnSgldChain* c, SgPlan* plan, bool bind) {
   p.al = c->alpha_n; p.be = c->beta_n; p.lgamma_al = lgammaf(c->alpha_n); p.log_be = logf(c->beta_n);
   p.precond_mode = c->precond_mode;
   p.seed = c->seed;
-  plan->smem = (size_t)kSgStages * (WT_M + WT_N) * kSgLds * 4;
+  plan->smem = (size_t)kSgStagesW * (WT_M + WT_N) * kSgLds * 4;
+  if ((size_t)kSgStagesF * (FT_M + FT_N) * kSgLds * 4 > plan->smem) plan->smem = (size_t)kSgStagesF * (FT_M + FT_N) * kSgLds * 4;
   int grid = sm_count();
   if (max_jobs < grid) grid = max_jobs;
   plan->grid = grid;
@@ -636,6 +710,9 @@ extern "C" int32_t bnn_sgld_init(const BnnSgldChain* c, int32_t cur, void* strea
   return 0;
 }
 
+static long long* g_sg_trace = nullptr;   // debug: set by bnn_sgld_trace
+static int g_sg_trace_grid = 0, g_sg_trace_L = 0;
+
 extern "C" int32_t bnn_sgld_run(const BnnSgldChain* c, int32_t cur, int64_t t0, int64_t perm_off, int32_t n_steps, float* loss_out,
                                 float* grad_out, void* stream) {
   if (!c || (cur != 0 && cur != 1) || n_steps < 1 || t0 < 0 || perm_off < 0) BNN_FAIL("bnn_sgld_run: bad arguments");
@@ -659,6 +736,9 @@ extern "C" int32_t bnn_sgld_run(const BnnSgldChain* c, int32_t cur, int64_t t0, 
   if (per_sm < 1) BNN_FAIL("bnn_sgld_run: the step kernel does not fit on an SM");
   int grid = plan.grid;
   if (grid > per_sm * sm_count()) grid = per_sm * sm_count();
+  p.trace = g_sg_trace;
+  if (const char* e = getenv("BNN_SGLD_DBG")) p.dbg = atoi(e);
+  g_sg_trace_grid = grid; g_sg_trace_L = p.L;
   void* args[] = {(void*)&p};
   BNN_CUDA(cudaLaunchCooperativeKernel((void*)sgld_step_kernel, dim3((unsigned)grid), dim3(kSgThreads), args, plan.smem, st));
   return 0;
@@ -671,6 +751,26 @@ extern "C" int32_t bnn_sgld_perm(uint64_t seed, uint32_t epoch, int64_t N, int64
   const int hb = (bits + 1) / 2;
   sgld_perm_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, epoch, N, offset, count, hb, (long long*)out);
   BNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// debug: enable = 1 allocates the per-CTA phase timeline written by the following bnn_sgld_run launches (last step of each
+// launch); with host_out != NULL copies it out: [grid][2 L][2] clock64 values (work done, barrier passed); returns grid in *grid_out
+extern "C" int32_t bnn_sgld_trace(int32_t enable, long long* host_out, int32_t* grid_out, int32_t* phases_out) {
+  if (enable && !g_sg_trace) {
+    BNN_CUDA(cudaMalloc(&g_sg_trace, (size_t)(1024 * 2 * BNN_MAX_LINEAR * 2 + 256) * sizeof(long long)));
+    BNN_CUDA(cudaMemset(g_sg_trace, 0, (size_t)(1024 * 2 * BNN_MAX_LINEAR * 2 + 256) * sizeof(long long)));
+  }
+  if (host_out && g_sg_trace) {
+    BNN_CUDA(cudaDeviceSynchronize());
+    BNN_CUDA(cudaMemcpy(host_out, g_sg_trace, (size_t)g_sg_trace_grid * 2 * g_sg_trace_L * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+    // fine-grained probes of CTA 1 (first job of each phase): appended behind the coarse timeline
+    BNN_CUDA(cudaMemcpy(host_out + (size_t)g_sg_trace_grid * 2 * g_sg_trace_L * 2, g_sg_trace + 1024 * 2 * BNN_MAX_LINEAR * 2,
+                        (size_t)2 * g_sg_trace_L * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  if (grid_out) *grid_out = g_sg_trace_grid;
+  if (phases_out) *phases_out = 2 * g_sg_trace_L;
+  if (!enable && g_sg_trace) { cudaFree(g_sg_trace); g_sg_trace = nullptr; }
   return 0;
 }
 
