@@ -1,16 +1,17 @@
 #!/usr/bin/env python
 """Headline benchmark: posterior-predictive sample.point MLP evals/s (BASELINE.json metric).
 
-Workload (BASELINE.json configs[3], "synthetic predictive sweep"): N = 1M points, 2x200 ReLU
-MLP (D = 16), SGLD samples sharded over the GPUs -- 1250 samples per GPU, so 8 GPUs are the
-full S = 10k config and every N runs the same per-GPU shard (weak scaling).  One "step" is one
-predict_mv over the whole shard: fused forward + Welford reduction (+ the NCCL all-gather and
-Chan merge of the per-point moments when N > 1).
+Workload (BASELINE.json configs[3], "synthetic predictive sweep"): N = 1M points x S = 10k SGLD samples, 2x200 ReLU MLP
+(D = 16).  The S = 10k samples are sharded over the GPUs (STRONG scaling: 1 GPU evaluates all 10k, 8 GPUs 1250 each); one
+"step" is one predict_mv over the whole job: operand-image prep + fused forward + Welford reduction on every rank, then --
+for more than one GPU -- the NCCL all-gather of the per-point float64 (mean, M2) and the Chan merge.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]           # our CUDA path
     python bench.py --impl reference ...                          # the reference's CPU torch loop
 
-Prints ONE JSON line (see the field notes in DESIGN.md "Measurement").
+Prints ONE JSON line (field notes: DESIGN.md "Measurement").  Secondary blocks on the same line: `configs` (cfg 1, 2, 3 and
+cfg 5's predictive pass through the drop-in classes, 1 GPU only), `sgld` (cfg 5: fused SGLD steps/s, one chain per GPU),
+`spot_check` (the timed result against the CPU oracle on a sample of points, outside the timed region).
 """
 import argparse
 import json
@@ -26,15 +27,23 @@ sys.path.insert(0, ROOT)
 DIMS = [16, 200, 200, 1]
 ACT = "relu"
 N_POINTS = 1_000_000
-S_PER_GPU = 1250
+S_TOTAL = 10_000
 METRIC = "posterior-predictive sample.point MLP evals/sec"
 UNIT = "evals/s"
 FLOP_PER_EVAL = 2 * sum(i * o for i, o in zip(DIMS[:-1], DIMS[1:]))   # 86,800
+SGLD_DIMS, SGLD_BATCH, SGLD_ROWS, SGLD_KEEP = [90, 512, 512, 512, 1], 128, 10_000_000, 50     # BASELINE.json configs[4]
+SGLD_FLOP_PER_STEP = 3 * SGLD_BATCH * 2 * sum(i * o for i, o in zip(SGLD_DIMS[:-1], SGLD_DIMS[1:]))   # ~438 MFLOP (fwd + bwd)
 
 
 def workload_name(n_gpus):
-    return (f"cfg4 synthetic predictive sweep: N={N_POINTS} points x S={S_PER_GPU * n_gpus} SGLD samples "
-            f"({S_PER_GPU}/GPU; 8 GPUs = the S=10k config), {DIMS[0]}-{DIMS[1]}-{DIMS[2]}-{DIMS[3]} {ACT} MLP")
+    return (f"cfg4 synthetic predictive sweep: N={N_POINTS} points x S={S_TOTAL} SGLD samples, "
+            f"{DIMS[0]}-{DIMS[1]}-{DIMS[2]}-{DIMS[3]} {ACT} MLP, samples sharded over {n_gpus} GPU(s)")
+
+
+def shard_range(S, rank, world):
+    base, extra = divmod(int(S), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
 
 
 # --------------------------------------------------------------------------------------
@@ -84,7 +93,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.gpus), "sample_per_step": f"S={S} x N={N} of the workload"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
@@ -144,6 +153,25 @@ class ClockSampler:
         return out
 
 
+def ncu_record(key):
+    """dram bytes / tensor-pipe activity of the dominant kernel from the committed ncu capture of THIS configuration
+    (profiles/r02_ncu_records.json, written by tools/ncu_records.py from the .ncu-rep of a bench run); None when the
+    configuration was never captured."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_records.json"))).get(key)
+    except Exception:
+        return None
+
+
+def make_bank(arch, rank_of_shard, lo, hi, dev):
+    """Shard [lo, hi) of the synthetic chain: xavier base + 0.05 N(0,1), one generator per shard."""
+    import torch
+    base = arch.pack(cpu_nets(1, 0)[:1])[0].to(dev)
+    gw = torch.Generator(device=dev).manual_seed(100 + rank_of_shard)
+    bank = (base[None, :] + 0.05 * torch.randn(hi - lo, arch.stride, generator=gw, device=dev)) * arch.valid_mask().to(dev)
+    return bank.contiguous()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -158,20 +186,32 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+
+    # ---- CPU legs: 1-GPU runs only, and before anything else is resident (at N > 1 the other ranks would otherwise spin
+    #      inside NCCL while rank 0 times the host loop)
+    cpu_base, sgld_cpu = None, None
+    cores = os.cpu_count() or 1
+    if world == 1:
+        cpu_val, cpu_t = time_cpu_sample(16, 250_000)
+        cpu_base = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"S=16 samples x N=250000 points of the same workload, torch CPU loop, {cores} threads, {cpu_t:.1f} s"}
+        if not args.no_sgld:
+            try:
+                sgld_cpu = sgld_cpu_baseline()
+            except Exception as e:
+                sgld_cpu = {"error": repr(e)[:200]}
+
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
     arch = Arch(DIMS, ACT)
-    S = S_PER_GPU
-    # synthetic inputs: X ~ N(0,1); nets = xavier base + 0.05 N(0,1), one chain shard per rank
+    lo, hi = shard_range(S_TOTAL, rank, world)
+    S = hi - lo
     g = torch.Generator(device=dev).manual_seed(1234 + 4)
-    X = torch.randn(N_POINTS, DIMS[0], generator=g, device=dev)
-    base = arch.pack(cpu_nets(1, 0)[:1])[0].to(dev)
-    gw = torch.Generator(device=dev).manual_seed(100 + rank)
-    bank = (base[None, :] + 0.05 * torch.randn(S, arch.stride, generator=gw, device=dev)) * arch.valid_mask().to(dev)
-    bank = bank.contiguous()
+    X = torch.randn(N_POINTS, DIMS[0], generator=g, device=dev)      # X ~ N(0,1), replicated
+    bank = make_bank(arch, rank, lo, hi, dev)
     X_host = X.cpu().pin_memory()
     bank_host = bank.cpu().pin_memory()
 
@@ -182,10 +222,17 @@ def run_ours(args):
             return merge_shards(out["part_mean"], out["part_m2"], S)
         return out["mean"], out["var"]
 
+    host_out = {}
+
     def step_e2e():
-        # host-resident inputs: X once, the bank in 5 chunks uploaded behind the evaluation of the previous chunk
-        out = ops.forward_streamed(arch, X_host, bank_host, chunk=250, precision=args.precision, want_partials=(world > 1))
-        mean, var = merge_shards(out["part_mean"], out["part_m2"], S) if world > 1 else (out["mean"], out["var"])
+        # the C ABI's host-buffer entry point: H2D of X and of the bank (in chunks behind the evaluation), launches, D2H
+        nonlocal host_out
+        if world == 1:
+            host_out = ops.forward_host(arch, X_host, bank_host, want_moments=True, precision=args.precision, out=host_out)
+            return host_out["mean"], host_out["var"]
+        host_out = ops.forward_host(arch, X_host, bank_host, want_moments=False, want_partials=True, precision=args.precision,
+                                    out=host_out)
+        mean, var = merge_shards(host_out["part_mean"].to(dev, non_blocking=True), host_out["part_m2"].to(dev, non_blocking=True), S)
         return mean.cpu(), var.cpu()
 
     def barrier():
@@ -198,23 +245,36 @@ def run_ours(args):
             fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             r = fn()
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = max(e0.elapsed_time(e1), 0.0)
+        wall_ms = (time.perf_counter() - t0) * 1e3
         if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            t = torch.tensor([ms, wall_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms, r
+            ms, wall_ms = float(t[0]), float(t[1])
+        return ms, wall_ms, r
 
+    warm = max(args.warmup, 3)
     clocks = ClockSampler(local) if rank == 0 else None
-    ms, (mean, var) = timed(step_device, args.steps, max(args.warmup, 3))
+    ms, _, (mean, var) = timed(step_device, args.steps, warm)
     clk = clocks.stop() if clocks else None
     e2e_steps = max(1, min(args.steps, 3))
-    ms_e2e, _ = timed(step_e2e, e2e_steps, 1)
+    # the host path synchronises inside the library (its own stream): its time is wall time around the calls
+    _, wall_e2e, (mean_h, var_h) = timed(step_e2e, e2e_steps, 1)
+    e2e_match = float((mean_h.to(dev).reshape(-1) - mean.reshape(-1)).abs().max())
+
+    # ---- spot check against the CPU oracle (outside the timed region): all S_TOTAL samples on a sample of points
+    spot = None
+    if rank == 0 and not args.no_check:
+        try:
+            spot = spot_check(arch, mean, var, X, dev, world)
+        except Exception as e:
+            spot = {"error": repr(e)[:200]}
 
     sgld = None
     if not args.no_sgld:
@@ -227,12 +287,21 @@ def run_ours(args):
             else:
                 sgld["steps_per_s_all_chains"] = sgld["steps_per_s_per_chain"]
             sgld["chains"] = world
+            if sgld_cpu is not None:
+                sgld["cpu"] = sgld_cpu
         except Exception as e:      # the secondary metric must never take the headline down
-            sgld = {"error": repr(e)[:200]}
+            sgld = {"error": repr(e)[:300]}
 
-    evals_per_step = float(S) * n_gpus * N_POINTS
+    configs = None
+    if world == 1 and not args.no_configs:
+        try:
+            configs = config_blocks(dev)
+        except Exception as e:
+            configs = {"error": repr(e)[:300]}
+
+    evals_per_step = float(S_TOTAL) * N_POINTS
     value = evals_per_step * args.steps / (ms * 1e-3)
-    e2e_value = evals_per_step * e2e_steps / (ms_e2e * 1e-3)
+    e2e_value = evals_per_step * e2e_steps / (wall_e2e * 1e-3)
     finite = bool(torch.isfinite(mean).all() and torch.isfinite(var).all())
 
     if rank == 0:
@@ -241,33 +310,29 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        bf16_peak, peak_src = (peaks.get("bf16_tflops_sustained"), "measured (MEASURED_PEAKS.json, sustained)") \
+        bf16_peak, peak_src = (peaks.get("bf16_tflops_sustained"), "measured (MEASURED_PEAKS.json, sustained: the kernel runs for seconds)") \
             if peaks.get("bf16_tflops_sustained") else (1400.0, "fallback (B200_PROFILING.md sustained)")
         fp32_peak = float(_lib.lib().bnn_measure_fp32_tflops())
         per_gpu_tflops = FLOP_PER_EVAL * float(S) * N_POINTS * args.steps / (ms * 1e-3) / 1e12
-        cpu_val, cpu_t = time_cpu_sample(16, 250_000)
-        cores = os.cpu_count() or 1
-        tc = args.precision in ("tf32_bf16", "tf32x3", "tf32")
-        # tensor work issued per algorithmic MAC, in bf16-equivalent passes: a TF32 MMA pass runs at half the bf16 rate
-        # (2 units), a BF16 pass at the full rate (1 unit)
-        units = {"tf32_bf16": 2 + 1 + 1, "tf32x3": 3 * 2, "tf32": 2}.get(args.precision, 0)
+        tc = args.precision in ("tf32_bf16", "tf32x3", "tf32", "bf16")
+        units = {"tf32_bf16": 2 + 1 + 1, "tf32x3": 3 * 2, "tf32": 2, "bf16": 1}.get(args.precision, 0)
         scheme = {"tf32_bf16": "one TF32 pass + two BF16 correction passes", "tf32x3": "three TF32 passes",
-                  "tf32": "one TF32 pass"}.get(args.precision, "")
+                  "tf32": "one TF32 pass", "bf16": "one BF16 pass"}.get(args.precision, "")
+        rec = ncu_record(f"fwd_tc_kernel|S={S}|N={N_POINTS}|{args.precision}") if tc else None
+        alg_bytes = 4.0 * (S * arch.n_params + N_POINTS * DIMS[0] + 2 * N_POINTS * DIMS[-1])
         if tc:
             roof = {"bound": "tensor", "achieved": per_gpu_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
                     "frac": per_gpu_tflops / bf16_peak,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this very launch (S=1250 x N=1M) from the committed
-                    # ncu --set full capture (profiles/r01_fwd_tc_ncu_full_summary.txt); algorithmic bytes are 0.297 GB -- the
-                    # sample-outer loop re-reads X and the float64 per-point state per sample out of L2 (8 % miss to DRAM,
-                    # 27 GB/s = 0.3 % of the HBM peak; the kernel is tensor bound)
-                    "traffic": 9.888e9 if args.precision == "tf32_bf16" else None, "traffic_unit": "bytes/launch",
-                    "kernel": "fwd_tc_kernel<2,relu> (tcgen05 kind::tf32 + kind::f16, cta_group::2, A operand of layer 2 in TMEM)",
-                    "flop_per_eval": FLOP_PER_EVAL,
-                    "peak_source": peak_src + "; dense bf16",
+                    "traffic": rec.get("dram_bytes") if rec else None, "traffic_unit": "bytes/launch",
+                    "traffic_source": ("ncu --set full capture of this configuration: " + rec.get("source", "")) if rec
+                    else "no ncu capture of this configuration committed",
+                    "algorithmic_bytes": alg_bytes,
+                    "kernel": "fwd_tc_kernel (tcgen05 kind::tf32 + kind::f16, cta_group::2, A operand of layer 2 in TMEM)",
+                    "flop_per_eval": FLOP_PER_EVAL, "peak_source": peak_src + "; dense bf16",
                     "note": f"achieved = ALGORITHMIC flop/s (2*sum in*out per eval).  {args.precision} issues {scheme} per algorithmic "
-                            f"MAC = {units} bf16-equivalent units, so frac is capped at {1.0 / units:.3f}; tensor_pipe_frac below is "
-                            "the share of the bf16 peak the issued MMAs occupy",
-                    "tensor_pipe_frac": units * per_gpu_tflops / bf16_peak}
+                            f"MAC = {units} bf16-equivalent units, so frac is capped at {1.0 / units:.3f}",
+                    "issued_bf16_equiv_frac": units * per_gpu_tflops / bf16_peak,
+                    "tensor_pipe_active_pct_ncu": rec.get("tensor_pipe_active_pct") if rec else None}
         else:
             roof = {"bound": "fp32", "achieved": per_gpu_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": per_gpu_tflops / fp32_peak if fp32_peak > 0 else None, "traffic": None,
@@ -276,95 +341,216 @@ def run_ours(args):
                                    "MEASURED_PEAKS.json has no FP32-SIMT figure",
                     "frac_of_bf16_tensor_peak": per_gpu_tflops / bf16_peak, "bf16_peak": bf16_peak}
         launches_per_step = (3 if tc else 2) + (1 if world > 1 else 0)
+        h2d = int((bank.numel() + X.numel()) * 4) + (int(2 * N_POINTS * 8) if world > 1 else 0)
+        d2h = int(2 * N_POINTS * DIMS[-1] * 4) + (int(2 * N_POINTS * 8) if world > 1 else 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"tf32_bf16": "tf32+bf16 (TF32 main term + two BF16 correction terms, FP32 accumulate; parity 1e-5)",
-                                           "tf32x3": "tf32x3 (3-pass error-compensated TF32, FP32 accumulate; parity 1e-5)",
-                                           "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
-            "config": {"workload": workload_name(n_gpus), "precision": args.precision,
+            "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": {"tf32_bf16": "tf32+bf16 (TF32 main term + two BF16 correction terms, FP32 accumulate; parity 1e-5)",
+                      "tf32x3": "tf32x3 (3-pass error-compensated TF32, FP32 accumulate; parity 1e-5)",
+                      "tf32": "tf32 (single pass, bound 5e-3)", "bf16": "bf16 (single pass, bound 2e-2)",
+                      "fp32": "f32"}[args.precision], "data": "synthetic",
+            "config": {"workload": workload_name(n_gpus), "precision": args.precision, "samples_per_gpu": S,
                        "l2": f"inputs {(bank.numel() + X.numel()) * 4 / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)",
-                       "parallelism": f"samples sharded x{n_gpus}, all-gather of float64 (mean, M2) + Chan merge"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((bank.numel() + X.numel()) * 4),
-                    "d2h_bytes_per_step": int(2 * N_POINTS * DIMS[-1] * 4), "ms_per_step": ms_e2e / e2e_steps,
-                    "steps": e2e_steps, "api": "bnn_b200.ops.forward_streamed on pinned host tensors (H2D of X + bank in 5 chunks overlapped with the evaluation, D2H of mean/var, per step)"},
+                       "parallelism": f"samples sharded x{n_gpus}" + (", all-gather of float64 (mean, M2) + Chan merge" if n_gpus > 1 else "")},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": wall_e2e / e2e_steps, "steps": e2e_steps,
+                    "api": "bnn_forward_host (C ABI, host pointers: H2D of X and of the bank in chunks overlapped with the "
+                           "evaluation, D2H of the result, per step)" + ("; shard moments re-uploaded for the NCCL merge" if world > 1 else ""),
+                    "max_abs_diff_vs_device_resident_mean": e2e_match},
             "gpu_launches": args.steps * launches_per_step,
             "roofline": roof,
             "fp32_ffma_peak_tflops": fp32_peak,
-            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"S=16 samples x N=250000 points of the same workload, torch CPU loop, "
-                                       f"{cores} threads, {cpu_t:.1f} s"},
-            "clocks": clk, "outputs_finite": finite, "sgld": sgld,
+            "cpu_baseline": cpu_base if cpu_base is not None else {"value": None, "unit": UNIT, "cores": cores, "kind": "port",
+                                                                   "sample": "not timed at N > 1 (rank 0 at N = 1 only)"},
+            "clocks": clk, "outputs_finite": finite, "spot_check": spot, "sgld": sgld, "configs": configs,
         }
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-SGLD_DIMS, SGLD_BATCH, SGLD_ROWS = [90, 512, 512, 512, 1], 128, 10_000_000     # BASELINE.json configs[4]
+def spot_check(arch, mean, var, X, dev, world, n_pts=256):
+    """The timed result against the CPU oracle (the reference's loop) on n_pts points x all S_TOTAL samples."""
+    import torch
+    from oracle import bnn_oracle as O
+    O.warmup()
+    torch.set_num_threads(os.cpu_count() or 1)
+    idx = torch.linspace(0, N_POINTS - 1, n_pts).long()
+    Xs = X[idx.to(dev)].cpu()
+    preds = []
+    t0 = time.perf_counter()
+    for r in range(world):
+        lo, hi = shard_range(S_TOTAL, r, world)
+        b = make_bank(arch, r, lo, hi, dev).cpu()
+        nets = [arch.unpack(b[s]) for s in range(b.shape[0])]
+        with torch.no_grad():
+            preds.append(O.sample_predict(nets, Xs, ACT, nout=1))
+    pred = torch.cat(preds)
+    m_ref, v_ref = O.predict_mv(pred, n_pts)
+    m, v = mean[idx.to(dev)].cpu().double(), var[idx.to(dev)].cpu().double()
+    return {"points": n_pts, "samples": int(pred.shape[0]),
+            "mean_max_norm_err": float((m - m_ref.double()).abs().max() / m_ref.abs().max()),
+            "var_max_norm_err": float((v - v_ref.double()).abs().max() / v_ref.abs().max()),
+            "tolerance": 1e-5, "oracle_s": time.perf_counter() - t0}
 
 
-def sgld_bench(dev, rank, steps, cpu=True):
-    """Secondary metric: SGLD steps/s of one pSGLD chain per GPU (cfg 5: synthetic 10M x 90 regression, 3x512 tanh MLP,
-    batch 128).  A step = minibatch gather + forward + backward (torch autograd captured in a CUDA graph: the stop-gap
-    SURVEY.md 8f ranks next) + the fused pSGLD update kernel + LR schedule."""
+# --------------------------------------------------------------------------------------
+def gpu_ms(fn, reps=20, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def config_blocks(dev):
+    """BASELINE.json configs 1, 2, 3 and cfg 5's predictive pass through the DROP-IN classes (sample + predict_mv, device
+    tensors in and out), each with its own roofline entry.  cfg 1-3 are 7 MFLOP .. 100 GFLOP problems: their time is launch
+    latency, which the fractions show."""
     import torch
     import torch.nn as nn
+    from bnn_b200 import _lib, ops
+    from bnn_b200.BNN_SGDMC import BNN_SGDMC
+    from bnn_b200.BNN_BBB import BNN_BBB
+    from bnn_b200.BNN_Dropout import BNN_Dropout
+    from bnn_b200.BNN_CDropout import BNN_CDropout
+    from bnn_b200.bank import SampleBank
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = peaks.get("bf16_tflops", 1590.0)
+    fp32 = float(_lib.lib().bnn_measure_fp32_tflops())
+    out = {}
+
+    def block(name, model, evals, fn, sampling):
+        arch = model.arch
+        ms = gpu_ms(fn)
+        tc = ops.tc_supported(arch, masked=sampling in ("dropout masks", "concrete-dropout masks")) and model.precision in ("auto", "tf32_bf16")
+        tf = arch.flops_per_eval * evals / (ms * 1e-3) / 1e12
+        peak = bf16 if tc else fp32
+        out[name] = {"evals": evals, "ms": ms, "evals_per_s": evals / (ms * 1e-3), "includes": sampling + " + forward + moments",
+                     "roofline": {"bound": "tensor" if tc else "fp32", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                                  "kernel": "fwd_tc_kernel" if tc else "fwd_simt_kernel", "flop_per_eval": arch.flops_per_eval}}
+
+    torch.manual_seed(0)
+    m = BNN_SGDMC(13, nn.ReLU(), [50], nout=1, conf={"device": str(dev)})
+    base = m.arch.pack([m.nn.nn])[0]
+    m.nns = SampleBank(m.arch, ((base[None] + 0.05 * torch.randn(100, m.arch.stride)) * m.arch.valid_mask()).to(dev))
+    X = torch.randn(51, 13, device=dev)
+    block("cfg1 SGDMC 13-50-1 relu, S=100, N=51", m, 100 * 51, lambda: m.predict_mv(X, m.nns), "bank")
+    m2 = BNN_BBB(1, nn.Tanh(), [50, 50], conf={"device": str(dev)})
+    X2 = torch.linspace(-3, 3, 1000, device=dev).view(-1, 1)
+    block("cfg2 BBB 1-50-50-1 tanh, S=1000 draws, N=1000", m2, 1000 * 1000, lambda: m2.predict_mv(X2, m2.sample(1000)), "1000 reparameterised draws")
+    X3 = torch.randn(4573, 9, device=dev)
+    m3 = BNN_Dropout(9, nn.Tanh(), [100, 100], conf={"device": str(dev)})
+    block("cfg3 Dropout 9-100-100-1 tanh, S=1000 masks, N=4573", m3, 1000 * 4573, lambda: m3.predict_mv(X3, m3.sample(1000)), "dropout masks")
+    m4 = BNN_CDropout(9, nn.Tanh(), [100, 100], conf={"device": str(dev)})
+    block("cfg3 CDropout 9-100-100-1 tanh, S=1000 masks, N=4573", m4, 1000 * 4573, lambda: m4.predict_mv(X3, m4.sample(1000)), "concrete-dropout masks")
+    m5 = BNN_SGDMC(90, nn.Tanh(), [512, 512, 512], nout=1, conf={"device": str(dev)})
+    base = m5.arch.pack([m5.nn.nn])[0]
+    m5.nns = SampleBank(m5.arch, ((base[None] + 0.02 * torch.randn(50, m5.arch.stride)) * m5.arch.valid_mask()).to(dev))
+    X5 = torch.randn(100_000, 90, device=dev)
+    block("cfg5 predictive 90-512-512-512-1 tanh, S=50, N=100k", m5, 50 * 100_000, lambda: m5.predict_mv(X5, m5.nns), "bank")
+    return out
+
+
+def sgld_cpu_baseline():
+    """The reference's sgld_steps body on the host cores: oracle energy (BNN_SGDMC.py:61-74,83) + torch autograd + the oracle's
+    pSGLD restatement as the optimizer (pybnn is absent); cfg 5 shape, batch 128."""
+    import torch
+    from oracle import bnn_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(7)
+    Xc, yc = torch.randn(100_000, SGLD_DIMS[0], generator=g), torch.randn(100_000, 1, generator=g)
+    params = []
+    for i, o in zip(SGLD_DIMS[:-1], SGLD_DIMS[1:]):
+        params += [torch.randn(o, i, generator=g) * (2.0 / (i + o)) ** 0.5, torch.zeros(o)]
+    params.append(torch.zeros(1))
+    Vs = [torch.ones_like(t) for t in params]
+
+    def cpu_step(t):
+        idx = torch.randint(0, Xc.shape[0], (SGLD_BATCH,))
+        ps = [q.clone().requires_grad_(True) for q in params]
+        nn_ = [(ps[2 * l], ps[2 * l + 1]) for l in range(len(SGLD_DIMS) - 1)]
+        U = O.sgdmc_neg_log_post(nn_, ps[-1], Xc[idx], yc[idx], "tanh", SGLD_ROWS, 1e-2, 1e-1)
+        gs = torch.autograd.grad(U, ps)
+        f = float(O.lr_factor(t))
+        for k, (q, gq) in enumerate(zip(params, gs)):
+            params[k], Vs[k] = O.psgld_step(q, gq, Vs[k], (1e-1 if k == len(params) - 1 else 2e-2) * f, torch.randn_like(q))
+
+    for t in range(5):
+        cpu_step(t)
+    t0 = time.perf_counter()
+    n_cpu = 100
+    for t in range(n_cpu):
+        cpu_step(5 + t)
+    return {"steps_per_s": n_cpu / (time.perf_counter() - t0), "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{n_cpu} steps, batch {SGLD_BATCH}, torch CPU autograd + oracle pSGLD"}
+
+
+def sgld_bench(dev, rank, steps):
+    """Secondary metric: SGLD steps/s of one pSGLD chain per GPU (cfg 5: synthetic 10M x 90 regression, 3x512 tanh MLP,
+    batch 128).  A step = minibatch gather + forward + backward + pSGLD update + LR schedule, all inside the persistent fused
+    step kernel (bnn_sgld_run; no library GEMM); the chain runs in launches of keep_every = 50 steps, each followed by the
+    thinning snapshot (one bank row copy) and preceded by the epoch-permutation kernel, as BNN_SGDMC.train does."""
+    import torch
+    import torch.nn as nn
+    from bnn_b200 import ops
     from bnn_b200.BNN_SGDMC import BNN_SGDMC
     g = torch.Generator(device=dev).manual_seed(7)
     X = torch.randn(SGLD_ROWS, SGLD_DIMS[0], generator=g, device=dev)
     teacher = BNN_SGDMC(SGLD_DIMS[0], nn.Tanh(), SGLD_DIMS[1:-1], nout=1, conf={"device": str(dev), "seed": 7})
     with torch.no_grad():
         bank = teacher.arch.pack([teacher.nn.nn]).to(dev)
-        from bnn_b200 import ops
-        y = ops.forward(teacher.arch, X[:1_000_000].contiguous(), bank, want_pred=True, want_moments=False)["pred"].reshape(-1)
+        y = ops.forward(teacher.arch, X[:1_000_000].contiguous(), bank, want_pred=True, want_moments=False, precision="fp32")["pred"].reshape(-1)
         reps = SGLD_ROWS // y.shape[0]
         y = y.repeat(reps) + 0.1 * torch.randn(SGLD_ROWS, generator=g, device=dev)   # teacher on a 1M slice, tiled (synthetic)
     model = BNN_SGDMC(SGLD_DIMS[0], nn.Tanh(), SGLD_DIMS[1:-1], nout=1,
-                      conf={"device": str(dev), "seed": 100 + rank, "batch_size": SGLD_BATCH})
-    model._chain_init(dev)
-    model._perm, model._perm_pos = None, 0
-    gen = torch.Generator(device=dev).manual_seed(100 + rank)
-    yv = y.view(-1, 1)
-    model.sgld_steps(50, X, yv, gen)                    # warm-up (builds the graph)
+                      conf={"device": str(dev), "seed": 100 + rank, "batch_size": SGLD_BATCH, "keep_every": SGLD_KEEP})
+    yv = y.view(-1, 1).contiguous()
+    model._chain = model._new_chain(dev)
+    model._chain.bind(X, yv)
+    model._epoch = 0
+    a = model.arch
+    n_keep = max(1, steps // SGLD_KEEP)
+    snap = torch.empty(n_keep, a.stride, device=dev)
+
+    def run(n_intervals):
+        for k in range(n_intervals):
+            model.sgld_steps(SGLD_KEEP, SGLD_ROWS)
+            snap[k % n_keep].copy_(model._chain.state[: a.stride])       # thinning snapshot (BNN_SGDMC.py:124)
+
+    run(2)                                                               # warm-up
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    model.sgld_steps(steps, X, yv, gen)
+    run(n_keep)
     e1.record()
     torch.cuda.synchronize()
-    sps = steps / (e0.elapsed_time(e1) * 1e-3)
-    out = {"steps_per_s_per_chain": sps, "steps": steps, "batch": SGLD_BATCH, "params": model.arch.n_params + 1,
+    model._chain.check()
+    n_steps = n_keep * SGLD_KEEP
+    sps = n_steps / (e0.elapsed_time(e1) * 1e-3)
+    loss = float(model._chain.loss)
+    out = {"steps_per_s_per_chain": sps, "us_per_step": 1e6 / sps, "steps": n_steps, "batch": SGLD_BATCH, "params": a.n_params + 1,
            "workload": f"cfg5: one pSGLD chain per GPU, synthetic {SGLD_ROWS}x{SGLD_DIMS[0]} regression, "
-                       f"{'-'.join(map(str, SGLD_DIMS))} tanh MLP, batch {SGLD_BATCH}",
-           "gradient": "hand-derived on the packed vector: bnn_sgld_gather + 10 cuBLAS SGEMMs + 6 activation kernels + bnn_sgld_prior + bnn_sgld_head, whole step = one CUDA-graph replay of 21 launches", "update": "bnn_psgld_step (fused, Philox in-kernel)",
-           "update_bytes_per_step": 20 * (model.arch.stride + 1)}
-    if cpu and rank == 0:
-        # CPU: the reference's sgld_steps body with the oracle's pSGLD restatement as the optimizer (pybnn is absent)
-        from oracle import bnn_oracle as O
-        torch.set_num_threads(os.cpu_count() or 1)
-        Xc, yc = X[:100_000].cpu(), yv[:100_000].cpu()
-        net = [(W.clone(), b.clone()) for W, b in teacher.arch.unpack(bank[0].cpu())]
-        params = [t for pair in net for t in pair] + [torch.zeros(1)]
-        Vs = [torch.ones_like(t) for t in params]
-        def cpu_step(t):
-            idx = torch.randint(0, Xc.shape[0], (SGLD_BATCH,))
-            ps = [q.clone().requires_grad_(True) for q in params]
-            nn_ = [(ps[0], ps[1]), (ps[2], ps[3]), (ps[4], ps[5]), (ps[6], ps[7])]
-            U = O.sgdmc_neg_log_post(nn_, ps[8], Xc[idx], yc[idx], "tanh", SGLD_ROWS, 1e-2, 1e-1)
-            gs = torch.autograd.grad(U, ps)
-            f = float(O.lr_factor(t))
-            for k, (q, gq) in enumerate(zip(params, gs)):
-                params[k], Vs[k] = O.psgld_step(q, gq, Vs[k], (1e-1 if k == 8 else 2e-2) * f, torch.randn_like(q))
-        for t in range(5):
-            cpu_step(t)
-        t0 = time.perf_counter()
-        n_cpu = 100
-        for t in range(n_cpu):
-            cpu_step(5 + t)
-        out["cpu_steps_per_s"] = n_cpu / (time.perf_counter() - t0)
-        out["cpu_cores"] = os.cpu_count() or 1
-    del X, y
+                       f"{'-'.join(map(str, SGLD_DIMS))} tanh MLP, batch {SGLD_BATCH}, launches of {SGLD_KEEP} steps + thinning snapshot",
+           "kernel": "sgld_step_kernel (persistent cooperative kernel: gather, forward, head, backward, pSGLD update with in-kernel "
+                     "Philox; FP32 FFMA tiles, 2L grid barriers per step; no library GEMM, no elementwise launches)",
+           "launches_per_50_steps": 3, "last_loss": loss, "state_finite": bool(torch.isfinite(model._chain.state).all()),
+           "roofline": {"bound": "latency (grid barriers + first-touch L2 latency per phase; see profiles/r02_sgld_step_notes.md)",
+                        "achieved": SGLD_FLOP_PER_STEP * sps / 1e12, "unit": "TFLOP/s", "flop_per_step": SGLD_FLOP_PER_STEP,
+                        "update_bytes_per_step": 20 * (a.stride + 1)}}
+    del X, y, yv
     torch.cuda.empty_cache()
     return out
 
@@ -398,6 +584,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-sgld", action="store_true", help="skip the secondary SGLD steps/s measurement")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config blocks (cfg 1, 2, 3, 5-predictive)")
+    ap.add_argument("--no-check", action="store_true", help="skip the spot check against the CPU oracle")
     ap.add_argument("--sgld-steps", type=int, default=2000)
     ap.add_argument("--precision", default="tf32_bf16", choices=["tf32_bf16", "tf32x3", "fp32", "tf32"],
                     help="tf32_bf16: tcgen05 TF32 main term + two BF16 correction terms (FP32-grade, default); tf32x3: 3-pass "

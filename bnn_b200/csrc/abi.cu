@@ -192,7 +192,7 @@ extern "C" int32_t bnn_forward_host(const BnnForwardArgs* ah) {
   //      previous chunk; every chunk is reduced to float64 (mean, M2) per point and the chunks are Chan-merged
   //      (bnn_moments_merge), which is the arithmetic of the multi-GPU shard merge
   const long long kChunk = 256;
-  if (a.w_stride != 0 && a.S >= 3 * kChunk && !ah->pred && !ah->part_mean && !ah->part_m2 && (ah->mean || ah->var)) {
+  if (a.w_stride != 0 && a.S >= 3 * kChunk && !ah->pred && (ah->mean || ah->var || ah->part_mean || ah->part_m2)) {
     long long chunk = kChunk;
     while ((a.S + chunk - 1) / chunk > 64) chunk *= 2;          // bnn_moments_merge takes at most 64 shards
     const int R = (int)((a.S + chunk - 1) / chunk);
@@ -232,9 +232,19 @@ extern "C" int32_t bnn_forward_host(const BnnForwardArgs* ah) {
       if (rc) return rc;
       BNN_CUDA(cudaEventRecord(g_ws.ev_free[i & 1], st));
     }
-    if (bnn_moments_merge(parts, parts + (long long)R * M, counts, R, M, ah->mean ? (float*)g_ws.buf[BMEAN] : nullptr,
-                          ah->var ? (float*)g_ws.buf[BVAR] : nullptr, st))
-      return -2;
+    if (ah->mean || ah->var) {
+      if (bnn_moments_merge(parts, parts + (long long)R * M, counts, R, M, ah->mean ? (float*)g_ws.buf[BMEAN] : nullptr,
+                            ah->var ? (float*)g_ws.buf[BVAR] : nullptr, st))
+        return -2;
+    }
+    if (ah->part_mean || ah->part_m2) {   // the shard's float64 moments (multi-GPU merge input)
+      if (g_ws.ensure(BPART, (size_t)M * 16)) return -2;
+      if (bnn_moments_merge_partials(parts, parts + (long long)R * M, counts, R, M, (double*)g_ws.buf[BPART],
+                                     (double*)g_ws.buf[BPART] + M, st))
+        return -2;
+      if (ah->part_mean) BNN_CUDA(cudaMemcpyAsync(ah->part_mean, g_ws.buf[BPART], (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+      if (ah->part_m2) BNN_CUDA(cudaMemcpyAsync(ah->part_m2, (double*)g_ws.buf[BPART] + M, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+    }
     if (ah->mean) BNN_CUDA(cudaMemcpyAsync(ah->mean, g_ws.buf[BMEAN], (size_t)M * 4, cudaMemcpyDeviceToHost, st));
     if (ah->var) BNN_CUDA(cudaMemcpyAsync(ah->var, g_ws.buf[BVAR], (size_t)M * 4, cudaMemcpyDeviceToHost, st));
     BNN_CUDA(cudaStreamSynchronize(st));

@@ -148,7 +148,8 @@ extern "C" int32_t bnn_moments(const float* pred, int64_t S, int64_t M, float* m
 // travel by value in the kernel arguments (no device buffer, graph-capturable)
 struct CountsArg { long long c[64]; };
 __global__ void merge_kernel(const double* __restrict__ pmean, const double* __restrict__ pm2, CountsArg counts, int R,
-                                   long long M, float* __restrict__ mean, float* __restrict__ var) {
+                                   long long M, float* __restrict__ mean, float* __restrict__ var,
+                                   double* __restrict__ out_mean = nullptr, double* __restrict__ out_m2 = nullptr) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += stride) {
     double n = 0.0, mu = 0.0, m2 = 0.0;
@@ -163,7 +164,21 @@ __global__ void merge_kernel(const double* __restrict__ pmean, const double* __r
     }
     if (mean) mean[m] = (float)mu;
     if (var) var[m] = (float)(m2 / (n - 1.0));
+    if (out_mean) out_mean[m] = mu;
+    if (out_m2) out_m2[m] = m2;
   }
+}
+
+// same merge, but the result stays a float64 (mean, M2) pair -- one shard made of several chunks (host-buffer path)
+extern "C" int32_t bnn_moments_merge_partials(const double* part_mean, const double* part_m2, const int64_t* counts_host, int32_t R,
+                                              int64_t M, double* out_mean, double* out_m2, void* stream) {
+  if (!part_mean || !part_m2 || !counts_host || R < 1 || R > 64 || M < 1 || (!out_mean && !out_m2))
+    BNN_FAIL("bnn_moments_merge_partials: bad arguments (R=%d)", R);
+  CountsArg c;
+  for (int r = 0; r < 64; ++r) c.c[r] = r < R ? counts_host[r] : 0;
+  merge_kernel<<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>(part_mean, part_m2, c, R, M, nullptr, nullptr, out_mean, out_m2);
+  BNN_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int32_t bnn_moments_merge(const double* part_mean, const double* part_m2, const int64_t* counts_host, int32_t R,

@@ -193,9 +193,12 @@ def tc_supported(arch: Arch, S=2, masked=False, precision="tf32_bf16"):
     return bool(_lib.lib().bnn_forward_tc_supported(C.byref(a)))
 
 
-def forward_host(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=False, want_moments=True, precision="fp32"):
-    """End-to-end variant: X / W / mask / outputs are HOST tensors (pin them); the library does the
-    H2D copies, the launch, the D2H copies and synchronises."""
+def forward_host(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=False, want_moments=True, want_partials=False,
+                 precision="fp32", out=None):
+    """End-to-end variant through the C ABI's host-buffer entry point (bnn_forward_host): X / W / mask / outputs are HOST
+    tensors (pin them); the library does the H2D copies (large banks in chunks on a copy stream behind the evaluation of the
+    previous chunk), the launches, the D2H copies and synchronises.  `out` (optional dict of pinned tensors from a previous
+    call) is reused instead of allocating new pinned outputs."""
     for name, t in (("X", X), ("W", W)):
         if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
             raise ValueError(f"{name} must be a contiguous float32 host tensor")
@@ -218,16 +221,30 @@ def forward_host(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=Fa
             a.mask = spec
         else:
             a.mask = mask.spec(arch)
-    a.precision = _PREC[precision]
+    if precision == "auto":
+        a.N = X.shape[0]
+        a.precision = _lib.PREC_TF32_BF16
+        if not _lib.lib().bnn_forward_tc_supported(C.byref(a)):
+            a.precision = _lib.PREC_FP32
+    else:
+        a.precision = _PREC[precision]
     N, O, Sn = X.shape[0], arch.nout, int(a.S)
-    out = {}
+    out = dict(out) if out is not None else {}
+
+    def pinned(name, shape, dtype):
+        t = out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype).pin_memory()
+            out[name] = t
+        return t
+
     if want_pred:
-        out["pred"] = torch.empty(Sn, N, O, dtype=torch.float32).pin_memory()
-        a.pred = out["pred"].data_ptr()
+        a.pred = pinned("pred", (Sn, N, O), torch.float32).data_ptr()
     if want_moments:
-        out["mean"] = torch.empty(N, O, dtype=torch.float32).pin_memory()
-        out["var"] = torch.empty(N, O, dtype=torch.float32).pin_memory()
-        a.mean, a.var = out["mean"].data_ptr(), out["var"].data_ptr()
+        a.mean, a.var = pinned("mean", (N, O), torch.float32).data_ptr(), pinned("var", (N, O), torch.float32).data_ptr()
+    if want_partials:
+        a.part_mean = pinned("part_mean", (N, O), torch.float64).data_ptr()
+        a.part_m2 = pinned("part_m2", (N, O), torch.float64).data_ptr()
     L = _lib.lib()
     _lib.check(L.bnn_set_device(torch.cuda.current_device()), "bnn_set_device")
     _lib.check(L.bnn_forward_host(C.byref(a)), "bnn_forward_host")

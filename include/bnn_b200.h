@@ -149,6 +149,10 @@ int64_t bnn_moments_workspace_bytes(int64_t S, int64_t M);
 int32_t bnn_moments_merge(const double* part_mean, const double* part_m2, const int64_t* counts_host,
                           int32_t R, int64_t M, float* mean, float* var, void* stream);
 
+/* same merge with a float64 (mean, M2) result: several chunks of one shard -> the shard's moments */
+int32_t bnn_moments_merge_partials(const double* part_mean, const double* part_m2, const int64_t* counts_host,
+                                   int32_t R, int64_t M, double* out_mean, double* out_m2, void* stream);
+
 /* replaces: BNN.validate's rmse / nll lines (BNN.py:30-31) and, with
  * noise_var != NULL (per output, device), experiments/SGDMC.py:83-93.
  * out = {rmse[nout], nll[nout]} floats followed by one float holding the count
