@@ -63,7 +63,6 @@ struct TcParams {
   int trace_mask;              // BNN_TC_TRACE value: bit 0 MMA per-stage events, bit 1 WG-A, bit 2 WG-B (tile ends always)
   // shared memory offsets (bytes)
   int sm_b1, sm_b2, sm_vec, sm_a1, sm_bar, sm_ypart, sm_mask;
-  int v2;                  // pipelined kernel (fwd_tc2_kernel): layer 1 issued just in time in 16-column batches, D2 double-buffered
 };
 
 // ---- operand image builder -------------------------------------------------------------------------
@@ -74,15 +73,7 @@ struct TcPrepParams {
   int vec_len;
   int mixed;   // second half of each operand region = two BF16 images (pairs per word) instead of the TF32 lo image
   long long S; // networks to convert (1 for a shared network)
-  int perm;    // v2 + CTA pair: hidden-1 units in the K order of layer 2 / in b1 follow the D1 column order of the batched layer-1 MMAs
 };
-
-// v2, CTA pair: a layer-1 MMA of N = 16 takes 8 weight rows from each CTA of the pair, so column c of the stream of D1
-// batches (c = 16 * batch + j) is hidden unit 8 * batch + j (j < 8, first CTA's half) or N1h + 8 * batch + j - 8 (second CTA's)
-__host__ __device__ __forceinline__ int tc_unit_of_col(int c, int n1h) {
-  const int blk = c >> 4, j = c & 15;
-  return j < 8 ? 8 * blk + j : n1h + 8 * blk + (j - 8);
-}
 
 __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ TcPrepParams q, const float* __restrict__ W,
                                                       float* __restrict__ img) {
@@ -108,10 +99,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Tc
       auto weight = [&](int ng, int k) {
         float w = 0.0f;
         if (layer == 0) { if (ng < q.H1 && k < q.D) w = Ws[off0 + ng * q.ld0 + k]; }
-        else {
-          if (q.perm) k = tc_unit_of_col(k, q.N1 / 2);     // K position -> hidden-1 unit
-          if (ng < q.H2 && k < q.H1) w = Ws[off1 + ng * q.ld1 + k];
-        }
+        else            { if (ng < q.H2 && k < q.H1) w = Ws[off1 + ng * q.ld1 + k]; }
         return w;
       };
       if (hl && q.mixed) {
@@ -136,7 +124,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Tc
       }
     } else {
       int j = r - part_stride * q.kpair;
-      if (j < q.N1) { const int u = q.perm ? tc_unit_of_col(j, q.N1 / 2) : j; if (u < q.H1) v = Ws[off0 + u * q.ld0 + q.D]; }   // b1
+      if (j < q.N1) { if (j < q.H1) v = Ws[off0 + j * q.ld0 + q.D]; }                      // b1
       else if ((j -= q.N1) < q.N2) { if (j < q.H2) v = Ws[off1 + j * q.ld1 + q.H1]; }      // b2
       else if ((j -= q.N2) < q.O * q.N2) {                                                 // w3[o][j]
         const int o = j / q.N2, c = j - o * q.N2;
@@ -887,516 +875,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
   if (warp == kTcMmaWarp) tmem_dealloc_n<kPair>(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-// =====================================================================================================================
-// Pipelined variant (v2).  The first kernel above keeps D1 [N1] and D2 [N2] single-buffered next to a 3-stage activation
-// ring: TMEM is full, every tile ends with the ~2.5k-cycle drain of D2 (tcgen05.ld is ~64 B/clk/SM) during which the tensor
-// pipe idles (ncu: 60 % active).  Here layer 1 no longer owns N1 columns: its K is tiny (Dp <= 64), so the MMA warp issues
-// it JUST IN TIME in batches of 16 output columns -- batch b + 2 while the layer-2 MMAs of batch b execute -- into two
-// 16-column slots that epilogue-1 empties into registers at once.  That frees enough tensor memory to double-buffer D2
-// (2 N2 + 2 * 16 + ring * 32 <= 512: cfg 4's N2 = 208 fits with a 2-stage ring), so epilogue-2 drains tile t while the
-// layer-2 MMAs of tile t + 1 run, and A1 is double-buffered in shared memory so that the look-ahead crosses tile boundaries.
-//   tensor memory : D2[0] | D2[1] | D1 slot 0 | D1 slot 1 | A2 ring
-//   batches       : gb = 13 * pair + b is a continuous stream; warp set (gb & 1) of WG-A owns D1 slot gb & 1 and ring stage
-//                   gb % ring, the MMA warp keeps layer 1 two batches ahead of layer 2
-// Barriers (leader = CTA 0 of the pair):
-//   W_FULL, SAMPLE_DONE, VEC_FREE  as above
-//   A1_FULL[2]    4 x kPair warp arrivals: A1 image of pair P in buffer P & 1 written
-//   D1_FULL[2]    commit (multicast): layer-1 MMAs of the batch in this slot done
-//   D1_FREE[2]    4 x kPair warp arrivals: the set has the slot's columns in registers
-//   A2_FULL / A2_EMPTY[ring], D2_FULL[2] (commit), D2_EMPTY[2] (8 x kPair warp arrivals)
-enum { B2_W_FULL = 0, B2_SAMPLE_DONE, B2_VEC_FREE, B2_A1_FULL, B2_D1_FULL = B2_A1_FULL + 2, B2_D1_FREE = B2_D1_FULL + 2,
-       B2_D2_FULL = B2_D1_FREE + 2, B2_D2_EMPTY = B2_D2_FULL + 2, B2_A2_FULL = B2_D2_EMPTY + 2, B2_A2_EMPTY = B2_A2_FULL + kTcRing,
-       B2_COUNT = B2_A2_EMPTY + kTcRing };
-
-template <int kPair, int kAct>
-__global__ void __launch_bounds__(kTcThreads, 1) fwd_tc2_kernel(const __grid_constant__ TcParams p) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.sm_bar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B2_COUNT);
-  const uint32_t s_b1 = smem_u32(smem + p.sm_b1), s_b2 = smem_u32(smem + p.sm_b2);
-  const uint32_t s_a1 = smem_u32(smem + p.sm_a1);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = kPair == 1 ? 0u : cluster_ctarank();
-  const bool leader = rank == 0;
-  const int slot = blockIdx.x / kPair;
-  const int g = blockIdx.y;
-  const int s0 = g * p.Sg, s1 = min(p.S, s0 + p.Sg);
-  const int pt0 = slot * p.tiles_per_slot, pt1 = min(p.n_tiles, pt0 + p.tiles_per_slot);
-  const int ntile = pt1 - pt0;
-  const int N1h = p.N1 / kPair, N2h = p.N2 / kPair;
-  const int n_k1 = p.Dp >> 3;
-  const int nb = p.K2 >> 4;            // 16-column batches per tile (K2 == N1, a multiple of 16)
-  const uint32_t b1_hl_bytes = (uint32_t)p.Dp * N1h * 4, b2_hl_bytes = (uint32_t)p.K2 * N2h * 4;
-  const uint32_t a1_hl_bytes = (uint32_t)p.Dp * 128 * 4;
-  const int vec_pad = (p.vec_len + 3) & ~3;
-  const int total_pairs = (s1 - s0) * ntile;
-
-  if (tid == 0) {
-    mbar_init(&bars[B2_W_FULL], 1);
-    mbar_init(&bars[B2_SAMPLE_DONE], 1);
-    mbar_init(&bars[B2_VEC_FREE], 8);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars[B2_A1_FULL + i], 4 * kPair);
-      mbar_init(&bars[B2_D1_FULL + i], 1);
-      mbar_init(&bars[B2_D1_FREE + i], 4 * kPair);
-      mbar_init(&bars[B2_D2_FULL + i], 1);
-      mbar_init(&bars[B2_D2_EMPTY + i], 8 * kPair);
-    }
-    for (int i = 0; i < kTcRing; ++i) {
-      mbar_init(&bars[B2_A2_FULL + i], 4 * kPair);
-      mbar_init(&bars[B2_A2_EMPTY + i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == kTcMmaWarp) tmem_alloc_n<kPair>(tmem_slot, (uint32_t)p.tmem_cols);
-  tc::fence_before_thread_sync();
-  __syncthreads();
-  if constexpr (kPair == 2) cluster_sync_all();
-  tc::fence_after_thread_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d2 = tmem_base, tmem_d1 = tmem_base + 2u * (uint32_t)p.N2, tmem_a2 = tmem_d1 + 32u;
-  if (total_pairs > 0) {
-  if (warp == kTcMmaWarp) {
-    // ===================== weight loader + MMA issuer (converged warp, one elected lane issues) =======================
-    const uint32_t idesc1 = tc::make_idesc_tf32(128 * kPair, 16), idesc2 = tc::make_idesc_tf32(128 * kPair, p.N2);
-    const uint32_t idesc1h = tc::make_idesc_bf16(128 * kPair, 16), idesc2h = tc::make_idesc_bf16(128 * kPair, p.N2);
-    const uint64_t b1_desc0 = tc::make_smem_desc(s_b1, (uint32_t)N1h * 16u, 128u);
-    const uint64_t b2_desc0 = tc::make_smem_desc(s_b2, (uint32_t)N2h * 16u, 128u);
-    const uint64_t b1_step = (uint64_t)(2 * N1h), b2_step = (uint64_t)(2 * N2h);   // 16-byte units per K = 8 step
-    const uint64_t a_step = (uint64_t)(2 * 128);
-    const uint64_t a1_lo_off = (uint64_t)(a1_hl_bytes >> 4), b1_lo_off = (uint64_t)(b1_hl_bytes >> 4), b2_lo_off = (uint64_t)(b2_hl_bytes >> 4);
-    const uint64_t a1_buf_step = (uint64_t)((2 * a1_hl_bytes) >> 4);
-    const uint64_t a1_desc0 = tc::make_smem_desc(s_a1, 2048u, 128u);
-    const bool three = p.passes == 3, mixed = p.passes == 2;
-    const int rows_per_batch = 16 / kPair;          // weight rows of one layer-1 batch held by each CTA
-    // layer-1 look-ahead cursor: next batch to issue (global batch index, its pair and batch inside the pair)
-    uint32_t cur_gb = 0, cur_P = 0;
-    int cur_b = 0;
-    // layer 1 of batch (cur_P, cur_b) into D1 slot cur_gb & 1
-    auto issue_mma1 = [&]() {
-      const uint32_t sl = cur_gb & 1u;
-      if (cur_b == 0) {
-        mbar_wait(&bars[B2_A1_FULL + (cur_P & 1u)], (cur_P >> 1) & 1u);
-      }
-      mbar_wait(&bars[B2_D1_FREE + sl], ((cur_gb >> 1) & 1u) ^ 1u);
-      tc::fence_after_thread_sync();
-      const uint64_t a0d = a1_desc0 + (uint64_t)(cur_P & 1u) * a1_buf_step;
-      const uint64_t b0d = b1_desc0 + (uint64_t)(cur_b * rows_per_batch);
-      const uint32_t dst = tmem_d1 + sl * 16u;
-      if (tc::elect_one()) {
-        uint64_t a_hi = a0d, b_hi = b0d;
-        for (int ks = 0; ks < n_k1; ++ks) {
-          mma_tf32<kPair>(dst, a_hi, b_hi, idesc1, ks > 0);
-          if (three) {
-            mma_tf32<kPair>(dst, a_hi + a1_lo_off, b_hi, idesc1, 1);
-            mma_tf32<kPair>(dst, a_hi, b_hi + b1_lo_off, idesc1, 1);
-          }
-          if (mixed && (ks & 1)) {
-            const uint64_t a16 = a0d + a1_lo_off + (uint64_t)(ks >> 1) * a_step;
-            const uint64_t b16 = b0d + b1_lo_off + (uint64_t)(ks >> 1) * b1_step;
-            mma_bf16<kPair>(dst, a16 + (a1_lo_off >> 1), b16, idesc1h, 1);   // lo(a) . b
-            mma_bf16<kPair>(dst, a16, b16 + (b1_lo_off >> 1), idesc1h, 1);   // a . lo(b)
-          }
-          a_hi += a_step;
-          b_hi += b1_step;
-        }
-        mma_commit_all<kPair>(&bars[B2_D1_FULL + sl]);
-      }
-      __syncwarp();
-      ++cur_gb;
-      if (++cur_b == nb) { cur_b = 0; ++cur_P; }
-    };
-    uint32_t gb = 0, ring_st = 0, ring_par = 0;
-    for (int s = s0; s < s1; ++s) {
-      const uint32_t spar = (uint32_t)(s - s0) & 1u;
-      const bool reload = !p.shared_w || s == s0;   // a shared network is loaded once and stays resident
-      if (reload && s > s0) mbar_wait(&bars[B2_SAMPLE_DONE], spar ^ 1u);
-      const long long s_img = p.shared_w ? 0 : s;
-      const float* src = p.img + s_img * p.img_stride + (long long)rank * p.part_stride;
-      const uint32_t b1_bytes = (three || mixed) ? 2 * b1_hl_bytes : b1_hl_bytes;
-      const uint32_t b2_bytes = (three || mixed) ? 2 * b2_hl_bytes : b2_hl_bytes;
-      if (reload && tc::elect_one()) {
-        mbar_arrive_expect_tx(&bars[B2_W_FULL], b1_bytes + b2_bytes + (uint32_t)vec_pad * 4);
-        bulk_g2s(smem + p.sm_b1, src, b1_bytes, &bars[B2_W_FULL]);
-        bulk_g2s(smem + p.sm_b2, src + 2 * (long long)(b1_hl_bytes / 4), b2_bytes, &bars[B2_W_FULL]);
-      }
-      __syncwarp();
-      if (reload && s > s0) mbar_wait(&bars[B2_VEC_FREE], spar ^ 1u);
-      if (reload && tc::elect_one())
-        bulk_g2s(smem + p.sm_vec, p.img + s_img * p.img_stride + p.part_stride * kPair, (uint32_t)vec_pad * 4,
-                 &bars[B2_W_FULL]);
-      __syncwarp();
-      if (!leader) continue;   // the peer CTA only loads; its tensor-core work is issued by the leader
-      if (reload) mbar_wait(&bars[B2_W_FULL], spar);
-      // batches that may use the weights now resident: this sample's (per-sample bank) or everything (shared network)
-      const uint32_t run_end = p.shared_w ? (uint32_t)total_pairs * (uint32_t)nb : (uint32_t)(s - s0 + 1) * (uint32_t)ntile * (uint32_t)nb;
-      for (int pt = pt0; pt < pt1; ++pt) {
-        const uint32_t P = (uint32_t)(s - s0) * (uint32_t)ntile + (uint32_t)(pt - pt0);
-        const uint32_t d2 = tmem_d2 + (P & 1u) * (uint32_t)p.N2;
-        for (int b = 0; b < nb; ++b, ++gb) {
-          // ---- layer 1, two batches ahead of layer 2
-          while (cur_gb < run_end && cur_gb <= gb + 2u) issue_mma1();
-          // ---- layer 2, batch b: D2[P & 1] (+)= A2[stage] * B2[16 K-columns]^T
-          if (b == 0) mbar_wait(&bars[B2_D2_EMPTY + (P & 1u)], ((P >> 1) & 1u) ^ 1u);   // epilogue-2 drained this buffer (pair P - 2)
-          mbar_wait(&bars[B2_A2_FULL + ring_st], ring_par);
-          tc::fence_after_thread_sync();
-          const uint32_t a0 = tmem_a2 + ring_st * (uint32_t)kTcStageCols;
-          const uint64_t bd0 = b2_desc0 + (uint64_t)(2 * b) * b2_step, bd1 = bd0 + b2_step;
-          const uint32_t acc0 = b > 0 ? 1u : 0u;
-          if (tc::elect_one()) {
-            if (three) {
-              mma_tf32_ts<kPair>(d2, a0, bd0, idesc2, acc0);
-              mma_tf32_ts<kPair>(d2, a0 + 16u, bd0, idesc2, 1);
-              mma_tf32_ts<kPair>(d2, a0, bd0 + b2_lo_off, idesc2, 1);
-              mma_tf32_ts<kPair>(d2, a0 + 8u, bd1, idesc2, 1);
-              mma_tf32_ts<kPair>(d2, a0 + 24u, bd1, idesc2, 1);
-              mma_tf32_ts<kPair>(d2, a0 + 8u, bd1 + b2_lo_off, idesc2, 1);
-            } else if (mixed) {
-              const uint64_t b16 = b2_desc0 + b2_lo_off + (uint64_t)b * b2_step;
-              mma_tf32_ts<kPair>(d2, a0, bd0, idesc2, acc0);
-              mma_tf32_ts<kPair>(d2, a0 + 8u, bd1, idesc2, 1);
-              mma_bf16_ts<kPair>(d2, a0 + 24u, b16, idesc2h, 1);                      // lo(a) . b
-              mma_bf16_ts<kPair>(d2, a0 + 16u, b16 + (b2_lo_off >> 1), idesc2h, 1);   // a . lo(b)
-            } else {
-              mma_tf32_ts<kPair>(d2, a0, bd0, idesc2, acc0);
-              mma_tf32_ts<kPair>(d2, a0 + 8u, bd1, idesc2, 1);
-            }
-            mma_commit_all<kPair>(&bars[B2_A2_EMPTY + ring_st]);
-            if (b + 1 == nb) {
-              mma_commit_all<kPair>(&bars[B2_D2_FULL + (P & 1u)]);
-              if (pt + 1 == pt1) mma_commit_all<kPair>(&bars[B2_SAMPLE_DONE]);
-            }
-          }
-          __syncwarp();
-          if (++ring_st == (uint32_t)p.ring) { ring_st = 0; ring_par ^= 1u; }
-        }
-      }
-    }
-  } else if (warp < 8) {
-    // ===================== WG-A: A1 images + epilogue 1; thread = one point (TMEM lane) ===============================
-    const int quarter = warp & 3, set = warp >> 2;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-    const bool three = p.passes == 3, mixed = p.passes == 2;
-    const float* b1s = reinterpret_cast<const float*>(smem + p.sm_vec);
-    float* mk_base = reinterpret_cast<float*>(smem + p.sm_mask);
-    const int mk_sz = p.Dp + p.N1;
-    const bool has_m0 = p.mask_mode != BNN_MASK_NONE && p.m_off[0] >= 0;
-    const bool has_m1 = p.mask_mode != BNN_MASK_NONE && p.m_off[1] >= 0;
-    const int n_kc = p.Dp >> 2;
-    constexpr int kPre = 4;
-    // A1 granule kc of this thread's point into buffer `buf`: hi/lo split of X[n][4kc .. 4kc+3] (zero beyond D / N)
-    auto store_a1 = [&](uint32_t buf, int kc, const float (&x)[4]) {
-      float4 hi, lo;
-      hi.x = tc::tf32_hi(x[0]); hi.y = tc::tf32_hi(x[1]); hi.z = tc::tf32_hi(x[2]); hi.w = tc::tf32_hi(x[3]);
-      lo.x = x[0] - hi.x; lo.y = x[1] - hi.y; lo.z = x[2] - hi.z; lo.w = x[3] - hi.w;
-      const uint32_t base = s_a1 + buf * 2u * a1_hl_bytes;
-      const uint32_t a = base + (uint32_t)(kc * 128 + row) * 16u;
-      sts128(a, hi);
-      if (mixed) {
-        const uint32_t a16 = base + a1_hl_bytes + (uint32_t)((kc >> 1) * 128 + row) * 16u + (uint32_t)(kc & 1) * 8u;
-        sts64(a16, make_float2(__uint_as_float(tc::pack_bf16x2(x[0], x[1])), __uint_as_float(tc::pack_bf16x2(x[2], x[3]))));
-        sts64(a16 + a1_hl_bytes / 2,
-              make_float2(__uint_as_float(tc::pack_bf16x2(lo.x, lo.y)), __uint_as_float(tc::pack_bf16x2(lo.z, lo.w))));
-      } else {
-        sts128(a + a1_hl_bytes, lo);
-      }
-    };
-    auto load_x = [&](long long n, int kc, float (&x)[4]) {
-      const float* xr = p.X + n * p.D;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int k = kc * 4 + e;
-        x[e] = (n < p.N && k < p.D) ? __ldg(xr + k) : 0.0f;
-      }
-    };
-    auto mask_x = [&](const float* m0, int kc, float (&x)[4]) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int k = kc * 4 + e;
-        if (k < p.D) x[e] *= m0[k];
-      }
-    };
-    auto draw_masks = [&](int sm) {   // masks of sample sm into the buffer of its parity (all 256 WG-A threads); m1 in D1 column order
-      float* m0 = mk_base + ((sm - s0) & 1) * mk_sz;
-      float* m1 = m0 + p.Dp;
-      const int t256 = warp * 32 + lane;
-      if (has_m0) for (int j = t256; j < p.D; j += 256) m0[j] = tc_mask_value(p, p.sample_offset + sm, sm, 0, p.m_off[0] + j);
-      if (has_m1) for (int j = t256; j < p.N1; j += 256) {
-        const int u = kPair == 2 ? tc_unit_of_col(j, N1h) : j;
-        m1[j] = u < p.H1 ? tc_mask_value(p, p.sample_offset + sm, sm, 1, p.m_off[1] + u) : 0.0f;
-      }
-    };
-    // A1 image of pair Pn (sample sn, tile ptn) into buffer Pn & 1, then signal the leader
-    auto build_a1 = [&](uint32_t Pn, int sn, int ptn, bool from_regs, float (&xn)[kPre][4]) {
-      const float* m0 = mk_base + ((sn - s0) & 1) * mk_sz;
-      const long long n = ((long long)ptn * kPair + rank) * 128 + row;
-      for (int kc = 0; kc < n_kc; ++kc) {
-        float x[4];
-        if (from_regs && kc < kPre) { x[0] = xn[kc][0]; x[1] = xn[kc][1]; x[2] = xn[kc][2]; x[3] = xn[kc][3]; }
-        else load_x(n, kc, x);
-        if (has_m0) mask_x(m0, kc, x);
-        store_a1(Pn & 1u, kc, x);
-      }
-    };
-    uint32_t ring_st = (uint32_t)set % (uint32_t)p.ring, ring_use = ((uint32_t)set / (uint32_t)p.ring) & 1u;   // stage / use parity of batch gb = set
-    const uint32_t ring_adv = 2u % (uint32_t)p.ring, ring_wrap2 = 2u / (uint32_t)p.ring;   // gb advances by 2: ring is 2..6
-    uint32_t gb = (uint32_t)set;
-    int b = set;                                  // batch inside the pair
-    for (uint32_t P = 0; P < (uint32_t)total_pairs; ++P) {
-      const int s = s0 + (int)(P / (uint32_t)ntile), pt = pt0 + (int)(P % (uint32_t)ntile);
-      const bool first_of_sample = pt == pt0;
-      const bool reload = !p.shared_w || s == s0;
-      if (first_of_sample && (has_m0 || has_m1)) {
-        // masks are drawn ONE SAMPLE AHEAD (the next sample's first A1 needs them during this sample's last tile); both warp
-        // sets pass here once per sample (named barrier 5, 256 threads)
-        named_bar_sync(5, 256);
-        if (s == s0) draw_masks(s0);
-        if (s + 1 < s1) draw_masks(s + 1);
-        named_bar_sync(5, 256);
-      }
-      const float* mk1 = mk_base + ((s - s0) & 1) * mk_sz + p.Dp;
-      // the pair after this one in the stream (if its weights are the ones resident now, its A1 is prepared during this pair)
-      const bool has_next = P + 1 < (uint32_t)total_pairs;
-      const int s_n = s0 + (int)((P + 1) / (uint32_t)ntile), pt_n = pt0 + (int)((P + 1) % (uint32_t)ntile);
-      const bool next_prepared = has_next && (p.shared_w || s_n == s);
-      float xn[kPre][4];
-      if (set == 0) {
-        const bool prepared = P > 0 && (p.shared_w || !first_of_sample);
-        if (!prepared) {
-          // first pair of the stream / of a freshly loaded sample: build A1 on the critical path; the operands of this sample
-          // must have landed in THIS CTA before the leader may use them, so wait for them before signalling
-          build_a1(P, s, pt, false, xn);
-          if (reload) mbar_wait(&bars[B2_W_FULL], (uint32_t)(s - s0) & 1u);
-          warp_signal_leader<kPair>(&bars[B2_A1_FULL + (P & 1u)], lane);
-        }
-        if (next_prepared) {
-          const long long n_next = ((long long)pt_n * kPair + rank) * 128 + row;
-#pragma unroll
-          for (int kc = 0; kc < kPre; ++kc)
-            if (kc < n_kc) load_x(n_next, kc, xn[kc]);
-        }
-      } else if (first_of_sample && reload) {
-        mbar_wait(&bars[B2_W_FULL], (uint32_t)(s - s0) & 1u);   // b1 of this sample
-      }
-      bool a1_next_done = !(set == 0 && next_prepared);
-      // ---- this set's batches of the pair
-      auto epilogue1 = [&](auto masked_tag) {
-        constexpr bool kMasked = decltype(masked_tag)::value;
-        for (; b < nb; b += 2, gb += 2) {
-          const uint32_t sl = (uint32_t)set;                       // gb & 1 == set
-          const int c0 = b * 16;
-          uint32_t d[16];
-          mbar_wait(&bars[B2_D1_FULL + sl], (gb >> 1) & 1u);
-          tc::fence_after_thread_sync();
-          tc::tmem_ld16_issue(tmem_d1 + lane_sel + sl * 16u, d);
-          tc::tmem_ld_wait(d);
-          // the slot is in registers: the MMA warp may refill it (layer 1 of batch gb + 2)
-          warp_signal_tmem<kPair>(&bars[B2_D1_FREE + sl], lane);
-          if (!a1_next_done) {
-            // all layer-1 MMAs of the previous pair are complete (they precede this batch's in issue order), so its A1 buffer
-            // -- the one pair P + 1 uses -- is free: build the next pair's image now, long before its first batch is issued
-            build_a1(P + 1, s_n, pt_n, true, xn);
-            warp_signal_leader<kPair>(&bars[B2_A1_FULL + ((P + 1) & 1u)], lane);
-            a1_next_done = true;
-          }
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 bq = *reinterpret_cast<const float4*>(b1s + c0 + q4 * 4);
-            float h[4];
-            h[0] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 0]) + bq.x);
-            h[1] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 1]) + bq.y);
-            h[2] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 2]) + bq.z);
-            h[3] = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 3]) + bq.w);
-            if constexpr (kMasked) {
-              const float4 mq = *reinterpret_cast<const float4*>(mk1 + c0 + q4 * 4);
-              h[0] *= mq.x; h[1] *= mq.y; h[2] *= mq.z; h[3] *= mq.w;
-            }
-            float l[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float hh = tc::tf32_hi_fast(h[e]);
-              hi[q4 * 4 + e] = __float_as_uint(hh);
-              l[e] = h[e] - hh;
-            }
-            if (mixed) {
-              lo[q4 * 2 + 0] = tc::pack_bf16x2(h[0], h[1]);
-              lo[q4 * 2 + 1] = tc::pack_bf16x2(h[2], h[3]);
-              lo[8 + q4 * 2 + 0] = tc::pack_bf16x2(l[0], l[1]);
-              lo[8 + q4 * 2 + 1] = tc::pack_bf16x2(l[2], l[3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) lo[q4 * 4 + e] = __float_as_uint(l[e]);
-            }
-          }
-          mbar_wait(&bars[B2_A2_EMPTY + ring_st], ring_use ^ 1u);   // the MMAs that read this stage's previous contents are done
-          tc::fence_after_thread_sync();
-          const uint32_t ta = tmem_a2 + lane_sel + ring_st * (uint32_t)kTcStageCols;
-          tc::tmem_st16(ta, hi);
-          if (three || mixed) tc::tmem_st16(ta + 16u, lo);
-          tc::tmem_st_wait();
-          warp_signal_tmem<kPair>(&bars[B2_A2_FULL + ring_st], lane);
-          ring_st += ring_adv;
-          ring_use ^= ring_wrap2 & 1u;
-          if (ring_st >= (uint32_t)p.ring) { ring_st -= (uint32_t)p.ring; ring_use ^= 1u; }
-        }
-        b -= nb;                                                    // first batch of this set in the next pair
-      };
-      if (has_m1) epilogue1(std::true_type{});
-      else epilogue1(std::false_type{});
-    }
-  } else {
-    // ===================== WG-B: epilogue 2 + predictive reduction; thread = one point ===============================
-    const int quarter = warp & 3, half = (warp - 8) >> 2;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-    const long long M = p.N * p.O;
-    double* st_mean = p.part ? p.part + (long long)g * 2 * M : nullptr;
-    double* st_m2 = p.part ? st_mean + M : nullptr;
-    const float* b3 = reinterpret_cast<const float*>(smem + p.sm_vec) + p.N1 + p.N2 + p.O * p.N2;
-    float* ypart = reinterpret_cast<float*>(smem + p.sm_ypart);   // [128][O] partial outputs of the half-1 warps
-    const int nb16 = p.N2 >> 4;
-    const int c_lo = half == 0 ? 0 : ((nb16 + 1) >> 1) * 16, c_hi = half == 0 ? ((nb16 + 1) >> 1) * 16 : p.N2;
-    float* w3m = reinterpret_cast<float*>(smem + p.sm_mask) + 2 * (p.Dp + p.N1);   // [O][N2]
-    const float* b2s = reinterpret_cast<const float*>(smem + p.sm_vec) + p.N1;
-    const float* w3s = b2s + p.N2;
-    const bool has_m2 = p.mask_mode != BNN_MASK_NONE && p.m_off[2] >= 0;
-    uint32_t P = 0;
-    for (int s = s0; s < s1; ++s) {
-      const double inv_cnt = 1.0 / (double)(s - s0 + 1);
-      if (!p.shared_w || s == s0) mbar_wait(&bars[B2_W_FULL], (uint32_t)(s - s0) & 1u);
-      if (has_m2) {
-        named_bar_sync(6, 256);
-        const int t256 = (warp - 8) * 32 + lane;
-        for (int j = t256; j < p.N2; j += 256) {
-          const float m = j < p.H2 ? tc_mask_value(p, p.sample_offset + s, s, 2, p.m_off[2] + j) : 0.0f;
-          for (int o = 0; o < p.O; ++o) w3m[o * p.N2 + j] = w3s[o * p.N2 + j] * m;
-        }
-        named_bar_sync(6, 256);
-      }
-      float y0[4] = {0.f, 0.f, 0.f, 0.f};
-      if (half == 0) { y0[0] = b3[0]; if (p.O > 1) y0[1] = b3[1]; if (p.O > 2) y0[2] = b3[2]; if (p.O > 3) y0[3] = b3[3]; }
-      for (int pt = pt0; pt < pt1; ++pt, ++P) {
-        const long long n = ((long long)pt * kPair + rank) * 128 + row;
-        const bool in_range = n < p.N;
-        const uint32_t d2 = tmem_d2 + (P & 1u) * (uint32_t)p.N2;
-        mbar_wait(&bars[B2_D2_FULL + (P & 1u)], (P >> 1) & 1u);
-        tc::fence_after_thread_sync();
-        float y[4] = {y0[0], y0[1], y0[2], y0[3]};
-        auto drain = [&](auto single_tag) {
-          constexpr bool kSingle = decltype(single_tag)::value;
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          const float* w3p = has_m2 ? w3m : w3s;
-          float4 bq[4], wq[4];
-          auto fetch = [&](int c) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              bq[q4] = *reinterpret_cast<const float4*>(b2s + c + q4 * 4);
-              if constexpr (kSingle) wq[q4] = *reinterpret_cast<const float4*>(w3p + c + q4 * 4);
-            }
-          };
-          auto reduce16 = [&](const uint32_t* d, int c) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const float t0 = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 0]) + bq[q4].x);
-              const float t1 = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 1]) + bq[q4].y);
-              const float t2 = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 2]) + bq[q4].z);
-              const float t3 = act_ct<kAct>(__uint_as_float(d[q4 * 4 + 3]) + bq[q4].w);
-              if constexpr (kSingle) {
-                acc[0] = fmaf(wq[q4].x, t0, acc[0]);
-                acc[1] = fmaf(wq[q4].y, t1, acc[1]);
-                acc[2] = fmaf(wq[q4].z, t2, acc[2]);
-                acc[3] = fmaf(wq[q4].w, t3, acc[3]);
-              } else {
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                  if (o < p.O) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(w3p + o * p.N2 + c + q4 * 4);
-                    acc[o] += fmaf(w4.x, t0, w4.y * t1) + fmaf(w4.z, t2, w4.w * t3);
-                  }
-                }
-              }
-            }
-          };
-          uint32_t d[32];
-          for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-            const bool wide = c_hi - c0 >= 32;
-            if (wide) tc::tmem_ld32_issue(d2 + lane_sel + (uint32_t)c0, d);
-            else tc::tmem_ld16_issue_lo(d2 + lane_sel + (uint32_t)c0, d);
-            fetch(c0);
-            tc::tmem_ld_wait32(d);
-            reduce16(d, c0);
-            if (wide) {
-              fetch(c0 + 16);
-              reduce16(d + 16, c0 + 16);
-            }
-          }
-          if constexpr (kSingle) y[0] += (acc[0] + acc[1]) + (acc[2] + acc[3]);
-          else {
-#pragma unroll
-            for (int o = 0; o < 4; ++o) y[o] += acc[o];
-          }
-        };
-        if (p.O == 1) drain(std::true_type{});
-        else drain(std::false_type{});
-        // this buffer of D2 is drained by this warp: the layer-2 MMAs of pair P + 2 may overwrite it; after the last tile of
-        // the sample the bias vector is free as well
-        tc::fence_before_thread_sync();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (kPair == 1) mbar_arrive(&bars[B2_D2_EMPTY + (P & 1u)]);
-          else mbar_arrive_cluster(&bars[B2_D2_EMPTY + (P & 1u)], 0);
-          if (pt + 1 == pt1) mbar_arrive(&bars[B2_VEC_FREE]);
-        }
-        double mu0[4] = {0.0, 0.0, 0.0, 0.0}, q0[4] = {0.0, 0.0, 0.0, 0.0};
-        if (half == 0 && in_range && st_mean && s != s0) {
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            if (o < p.O) {
-              mu0[o] = st_mean[n * p.O + o];
-              q0[o] = st_m2[n * p.O + o];
-            }
-          }
-        }
-        if (half == 1) {
-#pragma unroll
-          for (int o = 0; o < 4; ++o) if (o < p.O) ypart[row * p.O + o] = y[o];
-        }
-        named_bar_sync(1 + quarter, 64);
-        if (half == 0) {
-#pragma unroll
-          for (int o = 0; o < 4; ++o) if (o < p.O) y[o] += ypart[row * p.O + o];
-        }
-        named_bar_sync(1 + quarter, 64);   // ypart may be overwritten by the next tile
-        if (half == 0 && in_range) {
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            if (o < p.O) {
-              const long long m = n * p.O + o;
-              if (p.pred) p.pred[((long long)s * p.N + n) * p.O + o] = y[o];
-              if (st_mean) {
-                const double dlt = (double)y[o] - mu0[o];
-                const double mu = mu0[o] + dlt * inv_cnt;
-                st_mean[m] = mu;
-                st_m2[m] = q0[o] + dlt * ((double)y[o] - mu);
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-  }
-
-  // ---- teardown
-  tc::fence_before_thread_sync();
-  __syncthreads();
-  if constexpr (kPair == 2) cluster_sync_all();
-  if (warp == kTcMmaWarp) tmem_dealloc_n<kPair>(tmem_base, (uint32_t)p.tmem_cols);
-}
-
 // ---- self-test GEMM: D[128, N] = A[128, K] * B[N, K]^T through the same descriptors / split -----------------
 __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                              float* __restrict__ Dout, int K, int N, int passes) {
@@ -1664,54 +1142,40 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   p.D = D; p.H1 = H1; p.H2 = H2; p.O = O; p.act = L.act;
   p.passes = a->precision == BNN_PREC_TF32 ? 1 : a->precision == BNN_PREC_TF32_BF16 ? 2 : 3;
   const int kq = p.passes == 2 ? 16 : 8;   // the BF16 correction MMAs take K = 16 at a time
-  p.Dp = roundup(D, kq); p.N1 = roundup(H1, 16); p.N2 = roundup(H2, 16);
-  // Pipelined kernel (v2) whenever two D2 buffers + two 16-column D1 slots + a 2-stage ring fit tensor memory and the tile has
-  // at least two 16-column batches; BNN_TC_V1=1 forces the first kernel (debugging / A-B timing)
-  bool v2 = 2 * p.N2 + 32 + 2 * kTcStageCols <= 512 && p.N1 >= 32;
-  if (const char* e = getenv("BNN_TC_V1")) { if (atoi(e) != 0) v2 = false; }
-  p.K2 = v2 ? p.N1 : roundup(H1, kq);      // v2 walks layer 2's K in whole 16-column batches
+  p.Dp = roundup(D, kq); p.N1 = roundup(H1, 16); p.N2 = roundup(H2, 16); p.K2 = roundup(H1, kq);
   p.vec_len = p.N1 + p.N2 + O * p.N2 + 4;
   const int vec_pad = (p.vec_len + 3) & ~3;
-  const int n_bars = v2 ? (int)B2_COUNT : (int)BAR_COUNT;
   // try one CTA per tile first (weights fully resident in one SM's shared memory), else a CTA pair
   int kpair = 0;
-  for (int pass = 0; pass < 2 && !kpair; ++pass) {
-    if (pass == 1) {                       // v2 needs a second A1 buffer: if nothing fits with it, fall back to the first kernel
-      if (!v2) break;
-      v2 = false;
-      p.K2 = roundup(H1, kq);
-    }
-    for (int kp = 1; kp <= 2 && !kpair; ++kp) {
-      const int N1h = p.N1 / kp, N2h = p.N2 / kp;
-      if ((N1h & 7) || (N2h & 7)) continue;
+  for (int kp = 1; kp <= 2 && !kpair; ++kp) {
+    const int N1h = p.N1 / kp, N2h = p.N2 / kp;
+    if ((N1h & 7) || (N2h & 7)) continue;
+    {
       size_t o = 0;
       p.sm_b1 = (int)o; o += (size_t)2 * p.Dp * N1h * 4;
       p.sm_b2 = (int)o; o += (size_t)2 * p.K2 * N2h * 4;
-      p.sm_a1 = (int)o; o += (size_t)2 * p.Dp * 128 * 4 * (v2 ? 2 : 1);
+      p.sm_a1 = (int)o; o += (size_t)2 * p.Dp * 128 * 4;
       p.sm_vec = (int)o; o += (size_t)vec_pad * 4;
       p.sm_ypart = (int)o; o += (size_t)128 * O * 4;
       o = (o + 15) & ~(size_t)15;
       p.sm_mask = (int)o; if (a->mask.mode != BNN_MASK_NONE) o += (size_t)(2 * (p.Dp + p.N1) + p.O * p.N2) * 4;
       o = (o + 15) & ~(size_t)15;
-      p.sm_bar = (int)o; o += (size_t)(v2 ? (int)B2_COUNT : (int)BAR_COUNT) * 8 + 16;
+      p.sm_bar = (int)o; o += (size_t)BAR_COUNT * 8 + 16;
       if (o <= (size_t)227 * 1024) { kpair = kp; plan->smem = o; }
     }
   }
-  (void)n_bars;
   if (!kpair) { set_error("tensor-core forward: weights do not fit shared memory even as a CTA pair"); return 1; }
   plan->kpair = kpair;
-  p.v2 = v2 ? 1 : 0;
   const int N1h = p.N1 / kpair, N2h = p.N2 / kpair;
   p.part_stride = 2LL * p.Dp * N1h + 2LL * p.K2 * N2h;
   p.img_stride = p.part_stride * kpair + vec_pad;
-  // tensor memory.  v1: D1 [N1] | D2 [N2] | A2 ring;  v2: D2[0] | D2[1] | two 16-column D1 slots | A2 ring
-  int ring = v2 ? (512 - 2 * p.N2 - 32) / kTcStageCols : (512 - p.N1 - p.N2) / kTcStageCols;
+  // tensor memory: D1 [N1] | D2 [N2] | A2 ring (as many 32-column stages as fit, 2..kTcRing)
+  int ring = (512 - p.N1 - p.N2) / kTcStageCols;
   if (ring > kTcRing) ring = kTcRing;
-  if (v2 && ring > 4) ring = 4;
   if (const char* e = getenv("BNN_TC_RING")) { const int v = atoi(e); if (v >= 2 && v < ring) ring = v; }  // tuning knob
   if (ring < 2) { set_error("tensor-core forward: accumulators and the activation ring exceed TMEM"); return 1; }
   p.ring = ring;
-  int cols = v2 ? 2 * p.N2 + 32 + ring * kTcStageCols : p.N1 + p.N2 + ring * kTcStageCols, tc = 32;
+  int cols = p.N1 + p.N2 + ring * kTcStageCols, tc = 32;
   while (tc < cols) tc <<= 1;
   p.tmem_cols = tc;
   p.X = a->X; p.N = a->N; p.S = (int)a->S; p.pred = a->pred;
@@ -1749,7 +1213,6 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   q.ld0 = L.ld[0]; q.ld1 = L.ld[1]; q.ld2 = L.ld[2];
   q.off0 = L.off[0]; q.off1 = L.off[1]; q.off2 = L.off[2];
   q.w_stride = a->w_stride; q.part_stride = p.part_stride; q.img_stride = p.img_stride; q.vec_len = p.vec_len; q.mixed = p.passes == 2;
-  q.perm = (p.v2 && kpair == 2) ? 1 : 0;
   return 0;
 }
 
@@ -1814,19 +1277,13 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
     return 0;
   };
   int lrc = 0;
-#define BNN_TC_LAUNCH(ACT)                                                                             \
-  case ACT:                                                                                            \
-    if (p.v2) lrc = plan.kpair == 1 ? launch(fwd_tc2_kernel<1, ACT>) : launch(fwd_tc2_kernel<2, ACT>);  \
-    else lrc = plan.kpair == 1 ? launch(fwd_tc_kernel<1, ACT>) : launch(fwd_tc_kernel<2, ACT>);        \
-    break;
+#define BNN_TC_LAUNCH(ACT)                                                         \
+  case ACT: lrc = plan.kpair == 1 ? launch(fwd_tc_kernel<1, ACT>) : launch(fwd_tc_kernel<2, ACT>); break;
   switch (p.act) {
     BNN_TC_LAUNCH(BNN_ACT_RELU)
     BNN_TC_LAUNCH(BNN_ACT_TANH)
     BNN_TC_LAUNCH(BNN_ACT_SIGMOID)
-    default:
-      if (p.v2) lrc = plan.kpair == 1 ? launch(fwd_tc2_kernel<1, BNN_ACT_IDENTITY>) : launch(fwd_tc2_kernel<2, BNN_ACT_IDENTITY>);
-      else lrc = plan.kpair == 1 ? launch(fwd_tc_kernel<1, BNN_ACT_IDENTITY>) : launch(fwd_tc_kernel<2, BNN_ACT_IDENTITY>);
-      break;
+    default: lrc = plan.kpair == 1 ? launch(fwd_tc_kernel<1, BNN_ACT_IDENTITY>) : launch(fwd_tc_kernel<2, BNN_ACT_IDENTITY>); break;
   }
 #undef BNN_TC_LAUNCH
   if (lrc) return lrc;

@@ -5,7 +5,7 @@ sys.path.insert(0, ".")
 from bnn_b200 import _lib
 names = ["tf32 SS K=8", "tf32 TS K=8", "bf16 SS K=16", "bf16 TS K=16", "mixed stage (2 tf32 + 2 bf16, TS)", "3xTF32 stage (TS)"]
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
-for N in (208, 256, 112, 64):
+for N in (208, 256, 112, 64, 32, 16):
     for mode in range(6):
         for iters in (240,):
             _lib.check(_lib.lib().bnn_tc_mma_bench(mode, N, iters, out.data_ptr(), None), "bench")
