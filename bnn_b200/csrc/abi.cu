@@ -1,6 +1,7 @@
 // C-ABI glue: error state, layout queries, forward dispatch and the host-buffer
 // (end-to-end) convenience entry point.  No torch types anywhere.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -35,9 +36,32 @@ long long forward_simt_workspace_bytes(const BnnForwardArgs* a);
 int forward_tc(const BnnForwardArgs* a, cudaStream_t st);
 long long forward_tc_workspace_bytes(const BnnForwardArgs* a);
 int forward_tc_supported(const BnnForwardArgs* a);
+int forward_tcl(const BnnForwardArgs* a, cudaStream_t st);
+long long forward_tcl_workspace_bytes(const BnnForwardArgs* a);
+int forward_tcl_supported(const BnnForwardArgs* a);
 
 static bool use_tc(const BnnForwardArgs* a) {
   return a->precision == BNN_PREC_TF32X3 || a->precision == BNN_PREC_TF32 || a->precision == BNN_PREC_TF32_BF16;
+}
+
+// tensor-core requests: the resident-weights kernel (forward_tc.cu) when the shape fits it, else the streaming kernel for
+// deep / wide networks (forward_tcl.cu); neither -> error with the first kernel's reason (no silent fallback)
+static bool prefer_stream() {   // tuning knob: BNN_TC_STREAM=1 sends every supported shape to the streaming kernel
+  const char* e = getenv("BNN_TC_STREAM");
+  return e && atoi(e) != 0;
+}
+static long long tc_workspace_bytes(const BnnForwardArgs* a) {
+  if (prefer_stream() && forward_tcl_supported(a)) return forward_tcl_workspace_bytes(a);
+  if (forward_tc_supported(a)) return forward_tc_workspace_bytes(a);
+  if (forward_tcl_supported(a)) return forward_tcl_workspace_bytes(a);
+  forward_tc_supported(a);   // restore the first kernel's message
+  return -1;
+}
+static int tc_forward(const BnnForwardArgs* a, cudaStream_t st) {
+  if (prefer_stream() && forward_tcl_supported(a)) return forward_tcl(a, st);
+  if (forward_tc_supported(a)) return forward_tc(a, st);
+  if (forward_tcl_supported(a)) return forward_tcl(a, st);
+  return forward_tc(a, st);  // fails with the reason
 }
 
 static int check_forward_args(const BnnForwardArgs* a, bool host) {
@@ -67,7 +91,10 @@ extern "C" const char* bnn_last_error(void) { return g_err; }
 extern "C" int32_t bnn_sm_count(void) { return sm_count(); }
 extern "C" int32_t bnn_forward_tc_supported(const BnnForwardArgs* a) {
   if (!a) { set_error("null args"); return 0; }
-  return forward_tc_supported(a);
+  if (forward_tc_supported(a)) return 1;
+  if (forward_tcl_supported(a)) return 1;
+  forward_tc_supported(a);   // leave the resident-weights kernel's reason in bnn_last_error()
+  return 0;
 }
 extern "C" int32_t bnn_set_device(int32_t device) {
   BNN_CUDA(cudaSetDevice(device));
@@ -100,12 +127,12 @@ extern "C" int64_t bnn_mask_len(const BnnMlpDesc* d, const int32_t* layer_masked
 
 extern "C" int64_t bnn_forward_workspace_bytes(const BnnForwardArgs* a) {
   if (!a) { set_error("null args"); return -1; }
-  return use_tc(a) ? forward_tc_workspace_bytes(a) : forward_simt_workspace_bytes(a);
+  return use_tc(a) ? tc_workspace_bytes(a) : forward_simt_workspace_bytes(a);
 }
 
 extern "C" int32_t bnn_forward(const BnnForwardArgs* a, void* stream) {
   if (check_forward_args(a, false)) return -1;
-  return use_tc(a) ? forward_tc(a, (cudaStream_t)stream) : forward_simt(a, (cudaStream_t)stream);
+  return use_tc(a) ? tc_forward(a, (cudaStream_t)stream) : forward_simt(a, (cudaStream_t)stream);
 }
 
 // ---- host-buffer path ---------------------------------------------------------
@@ -209,7 +236,7 @@ extern "C" int32_t bnn_forward_host(const BnnForwardArgs* ah) {
     BnnForwardArgs c = a;
     c.mean = c.var = nullptr;
     c.S = chunk;
-    const long long wsb = use_tc(&c) ? forward_tc_workspace_bytes(&c) : forward_simt_workspace_bytes(&c);
+    const long long wsb = use_tc(&c) ? tc_workspace_bytes(&c) : forward_simt_workspace_bytes(&c);
     if (wsb < 0) return -1;
     if (g_ws.ensure(BWS, (size_t)(wsb > 16 ? wsb : 16))) return -2;
     c.workspace = g_ws.buf[BWS];
@@ -228,7 +255,7 @@ extern "C" int32_t bnn_forward_host(const BnnForwardArgs* ah) {
       if (a.mask.mode == BNN_MASK_EXTERNAL) c.mask.mask = a.mask.mask + lo * a.mask.mask_stride;
       c.mask.sample_offset = a.mask.sample_offset + lo;          // in-kernel Philox streams are indexed by the global sample
       counts[i] = n;
-      const int rc = use_tc(&c) ? forward_tc(&c, st) : forward_simt(&c, st);
+      const int rc = use_tc(&c) ? tc_forward(&c, st) : forward_simt(&c, st);
       if (rc) return rc;
       BNN_CUDA(cudaEventRecord(g_ws.ev_free[i & 1], st));
     }
@@ -264,12 +291,12 @@ extern "C" int32_t bnn_forward_host(const BnnForwardArgs* ah) {
     a.part_mean = ah->part_mean ? (double*)g_ws.buf[BPART] : nullptr;
     a.part_m2 = ah->part_m2 ? (double*)g_ws.buf[BPART] + M : nullptr;
   }
-  const long long wsb = use_tc(&a) ? forward_tc_workspace_bytes(&a) : forward_simt_workspace_bytes(&a);
+  const long long wsb = use_tc(&a) ? tc_workspace_bytes(&a) : forward_simt_workspace_bytes(&a);
   if (wsb < 0) return -1;
   if (g_ws.ensure(BWS, (size_t)(wsb > 16 ? wsb : 16))) return -2;
   a.workspace = g_ws.buf[BWS];
   a.workspace_bytes = wsb;
-  const int rc = use_tc(&a) ? forward_tc(&a, st) : forward_simt(&a, st);
+  const int rc = use_tc(&a) ? tc_forward(&a, st) : forward_simt(&a, st);
   if (rc) return rc;
   if (ah->pred) BNN_CUDA(cudaMemcpyAsync(ah->pred, a.pred, (size_t)a.S * M * 4, cudaMemcpyDeviceToHost, st));
   if (ah->mean) BNN_CUDA(cudaMemcpyAsync(ah->mean, a.mean, (size_t)M * 4, cudaMemcpyDeviceToHost, st));

@@ -243,3 +243,51 @@ def test_random_shape_sweep_tc_vs_simt():
             assert max_rel(b["mean"].cpu(), a["mean"].cpu()) <= 1e-5, (dims, act, S, N, masked, prec)
         done += 1
     assert done >= 15
+
+
+@pytest.mark.parametrize("dims,act,S,N", [
+    ([90, 512, 512, 512, 1], "tanh", 5, 1000),       # cfg 5's network: three hidden layers of 512
+    ([90, 512, 512, 512, 1], "relu", 3, 300),
+    ([7, 300, 1], "relu", 9, 777),                   # one hidden layer, width not a multiple of 32: N-tiles 256 + 48
+    ([20, 64, 96, 40, 3], "sigmoid", 4, 520),        # three hidden layers, uneven widths, nout = 3 (sigmoid(0) != 0 in the padding)
+    ([1000, 1024, 2], "tanh", 2, 260),               # widest supported: K = 1024 input, four N-tiles
+    ([16, 320, 320, 1], "relu", 1, 200),             # H > 256: outside the resident-weights family; S = 1 -> var NaN
+    ([33, 40, 40, 40, 40, 40, 2], "identity", 3, 130),   # five hidden layers
+])
+def test_deep_wide_streaming_kernel_matches_oracle(dims, act, S, N):
+    """fwd_tcl_kernel (forward_tcl.cu): any depth, widths up to 1024, FP32-grade TF32 + BF16 products; 1e-5 vs the oracle."""
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    arch = Arch(dims, act)
+    assert ops.tc_supported(arch, S=S)                      # ... through the streaming kernel
+    nets = random_nets(dims, S, seed=sum(dims) + S)
+    X = torch.randn(N, dims[0], generator=torch.Generator().manual_seed(N))
+    ref = O.sample_predict(nets, X, act, nout=dims[-1])
+    out = run(dims, act, nets, X, "tf32_bf16")
+    assert max_rel(out["pred"], ref) <= 1e-5, max_rel(out["pred"], ref)
+    mean_ref, var_ref = O.predict_mv(ref, N)
+    assert max_rel(out["mean"], mean_ref) <= 1e-5
+    if S > 1:
+        dv = (out["var"].double() - var_ref.double()).abs()
+        # the forward's own rounding grows with the length of the dot products (K up to 1024 here)
+        vb = var_bound(ref, c=256.0 * max(1.0, max(dims) / 128.0), depth=len(dims) - 1)
+        assert bool((dv <= vb).all()), float((dv / vb).max())
+    else:
+        assert bool(torch.isnan(out["var"]).all())
+
+
+def test_deep_wide_moments_only_and_sample_groups():
+    """Few points, many samples: sample groups (G > 1) + Chan merge of the groups; moments without materialising pred."""
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    dims, act, S, N = [12, 288, 288, 1], "tanh", 37, 300
+    arch = Arch(dims, act)
+    nets = random_nets(dims, S, seed=5)
+    X = torch.randn(N, 12, generator=torch.Generator().manual_seed(6))
+    out = ops.forward(arch, X.cuda(), arch.pack(nets).cuda(), want_pred=False, want_moments=True, want_partials=True, precision="tf32_bf16")
+    ref = O.sample_predict(nets, X, act, nout=1)
+    mean_ref, var_ref = O.predict_mv(ref, N)
+    assert max_rel(out["mean"].cpu(), mean_ref) <= 1e-5
+    dv = (out["var"].cpu().double() - var_ref.double()).abs()
+    assert bool((dv <= var_bound(ref, c=256.0, depth=3)).all())
+    assert max_rel(out["part_mean"].cpu(), ref.double().mean(0).reshape(N, 1)) <= 1e-5
