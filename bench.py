@@ -4,7 +4,7 @@
 Workload (BASELINE.json configs[3], "synthetic predictive sweep"): N = 1M points x S = 10k SGLD samples, 2x200 ReLU MLP
 (D = 16).  The S = 10k samples are sharded over the GPUs (STRONG scaling: 1 GPU evaluates all 10k, 8 GPUs 1250 each); one
 "step" is one predict_mv over the whole job: operand-image prep + fused forward + Welford reduction on every rank, then --
-for more than one GPU -- the NCCL all-gather of the per-point float64 (mean, M2) and the Chan merge.
+for more than one GPU -- bnn_moments_allreduce (NCCL reduce-scatter of float64 raw moments, slice finalisation, all-gather).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]           # our CUDA path
     python bench.py --impl reference ...                          # the reference's CPU torch loop
@@ -201,9 +201,12 @@ def run_ours(args):
             except Exception as e:
                 sgld_cpu = {"error": repr(e)[:200]}
 
+    nccl_merge = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
+        from bnn_b200.distributed import NcclMoments
+        nccl_merge = NcclMoments(dev)                             # the collective of the C ABI (bnn_moments_allreduce)
     n_gpus = world
 
     arch = Arch(DIMS, ACT)
@@ -219,7 +222,7 @@ def run_ours(args):
         out = ops.forward(arch, X, bank, want_pred=False, want_moments=(world == 1), want_partials=(world > 1),
                           precision=args.precision)
         if world > 1:
-            return merge_shards(out["part_mean"], out["part_m2"], S)
+            return nccl_merge.merge(out["part_mean"], out["part_m2"], S)
         return out["mean"], out["var"]
 
     host_out = {}
@@ -232,7 +235,7 @@ def run_ours(args):
             return host_out["mean"], host_out["var"]
         host_out = ops.forward_host(arch, X_host, bank_host, want_moments=False, want_partials=True, precision=args.precision,
                                     out=host_out)
-        mean, var = merge_shards(host_out["part_mean"].to(dev, non_blocking=True), host_out["part_m2"].to(dev, non_blocking=True), S)
+        mean, var = nccl_merge.merge(host_out["part_mean"].to(dev, non_blocking=True), host_out["part_m2"].to(dev, non_blocking=True), S)
         return mean.cpu(), var.cpu()
 
     def barrier():
@@ -340,7 +343,7 @@ def run_ours(args):
                     "peak_source": "FP32 FFMA microbenchmark measured live (bnn_measure_fp32_tflops); "
                                    "MEASURED_PEAKS.json has no FP32-SIMT figure",
                     "frac_of_bf16_tensor_peak": per_gpu_tflops / bf16_peak, "bf16_peak": bf16_peak}
-        launches_per_step = (3 if tc else 2) + (1 if world > 1 else 0)
+        launches_per_step = (3 if tc else 2) + (3 if world > 1 else 0)   # + pack / finalise / unpack kernels around the two NCCL calls
         h2d = int((bank.numel() + X.numel()) * 4) + (int(2 * N_POINTS * 8) if world > 1 else 0)
         d2h = int(2 * N_POINTS * DIMS[-1] * 4) + (int(2 * N_POINTS * 8) if world > 1 else 0)
         line = {
@@ -353,7 +356,7 @@ def run_ours(args):
                       "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": workload_name(n_gpus), "precision": args.precision, "samples_per_gpu": S,
                        "l2": f"inputs {(bank.numel() + X.numel()) * 4 / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)",
-                       "parallelism": f"samples sharded x{n_gpus}" + (", all-gather of float64 (mean, M2) + Chan merge" if n_gpus > 1 else "")},
+                       "parallelism": f"samples sharded x{n_gpus}" + (", bnn_moments_allreduce: NCCL reduce-scatter of float64 raw moments + slice finalisation + all-gather" if n_gpus > 1 else "")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e / e2e_steps, "steps": e2e_steps,
                     "api": "bnn_forward_host (C ABI, host pointers: H2D of X and of the bank in chunks overlapped with the "
@@ -368,6 +371,7 @@ def run_ours(args):
         }
         _emit(line)
     if world > 1:
+        nccl_merge.close()
         dist.destroy_process_group()
 
 

@@ -67,6 +67,10 @@ PROTOTYPES = {
                                       C.c_void_p, C.c_void_p]),
     "bnn_moments_merge_partials": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_int64, C.c_void_p,
                                                C.c_void_p, C.c_void_p]),
+    "bnn_nccl_load": (C.c_int32, [C.c_char_p]),
+    "bnn_moments_allreduce_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
+    "bnn_moments_allreduce": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "bnn_metrics": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                 C.c_void_p, C.c_void_p]),
     "bnn_reparam_kl": (C.c_int32, [C.POINTER(MlpDesc), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,

@@ -44,7 +44,7 @@ def build(force=False, verbose=False, trace=False):
             cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             subprocess.run(cmd, check=True)
     if force or _stale(lib, objs):
-        cmd = [nvcc, "-shared", "-cudart", "static", "-o", lib] + objs
+        cmd = [nvcc, "-shared", "-cudart", "static", "-o", lib] + objs + ["-ldl"]
         subprocess.run(cmd, check=True)
     return lib
 

@@ -41,3 +41,78 @@ def merge_shards(part_mean, part_m2, count, group=None, merge_fn=None):
     pm = gathered[:, 0].contiguous().view((R,) + shape)
     pm2 = gathered[:, 1].contiguous().view((R,) + shape)
     return merge_fn(pm, pm2, cnts.tolist())
+
+
+# ---- the collective inside the C ABI (bnn_moments_allreduce) ---------------------------------------------------------------
+import ctypes as _C
+import glob as _glob
+import os as _os
+
+
+def _nccl_path():
+    """The libnccl this process uses: the one bundled with torch (nvidia/nccl/lib), else the system's."""
+    import sys
+    for base in sys.path:
+        hits = _glob.glob(_os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2"))
+        if hits:
+            return hits[0]
+    return "libnccl.so.2"
+
+
+class _UniqueId(_C.Structure):
+    _fields_ = [("internal", _C.c_char * 128)]
+
+
+class NcclMoments:
+    """An NCCL communicator owned by this package (created with ncclCommInitRank from the process group's ranks; the unique id
+    travels through torch.distributed) + the C-ABI collective that merges sample-sharded predictive moments:
+    reduce-scatter of float64 raw moments, finalisation of this rank's slice of points, optional all-gather (see
+    include/bnn_b200.h).  One instance per process; all calls are stream-ordered on torch's current stream."""
+
+    def __init__(self, device, group=None):
+        from . import _lib
+        self.device = torch.device(device)
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        path = _nccl_path()
+        self._nccl = _C.CDLL(path, mode=_C.RTLD_GLOBAL)
+        _lib.check(_lib.lib().bnn_nccl_load(path.encode()), "bnn_nccl_load")
+        uid = _UniqueId()
+        if self.rank == 0:
+            rc = self._nccl.ncclGetUniqueId(_C.byref(uid))
+            if rc != 0:
+                raise RuntimeError(f"ncclGetUniqueId failed ({rc})")
+        t = torch.frombuffer(bytearray(bytes(uid.internal) if self.rank == 0 else bytes(128)), dtype=torch.uint8).clone()
+        t = t.to(self.device) if dist.get_backend(group) == "nccl" else t
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(t.cpu().numpy().tobytes())
+        _C.memmove(_C.byref(uid), raw, 128)
+        self.comm = _C.c_void_p()
+        torch.cuda.set_device(self.device)
+        self._nccl.ncclCommInitRank.argtypes = [_C.POINTER(_C.c_void_p), _C.c_int, _UniqueId, _C.c_int]
+        rc = self._nccl.ncclCommInitRank(_C.byref(self.comm), self.world, uid, self.rank)
+        if rc != 0:
+            raise RuntimeError(f"ncclCommInitRank failed ({rc})")
+        self._ws = None
+
+    def merge(self, part_mean, part_m2, count, gather=True):
+        """(mean, var) float32 [..] from this rank's float64 shard moments; gather=False leaves only this rank's slice valid."""
+        from . import _lib, ops
+        if part_mean.dtype != torch.float64 or not part_mean.is_cuda:
+            raise TypeError("shard moments must be float64 CUDA tensors")
+        M = part_mean.numel()
+        L = _lib.lib()
+        need = int(L.bnn_moments_allreduce_workspace_bytes(M, self.world))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        mean = torch.empty(part_mean.shape, dtype=torch.float32, device=self.device)
+        var = torch.empty(part_mean.shape, dtype=torch.float32, device=self.device)
+        _lib.check(L.bnn_moments_allreduce(self.comm, ops._ptr(part_mean.contiguous()), ops._ptr(part_m2.contiguous()), int(count), M,
+                                           ops._ptr(mean), ops._ptr(var), 1 if gather else 0, ops._ptr(self._ws), self._ws.numel(),
+                                           ops._stream(mean)), "bnn_moments_allreduce")
+        return mean, var
+
+    def close(self):
+        if self.comm:
+            self._nccl.ncclCommDestroy(self.comm)
+            self.comm = _C.c_void_p()

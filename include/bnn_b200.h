@@ -153,6 +153,19 @@ int32_t bnn_moments_merge(const double* part_mean, const double* part_m2, const 
 int32_t bnn_moments_merge_partials(const double* part_mean, const double* part_m2, const int64_t* counts_host,
                                    int32_t R, int64_t M, double* out_mean, double* out_m2, void* stream);
 
+/* ---- (e) multi-GPU: exchange of the per-point moments over NCCL ----------------- */
+/* One process per GPU, samples sharded over the ranks: every rank passes the float64 (mean, M2) of ITS `count`
+ * samples for all M points; float64 raw moments (n mean, M2 + n mean^2) are reduce-scattered (ncclSum), each rank finalises
+ * M / R points, and with gather != 0 an all-gather hands every rank the full float32 mean / unbiased var (what
+ * BNN.predict_mv returns, BNN.py:34-37); with gather == 0 a rank only writes its own slice [rank*ceil(M/R), ...) of mean / var.
+ * Payload per rank: 16 M bytes reduce-scatter (+ 8 M all-gather), independent of R; stream-ordered, no host sync.
+ * nccl_comm is an ncclComm_t created by the caller from the SAME libnccl that bnn_nccl_load opened (NULL path =
+ * "libnccl.so.2" on the default search path; call it first with the path of the NCCL your process uses).               */
+int32_t bnn_nccl_load(const char* path);
+int64_t bnn_moments_allreduce_workspace_bytes(int64_t M, int32_t n_ranks);
+int32_t bnn_moments_allreduce(void* nccl_comm, const double* part_mean, const double* part_m2, int64_t count, int64_t M,
+                              float* mean, float* var, int32_t gather, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* replaces: BNN.validate's rmse / nll lines (BNN.py:30-31) and, with
  * noise_var != NULL (per output, device), experiments/SGDMC.py:83-93.
  * out = {rmse[nout], nll[nout]} floats followed by one float holding the count
