@@ -1216,6 +1216,29 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   return 0;
 }
 
+// Bytes of the L2 set-aside a launch may pin (0: none).  The set-aside is sized once per device, on first use, to what the
+// device allows (it stays usable by normal accesses whenever no persisting lines occupy it).  BNN_TC_L2PERSIST=0 turns it off.
+static long long l2_persist_window(long long want) {
+  static long long cap[64];
+  static bool done[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (!done[dev]) {
+    done[dev] = true;
+    cap[dev] = 0;
+    const char* e = getenv("BNN_TC_L2PERSIST");
+    if (!(e && atoi(e) == 0)) {
+      int max_persist = 0, max_win = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+      long long c = max_persist < max_win ? max_persist : max_win;
+      if (c > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)c) == cudaSuccess) cap[dev] = c;
+      cudaGetLastError();
+    }
+  }
+  return want < cap[dev] ? want : cap[dev];
+}
+
 static unsigned long long* g_tc_trace = nullptr;
 unsigned long long* tc_trace_buffer() { return g_tc_trace; }
 
@@ -1264,13 +1287,27 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
   cfg.blockDim = dim3(kTcThreads, 1, 1);
   cfg.dynamicSmemBytes = plan.smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)plan.kpair;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // The running (mean, M2) state is read and written once per sample by the thread that owns the point; together with X it is
+  // the kernel's whole re-used working set.  Pin it in the L2 set-aside so that only X competes for the rest of the cache.
+  if (want_moments && plan.part_bytes > 0) {
+    const long long win = l2_persist_window(plan.part_bytes);
+    if (win > 0) {
+      attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+      attr[1].val.accessPolicyWindow.base_ptr = p.part;
+      attr[1].val.accessPolicyWindow.num_bytes = (size_t)(plan.part_bytes < win ? plan.part_bytes : win);
+      attr[1].val.accessPolicyWindow.hitRatio = 1.0f;
+      attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+      cfg.numAttrs = 2;
+    }
+  }
   auto launch = [&](auto kern) -> int {
     BNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     BNN_CUDA(cudaLaunchKernelEx(&cfg, kern, p));

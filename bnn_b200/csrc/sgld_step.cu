@@ -3,15 +3,15 @@
 //   minibatch gather (DataLoader batch, :80,110) -> L forward layers (util.py:31-33) -> Gaussian log-likelihood + priors and
 //   dU/d(out) (:61-74,83) -> backward (dW, dh; what loss.backward() computes, :85) -> preconditioned SGLD update with
 //   in-kernel Philox noise and the LambdaLR factor (:86-87,96-101).
-// No library GEMM, no elementwise launches: every phase is a set of tile jobs spread over the CTAs, phases are separated by
-// a grid barrier (2 L barriers per step).  The gradient never exists in memory: the CTA that finishes a dW tile applies the
-// update to that tile of (theta, V) in its epilogue.
+// No library GEMM, no elementwise launches, no grid barrier: a step is a list of tile jobs that the CTAs pull from a global
+// counter and whose inputs are tracked by completion counters (see "the step as a dataflow job list" below).  The gradient
+// never exists in memory: the CTA that finishes a dW tile applies the update to that tile of (theta, V) in its epilogue.
 //
 // Why FP32 FFMA and not tcgen05 here (north_star: "tensor cores only where width x S makes it a real contraction"): at
-// cfg 5 a step is 438 MFLOP spread over 8 dependent phases; one phase is a [128 x 512 x 512] product = 0.26 MFLOP per
-// CTA-tile when spread over 128 SMs, i.e. ~2k cycles of FFMA, the same order as the L2 -> SM ingest of the tile's operands
-// and as the grid barrier.  The step is latency / barrier bound, not FLOP bound; FP32 also keeps the gradient bit-comparable
-// (1e-6) with the reference's autograd.
+// cfg 5 a step is 438 MFLOP spread over a chain of 8 dependent products; one of them is [128 x 512 x 512] = 0.26 MFLOP per
+// CTA-tile when spread over 128 SMs, i.e. ~2k cycles of FFMA, the same order as the L2 -> SM ingest of the tile's operands.
+// The step is latency / dependency bound, not FLOP bound; FP32 also keeps the gradient bit-comparable (1e-6) with the
+// reference's autograd.
 //
 // Layout: every product is brought into the "NT" form C[m, n] = sum_k A[m, k] * B[n, k] with both operands K-contiguous:
 //   forward  l : C = z_l[b, j]        A = h_l[b, 0:ld_l]   (augmented (h | 1 | 0))   B = theta_l[j, 0:ld_l]  ((W | b | 0))
@@ -19,7 +19,7 @@
 //   dh       l : C = dh_l[b, k]       A = dz_l[b, 0:ldz_l]                           B = thetaT_l[k, 0:ldT_l]
 // so activations and output gradients are stored twice (row-major and transposed) by the producing epilogue, and the
 // weights of layers >= 1 carry a transposed copy maintained by the update epilogue.  theta / thetaT are double-buffered by
-// step parity: all reads of a step see theta_cur, all updates write theta_next -- no intra-step hazards, no extra barrier.
+// step parity: all reads of a step see theta_cur, all updates write theta_next -- no intra-step hazards.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -28,7 +28,10 @@
 
 namespace bnn {
 
-constexpr int kSgThreads = 256;
+constexpr int kSgThreads = 256;       // compute threads
+constexpr int kSgBlock = kSgThreads + 32;   // + the scheduler warp
+// compute-only barrier (the scheduler warp never joins): named barrier 1
+__device__ __forceinline__ void sg_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 constexpr int kSgKC = 64;            // K chunk (floats)
 constexpr int kSgLds = kSgKC + 4;    // smem row pitch: 68 words = 4 (mod 32) -> 8 consecutive rows hit 32 distinct banks
 // Stage counts per tile family.  A tile's operands are tiny (<= 110 KB) but every access is an L2 round trip of ~450
@@ -40,17 +43,33 @@ constexpr int kSgMaxStages = 12;
 
 struct SgLayer {
   int in, out, ld, ldz, ldT;
+  int ncb, nkb, ndw;         // 16-column tiles of the output / of the input, dW tiles (+ 1 for the last layer: the log-precision job)
   long long off, offT;       // float offsets into theta / thetaT
-  float* h;                  // input of Linear l, augmented: [Bp, ld]   (null for l = 0: gathered from X)
-  float* hT;                 // [ld, Bp]                                  (null for l = 0)
+  float* h[2];               // input of Linear l, augmented: [Bp, ld], by step parity   (null for l = 0: gathered from X)
+  float* hT[2];              // [ld, Bp]                                                  (null for l = 0)
   float* dz;                 // dU/d(pre-activation output of Linear l): [Bp, ldz]
   float* dzT;                // [out, Bp]
   float inv_var;             // 1 / std_l^2 of the weight prior, std_l = gain * sqrt(2 / (in + out))   (BNN_SGDMC.py:65)
 };
 
+// one run of same-kind jobs in a step's job list
+struct SgSeg { int type, l, first, count; };
+constexpr int kSgMaxSeg = 3 * BNN_MAX_LINEAR + 4;
+constexpr int kSgMaxRb = 32;           // 32-row blocks of a batch of <= 1024
+constexpr int kSgTraceRecs = 96;
+constexpr int kSgTraceW = 10;          // words per record       // debug timeline: job records per CTA
+// completion counters (unsigned int, zero at launch): [0] = next job index
+__host__ __device__ constexpr int sg_c_fwd(int l, int rb) { return 16 + l * kSgMaxRb + rb; }
+__host__ __device__ constexpr int sg_c_dh(int l, int rb) { return 16 + (BNN_MAX_LINEAR + l) * kSgMaxRb + rb; }
+__host__ __device__ constexpr int sg_c_dht(int l) { return 16 + 2 * BNN_MAX_LINEAR * kSgMaxRb + l; }
+__host__ __device__ constexpr int sg_c_dw(int l) { return 16 + 2 * BNN_MAX_LINEAR * kSgMaxRb + BNN_MAX_LINEAR + l; }
+constexpr int kSgCounters = 16 + 2 * BNN_MAX_LINEAR * kSgMaxRb + 2 * BNN_MAX_LINEAR;
+
 struct SgParams {
   int L, act, B, Bp, nout, D;
   SgLayer ly[BNN_MAX_LINEAR];
+  SgSeg seg[kSgMaxSeg];
+  int n_seg, jobs_per_step;
   float* theta[2];
   float* thetaT[2];
   float* V;
@@ -64,13 +83,15 @@ struct SgParams {
   float lr_w, lr_n, alpha, lam, al, be, lgamma_al, log_be, log_const;
   int precond_mode;                    // 0: G = 1 / (lam + sqrt(V))   1: G = 1 / sqrt(V + lam)
   unsigned long long seed;
-  double* acc;                         // [nout] sum r^2 per output | [nout] prior quad (one slot used) -- zero before launch
-  unsigned int* bar;                   // grid barrier counter, zero before launch
+  double* acc;                         // by step parity: [nout] sum r^2 per output | prior quad -- zero before launch
+  unsigned int* cnt;                   // job / completion counters [kSgCounters], zero before launch
+  float* fs;                           // [2] LambdaLR factor of the step, by step parity (written one step ahead by LOGP)
+  float f0;                            // ... of the launch's first step
   int* err;
   float* loss_out;                     // U of the LAST step of the launch (may be null)
   float* grad_out;                     // debug: when non-null the step writes dU/dtheta here and does NOT update
   int dbg;                             // debug (BNN_SGLD_DBG): 1 skip the FMA loop, 2 skip the dense loads, 4 skip the epilogues
-  long long* trace;                    // debug: [grid][2 * L phases][2] clock64 (work done, barrier passed) of the LAST step
+  long long* trace;                    // debug: [grid][kSgTraceRecs][6] = {job code, grabbed, inputs ready, done (clock64), grabbed, done (globaltimer ns)}, last two steps
 };
 
 // ---- small helpers ---------------------------------------------------------------------------------------------------
@@ -85,27 +106,6 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
-}
-
-// Grid barrier on a monotonically increasing counter.  Co-residency of all CTAs is guaranteed by the cooperative launch.
-// A spin limit turns a (never expected) deadlock into an error code instead of a hung GPU.
-__device__ __forceinline__ bool grid_barrier(unsigned int* counter, unsigned int& target, int* err, int* s_flag) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    target += gridDim.x;
-    // release at gpu scope: the CTA's writes (ordered before this by the bar.sync above) are visible to whoever acquires
-    // the counter; cheaper than __threadfence() (= fence.sc.gpu) followed by a relaxed add
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-    unsigned long long spins = 0;
-    int bad = 0;
-    while ((int)(ld_acquire_u32(counter) - target) < 0) {
-      if (++spins > (1ull << 26)) { atomicExch(err, 1); bad = 1; break; }
-      if ((spins & 1023) == 0 && *((volatile int*)err) != 0) { bad = 1; break; }
-    }
-    *s_flag = bad;
-  }
-  __syncthreads();
-  return *s_flag == 0;
 }
 
 __device__ __forceinline__ float act_fwd(float v, int act) { return apply_act(v, act); }
@@ -135,7 +135,7 @@ struct SgOperand {
 // what the gather kinds need (X[perm[b] * D + k]; batch rows >= rows_live are zero: short last batch of an epoch)
 struct SgGather {
   const float* __restrict__ X;
-  const long long* perm;   // this step's batch rows (shared-memory copy of perm[off .. off + B))
+  const long long* perm;   // this step's batch rows: perm + off (read-only for the whole launch)
   int D, B, rows_live;
 };
 
@@ -154,7 +154,7 @@ __device__ __forceinline__ void load_gather(const SgGather& gq, int row0, int k0
       const int b = kT ? k0 + kk : row0 + r, f = kT ? row0 + r : k0 + kk;
       v[u] = 0.0f;
       if (idx < ROWS * kSgKC && b < gq.rows_live) {
-        if (f < gq.D) v[u] = __ldg(gq.X + gq.perm[b] * gq.D + f);
+        if (f < gq.D) v[u] = __ldg(gq.X + __ldg(gq.perm + b) * gq.D + f);
         else if (f == gq.D) v[u] = 1.0f;
       }
     }
@@ -217,21 +217,28 @@ __device__ __forceinline__ void tile_core(const SgOperand& A, const SgOperand& B
     if (!a_dense) load_gather<TM, false>(gq, m0, c * kSgKC, st);
     if (!b_dense) load_gather<TN, true>(gq, n0, c * kSgKC, st + TM * kSgLds);
   };
-  // prologue: everything the ring holds
+  // prologue: the first chunks; the rest of what the ring holds is issued from inside the K loop, kLead chunks ahead of the
+  // chunk being consumed (every stage is used once per tile while K <= NS * 64, so no hand-shake is needed), which overlaps
+  // the cp.async issue (LSU bound, ~390 cycles per chunk) with the FMA work of the earlier chunks.  Gathered operands (Linear 0)
+  // are plain stores behind a __syncthreads and stay in the prologue.
+  constexpr int kLead = 3;
+  const int nring = min(nchunks, NS);
+  const bool gathered = !a_dense || !b_dense;
   {
-    const int npre = min(nchunks, NS);
+    const int npre = gathered ? nring : min(nring, kLead);
 #pragma unroll 1
     for (int c = 0; c < npre; ++c) issue_dense(c);
-    if (!a_dense || !b_dense) {
+    if (gathered) {
 #pragma unroll 1
       for (int c = 0; c < npre; ++c) issue_gather(c);
-      __syncthreads();                     // gathered rows are plain shared-memory stores
+      sg_sync();                     // gathered rows are plain shared-memory stores
     }
   }
   if (probe && tid == 0) probe[1] = clock64();
 #pragma unroll 1
   for (int c = 0; c < nchunks; ++c) {
     const int s = c % NS;
+    if (!gathered && c + kLead < nring) issue_dense(c + kLead);
     if (!(dbg & 2)) mbar_wait_spin(&bars[s], (phase_bits >> s) & 1u);
     phase_bits ^= 1u << s;
     const float* As = smem + s * STAGE + ty * kSgLds;
@@ -256,19 +263,19 @@ __device__ __forceinline__ void tile_core(const SgOperand& A, const SgOperand& B
         }
     }
     if (c + NS < nchunks) {                // refill this stage (only for K beyond the ring: layers wider than 768 / 384)
-      __syncthreads();                     // every warp is done with chunk c
+      sg_sync();                     // every warp is done with chunk c
       issue_dense(c + NS);
-      if (!a_dense || !b_dense) { issue_gather(c + NS); __syncthreads(); }
+      if (!a_dense || !b_dense) { issue_gather(c + NS); sg_sync(); }
     }
   }
-  __syncthreads();                         // all slices done with the stages: reuse them for the cross-slice reduction
+  sg_sync();                         // all slices done with the stages: reuse them for the cross-slice reduction
   if (probe && tid == 0) probe[2] = clock64();
   float* red = smem + TM * TN;             // [KS][TM * TN] partials behind the [TM * TN] result
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) red[ks * (TM * TN) + (ty + TY * i) * TN + tx + TX * j] = acc[i][j];
-  __syncthreads();
+  sg_sync();
 #pragma unroll 1
   for (int q = tid; q < TM * TN / 4; q += kSgThreads) {
     float4 v = *reinterpret_cast<const float4*>(red + q * 4);
@@ -279,7 +286,7 @@ __device__ __forceinline__ void tile_core(const SgOperand& A, const SgOperand& B
     }
     *reinterpret_cast<float4*>(smem + q * 4) = v;
   }
-  __syncthreads();
+  sg_sync();
   if (probe && tid == 0) probe[3] = clock64();
 }
 
@@ -291,28 +298,207 @@ __device__ __forceinline__ void psgld_update1(float& t, float& v, float g, float
 }
 
 constexpr int FT_M = 32, FT_N = 16;   // forward / dh tiles over [batch, features]
+constexpr int kSgHeadCols = 64;       // columns of the last hidden layer per HEAD job
 constexpr int WT_M = 64, WT_N = 32;   // dW tiles over [out, ld]
 
-__global__ void __launch_bounds__(kSgThreads, 1) sgld_step_kernel(const __grid_constant__ SgParams p) {
+// ---- the step as a dataflow job list ---------------------------------------------------------------------------------------
+// One step = a fixed, topologically ordered list of tile jobs; the launch's list is n_steps copies of it.  CTAs take jobs from
+// the head of the list with an atomic counter (the next index is fetched while the current job runs) and wait for the job's
+// inputs on monotonically increasing completion counters in global memory (red.release / ld.acquire at gpu scope) -- there is
+// no grid-wide barrier anywhere.  Because the list is topologically ordered and every CTA is resident (cooperative launch),
+// the oldest unfinished job always has its inputs complete: no deadlock.  Dependencies are per 32-row block of the batch where
+// the data flow allows it (forward and dh chains), so the layers of one step overlap, and the weight-update jobs (dW tile +
+// prior gradient + pSGLD update) are off the critical path: they only gate the NEXT step's use of that layer.
+//   FWD(l, rb, cb)   l <= L-2: h_{l+1}[rb rows, cb cols] = act(h_l theta_l^T)      needs FWD(l-1, rb, *), all DW(l) of step t-1
+//   HEAD(rb)         last Linear + Gaussian likelihood head + dz_{L-1} + dz_{L-2} for 32 batch rows (GEMV-sized: no tile core)
+//                                                                                needs FWD(L-2, rb, *), all DW(L-1) of step t-1
+//   DH(l, rb, kb)    1 <= l <= L-2: dz_{l-1} = (dz_l theta_l) * act'(h_l)          needs DH(l+1, rb, *)  (HEAD(rb) for l = L-2)
+//   DW(l, tile)      dW_l tile, + prior gradient, pSGLD update of theta/thetaT/V   needs every producer of dz_l
+//   LOGP             log-precision group                                          needs every HEAD
+//   LOSS             U of the launch's last step                                  needs everything of that step
+// Buffers: theta / thetaT by step parity (readers of step t see "cur", DW writes "next"); h / hT by step parity as well (DW(l+1)
+// of step t may still read hT_{l+1} while FWD(l) of step t+1 writes it); dz / dzT and V single (ordered by the chains above).
+enum { JT_FWD = 0, JT_HEAD = 1, JT_DH = 2, JT_DW = 3, JT_LOGP = 4, JT_LOSS = 5 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+__device__ __forceinline__ void red_release_inc(unsigned int* c) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_cta_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// A decoded job, handed from the scheduler warp to the compute warps through shared memory.
+struct SgJob {
+  int type;                 // JT_*, -1 = the list is exhausted, -2 = a dependency wait timed out
+  int l, jj, rb, cb, it;
+  int nd, ns;               // counters to wait for / to signal
+  int dc[2], sc[2];
+  unsigned int dt[2];
+  long long t_grab, g_grab, t_ready;   // debug timeline: clock64 / globaltimer at the grab, clock64 when the inputs were complete
+};
+
+__device__ __forceinline__ void sg_decode(const SgParams& p, unsigned int idx, unsigned int total, SgJob* J) {
+  J->nd = 0; J->ns = 0;
+  if (idx >= total) { J->type = -1; return; }
+  const int L = p.L;
+  const int bm = (p.B + FT_M - 1) / FT_M;
+  const int it = (int)(idx / (unsigned int)p.jobs_per_step);
+  const int j = (int)(idx - (unsigned int)it * (unsigned int)p.jobs_per_step);
+  int si = 0;
+  while (si + 1 < p.n_seg && j >= p.seg[si + 1].first) ++si;
+  const int type = p.seg[si].type, l = p.seg[si].l, jj = j - p.seg[si].first;
+  const SgLayer& Y = p.ly[l];
+  const unsigned int done = (unsigned int)it + 1u;                // completions of "this step" = done * per-step count
+  int rb = 0, cb = 0, nd = 0, ns = 0;
+  switch (type) {
+    case JT_FWD:
+      rb = jj / Y.ncb; cb = jj - rb * Y.ncb;
+      if (l > 0) { J->dc[nd] = sg_c_fwd(l - 1, rb); J->dt[nd++] = done * (unsigned int)p.ly[l - 1].ncb; }
+      if (it > 0) { J->dc[nd] = sg_c_dw(l); J->dt[nd++] = (unsigned int)it * (unsigned int)Y.ndw; }
+      J->sc[ns++] = sg_c_fwd(l, rb);
+      break;
+    case JT_HEAD:
+      rb = jj / Y.nkb; cb = jj - rb * Y.nkb;
+      if (L > 1) { J->dc[nd] = sg_c_fwd(L - 2, rb); J->dt[nd++] = done * (unsigned int)p.ly[L - 2].ncb; }
+      if (it > 0) { J->dc[nd] = sg_c_dw(L - 1); J->dt[nd++] = (unsigned int)it * (unsigned int)Y.ndw; }
+      J->sc[ns++] = sg_c_dh(L - 1, rb); J->sc[ns++] = sg_c_dht(L - 1);
+      break;
+    case JT_DH:
+      rb = jj / Y.nkb; cb = jj - rb * Y.nkb;
+      J->dc[nd] = sg_c_dh(l + 1, rb); J->dt[nd++] = done * (unsigned int)p.ly[l + 1].nkb;
+      J->sc[ns++] = sg_c_dh(l, rb); J->sc[ns++] = sg_c_dht(l);
+      break;
+    case JT_DW: {
+      const int pl = l + 1 < L - 1 ? l + 1 : L - 1;               // who produces dz_l: DH(l + 1), or HEAD for the last two layers
+      J->dc[nd] = sg_c_dht(pl); J->dt[nd++] = done * (unsigned int)(bm * p.ly[pl].nkb);
+      J->sc[ns++] = sg_c_dw(l);
+      break;
+    }
+    case JT_LOGP:
+      J->dc[nd] = sg_c_dht(L - 1); J->dt[nd++] = done * (unsigned int)(bm * Y.nkb);
+      J->sc[ns++] = sg_c_dw(L - 1);
+      break;
+    default: break;                                                 // LOSS waits for everything, see the kernel
+  }
+  J->type = type; J->l = l; J->jj = jj; J->rb = rb; J->cb = cb; J->it = it; J->nd = nd; J->ns = ns;
+}
+
+// Block = 8 compute warps + 1 scheduler warp.  The scheduler warp (one lane) runs one job ahead of the compute warps: it takes
+// the next index from the global job counter, decodes it, waits for the job's inputs on the completion counters (ld.acquire at
+// gpu scope) and only then posts the job in a two-slot shared-memory mailbox (mbarrier per slot).  The compute warps therefore
+// never see the grab / decode / poll latencies (0.6-2.2k cycles per job when done inline): they go from the end of one job to the
+// start of the next through one mbarrier wait.  Compute-only synchronisation uses named barrier 1 (256 threads).
+__global__ void __launch_bounds__(kSgBlock, 1) sgld_step_kernel(const __grid_constant__ SgParams p) {
   extern __shared__ __align__(16) float sg_smem[];
-  __shared__ int s_flag;
-  __shared__ long long s_perm[1024];   // this step's batch rows
+  __shared__ SgJob s_job[2];
+  __shared__ __align__(8) uint64_t s_full[2];              // scheduler -> compute: slot holds a job whose inputs are complete
+  __shared__ unsigned int s_go_n, s_done_n;                // compute -> scheduler: jobs started / finished so far
   __shared__ __align__(8) uint64_t s_bars[kSgMaxStages];   // one per ring stage: "the chunk's bytes have landed"
-  unsigned int bar_target = 0;
   uint32_t phase_bits = 0;             // parity to wait for next, per stage (uniform across the CTA)
   const int tid = threadIdx.x;
+  const unsigned int total = (unsigned int)p.n_steps * (unsigned int)p.jobs_per_step;
+  const int L = p.L;
+  const int bm = (p.B + FT_M - 1) / FT_M;                           // batch-row blocks
   if (tid == 0) {
     for (int i = 0; i < kSgMaxStages; ++i) mbar_init(&s_bars[i], kSgThreads);   // every thread posts one (deferred) arrival per use
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    s_go_n = 0; s_done_n = 0;
     fence_barrier_init();
   }
   __syncthreads();
-  const int L = p.L;
-  const bool debug = p.grad_out != nullptr;
 
+  if (tid >= kSgThreads) {
+    // ===================================== scheduler warp =====================================
+    if (tid != kSgThreads) return;
+    unsigned int lo = 0;                 // oldest handed-over job whose completion has not been published yet
+    int bad = 0;
+    // publish finished jobs: the compute warps only bump a shared-memory counter at the end of a job; the release at gpu scope
+    // (which has to wait for the SM's outstanding stores) is paid here, off their path.  Called from every wait loop.
+    auto service = [&]() {
+      while (lo < ld_acquire_cta_u32(&s_done_n)) {
+        const SgJob* Jd = &s_job[lo & 1u];
+        if (Jd->ns > 0) red_release_inc(p.cnt + Jd->sc[0]);
+        if (Jd->ns > 1) red_release_inc(p.cnt + Jd->sc[1]);
+        ++lo;
+      }
+    };
+    // relaxed polls (an acquire per poll would drop the SM's L1 lines under the compute warps every time), then ONE acquire
+    // fence once everything the job needs has been seen complete
+    auto wait_for = [&](int c, unsigned int target) {
+      unsigned long long spins = 0;
+      while ((int)(ld_relaxed_u32(p.cnt + c) - target) < 0) {
+        service();
+        if (++spins > (1ull << 25)) { atomicExch(p.err, 1); bad = 1; break; }     // never expected: error instead of a hung GPU
+        if ((spins & 1023) == 0 && *((volatile int*)p.err) != 0) { bad = 1; break; }
+      }
+    };
 #pragma unroll 1
-  for (int it = 0; it < p.n_steps; ++it) {
+    for (unsigned int n = 0;; ++n) {
+      // one job ahead, not more (load balance): job n is fetched when job n - 1 has started.  Slot n & 1 was last used by job
+      // n - 2, which is finished AND published by then (its completion precedes the start of job n - 1).
+      if (n > 0) {
+        while (ld_acquire_cta_u32(&s_go_n) < n) service();
+        service();
+      }
+      SgJob* J = &s_job[n & 1u];
+      const unsigned int idx = atomicAdd(&p.cnt[0], 1u);
+      if (p.trace) { J->t_grab = clock64(); J->g_grab = (long long)globaltimer_ns(); }
+      sg_decode(p, idx, total, J);
+      if (J->type >= 0) {
+        for (int d = 0; d < J->nd && !bad; ++d) wait_for(J->dc[d], J->dt[d]);
+        if (J->type == JT_LOSS && p.loss_out != nullptr && J->it == p.n_steps - 1) {
+          const unsigned int done = (unsigned int)J->it + 1u;
+          wait_for(sg_c_dht(L - 1), done * (unsigned int)(bm * p.ly[L - 1].nkb));
+          for (int q = 0; q < L && !bad; ++q) wait_for(sg_c_dw(q), done * (unsigned int)p.ly[q].ndw);
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      }
+      if (bad) J->type = -2;
+      if (p.trace) J->t_ready = clock64();
+      const int ty = J->type;
+      mbar_arrive(&s_full[n & 1u]);                                 // releases the slot's contents to the compute warps
+      if (ty < 0) {
+        // drain: publish what is still running (all of it finishes: compute warps never wait for this warp except for new jobs)
+        if (ty == -1) while (lo < n) service();
+        return;
+      }
+    }
+  }
+
+  // ======================================== compute warps ========================================
+  const bool debug = p.grad_out != nullptr;
+  int trec = 0;
+  long long t_prev_end = 0;
+#pragma unroll 1
+  for (unsigned int n = 0;; ++n) {
+    long long t_start = 0, pr[4] = {0, 0, 0, 0};
+    const SgJob* J = &s_job[n & 1u];
+    mbar_wait_spin(&s_full[n & 1u], (n >> 1) & 1u);
+    const int type = J->type;
+    if (type < 0) return;
+    const int l = J->l, jj = J->jj, rb = J->rb, cb = J->cb, it = J->it;
+    const long long t_grab = J->t_grab, g_grab = J->g_grab, t_ready = J->t_ready;
+    sg_sync();                                                      // everybody has read the slot
+    if (tid == 0) st_release_cta_u32(&s_go_n, n + 1u);
+    if (p.trace && tid == 0) t_start = clock64();
+
     const long long t = p.t0 + it;
-    const int cur = (p.cur + it) & 1;
+    const int cur = (p.cur + it) & 1, par = it & 1;
     const float* th = p.theta[cur];
     const float* thT = p.thetaT[cur];
     float* th_next = p.theta[cur ^ 1];
@@ -320,216 +506,340 @@ __global__ void __launch_bounds__(kSgThreads, 1) sgld_step_kernel(const __grid_c
     const long long boff = p.perm_off + (long long)it * p.B;
     const long long left = p.num_train - boff;
     const int rows = left < p.B ? (int)left : p.B;                 // the last batch of an epoch may be short (:80)
-    // the batch's rows, read once per step per CTA (the gathers and the head index X / y through it); the previous step's
-    // readers are behind that step's last grid barrier
-    for (int b = tid; b < rows; b += kSgThreads) s_perm[b] = p.perm[boff + b];
-    __syncthreads();
     SgGather gq;
-    gq.X = p.X; gq.perm = s_perm; gq.D = p.D; gq.B = p.B; gq.rows_live = rows;
+    gq.X = p.X; gq.perm = p.perm + boff; gq.D = p.D; gq.B = p.B; gq.rows_live = rows;
     const float scale = (float)((double)p.num_train / (double)rows);   // N / |b|  (:83)
-    const float f = (float)pow((double)(1 + t), -0.33);            // LambdaLR: np.float32((1 + it) ** -0.33)  (:101)
-    const float lr_w = p.lr_w * f, lr_n = p.lr_n * f;
     const bool want_loss = p.loss_out != nullptr && it == p.n_steps - 1;
-    const int bm = (p.B + FT_M - 1) / FT_M;                         // batch-row tiles
+    double* acc = p.acc + par * (p.nout + 1);
+    const SgLayer& Y = p.ly[l];
 
-    // phases 0 .. L-1: forward of Linear ph; phases L .. 2L-1: backward + update of Linear 2L-1-ph
+    // =================================== part A: the job's main work ===================================
+    const bool tile_job = type == JT_DW || type == JT_FWD || type == JT_DH;
+    const bool big = type == JT_DW && l > 0;                        // 64 x 32 dW tiles; Linear 0's dW (gathered operand, on the
+    const int tm = big ? WT_M : FT_M, tn_sh = big ? 5 : 4;          // critical path into the next step) uses 32 x 16 tiles
+    int m0 = 0, n0 = 0;
+    if (tile_job) {
+      SgOperand A, Bo;
+      A.kind = OP_DENSE; Bo.kind = OP_DENSE;
+      A.k_valid = 0; Bo.k_valid = 0;
+      int K;
+      if (type == JT_DW) {
+        // dW_l tile over K = batch
+        const int wm = (Y.out + tm - 1) / tm;
+        m0 = (jj % wm) * tm; n0 = (jj / wm) << tn_sh;
+        A.p = Y.dzT; A.ld = p.Bp; A.rows_valid = Y.out;
+        if (l == 0) Bo.kind = OP_GATHER_XT;
+        Bo.p = Y.hT[par]; Bo.ld = p.Bp; Bo.rows_valid = Y.ld;
+        K = p.Bp;
+      } else if (type == JT_FWD) {
+        m0 = rb * FT_M; n0 = cb * FT_N;
+        if (l == 0) A.kind = OP_GATHER_X;
+        A.p = Y.h[par]; A.ld = Y.ld; A.rows_valid = p.B;
+        Bo.p = th + Y.off; Bo.ld = Y.ld; Bo.rows_valid = Y.out;
+        K = Y.ld;
+      } else {
+        m0 = rb * FT_M; n0 = cb * FT_N;
+        A.p = Y.dz; A.ld = Y.ldz; A.rows_valid = p.B;
+        Bo.p = thT + Y.offT; Bo.ld = Y.ldT; Bo.rows_valid = Y.in;
+        K = Y.ldz;
+      }
+      if (big) tile_core<WT_M, WT_N, kSgStagesW>(A, Bo, gq, m0, n0, K, sg_smem, s_bars, phase_bits, p.dbg, nullptr);
+      else tile_core<FT_M, FT_N, kSgStagesF>(A, Bo, gq, m0, n0, K, sg_smem, s_bars, phase_bits, p.dbg, nullptr);
+    }
+    // HEAD(rb, chunk): last Linear, residual, dU/d(out), per-output sum of squares (BNN_SGDMC.py:69-74, :83) for 32 batch rows,
+    // then dz of the last hidden layer for a 64-column chunk of those rows.  GEMV-sized work (nout is 1..few): eight threads per
+    // row along K, no tile core.  The (cheap) first part is recomputed by every chunk's job so that the second part spreads over
+    // bm x (width / 64) CTAs without another dependency hop; chunk 0 owns the side effects (dz_{L-1}, sums of squares).
+    const SgLayer& Yl = p.ly[L - 1];
+    float* s_dz = sg_smem;                                          // [FT_M][nout]
+    float* s_w = sg_smem + ((FT_M * p.nout + 3) & ~3);              // [nout][ld]: the last Linear's rows
+    float* s_h = s_w + p.nout * Yl.ld;                              // [FT_M][ld]: this row block of the last hidden layer
+    if (type == JT_HEAD) {
+      const int r0 = rb * FT_M;
+      const int nw = p.nout * Y.ld;
+      // everything the job reads from other SMs' output arrives in ONE round trip: 16-byte cp.async for W and the h rows
+      for (int i = tid * 4; i < nw; i += kSgThreads * 4) cp_async16(smem_u32(s_w + i), th + Y.off + i, 16);
+      if (L > 1) {
+        const int q4 = Y.ld >> 2;
+        const float* hsrc = Y.h[par] + (long long)r0 * Y.ld;
+        const int nrow = min(FT_M, p.B - r0);
+        for (int i = tid; i < nrow * q4; i += kSgThreads) cp_async16(smem_u32(s_h + i * 4), hsrc + (long long)i * 4, 16);
+      }
+      cp_async_commit();
+      const int row = tid >> 3, sub = tid & 7, b = r0 + row;
+      const bool live = b < rows;
+      long long prow = 0;
+      float ytrue = 0.0f;
+      if (live) {
+        prow = __ldg(gq.perm + b);
+        if (sub < p.nout) ytrue = __ldg(p.y + prow * p.nout + sub);   // targets of outputs 0..7 travel with the operands
+      }
+      cp_async_wait<0>();
+      sg_sync();
+      if (p.trace && tid == 0) pr[0] = clock64();
+      const float* hin = s_h + row * Y.ld;
 #pragma unroll 1
-    for (int ph = 0; ph < 2 * L; ++ph) {
-      const bool fwd = ph < L;
-      const int l = fwd ? ph : 2 * L - 1 - ph;
-      const SgLayer& Y = p.ly[l];
-      const int wm = (Y.out + WT_M - 1) / WT_M;
-      const int n_dw = fwd ? 0 : wm * ((Y.ld + WT_N - 1) / WT_N);
-      const int n_ft = bm * (fwd ? (Y.out + FT_N - 1) / FT_N : (l > 0 ? (Y.in + FT_N - 1) / FT_N : 0));
-      const int n_jobs = n_dw + n_ft + ((!fwd && l == L - 1) ? 1 : 0);
-      long long* probe = (p.trace && it == p.n_steps - 1 && blockIdx.x == 1) ? p.trace + 1024 * 2 * BNN_MAX_LINEAR * 2 + ph * 8 : nullptr;
-      if (probe && tid == 0) probe[5] = clock64();
-#pragma unroll 1
-      for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
-        if (job < n_dw) {
-          // ---- dW_l tile [64 x 32] over K = batch, then the pSGLD update of that tile of theta / V
-          SgOperand A, Bo;
-          A.kind = OP_DENSE; A.p = Y.dzT; A.ld = p.Bp; A.rows_valid = Y.out; A.k_valid = p.Bp;
-          Bo.kind = l == 0 ? OP_GATHER_XT : OP_DENSE; Bo.p = Y.hT; Bo.ld = p.Bp; Bo.rows_valid = Y.ld; Bo.k_valid = p.Bp;
-          const int m0 = (job % wm) * WT_M, n0 = (job / wm) * WT_N;
-          tile_core<WT_M, WT_N, kSgStagesW>(A, Bo, gq, m0, n0, p.Bp, sg_smem, s_bars, phase_bits, p.dbg, job == blockIdx.x ? probe : nullptr);
-          double quad_local = 0.0;
-          if (!(p.dbg & 4)) {
-#pragma unroll 1
-            for (int q = tid; q < WT_M * WT_N / 4; q += kSgThreads) {
-              const int j = m0 + (q * 4) / WT_N, k0 = n0 + (q * 4) % WT_N;
-              if (j >= Y.out || k0 >= Y.ld) continue;
-              const float4 v = *reinterpret_cast<const float4*>(sg_smem + q * 4);
-              const long long e = Y.off + (long long)j * Y.ld + k0;          // multiple of 4: one Philox block per quad
-              const float4 t4 = *reinterpret_cast<const float4*>(th + e);
-              float tt[4] = {t4.x, t4.y, t4.z, t4.w};
-              float g[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const int k = k0 + c;
-                if (k < Y.in) {                                                // weight entry: + d(-log prior)/dW = W / std^2  (:65-66)
-                  g[c] = fmaf(Y.inv_var, tt[c], g[c]);
-                  quad_local += (double)(Y.inv_var * tt[c]) * (double)tt[c];
-                } else if (k > Y.in) g[c] = 0.0f;                              // layout padding: no gradient, no noise, stays zero
-              }
-              if (debug) {
-                *reinterpret_cast<float4*>(p.grad_out + e) = make_float4(g[0], g[1], g[2], g[3]);
-                continue;
-              }
-              const float4 v4 = *reinterpret_cast<const float4*>(p.V + e);
-              float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-              float z[4];
-              philox_normal4(p.seed, (uint32_t)t, STREAM_SGLD, (uint64_t)(e >> 2), z);
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const int k = k0 + c;
-                if (k <= Y.in) psgld_update1(tt[c], vv[c], g[c], z[c], lr_w, p.alpha, p.lam, p.precond_mode);
-                else tt[c] = 0.0f;
-              }
-              *reinterpret_cast<float4*>(th_next + e) = make_float4(tt[0], tt[1], tt[2], tt[3]);
-              *reinterpret_cast<float4*>(p.V + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-              if (l > 0) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const int k = k0 + c;
-                  if (k < Y.in) thT_next[Y.offT + (long long)k * Y.ldT + j] = tt[c];
-                }
-              }
+      for (int o = 0; o < p.nout; ++o) {
+        const float* w = s_w + o * Y.ld;
+        float a = 0.0f;
+        if (b < p.B) {
+          if (L > 1) {
+#pragma unroll 4
+            for (int k = sub * 4; k < Y.ld; k += 32) {
+              const float4 hv = *reinterpret_cast<const float4*>(hin + k);
+              const float4 wv = *reinterpret_cast<const float4*>(w + k);
+              a = fmaf(hv.x, wv.x, a); a = fmaf(hv.y, wv.y, a); a = fmaf(hv.z, wv.z, a); a = fmaf(hv.w, wv.w, a);
             }
+          } else if (live) {
+            for (int k = sub; k <= p.D; k += 8) a = fmaf(k < p.D ? __ldg(p.X + prow * p.D + k) : 1.0f, w[k], a);
           }
-          __syncthreads();                 // the result tile in shared memory is free for the next job's loads
-          if (want_loss) {
-            // prior energy sum W^2 / std^2 of the step's INPUT parameters (the loss is evaluated before the update, :81-83)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) quad_local += __shfl_xor_sync(0xffffffffu, quad_local, o);
-            if ((tid & 31) == 0 && quad_local != 0.0) atomicAdd(&p.acc[p.nout], quad_local);
+        }
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        // the row's target for output o sits in lane (o & 7) of the row's eight lanes for o < 8
+        float yt = __shfl_sync(0xffffffffu, ytrue, (tid & 24) | (o & 7));
+        if (o >= 8 && live) yt = __ldg(p.y + prow * p.nout + o);
+        float dzv = 0.0f;
+        double r2 = 0.0;
+        if (sub == 0) {
+          if (live) {
+            const float r = a - yt;
+            dzv = scale * expf(th[p.n_head + o]) * r;
+            r2 = (double)r * (double)r;
           }
-        } else if (job < n_dw + n_ft) {
-          // ---- [32 x 16] tile over [batch, features]: forward of Linear l, or dh of Linear l (-> dz of Linear l - 1)
-          const int jj = job - n_dw;
-          const int m0 = (jj % bm) * FT_M, n0 = (jj / bm) * FT_N;
-          SgOperand A, Bo;
-          A.kind = OP_DENSE; Bo.kind = OP_DENSE;
-          int K;
-          if (fwd) {
-            if (l == 0) A.kind = OP_GATHER_X;
-            A.p = Y.h; A.ld = Y.ld; A.rows_valid = p.B; A.k_valid = Y.ld;
-            Bo.p = th + Y.off; Bo.ld = Y.ld; Bo.rows_valid = Y.out; Bo.k_valid = Y.ld;
-            K = Y.ld;
-          } else {
-            A.p = Y.dz; A.ld = Y.ldz; A.rows_valid = p.B; A.k_valid = Y.ldz;
-            Bo.p = thT + Y.offT; Bo.ld = Y.ldT; Bo.rows_valid = Y.in; Bo.k_valid = Y.ldT;
-            K = Y.ldz;
+          if (b < p.B && cb == 0) {
+            Y.dz[(long long)b * Y.ldz + o] = dzv;
+            Y.dzT[(long long)o * p.Bp + b] = dzv;
           }
-          tile_core<FT_M, FT_N, kSgStagesF>(A, Bo, gq, m0, n0, K, sg_smem, s_bars, phase_bits, p.dbg, job == blockIdx.x ? probe : nullptr);
-          if (!(p.dbg & 4) && tid < FT_M * FT_N / 4) {
-            const int b = m0 + (tid * 4) / FT_N, c0 = n0 + (tid * 4) % FT_N;
-            const float4 v = *reinterpret_cast<const float4*>(sg_smem + tid * 4);
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-            if (b < p.B) {
-              if (fwd && l < L - 1) {
-                // hidden layer: h_{l+1} = act(z), stored row-major and transposed
-                const SgLayer& Nx = p.ly[l + 1];
+          s_dz[row * p.nout + o] = dzv;
+        }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const int j = c0 + c;
-                  if (j < Y.out) {
-                    const float a = act_fwd(vv[c], p.act);
-                    Nx.h[(long long)b * Nx.ld + j] = a;
-                    Nx.hT[(long long)j * p.Bp + b] = a;
-                  }
-                }
-              } else if (fwd) {
-                // head: residual, dU/d(out) and the per-output sum of squares (BNN_SGDMC.py:69-74, :83)
+        for (int q = 16; q > 0; q >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, q);
+        if ((tid & 31) == 0 && r2 != 0.0 && cb == 0) atomicAdd(&acc[o], r2);
+      }
+      if (p.trace && tid == 0) pr[1] = clock64();
+      sg_sync();
+    }
+
+    // =================================== part B: epilogues ===================================
+    if (type == JT_DW) {
+      // ---- prior gradient + pSGLD update of the tile of theta / V (the gradient itself is never stored)
+      double quad_local = 0.0;
+      if (!(p.dbg & 4)) {
+        const float lr_w = p.lr_w * (it == 0 ? p.f0 : p.fs[par]);    // LambdaLR factor of this step (:101)
+        const int nquads = (tm << tn_sh) >> 2, tn_mask = (1 << tn_sh) - 1;
+        // a thread owns up to two quads of the tile (q = tid, tid + 256): both quads' theta / V loads are issued before any
+        // arithmetic so their L2 latency is paid once
+        float4 t4[2], v4[2];
+        bool on[2];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const int o = c0 + c;
-                  if (o < Y.out) {
-                    float dzv = 0.0f;
-                    if (b < rows) {
-                      const float r = vv[c] - __ldg(p.y + s_perm[b] * p.nout + o);
-                      dzv = scale * expf(th[p.n_head + o]) * r;
-                      atomicAdd(&p.acc[o], (double)r * (double)r);
-                    }
-                    Y.dz[(long long)b * Y.ldz + o] = dzv;
-                    Y.dzT[(long long)o * p.Bp + b] = dzv;
-                  }
-                }
-              } else {
-                // dz_{l-1} = dh * act'(h_l)
-                const SgLayer& Pv = p.ly[l - 1];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const int k = c0 + c;
-                  if (k < Y.in) {
-                    const float hv = __ldcg(Y.h + (long long)b * Y.ld + k);
-                    const float d = vv[c] * act_bwd(hv, p.act);
-                    Pv.dz[(long long)b * Pv.ldz + k] = d;
-                    Pv.dzT[(long long)k * p.Bp + b] = d;
-                  }
-                }
-              }
-            }
+        for (int u = 0; u < 2; ++u) {
+          const int q = tid + u * kSgThreads;
+          const int jr = m0 + ((q * 4) >> tn_sh), k0 = n0 + ((q * 4) & tn_mask);
+          on[u] = q < nquads && jr < Y.out && k0 < Y.ld;
+          if (on[u]) {
+            const long long e = Y.off + (long long)jr * Y.ld + k0;
+            // plain (L1-allocating) loads are coherent here: every job starts behind an acquire at gpu scope, which drops
+            // this SM's stale L1 lines; ld.global.cg (LDG.STRONG.GPU) costs ~3x the latency on this part
+            t4[u] = *reinterpret_cast<const float4*>(th + e);
+            if (!debug) v4[u] = *reinterpret_cast<const float4*>(p.V + e);
           }
-          __syncthreads();                 // the result tile in shared memory is free for the next job's loads
-        } else {
-          // ---- log-precision group (BNN_SGDMC.py:62, :96-98): closed-form gradient, same update rule, lr_noise
-          if (tid < ((p.n_theta - p.n_head) >> 2)) {
-            const long long e = p.n_head + (long long)tid * 4;
-            float tt[4], vv[4], g[4], z[4];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (!on[u]) continue;
+          const int q = tid + u * kSgThreads;
+          const int jr = m0 + ((q * 4) >> tn_sh), k0 = n0 + ((q * 4) & tn_mask);
+          const float4 v = *reinterpret_cast<const float4*>(sg_smem + q * 4);
+          const long long e = Y.off + (long long)jr * Y.ld + k0;         // multiple of 4: one Philox block per quad
+          float tt[4] = {t4[u].x, t4[u].y, t4[u].z, t4[u].w};
+          float g[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int k = k0 + c;
+            if (k < Y.in) {                                                // weight entry: + d(-log prior)/dW = W / std^2  (:65-66)
+              g[c] = fmaf(Y.inv_var, tt[c], g[c]);
+              quad_local += (double)(Y.inv_var * tt[c]) * (double)tt[c];
+            } else if (k > Y.in) g[c] = 0.0f;                              // layout padding: no gradient, no noise, stays zero
+          }
+          if (debug) {
+            *reinterpret_cast<float4*>(p.grad_out + e) = make_float4(g[0], g[1], g[2], g[3]);
+            continue;
+          }
+          float vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+          float z[4];
+          philox_normal4(p.seed, (uint32_t)t, STREAM_SGLD, (uint64_t)(e >> 2), z);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int k = k0 + c;
+            if (k <= Y.in) psgld_update1(tt[c], vv[c], g[c], z[c], lr_w, p.alpha, p.lam, p.precond_mode);
+            else tt[c] = 0.0f;
+          }
+          *reinterpret_cast<float4*>(th_next + e) = make_float4(tt[0], tt[1], tt[2], tt[3]);
+          *reinterpret_cast<float4*>(p.V + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+          if (l > 0) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              tt[c] = th[e + c];
-              vv[c] = p.V[e + c];
-              g[c] = 0.0f;
-              const long long o = e + c - p.n_head;
-              if (o < p.nout) {
-                const float prec = expf(tt[c]);
-                const float s2 = (float)__ldcg(&p.acc[o]);
-                g[c] = -scale * (-0.5f * prec * s2 + 0.5f * (float)rows) - (p.al - p.be * prec);
+              const int k = k0 + c;
+              if (k < Y.in) thT_next[Y.offT + (long long)k * Y.ldT + jr] = tt[c];
+            }
+          }
+        }
+      }
+      if (want_loss) {
+        // prior energy sum W^2 / std^2 of the step's INPUT parameters (the loss is evaluated before the update, :81-83)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) quad_local += __shfl_xor_sync(0xffffffffu, quad_local, o);
+        if ((tid & 31) == 0 && quad_local != 0.0) atomicAdd(&acc[p.nout], quad_local);
+      }
+    } else if (type == JT_FWD || type == JT_DH) {
+      if (!(p.dbg & 4) && tid < FT_M * FT_N / 4) {
+        const int b = m0 + (tid * 4) / FT_N, c0 = n0 + (tid * 4) % FT_N;
+        const float4 v = *reinterpret_cast<const float4*>(sg_smem + tid * 4);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        if (b < p.B) {
+          if (type == JT_FWD) {
+            // hidden layer: h_{l+1} = act(z), stored row-major and transposed
+            const SgLayer& Nx = p.ly[l + 1];
+            float* hn = Nx.h[par];
+            float* hnT = Nx.hT[par];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int jc = c0 + c;
+              if (jc < Y.out) {
+                const float a = act_fwd(vv[c], p.act);
+                hn[(long long)b * Nx.ld + jc] = a;
+                hnT[(long long)jc * p.Bp + b] = a;
               }
             }
-            if (debug) {
+          } else {
+            // dz_{l-1} = dh * act'(h_l)
+            const SgLayer& Pv = p.ly[l - 1];
+            const float* hl = Y.h[par];
 #pragma unroll
-              for (int c = 0; c < 4; ++c) p.grad_out[e + c] = g[c];
-            } else {
-              philox_normal4(p.seed, (uint32_t)t, STREAM_SGLD, (uint64_t)(e >> 2), z);
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                if (e + c - p.n_head < p.nout) psgld_update1(tt[c], vv[c], g[c], z[c], lr_n, p.alpha, p.lam, p.precond_mode);
-                else tt[c] = 0.0f;
-                th_next[e + c] = tt[c];
-                p.V[e + c] = vv[c];
+            for (int c = 0; c < 4; ++c) {
+              const int k = c0 + c;
+              if (k < Y.in) {
+                const float hv = hl[(long long)b * Y.ld + k];
+                const float d = vv[c] * act_bwd(hv, p.act);
+                Pv.dz[(long long)b * Pv.ldz + k] = d;
+                Pv.dzT[(long long)k * p.Bp + b] = d;
               }
             }
           }
         }
       }
-      if (probe && tid == 0) probe[4] = clock64();
-      if (p.trace && it == p.n_steps - 1 && tid == 0) p.trace[((long long)blockIdx.x * 2 * L + ph) * 2] = clock64();
-      if (!grid_barrier(p.bar, bar_target, p.err, &s_flag)) return;
-      if (p.trace && it == p.n_steps - 1 && tid == 0) p.trace[((long long)blockIdx.x * 2 * L + ph) * 2 + 1] = clock64();
-    }
-
-    // ================= end of step: loss of the last step, reset of the accumulators =================
-    if (blockIdx.x == 0 && tid == 0) {
-      if (want_loss) {
+    } else if (type == JT_HEAD) {
+      if (L > 1) {
+        // dz_{L-2}[b, k] = (sum_o dz_{L-1}[b, o] W[o, k]) * act'(h[b, k]) for k in this job's 64-column chunk.  Pass 1: thread =
+        // (column, 8-row group), coalesced row-major stores, the value also replaces h in shared memory; pass 2: lane = batch
+        // row, so the transposed copy goes out as full 128-byte rows too.
+        const int r0 = rb * FT_M, kc0 = cb * kSgHeadCols;
+        const SgLayer& Pv = p.ly[L - 2];
+        const int nrow = min(FT_M, p.B - r0);
+        {
+          const int k = kc0 + (tid & (kSgHeadCols - 1)), u0 = (tid / kSgHeadCols) * 8;
+          if (k < Y.in) {
+            float* dzp = Pv.dz + (long long)r0 * Pv.ldz + k;
+            float wk[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) wk[o] = o < p.nout ? s_w[o * Y.ld + k] : 0.0f;
+#pragma unroll
+            for (int uu = 0; uu < 8; ++uu) {
+              const int u = u0 + uu;
+              float dh = s_dz[u * p.nout] * wk[0];
+              if (p.nout > 1) {
+#pragma unroll
+                for (int o = 1; o < 4; ++o) if (o < p.nout) dh = fmaf(s_dz[u * p.nout + o], wk[o], dh);
+#pragma unroll 1
+                for (int o = 4; o < p.nout; ++o) dh = fmaf(s_dz[u * p.nout + o], s_w[o * Y.ld + k], dh);
+              }
+              const float d = u < nrow ? dh * act_bwd(s_h[u * Y.ld + k], p.act) : 0.0f;
+              s_h[u * Y.ld + k] = d;
+              if (u < nrow) dzp[(long long)u * Pv.ldz] = d;
+            }
+          }
+        }
+        sg_sync();
+        const int lane = tid & 31;
+        if (r0 + lane < p.Bp) {
+#pragma unroll
+          for (int kk = tid >> 5; kk < kSgHeadCols; kk += kSgThreads / 32) {
+            const int k = kc0 + kk;
+            if (k < Y.in) Pv.dzT[(long long)k * p.Bp + r0 + lane] = s_h[lane * Y.ld + k];
+          }
+        }
+      }
+    } else if (type == JT_LOGP) {
+      // ---- log-precision group (BNN_SGDMC.py:62, :96-98): closed-form gradient, same update rule, lr_noise
+      if (tid < ((p.n_theta - p.n_head) >> 2)) {
+        const float lr_n = p.lr_n * (it == 0 ? p.f0 : p.fs[par]);
+        const long long e = p.n_head + (long long)tid * 4;
+        float tt[4], vv[4], g[4], z[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tt[c] = th[e + c];
+          vv[c] = p.V[e + c];
+          g[c] = 0.0f;
+          const long long o = e + c - p.n_head;
+          if (o < p.nout) {
+            const float prec = expf(tt[c]);
+            const float s2 = (float)acc[o];
+            g[c] = -scale * (-0.5f * prec * s2 + 0.5f * (float)rows) - (p.al - p.be * prec);
+          }
+        }
+        if (debug) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) p.grad_out[e + c] = g[c];
+        } else {
+          philox_normal4(p.seed, (uint32_t)t, STREAM_SGLD, (uint64_t)(e >> 2), z);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (e + c - p.n_head < p.nout) psgld_update1(tt[c], vv[c], g[c], z[c], lr_n, p.alpha, p.lam, p.precond_mode);
+            else tt[c] = 0.0f;
+            th_next[e + c] = tt[c];
+            p.V[e + c] = vv[c];
+          }
+        }
+      }
+      // the other parity's sums of squares were consumed by the previous step's LOGP (which every HEAD of this step waited
+      // for) and are next written by the HEADs of step t + 1, which wait for this job: reset them here
+      if (tid < p.nout) p.acc[(par ^ 1) * (p.nout + 1) + tid] = 0.0;
+      // LambdaLR: np.float32((1 + it) ** -0.33) of the NEXT step, in double on one thread; its readers (the update jobs of
+      // step t + 1) are behind this job, the slot's previous readers (step t - 1) before it
+      if (tid == 64) p.fs[par ^ 1] = (float)pow((double)(2 + t), -0.33);
+    } else if (type == JT_LOSS) {
+      if (want_loss && tid == 0) {
         float total_ll = 0.0f, total_lp = 0.0f;
         for (int o = 0; o < p.nout; ++o) {
           const float lp = th[p.n_head + o], prec = expf(lp);
-          const float s2 = (float)__ldcg(&p.acc[o]);
+          const float s2 = (float)acc[o];
           total_ll += -0.5f * prec * s2 + (float)rows * (0.5f * lp - 0.91893853320467274178f);
           total_lp += p.al * p.log_be + (p.al - 1.0f) * lp - p.be * prec - p.lgamma_al + lp;
         }
-        const float quad = (float)__ldcg(&p.acc[p.nout]);
+        const float quad = (float)acc[p.nout];
         const float logp = -0.5f * quad - p.log_const + total_lp;
         p.loss_out[0] = -(total_ll * scale + logp);
       }
-      for (int o = 0; o <= p.nout; ++o) p.acc[o] = 0.0;
-      __threadfence();
     }
-    // the next accumulation into acc happens after L - 1 more grid barriers (or, for L == 1, after none: guard that case)
-    if (L == 1 && !grid_barrier(p.bar, bar_target, p.err, &s_flag)) return;
+
+    // ---- done: tell the scheduler warp, which publishes the completion
+    sg_sync();                           // the job's global writes are issued; its shared memory is free for the next job
+    if (tid == 0) {
+      st_release_cta_u32(&s_done_n, n + 1u);
+      if (p.trace) {
+        const long long t_end = clock64();
+        if (it >= p.n_steps - 2) {
+          long long* r = p.trace + ((long long)blockIdx.x * kSgTraceRecs + (trec < kSgTraceRecs ? trec : kSgTraceRecs - 1)) * kSgTraceW;
+          r[0] = ((long long)it << 32) | ((long long)type << 24) | ((long long)l << 16) | (long long)(jj & 0xffff);
+          r[1] = t_grab; r[2] = t_start; r[3] = t_end; r[4] = g_grab; r[5] = (long long)globaltimer_ns();
+          r[6] = pr[0]; r[7] = pr[1]; r[8] = t_ready; r[9] = t_prev_end;
+          ++trec;
+        }
+        t_prev_end = t_end;
+      }
+    }
   }
 }
 
@@ -550,8 +860,10 @@ __global__ void sgld_ones_kernel(const __grid_constant__ SgParams p) {
   for (int l = 1; l < p.L; ++l) {
     const SgLayer& Y = p.ly[l];
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < p.B; b += gridDim.x * blockDim.x) {
-      Y.h[(long long)b * Y.ld + Y.in] = 1.0f;
-      Y.hT[(long long)Y.in * p.Bp + b] = 1.0f;
+      for (int q = 0; q < 2; ++q) {
+        Y.h[q][(long long)b * Y.ld + Y.in] = 1.0f;
+        Y.hT[q][(long long)Y.in * p.Bp + b] = 1.0f;
+      }
     }
   }
 }
@@ -588,12 +900,12 @@ struct SgPlan {
   SgParams p;
   long long nT;            // floats of ONE thetaT buffer
   long long ws_floats;     // activation workspace (floats), followed by acc / barrier / err
-  long long ws_bytes;
+  long long ws_bytes, tail_bytes;
   int grid;
   size_t smem;
 };
 
-static int sg_plan(const BnnSgldChain* c, SgPlan* plan, bool bind) {
+static int sg_plan(const BnnSgldChain* c, SgPlan* plan, bool bind, bool want_loss = false) {
   Layout Lo;
   if (make_layout(&c->desc, &Lo)) return -1;
   if (c->batch < 1 || c->batch > 1024) BNN_FAIL("bnn_sgld: batch must be in [1, 1024] (got %d)", c->batch);
@@ -606,7 +918,7 @@ static int sg_plan(const BnnSgldChain* c, SgPlan* plan, bool bind) {
   long long oT = 0, ow = 0;
   double log_const = 0.0;
   const double gain = c->gain > 0.f ? c->gain : 5.0 / 3.0;
-  int max_jobs = 1;
+  const int bm = (p.B + FT_M - 1) / FT_M;
   for (int l = 0; l < p.L; ++l) {
     SgLayer& Y = p.ly[l];
     Y.in = Lo.in[l]; Y.out = Lo.out[l]; Y.ld = Lo.ld[l]; Y.off = Lo.off[l];
@@ -616,32 +928,64 @@ static int sg_plan(const BnnSgldChain* c, SgPlan* plan, bool bind) {
     const double std = gain * sqrt(2.0 / (double)(Y.in + Y.out));
     Y.inv_var = (float)(1.0 / (std * std));
     log_const += (double)Y.in * Y.out * (log(std) + 0.5 * log(2.0 * 3.14159265358979323846));
-    const int fwd = ((p.B + FT_M - 1) / FT_M) * ((Y.out + FT_N - 1) / FT_N);
-    const int bwd = ((Y.out + WT_M - 1) / WT_M) * ((Y.ld + WT_N - 1) / WT_N) +
-                    (l > 0 ? ((p.B + FT_M - 1) / FT_M) * ((Y.in + FT_N - 1) / FT_N) : 0) + 1;
-    if (fwd > max_jobs) max_jobs = fwd;
-    if ((bwd + 1) / 2 > max_jobs) max_jobs = (bwd + 1) / 2;   // backward phases may take two rounds
+    Y.ncb = (Y.out + FT_N - 1) / FT_N;
+    Y.nkb = (Y.in + FT_N - 1) / FT_N;
+    if (l == p.L - 1) Y.nkb = l > 0 ? (Y.in + kSgHeadCols - 1) / kSgHeadCols : 1;   // last layer: column chunks of the HEAD jobs
+    // dW tiles: 64 x 32, except Linear 0 (32 x 16: its update is on the critical path into the next step)
+    Y.ndw = (l > 0 ? ((Y.out + WT_M - 1) / WT_M) * ((Y.ld + WT_N - 1) / WT_N) : ((Y.out + FT_M - 1) / FT_M) * ((Y.ld + FT_N - 1) / FT_N)) +
+            (l == p.L - 1 ? 1 : 0);
+  }
+  plan->smem = (size_t)kSgStagesW * (WT_M + WT_N) * kSgLds * 4;
+  if ((size_t)kSgStagesF * (FT_M + FT_N) * kSgLds * 4 > plan->smem) plan->smem = (size_t)kSgStagesF * (FT_M + FT_N) * kSgLds * 4;
+  // the head job keeps the last Linear's rows, 32 rows of the last hidden layer and of dU/d(out) in shared memory
+  {
+    const size_t head = ((size_t)FT_M * p.nout + 4 + (size_t)(p.nout + FT_M) * p.ly[p.L - 1].ld) * 4;
+    if (head > (size_t)227 * 1024)
+      BNN_FAIL("bnn_sgld: (nout + 32) * (last hidden width) = %d * %d does not fit the fused head's shared memory", p.nout + FT_M, p.ly[p.L - 1].ld);
+    if (head > plan->smem) plan->smem = head;
+  }
+  // the step's job list (topological; see the kernel): forward chain, head, then dh chain with the updates slotted behind
+  // the dh segment that runs while their input is being finished
+  {
+    int n = 0, first = 0;
+    auto add = [&](int type, int l, int count) {
+      if (count <= 0) return;
+      p.seg[n].type = type; p.seg[n].l = l; p.seg[n].first = first; p.seg[n].count = count;
+      first += count; ++n;
+    };
+    const int Ln = p.L;
+    auto n_dw = [&](int l) { return p.ly[l].ndw - (l == Ln - 1 ? 1 : 0); };
+    for (int l = 0; l + 1 < Ln; ++l) add(JT_FWD, l, bm * p.ly[l].ncb);
+    add(JT_HEAD, Ln - 1, bm * p.ly[Ln - 1].nkb);
+    for (int l = Ln - 2; l >= 1; --l) {
+      add(JT_DH, l, bm * p.ly[l].nkb);
+      add(JT_DW, l + 1, n_dw(l + 1));
+      if (l + 1 == Ln - 1) add(JT_LOGP, Ln - 1, 1);
+    }
+    add(JT_DW, 0, n_dw(0));
+    if (Ln >= 2) add(JT_DW, 1, n_dw(1));
+    if (Ln <= 2) add(JT_LOGP, Ln - 1, 1);
+    if (want_loss) add(JT_LOSS, 0, 1);
+    p.n_seg = n; p.jobs_per_step = first;
   }
   plan->nT = oT > 0 ? oT : 4;
-  // workspace: per layer h, hT (l >= 1), dz, dzT
+  // workspace: per layer h, hT (l >= 1; two copies, by step parity), dz, dzT
   for (int l = 0; l < p.L; ++l) {
     SgLayer& Y = p.ly[l];
-    if (l > 0) { ow += r4((long long)p.Bp * Y.ld); ow += r4((long long)Y.ld * p.Bp); }
+    if (l > 0) ow += 2 * (r4((long long)p.Bp * Y.ld) + r4((long long)Y.ld * p.Bp));
     ow += r4((long long)p.Bp * Y.ldz);
     ow += r4((long long)Y.out * p.Bp);
   }
   plan->ws_floats = ow;
-  const long long tail = 8LL * (p.nout + 1) + 64;          // acc doubles, barrier counter, error flag
-  plan->ws_bytes = ((ow * 4 + 15) & ~15LL) + tail;
+  plan->tail_bytes = 16LL * (p.nout + 1) + 4LL * kSgCounters + 64;   // acc doubles (two parities), counters, fs[2], error flag
+  plan->ws_bytes = ((ow * 4 + 15) & ~15LL) + plan->tail_bytes;
   p.log_const = (float)log_const;
   p.lr_w = c->lr_weight; p.lr_n = c->lr_noise; p.alpha = c->precond_decay; p.lam = c->diagonal_bias;
   p.al = c->alpha_n; p.be = c->beta_n; p.lgamma_al = lgammaf(c->alpha_n); p.log_be = logf(c->beta_n);
   p.precond_mode = c->precond_mode;
   p.seed = c->seed;
-  plan->smem = (size_t)kSgStagesW * (WT_M + WT_N) * kSgLds * 4;
-  if ((size_t)kSgStagesF * (FT_M + FT_N) * kSgLds * 4 > plan->smem) plan->smem = (size_t)kSgStagesF * (FT_M + FT_N) * kSgLds * 4;
   int grid = sm_count();
-  if (max_jobs < grid) grid = max_jobs;
+  if (p.jobs_per_step < grid) grid = p.jobs_per_step;
   plan->grid = grid;
   if (bind) {
     if (!c->theta || !c->thetaT || !c->V || !c->workspace) BNN_FAIL("bnn_sgld: null chain buffers");
@@ -654,14 +998,16 @@ static int sg_plan(const BnnSgldChain* c, SgPlan* plan, bool bind) {
     long long o = 0;
     for (int l = 0; l < p.L; ++l) {
       SgLayer& Y = p.ly[l];
-      if (l > 0) { Y.h = w + o; o += r4((long long)p.Bp * Y.ld); Y.hT = w + o; o += r4((long long)Y.ld * p.Bp); }
+      if (l > 0)
+        for (int q = 0; q < 2; ++q) { Y.h[q] = w + o; o += r4((long long)p.Bp * Y.ld); Y.hT[q] = w + o; o += r4((long long)Y.ld * p.Bp); }
       Y.dz = w + o; o += r4((long long)p.Bp * Y.ldz);
       Y.dzT = w + o; o += r4((long long)Y.out * p.Bp);
     }
     char* tailp = reinterpret_cast<char*>(c->workspace) + ((ow * 4 + 15) & ~15LL);
     p.acc = reinterpret_cast<double*>(tailp);
-    p.bar = reinterpret_cast<unsigned int*>(tailp + 8LL * (p.nout + 1));
-    p.err = reinterpret_cast<int*>(tailp + 8LL * (p.nout + 1) + 16);
+    p.cnt = reinterpret_cast<unsigned int*>(tailp + 16LL * (p.nout + 1));
+    p.fs = reinterpret_cast<float*>(tailp + 16LL * (p.nout + 1) + 4LL * kSgCounters);
+    p.err = reinterpret_cast<int*>(tailp + 16LL * (p.nout + 1) + 4LL * kSgCounters + 16);
   }
   return 0;
 }
@@ -711,7 +1057,7 @@ extern "C" int32_t bnn_sgld_init(const BnnSgldChain* c, int32_t cur, void* strea
 }
 
 static long long* g_sg_trace = nullptr;   // debug: set by bnn_sgld_trace
-static int g_sg_trace_grid = 0, g_sg_trace_L = 0;
+static int g_sg_trace_grid = 0;
 
 extern "C" int32_t bnn_sgld_run(const BnnSgldChain* c, int32_t cur, int64_t t0, int64_t perm_off, int32_t n_steps, float* loss_out,
                                 float* grad_out, void* stream) {
@@ -722,25 +1068,28 @@ extern "C" int32_t bnn_sgld_run(const BnnSgldChain* c, int32_t cur, int64_t t0, 
     BNN_FAIL("bnn_sgld_run: %d steps of batch %d from offset %lld run past the epoch (%lld rows)", n_steps, c->batch,
              (long long)perm_off, (long long)c->num_train);
   SgPlan plan;
-  if (sg_plan(c, &plan, true)) return -1;
+  if (sg_plan(c, &plan, true, loss_out != nullptr)) return -1;
   SgParams& p = plan.p;
+  if ((long long)n_steps * p.jobs_per_step >= (1LL << 31)) BNN_FAIL("bnn_sgld_run: too many steps in one launch (%d x %d jobs)", n_steps, p.jobs_per_step);
+  p.f0 = (float)pow((double)(1 + t0), -0.33);                  // LambdaLR factor of the first step; later ones are computed in-kernel
   p.X = c->X; p.y = c->y; p.perm = (const long long*)c->perm; p.num_train = c->num_train; p.perm_off = perm_off;
   p.t0 = t0; p.n_steps = n_steps; p.cur = cur;
   p.loss_out = loss_out; p.grad_out = grad_out;
   cudaStream_t st = (cudaStream_t)stream;
-  // accumulators, barrier counter and error flag start at zero for every launch
-  BNN_CUDA(cudaMemsetAsync(p.acc, 0, (size_t)(8LL * (p.nout + 1) + 64), st));
+  // accumulators, job / completion counters and error flag start at zero for every launch
+  BNN_CUDA(cudaMemsetAsync(p.acc, 0, (size_t)plan.tail_bytes, st));
   BNN_CUDA(cudaFuncSetAttribute(sgld_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
   int per_sm = 0;
-  BNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgld_step_kernel, kSgThreads, plan.smem));
+  BNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgld_step_kernel, kSgBlock, plan.smem));
   if (per_sm < 1) BNN_FAIL("bnn_sgld_run: the step kernel does not fit on an SM");
   int grid = plan.grid;
   if (grid > per_sm * sm_count()) grid = per_sm * sm_count();
   p.trace = g_sg_trace;
   if (const char* e = getenv("BNN_SGLD_DBG")) p.dbg = atoi(e);
-  g_sg_trace_grid = grid; g_sg_trace_L = p.L;
+  g_sg_trace_grid = grid;
+  if (p.trace) BNN_CUDA(cudaMemsetAsync(p.trace, 0, (size_t)grid * kSgTraceRecs * kSgTraceW * sizeof(long long), st));
   void* args[] = {(void*)&p};
-  BNN_CUDA(cudaLaunchCooperativeKernel((void*)sgld_step_kernel, dim3((unsigned)grid), dim3(kSgThreads), args, plan.smem, st));
+  BNN_CUDA(cudaLaunchCooperativeKernel((void*)sgld_step_kernel, dim3((unsigned)grid), dim3(kSgBlock), args, plan.smem, st));
   return 0;
 }
 
@@ -754,27 +1103,26 @@ extern "C" int32_t bnn_sgld_perm(uint64_t seed, uint32_t epoch, int64_t N, int64
   return 0;
 }
 
-// debug: enable = 1 allocates the per-CTA phase timeline written by the following bnn_sgld_run launches (last step of each
-// launch); with host_out != NULL copies it out: [grid][2 L][2] clock64 values (work done, barrier passed); returns grid in *grid_out
-extern "C" int32_t bnn_sgld_trace(int32_t enable, long long* host_out, int32_t* grid_out, int32_t* phases_out) {
+// debug: enable = 1 allocates the per-CTA job timeline written by the following bnn_sgld_run launches (jobs of the last two
+// steps of each launch); with host_out != NULL copies it out: [grid][recs][6] = {it << 32 | type << 24 | layer << 16 | tile,
+// clock64 at grab, at inputs-ready, at done, globaltimer (ns) at grab, at done}; returns grid in *grid_out and recs in *recs_out
+extern "C" int32_t bnn_sgld_trace(int32_t enable, long long* host_out, int32_t* grid_out, int32_t* recs_out) {
+  const size_t bytes = (size_t)1024 * kSgTraceRecs * kSgTraceW * sizeof(long long);
   if (enable && !g_sg_trace) {
-    BNN_CUDA(cudaMalloc(&g_sg_trace, (size_t)(1024 * 2 * BNN_MAX_LINEAR * 2 + 256) * sizeof(long long)));
-    BNN_CUDA(cudaMemset(g_sg_trace, 0, (size_t)(1024 * 2 * BNN_MAX_LINEAR * 2 + 256) * sizeof(long long)));
+    BNN_CUDA(cudaMalloc(&g_sg_trace, bytes));
+    BNN_CUDA(cudaMemset(g_sg_trace, 0, bytes));
   }
   if (host_out && g_sg_trace) {
     BNN_CUDA(cudaDeviceSynchronize());
-    BNN_CUDA(cudaMemcpy(host_out, g_sg_trace, (size_t)g_sg_trace_grid * 2 * g_sg_trace_L * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
-    // fine-grained probes of CTA 1 (first job of each phase): appended behind the coarse timeline
-    BNN_CUDA(cudaMemcpy(host_out + (size_t)g_sg_trace_grid * 2 * g_sg_trace_L * 2, g_sg_trace + 1024 * 2 * BNN_MAX_LINEAR * 2,
-                        (size_t)2 * g_sg_trace_L * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    BNN_CUDA(cudaMemcpy(host_out, g_sg_trace, (size_t)g_sg_trace_grid * kSgTraceRecs * kSgTraceW * sizeof(long long), cudaMemcpyDeviceToHost));
   }
   if (grid_out) *grid_out = g_sg_trace_grid;
-  if (phases_out) *phases_out = 2 * g_sg_trace_L;
+  if (recs_out) *recs_out = kSgTraceRecs;
   if (!enable && g_sg_trace) { cudaFree(g_sg_trace); g_sg_trace = nullptr; }
   return 0;
 }
 
-// 0 = ok; 1 = a grid barrier of the last launches timed out (never expected; the chain state is then undefined)
+// 0 = ok; 1 = a dependency wait of the last launches timed out (never expected; the chain state is then undefined)
 extern "C" int32_t bnn_sgld_status(const BnnSgldChain* c, int32_t* status_host, void* stream) {
   if (!c || !status_host) BNN_FAIL("bnn_sgld_status: bad arguments");
   SgPlan plan;

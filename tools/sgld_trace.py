@@ -1,5 +1,5 @@
-"""Per-phase timeline of the fused SGLD step (cfg 5 shape by default): for every phase, the distribution over CTAs of
-(work time, barrier wait) in cycles.   python tools/sgld_trace.py [B]"""
+"""Job timeline of the fused SGLD step (cfg 5 shape by default): per job kind, how long the jobs of the launch's last step
+took, how long they waited for their inputs, and how busy the CTAs were.   python tools/sgld_trace.py [B] [dims]"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -22,28 +22,60 @@ torch.cuda.synchronize()
 L.bnn_sgld_trace(1, None, None, None)
 chain.run(perm, 0, 50)
 torch.cuda.synchronize()
-grid, ph = C.c_int32(0), C.c_int32(0)
-buf = np.zeros(1024 * 64, dtype=np.int64)
-L.bnn_sgld_trace(1, buf.ctypes.data_as(C.c_void_p), C.byref(grid), C.byref(ph))
-grid, ph = grid.value, ph.value
-t = buf[: grid * ph * 2].reshape(grid, ph, 2)
-nl = ph // 2
-names = [f"F{l}" for l in range(nl)] + [f"B{l}" for l in range(nl - 1, -1, -1)]
-print(f"grid {grid}, {ph} phases; cycles per CTA: work = barrier-entry minus previous barrier-exit, wait = barrier exit minus entry")
-tot = 0
-for k in range(ph):
-    wait = t[:, k, 1] - t[:, k, 0]
-    work = t[:, k, 0] - t[:, k - 1, 1] if k > 0 else None
-    line = f"{names[k]:4s} wait min/med/max {wait.min():7d} {int(np.median(wait)):7d} {wait.max():7d}"
-    if work is not None:
-        line += f"   work min/med/max {work.min():7d} {int(np.median(work)):7d} {work.max():7d}"
-    print(line)
-pr = buf[grid * ph * 2: grid * ph * 2 + ph * 8].reshape(ph, 8)
-print("CTA 1, first job of each phase: phase-start->job-start | prologue issue | K loop | reduction | epilogue+rest -> barrier entry")
-for k in range(ph):
-    a = pr[k]
-    if a[0] == 0:
-        print(f"{names[k]:4s} (no job)"); continue
-    print(f"{names[k]:4s} {a[0] - a[5]:7d} | {a[1] - a[0]:7d} | {a[2] - a[1]:7d} | {a[3] - a[2]:7d} | {a[4] - a[3]:7d}")
-span = t[:, ph - 1, 1] - t[:, 0, 0]
-print("F0-entry .. last barrier exit (cycles), median over CTAs:", int(np.median(span)))
+grid, recs = C.c_int32(0), C.c_int32(0)
+buf = np.zeros(1024 * 96 * 10, dtype=np.int64)
+L.bnn_sgld_trace(1, buf.ctypes.data_as(C.c_void_p), C.byref(grid), C.byref(recs))
+grid, recs = grid.value, recs.value
+t = buf[: grid * recs * 10].reshape(grid, recs, 10)
+ok = t[:, :, 3] > 0
+code, grab, ready, done, ggrab, gdone = (t[..., i][ok] for i in range(6))
+probes = t[..., 6:10][ok]
+cta = np.broadcast_to(np.arange(grid)[:, None], ok.shape)[ok]
+it, typ, lay = code >> 32, (code >> 24) & 0xff, (code >> 16) & 0xff
+last = it.max()
+names = {0: "FWD", 1: "HEAD", 2: "DH", 3: "DW", 4: "LOGP", 5: "LOSS"}
+print(f"grid {grid}; jobs recorded {ok.sum()}; steps {it.min()}..{last}")
+for step in (last - 1, last):
+    m = it == step
+    if not m.any():
+        continue
+    t0 = ggrab[m].min()
+    print(f"step {step}: span {gdone[m].max() - t0} ns (first grab .. last done), {m.sum()} jobs")
+    print("  kind  layer  jobs   run med/max (cyc)  idle-before-start med/max (cyc)  first grab .. last done (ns from the step's first grab)")
+    for ty in range(6):
+        for l in sorted(set(lay[m & (typ == ty)])):
+            q = m & (typ == ty) & (lay == l)
+            run = done[q] - ready[q]
+            wait = np.where(probes[q][:, 3] > 0, ready[q] - probes[q][:, 3], 0)     # compute warps idle since the previous job ended
+            print(f"  {names[ty]:5s} {l:3d} {q.sum():6d}   {int(np.median(run)):7d} {run.max():7d}      {int(np.median(wait)):7d} {wait.max():7d}"
+                  f"          {ggrab[q].min() - t0:7d} .. {gdone[q].max() - t0:7d}")
+    busy = np.zeros(grid)
+    for c in range(grid):
+        q = m & (cta == c)
+        busy[c] = (done[q] - ready[q]).sum()
+    print(f"  CTA busy cycles (running jobs) min/med/max: {int(busy.min())} {int(np.median(busy))} {int(busy.max())}")
+# step period: distance between the first FWD grabs of the last two steps
+a, b = ggrab[(it == last - 1) & (typ == 0)], ggrab[(it == last) & (typ == 0)]
+if len(a) and len(b):
+    print("step period (first FWD grab to first FWD grab):", b.min() - a.min(), "ns")
+
+q = (it == last) & (typ == 1)
+print("HEAD jobs of the last step: start -> operands staged | y + head loop | dz of the last hidden layer -> done")
+for r, pz, d in zip(ready[q], probes[q], done[q]):
+    print("  ", pz[0] - r, pz[1] - pz[0], d - pz[1])
+m = (it == last) & (probes[:, 3] > 0)
+idle = (ready - probes[:, 3])[m]
+print(f"last step: compute-warp idle time between jobs: median {int(np.median(idle))}, mean {int(idle.mean())}, total per CTA {int(idle.sum() / grid)} cycles;"
+      f" scheduler grab -> inputs complete: median {int(np.median((probes[:, 2] - grab)[m]))}")
+# does a job run faster when the CTA's previous job had the same kind (same code, warm instruction cache)?
+order = np.lexsort((grab, cta))
+prev_same = np.zeros(len(code), dtype=bool)
+for a_, b_ in zip(order[:-1], order[1:]):
+    if cta[a_] == cta[b_]:
+        prev_same[b_] = typ[a_] == typ[b_]
+run_all = done - ready
+for ty in (0, 2, 3):
+    for same in (True, False):
+        q = (typ == ty) & (prev_same == same) & (lay != 0)
+        if q.any():
+            print(f"{names[ty]} (layers >= 1), previous job on the CTA same kind = {same}: n = {q.sum()}, run median {int(np.median(run_all[q]))}")
