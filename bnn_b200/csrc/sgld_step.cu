@@ -32,21 +32,12 @@ constexpr int kSgThreads = 256;       // compute threads
 constexpr int kSgBlock = kSgThreads + 32;   // + the scheduler warp
 // compute-only barrier (the scheduler warp never joins): named barrier 1
 __device__ __forceinline__ void sg_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-constexpr int kSgKC = 64;            // K chunk (floats)
-constexpr int kSgLds = kSgKC + 4;    // smem row pitch: 68 words = 4 (mod 32) -> 8 consecutive rows hit 32 distinct banks
-// Stage counts per tile family.  A tile's operands are tiny (<= 110 KB) but every access is an L2 round trip of ~450
-// cycles (DRAM ~1000), so the ring is deep enough to put the WHOLE K extent of a tile in flight at once (K <= 768 resp.
-// 384): tile time = one latency + transfer, instead of one latency per two chunks.
-constexpr int kSgStagesF = 12;   // 32 x 16 tiles: 12 x 13,056 B
-constexpr int kSgStagesW = 6;    // 64 x 32 tiles:  6 x 26,112 B
-constexpr int kSgMaxStages = 12;
-
 struct SgLayer {
   int in, out, ld, ldz, ldT;
   int ncb, nkb, ndw;         // 16-column tiles of the output / of the input, dW tiles (+ 1 for the last layer: the log-precision job)
   long long off, offT;       // float offsets into theta / thetaT
-  float* h[2];               // input of Linear l, augmented: [Bp, ld], by step parity   (null for l = 0: gathered from X)
-  float* hT[2];              // [ld, Bp]                                                  (null for l = 0)
+  float* h[2];               // input of Linear l, augmented: [Bp, ld], by step parity   (l = 0: the gathered batch rows (x | 1 | 0))
+  float* hT[2];              // [ld, Bp]
   float* dz;                 // dU/d(pre-activation output of Linear l): [Bp, ldz]
   float* dzT;                // [out, Bp]
   float inv_var;             // 1 / std_l^2 of the weight prior, std_l = gain * sqrt(2 / (in + out))   (BNN_SGDMC.py:65)
@@ -57,13 +48,14 @@ struct SgSeg { int type, l, first, count; };
 constexpr int kSgMaxSeg = 3 * BNN_MAX_LINEAR + 4;
 constexpr int kSgMaxRb = 32;           // 32-row blocks of a batch of <= 1024
 constexpr int kSgTraceRecs = 96;
-constexpr int kSgTraceW = 10;          // words per record       // debug timeline: job records per CTA
+constexpr int kSgTraceW = 12;          // words per record       // debug timeline: job records per CTA
 // completion counters (unsigned int, zero at launch): [0] = next job index
 __host__ __device__ constexpr int sg_c_fwd(int l, int rb) { return 16 + l * kSgMaxRb + rb; }
 __host__ __device__ constexpr int sg_c_dh(int l, int rb) { return 16 + (BNN_MAX_LINEAR + l) * kSgMaxRb + rb; }
 __host__ __device__ constexpr int sg_c_dht(int l) { return 16 + 2 * BNN_MAX_LINEAR * kSgMaxRb + l; }
 __host__ __device__ constexpr int sg_c_dw(int l) { return 16 + 2 * BNN_MAX_LINEAR * kSgMaxRb + BNN_MAX_LINEAR + l; }
-constexpr int kSgCounters = 16 + 2 * BNN_MAX_LINEAR * kSgMaxRb + 2 * BNN_MAX_LINEAR;
+__host__ __device__ constexpr int sg_c_ga(int rb) { return 16 + 2 * BNN_MAX_LINEAR * kSgMaxRb + 2 * BNN_MAX_LINEAR + rb; }
+constexpr int kSgCounters = 16 + 2 * BNN_MAX_LINEAR * kSgMaxRb + 2 * BNN_MAX_LINEAR + kSgMaxRb;
 
 struct SgParams {
   int L, act, B, Bp, nout, D;
@@ -124,64 +116,87 @@ __device__ __forceinline__ float act_bwd(float h, int act) {
 // phases): a step executes every phase's code exactly once per tile, so straight-line code is instruction-fetch bound -- the
 // first version (fully unrolled prefetch prologues, three inlined copies of the core, ~130 KB of SASS) spent 3.5k of a tile's
 // 12.9k cycles with the FMAs, the loads and the epilogue all switched off.
-enum { OP_DENSE = 0, OP_GATHER_X = 1, OP_GATHER_XT = 2 };
 struct SgOperand {
-  int kind;
-  const float* p;      // DENSE: [rows, ld]
+  const float* p;      // [rows, ld], K-contiguous
   int ld;
-  int rows_valid;      // rows >= rows_valid read as zero
-  int k_valid;         // k >= k_valid reads as zero (multiple of 4)
-};
-// what the gather kinds need (X[perm[b] * D + k]; batch rows >= rows_live are zero: short last batch of an epoch)
-struct SgGather {
-  const float* __restrict__ X;
-  const long long* perm;   // this step's batch rows: perm + off (read-only for the whole launch)
-  int D, B, rows_live;
+  int rows_valid;      // rows >= rows_valid are not loaded
 };
 
-// gathered operands (synchronous): rows = batch index b, K = input feature (forward of Linear 0: kT = false) or rows = input
-// feature, K = batch index (dW of Linear 0: kT = true); augmented with the ones column / row at feature == D.  Four
-// independent loads are in flight per thread before the first store.
-template <int ROWS, bool kT>
-__device__ __forceinline__ void load_gather(const SgGather& gq, int row0, int k0, float* dst) {
+// ---- minibatch gather (DataLoader batch, BNN_SGDMC.py:80,110): 32 rows of the step's batch -> h_0 (augmented (x | 1 | 0), row-
+// major) and its transpose.  Done one step AHEAD by a job of the previous step's list (the first step of a launch by a small
+// kernel in front), so Linear 0's forward and dW tiles are ordinary dense tiles and the random-row DRAM latency of the gather
+// is off the step's critical path.  Rows beyond the live batch (short last batch of an epoch) are zero, ones column included.
+__device__ __forceinline__ void sg_gather_rows(const SgParams& p, int it, int rb, float* smem) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const SgLayer& Y = p.ly[0];
+  const int par = it & 1, r0 = rb * 32;
+  const long long boff = p.perm_off + (long long)it * p.B;
+  const long long left = p.num_train - boff;
+  const int rows = left < p.B ? (int)left : p.B;
+  const int pitch = Y.ld + 1;                        // odd pitch: the transposed read below is conflict-free
+  float* h0 = Y.h[par];
+  float* h0T = Y.hT[par];
+  // warp w takes rows w, w + 8, w + 16, w + 24: the four permutation entries first, then the rows with up to 16 loads in flight
+  long long prow[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int b = r0 + w + 8 * i;
+    prow[i] = b < rows ? __ldg(p.perm + boff + b) : -1;
+  }
 #pragma unroll 1
-  for (int base = threadIdx.x; base < ROWS * kSgKC; base += 4 * kSgThreads) {
-    float v[4];
+  for (int kk0 = 0; kk0 < Y.ld; kk0 += 128) {
+    float v[4][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int idx = base + u * kSgThreads;
-      const int r = kT ? idx % ROWS : idx >> 6, kk = kT ? idx / ROWS : idx & 63;
-      const int b = kT ? k0 + kk : row0 + r, f = kT ? row0 + r : k0 + kk;
-      v[u] = 0.0f;
-      if (idx < ROWS * kSgKC && b < gq.rows_live) {
-        if (f < gq.D) v[u] = __ldg(gq.X + __ldg(gq.perm + b) * gq.D + f);
-        else if (f == gq.D) v[u] = 1.0f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = kk0 + u * 32 + lane;
+        v[i][u] = 0.0f;
+        if (prow[i] >= 0) {
+          if (k < p.D) v[i][u] = __ldg(p.X + prow[i] * p.D + k);
+          else if (k == p.D) v[i][u] = 1.0f;
+        }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int idx = base + u * kSgThreads;
-      if (idx < ROWS * kSgKC) dst[(kT ? idx % ROWS : idx >> 6) * kSgLds + (kT ? idx / ROWS : idx & 63)] = v[u];
-    }
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = kk0 + u * 32 + lane, r = w + 8 * i;
+        if (k < Y.ld) {
+          smem[r * pitch + k] = v[i][u];
+          if (r0 + r < p.Bp) h0[(long long)(r0 + r) * Y.ld + k] = v[i][u];
+        }
+      }
+  }
+  sg_sync();
+  if (r0 + lane < p.Bp) {
+#pragma unroll 4
+    for (int k = w; k < Y.ld; k += kSgThreads / 32) h0T[(long long)k * p.Bp + r0 + lane] = smem[lane * pitch + k];
   }
 }
 
 // ---- tile core: red[TM x TN] = sum_k A[m0 + ., k] B[n0 + ., k], left in shared memory (row-major, after the K-slices are summed)
-// Operands: 16-byte cp.async into padded shared-memory rows, completion per ring stage on an mbarrier (every thread posts a
-// deferred arrival that fires when its own copies of the stage have landed: no per-chunk __syncthreads).  Rows beyond the
-// operand are not copied (garbage rows only feed output rows / columns the epilogues discard); the K tail is skipped.
+// Operands: every row of the tile arrives WHOLE (its full K extent) through the bulk-copy engine: one cp.async.bulk per row
+// and K-half, completion on two mbarriers (transaction bytes).  The first version used 16-byte cp.async per thread: those
+// LDGSTS go through the same load/store pipe as the LDS of the FMA loop (194 of them per tile on top of 1,024 LDS.128), and the
+// two were additive -- the K loop took 9.8k cycles for 2k cycles of FFMA.  Few large bulk copies matter: the engine retires a
+// copy every ~20 cycles whatever its size (432 copies of 256 B per tile took 8k cycles), so rows are not chunked along K.
+// Shared-memory row pitch = K rounded up to 32 words + 4: 8 consecutive rows hit 32 distinct banks for float4 reads.
+// Rows beyond the operand are not copied (garbage rows only feed output rows / columns the epilogues discard).
+// K extents that do not fit shared memory (batch or width > ~800 / ~380) are processed in rounds with a barrier in between.
 // Compute: FP32 FFMA, thread tile 4 x 4 (rows ty + TY * i, columns tx + TX * j); the 256 threads form KS = 256 / (TY * TX)
-// K-slices, slice ks takes the float4 groups g = ks, ks + KS, ... of every chunk.
+// K-slices, slice ks takes the float4 groups g = ks, ks + KS, ...
 // Measured alternatives (profiles/r02_sgld_step_notes.md): mma.sync m16n8k8 TF32 with 3xTF32 compensation is NOT faster --
 // the legacy warp-level tensor path of this chip issues one TF32 mma per ~32 cycles per SM sub-partition, i.e. the FFMA
-// rate, and the compensation needs three of them; one cp.async.bulk per 256-byte operand row was slower than 16-byte
-// cp.async (432 small bulk copies per tile); 16 warps instead of 8 did not change the K loop.
-template <int TM, int TN, int NS>
-__device__ __forceinline__ void tile_core(const SgOperand& A, const SgOperand& Bop, const SgGather& gq, int m0, int n0, int K,
+// rate, and the compensation needs three of them; 8 x 8 thread tiles (half the LDS per FFMA) were slower (more slices to
+// reduce, register pressure); 16 warps instead of 8 did not change the K loop.
+constexpr int kSgStageFloats = 39168;     // shared-memory floats for a tile's operands (153 KB)
+template <int TM, int TN>
+__device__ __forceinline__ void tile_core(const SgOperand& A, const SgOperand& Bop, int m0, int n0, int K,
                                           float* smem, uint64_t* bars, uint32_t& phase_bits, int dbg, long long* probe) {
   constexpr int TY = TM / 4, TX = TN / 4, THR = TY * TX, KS = kSgThreads / THR;
-  constexpr int STAGE = (TM + TN) * kSgLds;
-  static_assert(KS >= 1 && KS * THR == kSgThreads && NS <= kSgMaxStages, "tile shape");
+  constexpr int KRMAX = ((kSgStageFloats / (TM + TN)) - 4) & ~31;
+  static_assert(KS >= 1 && KS * THR == kSgThreads && 2 * (TM + TN) <= kSgThreads, "tile shape");
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = (tid / TX) % TY, ks = tid / THR;
   float acc[4][4];
@@ -191,67 +206,48 @@ __device__ __forceinline__ void tile_core(const SgOperand& A, const SgOperand& B
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
   if (probe && tid == 0) probe[0] = clock64();
-  const int nchunks = (K + kSgKC - 1) / kSgKC;
-  const bool a_dense = A.kind == OP_DENSE, b_dense = Bop.kind == OP_DENSE;
   const int va = min(TM, A.rows_valid - m0), vb = min(TN, Bop.rows_valid - n0);   // valid rows of the tile (>= 1)
-  auto issue_dense = [&](int c) {
-    if (dbg & 2) return;
-    const int k0 = c * kSgKC;
-    const int kq = (min(kSgKC, K - k0) + 3) >> 2;                  // float4s per row in this chunk
-    float* st = smem + (c % NS) * STAGE;
-    const uint32_t d0 = smem_u32(st);
-#pragma unroll
-    for (int idx = tid; idx < (TM + TN) * (kSgKC / 4); idx += kSgThreads) {
-      const int r = idx >> 4, c4 = idx & 15;
-      const bool isA = r < TM;
-      const int rr = isA ? r : r - TM;
-      const SgOperand& op = isA ? A : Bop;
-      if (c4 < kq && rr < (isA ? va : vb) && (isA ? a_dense : b_dense))
-        cp_async16(d0 + (uint32_t)(r * kSgLds + c4 * 4) * 4u, op.p + (long long)((isA ? m0 : n0) + rr) * op.ld + k0 + c4 * 4, 16);
+#pragma unroll 1
+  for (int k0 = 0; k0 < K; k0 += KRMAX) {            // one round for every shape of the reference's configurations
+    const int Kr = min(KRMAX, K - k0);               // multiple of 4
+    const int pitch = ((Kr + 31) & ~31) + 4;
+    const int ngr = Kr >> 2;                         // float4 groups along K
+    const int nseg = ngr >= 64 ? 2 : 1;              // K-halves with their own barrier: the FMAs start on the first half
+    const int gs = nseg == 2 ? ((ngr >> 1) + 3) & ~3 : ngr;
+    if (k0 > 0) sg_sync();                           // the previous round's operands are consumed
+    if (!(dbg & 2)) {
+      if (tid == 0) {
+        const uint32_t nrows = (uint32_t)(va + vb);
+        mbar_arrive_expect_tx(&bars[0], nrows * (uint32_t)(gs * 16));
+        if (nseg == 2) mbar_arrive_expect_tx(&bars[1], nrows * (uint32_t)((ngr - gs) * 16));
+      }
+      // copy c = row * nseg + half is issued by lane c / 8 of warp c % 8: a warp's lanes issue their bulk copies one after the
+      // other (~45 cycles each), so the copies are spread over all eight warps
+      {
+        const int c = (tid & 31) * (kSgThreads / 32) + (tid >> 5);
+        const int row = nseg == 2 ? c >> 1 : c, half = nseg == 2 ? c & 1 : 0;
+        if (row < TM + TN) {
+          const bool isA = row < TM;
+          const int rr = isA ? row : row - TM;
+          const SgOperand& op = isA ? A : Bop;
+          if (rr < (isA ? va : vb)) {
+            const float* src = op.p + (long long)((isA ? m0 : n0) + rr) * op.ld + k0;
+            float* dst = smem + row * pitch;
+            if (half == 0) bulk_g2s(dst, src, (uint32_t)(gs * 16), &bars[0]);
+            else bulk_g2s(dst + gs * 4, src + gs * 4, (uint32_t)((ngr - gs) * 16), &bars[1]);
+          }
+        }
+      }
     }
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[c % NS])) : "memory");
-  };
-  auto issue_gather = [&](int c) {
-    if (dbg & 2) return;
-    float* st = smem + (c % NS) * STAGE;
-    if (!a_dense) load_gather<TM, false>(gq, m0, c * kSgKC, st);
-    if (!b_dense) load_gather<TN, true>(gq, n0, c * kSgKC, st + TM * kSgLds);
-  };
-  // prologue: the first chunks; the rest of what the ring holds is issued from inside the K loop, kLead chunks ahead of the
-  // chunk being consumed (every stage is used once per tile while K <= NS * 64, so no hand-shake is needed), which overlaps
-  // the cp.async issue (LSU bound, ~390 cycles per chunk) with the FMA work of the earlier chunks.  Gathered operands (Linear 0)
-  // are plain stores behind a __syncthreads and stay in the prologue.
-  constexpr int kLead = 3;
-  const int nring = min(nchunks, NS);
-  const bool gathered = !a_dense || !b_dense;
-  {
-    const int npre = gathered ? nring : min(nring, kLead);
-#pragma unroll 1
-    for (int c = 0; c < npre; ++c) issue_dense(c);
-    if (gathered) {
-#pragma unroll 1
-      for (int c = 0; c < npre; ++c) issue_gather(c);
-      sg_sync();                     // gathered rows are plain shared-memory stores
-    }
-  }
-  if (probe && tid == 0) probe[1] = clock64();
-#pragma unroll 1
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c % NS;
-    if (!gathered && c + kLead < nring) issue_dense(c + kLead);
-    if (!(dbg & 2)) mbar_wait_spin(&bars[s], (phase_bits >> s) & 1u);
-    phase_bits ^= 1u << s;
-    const float* As = smem + s * STAGE + ty * kSgLds;
-    const float* Bs = smem + s * STAGE + (TM + tx) * kSgLds;
-    const int rem = K - c * kSgKC;
-    const int gmax = (dbg & 1) ? 0 : (rem >= kSgKC ? kSgKC / 4 : (rem + 3) >> 2);
-#pragma unroll 1
-    for (int g = ks; g < gmax; g += KS) {
+    if (probe && tid == 0 && k0 == 0) probe[1] = clock64();
+    const float* As = smem + ty * pitch;
+    const float* Bs = smem + (TM + tx) * pitch;
+    auto body = [&](int g) {
       float4 a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(As + TY * i * kSgLds + g * 4);
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(As + TY * i * pitch + g * 4);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + TX * j * kSgLds + g * 4);
+      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + TX * j * pitch + g * 4);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -261,14 +257,24 @@ __device__ __forceinline__ void tile_core(const SgOperand& A, const SgOperand& B
           acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
           acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
         }
+    };
+    if (!(dbg & 2)) mbar_wait_spin(&bars[0], phase_bits & 1u);
+    phase_bits ^= 1u;
+    int g = ks;
+    if (!(dbg & 1)) {
+#pragma unroll 1
+      for (; g < gs; g += KS) body(g);
     }
-    if (c + NS < nchunks) {                // refill this stage (only for K beyond the ring: layers wider than 768 / 384)
-      sg_sync();                     // every warp is done with chunk c
-      issue_dense(c + NS);
-      if (!a_dense || !b_dense) { issue_gather(c + NS); sg_sync(); }
+    if (nseg == 2) {
+      if (!(dbg & 2)) mbar_wait_spin(&bars[1], (phase_bits >> 1) & 1u);
+      phase_bits ^= 2u;
+      if (!(dbg & 1)) {
+#pragma unroll 1
+        for (; g < ngr; g += KS) body(g);
+      }
     }
   }
-  sg_sync();                         // all slices done with the stages: reuse them for the cross-slice reduction
+  sg_sync();                               // all slices done with the operands: reuse the memory for the cross-slice reduction
   if (probe && tid == 0) probe[2] = clock64();
   float* red = smem + TM * TN;             // [KS][TM * TN] partials behind the [TM * TN] result
 #pragma unroll
@@ -286,6 +292,8 @@ __device__ __forceinline__ void tile_core(const SgOperand& A, const SgOperand& B
     }
     *reinterpret_cast<float4*>(smem + q * 4) = v;
   }
+  // the next job's bulk copies (async proxy) overwrite what was written here through the generic proxy: order them
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   sg_sync();
   if (probe && tid == 0) probe[3] = clock64();
 }
@@ -318,7 +326,7 @@ constexpr int WT_M = 64, WT_N = 32;   // dW tiles over [out, ld]
 //   LOSS             U of the launch's last step                                  needs everything of that step
 // Buffers: theta / thetaT by step parity (readers of step t see "cur", DW writes "next"); h / hT by step parity as well (DW(l+1)
 // of step t may still read hT_{l+1} while FWD(l) of step t+1 writes it); dz / dzT and V single (ordered by the chains above).
-enum { JT_FWD = 0, JT_HEAD = 1, JT_DH = 2, JT_DW = 3, JT_LOGP = 4, JT_LOSS = 5 };
+enum { JT_FWD = 0, JT_HEAD = 1, JT_DH = 2, JT_DW = 3, JT_LOGP = 4, JT_LOSS = 5, JT_GATHER = 6 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long v;
@@ -366,15 +374,22 @@ __device__ __forceinline__ void sg_decode(const SgParams& p, unsigned int idx, u
   const unsigned int done = (unsigned int)it + 1u;                // completions of "this step" = done * per-step count
   int rb = 0, cb = 0, nd = 0, ns = 0;
   switch (type) {
+    case JT_GATHER:                                                 // batch rows of step it + 1 (buffer parity of step it - 1)
+      rb = jj;
+      if (it > 0) { J->dc[nd] = sg_c_dw(0); J->dt[nd++] = (unsigned int)it * (unsigned int)p.ly[0].ndw; }
+      J->sc[ns++] = sg_c_ga(rb);
+      break;
     case JT_FWD:
       rb = jj / Y.ncb; cb = jj - rb * Y.ncb;
       if (l > 0) { J->dc[nd] = sg_c_fwd(l - 1, rb); J->dt[nd++] = done * (unsigned int)p.ly[l - 1].ncb; }
+      else if (it > 0) { J->dc[nd] = sg_c_ga(rb); J->dt[nd++] = (unsigned int)it; }
       if (it > 0) { J->dc[nd] = sg_c_dw(l); J->dt[nd++] = (unsigned int)it * (unsigned int)Y.ndw; }
       J->sc[ns++] = sg_c_fwd(l, rb);
       break;
     case JT_HEAD:
       rb = jj / Y.nkb; cb = jj - rb * Y.nkb;
       if (L > 1) { J->dc[nd] = sg_c_fwd(L - 2, rb); J->dt[nd++] = done * (unsigned int)p.ly[L - 2].ncb; }
+      else if (it > 0) { J->dc[nd] = sg_c_ga(rb); J->dt[nd++] = (unsigned int)it; }   // orders the gather before this step's dW_0
       if (it > 0) { J->dc[nd] = sg_c_dw(L - 1); J->dt[nd++] = (unsigned int)it * (unsigned int)Y.ndw; }
       J->sc[ns++] = sg_c_dh(L - 1, rb); J->sc[ns++] = sg_c_dht(L - 1);
       break;
@@ -408,14 +423,14 @@ __global__ void __launch_bounds__(kSgBlock, 1) sgld_step_kernel(const __grid_con
   __shared__ SgJob s_job[2];
   __shared__ __align__(8) uint64_t s_full[2];              // scheduler -> compute: slot holds a job whose inputs are complete
   __shared__ unsigned int s_go_n, s_done_n;                // compute -> scheduler: jobs started / finished so far
-  __shared__ __align__(8) uint64_t s_bars[kSgMaxStages];   // one per ring stage: "the chunk's bytes have landed"
+  __shared__ __align__(8) uint64_t s_bars[2];              // "the operands' first / second K-half has landed" (transaction bytes)
   uint32_t phase_bits = 0;             // parity to wait for next, per stage (uniform across the CTA)
   const int tid = threadIdx.x;
   const unsigned int total = (unsigned int)p.n_steps * (unsigned int)p.jobs_per_step;
   const int L = p.L;
   const int bm = (p.B + FT_M - 1) / FT_M;                           // batch-row blocks
   if (tid == 0) {
-    for (int i = 0; i < kSgMaxStages; ++i) mbar_init(&s_bars[i], kSgThreads);   // every thread posts one (deferred) arrival per use
+    mbar_init(&s_bars[0], 1); mbar_init(&s_bars[1], 1);     // one arrival (with the expected bytes) per use
     mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
     s_go_n = 0; s_done_n = 0;
     fence_barrier_init();
@@ -506,8 +521,6 @@ __global__ void __launch_bounds__(kSgBlock, 1) sgld_step_kernel(const __grid_con
     const long long boff = p.perm_off + (long long)it * p.B;
     const long long left = p.num_train - boff;
     const int rows = left < p.B ? (int)left : p.B;                 // the last batch of an epoch may be short (:80)
-    SgGather gq;
-    gq.X = p.X; gq.perm = p.perm + boff; gq.D = p.D; gq.B = p.B; gq.rows_live = rows;
     const float scale = (float)((double)p.num_train / (double)rows);   // N / |b|  (:83)
     const bool want_loss = p.loss_out != nullptr && it == p.n_steps - 1;
     double* acc = p.acc + par * (p.nout + 1);
@@ -520,20 +533,16 @@ __global__ void __launch_bounds__(kSgBlock, 1) sgld_step_kernel(const __grid_con
     int m0 = 0, n0 = 0;
     if (tile_job) {
       SgOperand A, Bo;
-      A.kind = OP_DENSE; Bo.kind = OP_DENSE;
-      A.k_valid = 0; Bo.k_valid = 0;
       int K;
       if (type == JT_DW) {
         // dW_l tile over K = batch
         const int wm = (Y.out + tm - 1) / tm;
         m0 = (jj % wm) * tm; n0 = (jj / wm) << tn_sh;
         A.p = Y.dzT; A.ld = p.Bp; A.rows_valid = Y.out;
-        if (l == 0) Bo.kind = OP_GATHER_XT;
         Bo.p = Y.hT[par]; Bo.ld = p.Bp; Bo.rows_valid = Y.ld;
         K = p.Bp;
       } else if (type == JT_FWD) {
         m0 = rb * FT_M; n0 = cb * FT_N;
-        if (l == 0) A.kind = OP_GATHER_X;
         A.p = Y.h[par]; A.ld = Y.ld; A.rows_valid = p.B;
         Bo.p = th + Y.off; Bo.ld = Y.ld; Bo.rows_valid = Y.out;
         K = Y.ld;
@@ -543,8 +552,8 @@ __global__ void __launch_bounds__(kSgBlock, 1) sgld_step_kernel(const __grid_con
         Bo.p = thT + Y.offT; Bo.ld = Y.ldT; Bo.rows_valid = Y.in;
         K = Y.ldz;
       }
-      if (big) tile_core<WT_M, WT_N, kSgStagesW>(A, Bo, gq, m0, n0, K, sg_smem, s_bars, phase_bits, p.dbg, nullptr);
-      else tile_core<FT_M, FT_N, kSgStagesF>(A, Bo, gq, m0, n0, K, sg_smem, s_bars, phase_bits, p.dbg, nullptr);
+      if (big) tile_core<WT_M, WT_N>(A, Bo, m0, n0, K, sg_smem, s_bars, phase_bits, p.dbg, p.trace ? pr : nullptr);
+      else tile_core<FT_M, FT_N>(A, Bo, m0, n0, K, sg_smem, s_bars, phase_bits, p.dbg, p.trace ? pr : nullptr);
     }
     // HEAD(rb, chunk): last Linear, residual, dU/d(out), per-output sum of squares (BNN_SGDMC.py:69-74, :83) for 32 batch rows,
     // then dz of the last hidden layer for a 64-column chunk of those rows.  GEMV-sized work (nout is 1..few): eight threads per
@@ -571,7 +580,7 @@ __global__ void __launch_bounds__(kSgBlock, 1) sgld_step_kernel(const __grid_con
       long long prow = 0;
       float ytrue = 0.0f;
       if (live) {
-        prow = __ldg(gq.perm + b);
+        prow = __ldg(p.perm + boff + b);
         if (sub < p.nout) ytrue = __ldg(p.y + prow * p.nout + sub);   // targets of outputs 0..7 travel with the operands
       }
       cp_async_wait<0>();
@@ -771,6 +780,8 @@ __global__ void __launch_bounds__(kSgBlock, 1) sgld_step_kernel(const __grid_con
           }
         }
       }
+    } else if (type == JT_GATHER) {
+      if (it + 1 < p.n_steps) sg_gather_rows(p, it + 1, rb, sg_smem);
     } else if (type == JT_LOGP) {
       // ---- log-precision group (BNN_SGDMC.py:62, :96-98): closed-form gradient, same update rule, lr_noise
       if (tid < ((p.n_theta - p.n_head) >> 2)) {
@@ -824,7 +835,11 @@ __global__ void __launch_bounds__(kSgBlock, 1) sgld_step_kernel(const __grid_con
       }
     }
 
-    // ---- done: tell the scheduler warp, which publishes the completion
+    // ---- done: tell the scheduler warp, which publishes the completion.  The next job's bulk copies (async proxy) overwrite
+    // shared memory this job wrote through the generic proxy: order them.  (Global memory needs no proxy fence here: the bulk
+    // copies read L2, where the producers' stores are before their completion is published with release / acquire at gpu scope;
+    // a full fence.proxy.async on either side was measured at 2.5-5k cycles per job.)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     sg_sync();                           // the job's global writes are issued; its shared memory is free for the next job
     if (tid == 0) {
       st_release_cta_u32(&s_done_n, n + 1u);
@@ -834,13 +849,19 @@ __global__ void __launch_bounds__(kSgBlock, 1) sgld_step_kernel(const __grid_con
           long long* r = p.trace + ((long long)blockIdx.x * kSgTraceRecs + (trec < kSgTraceRecs ? trec : kSgTraceRecs - 1)) * kSgTraceW;
           r[0] = ((long long)it << 32) | ((long long)type << 24) | ((long long)l << 16) | (long long)(jj & 0xffff);
           r[1] = t_grab; r[2] = t_start; r[3] = t_end; r[4] = g_grab; r[5] = (long long)globaltimer_ns();
-          r[6] = pr[0]; r[7] = pr[1]; r[8] = t_ready; r[9] = t_prev_end;
+          r[6] = pr[0]; r[7] = pr[1]; r[8] = t_ready; r[9] = t_prev_end; r[10] = pr[2]; r[11] = pr[3];
           ++trec;
         }
         t_prev_end = t_end;
       }
     }
   }
+}
+
+// batch rows of a launch's FIRST step (later steps are gathered by jobs of the step before)
+__global__ void __launch_bounds__(kSgThreads, 1) sgld_gather_kernel(const __grid_constant__ SgParams p) {
+  extern __shared__ __align__(16) float sg_smem[];
+  sg_gather_rows(p, 0, blockIdx.x, sg_smem);
 }
 
 // theta[cur] -> thetaT[cur] (layers >= 1), once per chain initialisation
@@ -935,9 +956,10 @@ static int sg_plan(const BnnSgldChain* c, SgPlan* plan, bool bind, bool want_los
     Y.ndw = (l > 0 ? ((Y.out + WT_M - 1) / WT_M) * ((Y.ld + WT_N - 1) / WT_N) : ((Y.out + FT_M - 1) / FT_M) * ((Y.ld + FT_N - 1) / FT_N)) +
             (l == p.L - 1 ? 1 : 0);
   }
-  plan->smem = (size_t)kSgStagesW * (WT_M + WT_N) * kSgLds * 4;
-  if ((size_t)kSgStagesF * (FT_M + FT_N) * kSgLds * 4 > plan->smem) plan->smem = (size_t)kSgStagesF * (FT_M + FT_N) * kSgLds * 4;
+  plan->smem = (size_t)kSgStageFloats * 4;
   // the head job keeps the last Linear's rows, 32 rows of the last hidden layer and of dU/d(out) in shared memory
+  if ((size_t)32 * (p.ly[0].ld + 1) > (size_t)kSgStageFloats)
+    BNN_FAIL("bnn_sgld: input dimension %d is too large for the in-kernel batch gather", p.D);
   {
     const size_t head = ((size_t)FT_M * p.nout + 4 + (size_t)(p.nout + FT_M) * p.ly[p.L - 1].ld) * 4;
     if (head > (size_t)227 * 1024)
@@ -957,8 +979,10 @@ static int sg_plan(const BnnSgldChain* c, SgPlan* plan, bool bind, bool want_los
     auto n_dw = [&](int l) { return p.ly[l].ndw - (l == Ln - 1 ? 1 : 0); };
     for (int l = 0; l + 1 < Ln; ++l) add(JT_FWD, l, bm * p.ly[l].ncb);
     add(JT_HEAD, Ln - 1, bm * p.ly[Ln - 1].nkb);
+    if (Ln <= 2) add(JT_GATHER, 0, bm);
     for (int l = Ln - 2; l >= 1; --l) {
       add(JT_DH, l, bm * p.ly[l].nkb);
+      if (l == Ln - 2) add(JT_GATHER, 0, bm);            // the next step's batch rows, off the critical path
       add(JT_DW, l + 1, n_dw(l + 1));
       if (l + 1 == Ln - 1) add(JT_LOGP, Ln - 1, 1);
     }
@@ -969,10 +993,10 @@ static int sg_plan(const BnnSgldChain* c, SgPlan* plan, bool bind, bool want_los
     p.n_seg = n; p.jobs_per_step = first;
   }
   plan->nT = oT > 0 ? oT : 4;
-  // workspace: per layer h, hT (l >= 1; two copies, by step parity), dz, dzT
+  // workspace: per layer h, hT (two copies, by step parity; layer 0: the gathered batch), dz, dzT
   for (int l = 0; l < p.L; ++l) {
     SgLayer& Y = p.ly[l];
-    if (l > 0) ow += 2 * (r4((long long)p.Bp * Y.ld) + r4((long long)Y.ld * p.Bp));
+    ow += 2 * (r4((long long)p.Bp * Y.ld) + r4((long long)Y.ld * p.Bp));
     ow += r4((long long)p.Bp * Y.ldz);
     ow += r4((long long)Y.out * p.Bp);
   }
@@ -998,8 +1022,7 @@ static int sg_plan(const BnnSgldChain* c, SgPlan* plan, bool bind, bool want_los
     long long o = 0;
     for (int l = 0; l < p.L; ++l) {
       SgLayer& Y = p.ly[l];
-      if (l > 0)
-        for (int q = 0; q < 2; ++q) { Y.h[q] = w + o; o += r4((long long)p.Bp * Y.ld); Y.hT[q] = w + o; o += r4((long long)Y.ld * p.Bp); }
+      for (int q = 0; q < 2; ++q) { Y.h[q] = w + o; o += r4((long long)p.Bp * Y.ld); Y.hT[q] = w + o; o += r4((long long)Y.ld * p.Bp); }
       Y.dz = w + o; o += r4((long long)p.Bp * Y.ldz);
       Y.dzT = w + o; o += r4((long long)Y.out * p.Bp);
     }
@@ -1088,6 +1111,12 @@ extern "C" int32_t bnn_sgld_run(const BnnSgldChain* c, int32_t cur, int64_t t0, 
   if (const char* e = getenv("BNN_SGLD_DBG")) p.dbg = atoi(e);
   g_sg_trace_grid = grid;
   if (p.trace) BNN_CUDA(cudaMemsetAsync(p.trace, 0, (size_t)grid * kSgTraceRecs * kSgTraceW * sizeof(long long), st));
+  {
+    const size_t gsmem = (size_t)32 * (p.ly[0].ld + 1) * 4;
+    BNN_CUDA(cudaFuncSetAttribute(sgld_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    sgld_gather_kernel<<<(unsigned)((p.B + FT_M - 1) / FT_M), kSgThreads, gsmem, st>>>(p);
+    BNN_CUDA(cudaGetLastError());
+  }
   void* args[] = {(void*)&p};
   BNN_CUDA(cudaLaunchCooperativeKernel((void*)sgld_step_kernel, dim3((unsigned)grid), dim3(kSgBlock), args, plan.smem, st));
   return 0;

@@ -23,13 +23,14 @@ L.bnn_sgld_trace(1, None, None, None)
 chain.run(perm, 0, 50)
 torch.cuda.synchronize()
 grid, recs = C.c_int32(0), C.c_int32(0)
-buf = np.zeros(1024 * 96 * 10, dtype=np.int64)
+buf = np.zeros(1024 * 96 * 12, dtype=np.int64)
 L.bnn_sgld_trace(1, buf.ctypes.data_as(C.c_void_p), C.byref(grid), C.byref(recs))
 grid, recs = grid.value, recs.value
-t = buf[: grid * recs * 10].reshape(grid, recs, 10)
+t = buf[: grid * recs * 12].reshape(grid, recs, 12)
 ok = t[:, :, 3] > 0
 code, grab, ready, done, ggrab, gdone = (t[..., i][ok] for i in range(6))
 probes = t[..., 6:10][ok]
+probes2 = t[..., 10:12][ok]
 cta = np.broadcast_to(np.arange(grid)[:, None], ok.shape)[ok]
 it, typ, lay = code >> 32, (code >> 24) & 0xff, (code >> 16) & 0xff
 last = it.max()
@@ -79,3 +80,12 @@ for ty in (0, 2, 3):
         q = (typ == ty) & (prev_same == same) & (lay != 0)
         if q.any():
             print(f"{names[ty]} (layers >= 1), previous job on the CTA same kind = {same}: n = {q.sum()}, run median {int(np.median(run_all[q]))}")
+
+print("tile jobs of the last step, medians (cycles): start -> core entry | prologue issue | K loop | slice reduction | epilogue -> done")
+for ty, lsel, nm in ((0, 0, "FWD 0"), (0, 1, "FWD 1+"), (2, 1, "DH"), (3, 0, "DW 0"), (3, 1, "DW 1+")):
+    q = (it == last) & (typ == ty) & ((lay == 0) if lsel == 0 else (lay > 0))
+    if not q.any():
+        continue
+    p0, p1, p2, p3 = probes[q][:, 0], probes[q][:, 1], probes2[q][:, 0], probes2[q][:, 1]
+    med = lambda v: int(np.median(v))
+    print(f"  {nm:7s} {med(p0 - ready[q]):6d} | {med(p1 - p0):6d} | {med(p2 - p1):6d} | {med(p3 - p2):6d} | {med(done[q] - p3):6d}")
