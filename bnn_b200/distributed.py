@@ -60,7 +60,7 @@ def _nccl_path():
 
 
 class _UniqueId(_C.Structure):
-    _fields_ = [("internal", _C.c_char * 128)]
+    _fields_ = [("internal", _C.c_ubyte * 128)]       # NOT c_char: ctypes truncates c_char arrays at the first NUL on read
 
 
 class NcclMoments:
@@ -82,10 +82,11 @@ class NcclMoments:
             rc = self._nccl.ncclGetUniqueId(_C.byref(uid))
             if rc != 0:
                 raise RuntimeError(f"ncclGetUniqueId failed ({rc})")
-        t = torch.frombuffer(bytearray(bytes(uid.internal) if self.rank == 0 else bytes(128)), dtype=torch.uint8).clone()
+        t = torch.frombuffer(bytearray(_C.string_at(_C.byref(uid), 128)), dtype=torch.uint8).clone()     # all 128 bytes
         t = t.to(self.device) if dist.get_backend(group) == "nccl" else t
         dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         raw = bytes(t.cpu().numpy().tobytes())
+        assert len(raw) == 128
         _C.memmove(_C.byref(uid), raw, 128)
         self.comm = _C.c_void_p()
         torch.cuda.set_device(self.device)
