@@ -444,7 +444,9 @@ def config_blocks(dev):
         peak = bf16 if tc else fp32
         out[name] = {"evals": evals, "ms": ms, "evals_per_s": evals / (ms * 1e-3), "includes": sampling + " + forward + moments",
                      "roofline": {"bound": "tensor" if tc else "fp32", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
-                                  "kernel": "fwd_tc_kernel" if tc else "fwd_simt_kernel", "flop_per_eval": arch.flops_per_eval}}
+                                  "kernel": (("fwd_tc_kernel" if len(arch.dims) == 4 and arch.dims[0] <= 64 and max(arch.dims[1:3]) <= 256
+                                              else "fwd_tcl_kernel") if tc else "fwd_simt_kernel"),
+                                  "flop_per_eval": arch.flops_per_eval}}
 
     torch.manual_seed(0)
     m = BNN_SGDMC(13, nn.ReLU(), [50], nout=1, conf={"device": str(dev)})
@@ -548,10 +550,12 @@ def sgld_bench(dev, rank, steps):
     out = {"steps_per_s_per_chain": sps, "us_per_step": 1e6 / sps, "steps": n_steps, "batch": SGLD_BATCH, "params": a.n_params + 1,
            "workload": f"cfg5: one pSGLD chain per GPU, synthetic {SGLD_ROWS}x{SGLD_DIMS[0]} regression, "
                        f"{'-'.join(map(str, SGLD_DIMS))} tanh MLP, batch {SGLD_BATCH}, launches of {SGLD_KEEP} steps + thinning snapshot",
-           "kernel": "sgld_step_kernel (persistent cooperative kernel: gather, forward, head, backward, pSGLD update with in-kernel "
-                     "Philox; FP32 FFMA tiles, 2L grid barriers per step; no library GEMM, no elementwise launches)",
+           "kernel": "sgld_step_kernel (persistent cooperative kernel, one launch per 50 steps: batch gather, forward, head, backward, "
+                     "pSGLD update with in-kernel Philox as a dataflow job list -- tile jobs pulled from a global counter, inputs "
+                     "tracked by completion counters, a scheduler warp per CTA, no grid barrier; FP32 FFMA tiles fed by bulk copies; "
+                     "no library GEMM, no elementwise launches)",
            "launches_per_50_steps": 3, "last_loss": loss, "state_finite": bool(torch.isfinite(model._chain.state).all()),
-           "roofline": {"bound": "latency (grid barriers + first-touch L2 latency per phase; see profiles/r02_sgld_step_notes.md)",
+           "roofline": {"bound": "latency (dependency chain of 7 tile stages per step, ~10k cycles each; see profiles/r02_sgld_step_notes.md)",
                         "achieved": SGLD_FLOP_PER_STEP * sps / 1e12, "unit": "TFLOP/s", "flop_per_step": SGLD_FLOP_PER_STEP,
                         "update_bytes_per_step": 20 * (a.stride + 1)}}
     del X, y, yv
