@@ -296,11 +296,18 @@ def run_ours(args):
             sgld = {"error": repr(e)[:300]}
 
     configs = None
+    precisions = None
     if world == 1 and not args.no_configs:
         try:
             configs = config_blocks(dev)
         except Exception as e:
             configs = {"error": repr(e)[:300]}
+        try:
+            del mean_h, var_h
+            torch.cuda.empty_cache()
+            precisions = precision_blocks(dev)
+        except Exception as e:
+            precisions = {"error": repr(e)[:300]}
 
     evals_per_step = float(S_TOTAL) * N_POINTS
     value = evals_per_step * args.steps / (ms * 1e-3)
@@ -368,6 +375,7 @@ def run_ours(args):
             "cpu_baseline": cpu_base if cpu_base is not None else {"value": None, "unit": UNIT, "cores": cores, "kind": "port",
                                                                    "sample": "not timed at N > 1 (rank 0 at N = 1 only)"},
             "clocks": clk, "outputs_finite": finite, "spot_check": spot, "sgld": sgld, "configs": configs,
+            "precision_modes": precisions,
         }
         _emit(line)
     if world > 1:
@@ -413,6 +421,42 @@ def gpu_ms(fn, reps=20, warm=3):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     return statistics.median(ts)
+
+
+def precision_blocks(dev):
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    _precision_doc = """The other arithmetic modes of the resident tensor-core forward on a slice of cfg 4 (N = 1M points x 256 samples), each
+    with the error it actually makes against the CPU oracle on 256 points -- the "stated looser bound" of the faster modes."""
+    import torch
+    from oracle import bnn_oracle as O
+    O.warmup()
+    arch = Arch(DIMS, ACT)
+    Sb = 256
+    g = torch.Generator(device=dev).manual_seed(99)
+    Xb = torch.randn(N_POINTS, DIMS[0], generator=g, device=dev)
+    bank = make_bank(arch, 0, 0, Sb, dev)
+    idx = torch.linspace(0, N_POINTS - 1, 256).long()
+    nets = [arch.unpack(b) for b in bank.cpu()]
+    with torch.no_grad():
+        ref = O.sample_predict(nets, Xb[idx.to(dev)].cpu(), ACT, nout=1)
+    m_ref, v_ref = O.predict_mv(ref, 256)
+    out = {}
+    for prec, units in (("tf32_bf16", 4), ("tf32x3", 6), ("tf32", 2), ("fp32", 0)):
+        box = {}
+
+        def fn():
+            box["r"] = ops.forward(arch, Xb, bank, precision=prec)
+        ms = gpu_ms(fn, reps=5, warm=2)
+        r = box["r"]
+        m, v = r["mean"][idx.to(dev)].cpu().double().reshape(-1), r["var"][idx.to(dev)].cpu().double().reshape(-1)
+        out[prec] = {"evals_per_s": Sb * N_POINTS / (ms * 1e-3), "ms": ms, "samples": Sb,
+                     "tflops_algorithmic": FLOP_PER_EVAL * Sb * N_POINTS / (ms * 1e-3) / 1e12,
+                     "bf16_equiv_units_per_mac": units or None,
+                     "mean_max_norm_err": float((m - m_ref.double().reshape(-1)).abs().max() / m_ref.abs().max()),
+                     "var_max_norm_err": float((v - v_ref.double().reshape(-1)).abs().max() / v_ref.abs().max()),
+                     "kernel": "fwd_simt_kernel" if prec == "fp32" else "fwd_tc_kernel"}
+    return out
 
 
 def config_blocks(dev):

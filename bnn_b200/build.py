@@ -32,6 +32,9 @@ def build(force=False, verbose=False, trace=False):
     objdir = os.path.join(HERE, "build_trace" if trace else "build")
     lib = LIB.replace(".so", "_trace.so") if trace else LIB
     flags = NVCC_FLAGS + (["-DBNN_TC_TRACE_BUILD"] if trace else [])
+    for knob in ("BNN_SG_MI",):                 # experiment knobs (compile-time)
+        if os.environ.get(knob):
+            flags = flags + [f"-D{knob}=" + os.environ[knob]]
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "bnn_b200.h"))

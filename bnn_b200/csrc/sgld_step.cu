@@ -82,7 +82,7 @@ struct SgParams {
   int* err;
   float* loss_out;                     // U of the LAST step of the launch (may be null)
   float* grad_out;                     // debug: when non-null the step writes dU/dtheta here and does NOT update
-  int dbg;                             // debug (BNN_SGLD_DBG): 1 skip the FMA loop, 2 skip the dense loads, 4 skip the epilogues
+  int dbg;                             // debug (BNN_SGLD_DBG): 1 skip the FMA loop, 2 skip the operand loads, 4 skip the epilogues, 8 no noise, 16 no thetaT stores
   long long* trace;                    // debug: [grid][kSgTraceRecs][6] = {job code, grabbed, inputs ready, done (clock64), grabbed, done (globaltimer ns)}, last two steps
 };
 
@@ -184,24 +184,31 @@ __device__ __forceinline__ void sg_gather_rows(const SgParams& p, int it, int rb
 // Shared-memory row pitch = K rounded up to 32 words + 4: 8 consecutive rows hit 32 distinct banks for float4 reads.
 // Rows beyond the operand are not copied (garbage rows only feed output rows / columns the epilogues discard).
 // K extents that do not fit shared memory (batch or width > ~800 / ~380) are processed in rounds with a barrier in between.
-// Compute: FP32 FFMA, thread tile 4 x 4 (rows ty + TY * i, columns tx + TX * j); the 256 threads form KS = 256 / (TY * TX)
-// K-slices, slice ks takes the float4 groups g = ks, ks + KS, ...
+// Compute: FP32 FFMA, thread tile 8 x 4 (rows ty + TY * i, columns tx + TX * j; 12 LDS.128 per 128 FFMA -- measured 8 % faster per
+// step than 4 x 4 with its 16 per 128: the shared-memory pipe is the K loop's bound); the 256 threads form KS = 256 / (TY * TX)
+// K-slices, slice ks takes the float4 groups g = ks, ks + KS, ...; slices that share a warp are summed with shuffles.
 // Measured alternatives (profiles/r02_sgld_step_notes.md): mma.sync m16n8k8 TF32 with 3xTF32 compensation is NOT faster --
 // the legacy warp-level tensor path of this chip issues one TF32 mma per ~32 cycles per SM sub-partition, i.e. the FFMA
-// rate, and the compensation needs three of them; 8 x 8 thread tiles (half the LDS per FFMA) were slower (more slices to
-// reduce, register pressure); 16 warps instead of 8 did not change the K loop.
+// rate, and the compensation needs three of them; 8 x 8 thread tiles (half the LDS per FFMA again) were slower (32 slices to
+// reduce, register pressure); 16 warps instead of 8 did not change the K loop; requesting the NEXT job's operands under this
+// job's epilogue (look-ahead through the scheduler mailbox) was built and measured slower (64.9 vs 60.5 us per step).
+#ifndef BNN_SG_MI
+#define BNN_SG_MI 8
+#endif
+constexpr int kSgMI = BNN_SG_MI;          // rows of a thread's register tile (4 or 8)
 constexpr int kSgStageFloats = 39168;     // shared-memory floats for a tile's operands (153 KB)
 template <int TM, int TN>
 __device__ __forceinline__ void tile_core(const SgOperand& A, const SgOperand& Bop, int m0, int n0, int K,
                                           float* smem, uint64_t* bars, uint32_t& phase_bits, int dbg, long long* probe) {
-  constexpr int TY = TM / 4, TX = TN / 4, THR = TY * TX, KS = kSgThreads / THR;
+  constexpr int MI = kSgMI;                          // rows per thread (columns per thread: 4)
+  constexpr int TY = TM / MI, TX = TN / 4, THR = TY * TX, KS = kSgThreads / THR, SPW = THR >= 32 ? 1 : 32 / THR;
   constexpr int KRMAX = ((kSgStageFloats / (TM + TN)) - 4) & ~31;
-  static_assert(KS >= 1 && KS * THR == kSgThreads && 2 * (TM + TN) <= kSgThreads, "tile shape");
+  static_assert(KS >= 1 && KS * THR == kSgThreads && 2 * (TM + TN) <= kSgThreads && (SPW == 1 || SPW * THR == 32), "tile shape");
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = (tid / TX) % TY, ks = tid / THR;
-  float acc[4][4];
+  float acc[MI][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
@@ -243,13 +250,13 @@ __device__ __forceinline__ void tile_core(const SgOperand& A, const SgOperand& B
     const float* As = smem + ty * pitch;
     const float* Bs = smem + (TM + tx) * pitch;
     auto body = [&](int g) {
-      float4 a[4], b[4];
+      float4 a[MI], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(As + TY * i * pitch + g * 4);
+      for (int i = 0; i < MI; ++i) a[i] = *reinterpret_cast<const float4*>(As + TY * i * pitch + g * 4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + TX * j * pitch + g * 4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
@@ -276,17 +283,33 @@ __device__ __forceinline__ void tile_core(const SgOperand& A, const SgOperand& B
   }
   sg_sync();                               // all slices done with the operands: reuse the memory for the cross-slice reduction
   if (probe && tid == 0) probe[2] = clock64();
-  float* red = smem + TM * TN;             // [KS][TM * TN] partials behind the [TM * TN] result
+  // slices that share a warp are summed with shuffles first; then one partial per remaining slice goes through shared memory
+  if (SPW > 1) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[ks * (TM * TN) + (ty + TY * i) * TN + tx + TX * j] = acc[i][j];
+      for (int j = 0; j < 4; ++j) {
+        float v = acc[i][j];
+#pragma unroll
+        for (int off = THR; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        acc[i][j] = v;
+      }
+  }
+  constexpr int NP = KS / SPW;             // partials left
+  float* red = smem + TM * TN;             // [NP][TM * TN] partials behind the [TM * TN] result
+  if (SPW == 1 || (tid & 31) < THR) {
+    const int pi = ks / SPW;
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[pi * (TM * TN) + (ty + TY * i) * TN + tx + TX * j] = acc[i][j];
+  }
   sg_sync();
 #pragma unroll 1
   for (int q = tid; q < TM * TN / 4; q += kSgThreads) {
     float4 v = *reinterpret_cast<const float4*>(red + q * 4);
 #pragma unroll
-    for (int s2 = 1; s2 < KS; ++s2) {
+    for (int s2 = 1; s2 < NP; ++s2) {
       const float4 w = *reinterpret_cast<const float4*>(red + s2 * (TM * TN) + q * 4);
       v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
     }
@@ -678,7 +701,8 @@ __global__ void __launch_bounds__(kSgBlock, 1) sgld_step_kernel(const __grid_con
           }
           float vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
           float z[4];
-          philox_normal4(p.seed, (uint32_t)t, STREAM_SGLD, (uint64_t)(e >> 2), z);
+          if (p.dbg & 8) { z[0] = z[1] = z[2] = z[3] = 0.0f; }
+          else philox_normal4(p.seed, (uint32_t)t, STREAM_SGLD, (uint64_t)(e >> 2), z);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int k = k0 + c;
@@ -687,7 +711,7 @@ __global__ void __launch_bounds__(kSgBlock, 1) sgld_step_kernel(const __grid_con
           }
           *reinterpret_cast<float4*>(th_next + e) = make_float4(tt[0], tt[1], tt[2], tt[3]);
           *reinterpret_cast<float4*>(p.V + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-          if (l > 0) {
+          if (l > 0 && !(p.dbg & 16)) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const int k = k0 + c;
