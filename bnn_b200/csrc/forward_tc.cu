@@ -50,6 +50,8 @@ struct TcParams {
   int tiles_per_slot, n_tiles;   // pair-tiles (128 * kPair points each)
   float* pred;
   double* part;            // [G][2][M]  Welford state = shard moments
+  unsigned int* progress;  // [G][slots] samples started per CTA pair (pacing, see the loader warp), zero before launch; may be null
+  int pace;                // samples a pair may run ahead of the slowest pair of its group
   int tmem_cols;
   // per-sample input-unit masks (dropout family): m_off[l] = offset of Linear l's input mask in the mask vector, -1 = none
   int mask_mode, mask_len, m_off[3];
@@ -398,6 +400,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     const bool three = p.passes == 3, mixed = p.passes == 2;
     const uint32_t idesc1h = tc::make_idesc_bf16(128 * kPair, p.N1), idesc2h = tc::make_idesc_bf16(128 * kPair, p.N2);
     trace_ev(tr, 0, tn, 20, 0);
+    bool pace_on = true;
     for (int s = s0; s < s1; ++s) {
       const uint32_t spar = (uint32_t)(s - s0) & 1u;
       const bool reload = !p.shared_w || s == s0;   // a shared network is loaded once and stays resident
@@ -407,6 +410,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
       const float* src = p.img + s_img * p.img_stride + (long long)rank * p.part_stride;
       const uint32_t b1_bytes = (three || mixed) ? 2 * b1_hl_bytes : b1_hl_bytes;
       const uint32_t b2_bytes = (three || mixed) ? 2 * b2_hl_bytes : b2_hl_bytes;
+      // Pacing.  Pairs own 52 or 53 tiles at cfg 4, so over thousands of samples the fast pairs drift hundreds of samples ahead
+      // and every pair ends up fetching "its" copy of each sample's operand image from DRAM (ncu: 44 MB of DRAM traffic per
+      // sample at S = 10,000 vs 5 MB at S = 2,048).  A pair therefore does not start sample s before the slowest pair of its
+      // group has started sample s - pace: the group's image loads stay within what L2 holds.  Progress counters are plain
+      // relaxed stores / loads; a wait gives up for good after ~2 ms (not all CTAs resident: no deadlock, just no pacing).
+      if (reload && p.progress != nullptr) {
+        unsigned int* prog = p.progress + (long long)g * gridDim.x / kPair;
+        const unsigned int rel = (unsigned int)(s - s0);
+        if (leader && lane == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(prog + slot), "r"(rel + 1u) : "memory");
+        if (pace_on && rel > (unsigned int)p.pace) {
+          const unsigned int need = rel - (unsigned int)p.pace;
+          const int npairs = (int)(gridDim.x / kPair);
+          const long long t_start = clock64();
+          for (;;) {
+            unsigned int mn = 0xffffffffu;
+            for (int j = lane; j < npairs; j += 32) {
+              unsigned int v;
+              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(prog + j) : "memory");
+              mn = min(mn, v);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            if (mn >= need) break;
+            const int late = __shfl_sync(0xffffffffu, (int)(clock64() - t_start > 4000000LL), 0);   // warp-uniform decision
+            if (late) { pace_on = false; break; }
+          }
+        }
+      }
       if (reload && tc::elect_one()) {
         mbar_arrive_expect_tx(&bars[BAR_W_FULL], b1_bytes + b2_bytes + (uint32_t)vec_pad * 4);
         bulk_g2s(smem + p.sm_b1, src, b1_bytes, &bars[BAR_W_FULL]);
@@ -1123,7 +1154,7 @@ struct TcPlan {
   TcPrepParams q;
   int kpair;
   size_t smem;
-  long long img_bytes, part_bytes, x_bytes;   // x_bytes: copy of X next to the Welford state (one L2 window over both), or 0
+  long long img_bytes, part_bytes, x_bytes, prog_bytes;   // x_bytes: copy of X next to the Welford state (one L2 window over both), or 0
   int slots;
 };
 
@@ -1213,6 +1244,7 @@ static int plan_tc(const BnnForwardArgs* a, TcPlan* plan) {
   // x_bytes stays 0: pinning a copy of X together with the Welford state (one 80 MB window at cfg 4) was measured WORSE than
   // pinning the state alone (20.7 vs 10.2 GB of DRAM traffic per 2048 samples; 35 GB with no window): the set-aside overflows.
   plan->x_bytes = 0;
+  plan->prog_bytes = ((long long)G * max_slots * 4 + 255) & ~255LL;
   TcPrepParams& q = plan->q;
   q.D = D; q.H1 = H1; q.H2 = H2; q.O = O; q.Dp = p.Dp; q.N1 = p.N1; q.N2 = p.N2; q.K2 = p.K2; q.kpair = kpair;
   q.ld0 = L.ld[0]; q.ld1 = L.ld[1]; q.ld2 = L.ld[2];
@@ -1251,7 +1283,7 @@ long long forward_tc_workspace_bytes(const BnnForwardArgs* a) {
   TcPlan plan;
   const int rc = plan_tc(a, &plan);
   if (rc) return -1;
-  return plan.img_bytes + plan.part_bytes + plan.x_bytes;
+  return plan.img_bytes + plan.part_bytes + plan.x_bytes + plan.prog_bytes;
 }
 
 int forward_tc_supported(const BnnForwardArgs* a) {
@@ -1264,7 +1296,7 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
   const int rc = plan_tc(a, &plan);
   if (rc) return -1;
   TcParams& p = plan.p;
-  const long long need = plan.img_bytes + plan.part_bytes + plan.x_bytes;
+  const long long need = plan.img_bytes + plan.part_bytes + plan.x_bytes + plan.prog_bytes;
   if (!a->workspace || a->workspace_bytes < need)
     BNN_FAIL("workspace too small: need %lld bytes, got %lld", need, (long long)a->workspace_bytes);
   float* img = reinterpret_cast<float*>(a->workspace);
@@ -1276,6 +1308,13 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
     if (cudaMalloc(&tb, 5 * 4096 * 16) == cudaSuccess) { cudaMemsetAsync(tb, 0, 5 * 4096 * 16, st); p.trace = tb; g_tc_trace = tb; p.trace_mask = atoi(getenv("BNN_TC_TRACE")); }
   }
 #endif
+  {
+    p.progress = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(a->workspace) + plan.img_bytes + plan.part_bytes + plan.x_bytes);
+    p.pace = 4;
+    if (const char* e = getenv("BNN_TC_PACE")) p.pace = atoi(e);     // tuning knob; 0 = off
+    if (p.pace <= 0 || p.shared_w) p.progress = nullptr;
+    else BNN_CUDA(cudaMemsetAsync(p.progress, 0, (size_t)plan.prog_bytes, st));
+  }
   const bool want_moments = a->mean || a->var || a->part_mean || a->part_m2;
   p.part = want_moments ? reinterpret_cast<double*>(reinterpret_cast<char*>(a->workspace) + plan.img_bytes) : nullptr;
   {
