@@ -334,7 +334,7 @@ def run_ours(args):
             roof = {"bound": "tensor", "achieved": per_gpu_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
                     "frac": per_gpu_tflops / bf16_peak,
                     "traffic": rec.get("dram_bytes") if rec else None, "traffic_unit": "bytes/launch",
-                    "traffic_source": ("ncu --set full capture of this configuration: " + rec.get("source", "")) if rec
+                    "traffic_source": ("ncu capture of this configuration: " + rec.get("source", "")) if rec
                     else "no ncu capture of this configuration committed",
                     "algorithmic_bytes": alg_bytes,
                     "kernel": "fwd_tc_kernel (tcgen05 kind::tf32 + kind::f16, cta_group::2, A operand of layer 2 in TMEM)",

@@ -456,7 +456,7 @@ class SgldChain:
         st = C.c_int32(0)
         _lib.check(_lib.lib().bnn_sgld_status(C.byref(self._c), C.byref(st), _stream(self.theta)), "bnn_sgld_status")
         if st.value != 0:
-            raise RuntimeError("fused SGLD step: a grid barrier timed out; the chain state is undefined")
+            raise RuntimeError("fused SGLD step: a dependency wait timed out; the chain state is undefined")
 
     @property
     def state(self):

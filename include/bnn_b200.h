@@ -255,9 +255,10 @@ int32_t bnn_sgld_run(const BnnSgldChain* c, int32_t cur, int64_t t0, int64_t per
 /* entries [offset, offset + count) of the pseudo-random permutation of [0, N) keyed by (seed, epoch): the shuffled order of
  * DataLoader(shuffle=True) (BNN_SGDMC.py:110) without materialising all N entries -- a chain only consumes a prefix */
 int32_t bnn_sgld_perm(uint64_t seed, uint32_t epoch, int64_t N, int64_t offset, int64_t count, int64_t* out, void* stream);
-/* debug: per-CTA phase timeline of the last step of the following bnn_sgld_run launches (see tools/sgld_trace.py) */
-int32_t bnn_sgld_trace(int32_t enable, long long* host_out, int32_t* grid_out, int32_t* phases_out);
-/* synchronises; *status_host = 0 ok, 1 = a grid barrier of the last launch timed out (chain state undefined) */
+/* debug: per-CTA job timeline of the last two steps of the following bnn_sgld_run launches: [grid][recs][12] words
+ * (see tools/sgld_trace.py); *recs_out = records per CTA */
+int32_t bnn_sgld_trace(int32_t enable, long long* host_out, int32_t* grid_out, int32_t* recs_out);
+/* synchronises; *status_host = 0 ok, 1 = a dependency wait of the last launch timed out (chain state undefined) */
 int32_t bnn_sgld_status(const BnnSgldChain* c, int32_t* status_host, void* stream);
 
 /* raw Philox stream dump for tests: out[n] 32-bit words / normals */
