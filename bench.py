@@ -484,6 +484,8 @@ def config_blocks(dev):
         arch = model.arch
         ms = gpu_ms(fn)
         tc = ops.tc_supported(arch, masked=sampling in ("dropout masks", "concrete-dropout masks")) and model.precision in ("auto", "tf32_bf16")
+        if model.precision == "auto" and evals * arch.flops_per_eval < ops._AUTO_TC_MIN_FLOP:
+            tc = False     # precision="auto" keeps launch-bound problems on the single-launch FP32 kernel
         tf = arch.flops_per_eval * evals / (ms * 1e-3) / 1e12
         peak = bf16 if tc else fp32
         out[name] = {"evals": evals, "ms": ms, "evals_per_s": evals / (ms * 1e-3), "includes": sampling + " + forward + moments",

@@ -61,6 +61,9 @@ class MaskConfig:
         return s
 
 
+_AUTO_TC_MIN_FLOP = 5e7   # below this much work per call, precision="auto" stays on the single-launch FP32 kernel
+
+
 def forward(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=False, want_moments=True,
             want_partials=False, precision="fp32"):
     """Fused S x N batched MLP forward (+ predictive moments).
@@ -94,7 +97,10 @@ def forward(arch: Arch, X, W, S=None, mask: MaskConfig = None, want_pred=False, 
             raise ValueError("mask rows != S")
     if precision == "auto":     # tensor cores (FP32-grade TF32 + BF16 corrections) when the shape is supported, else the FP32 SIMT kernel
         a.precision = _lib.PREC_TF32_BF16
-        if not _lib.lib().bnn_forward_tc_supported(C.byref(a)):
+        # tiny problems (cfg 1: 100 samples x 51 points of a 13-50-1 net) are launch-bound: the SIMT kernel is ONE launch + the
+        # finalisation, the tensor-core paths need their operand-image passes first
+        tiny = float(a.S) * float(X.shape[0]) * arch.flops_per_eval < _AUTO_TC_MIN_FLOP
+        if tiny or not _lib.lib().bnn_forward_tc_supported(C.byref(a)):
             a.precision = _lib.PREC_FP32
     else:
         a.precision = _PREC[precision]
