@@ -76,6 +76,48 @@ def test_short_last_batch_and_permuted_rows():
         assert float((glp - gs[-1]).abs().max()) <= 2e-5 * float(gs[-1].abs().max())
 
 
+@pytest.mark.parametrize("dims,act,B", [
+    ([6, 1000, 40, 1], "tanh", 48),        # K = 1004 > 800: the forward / dh tiles take two K rounds
+    ([11, 72, 72, 2], "relu", 512),        # K = batch = 512 > 384: the dW tiles take two K rounds; 16 row blocks
+    ([9, 33, 12], "tanh", 20),             # 12 outputs: the head's o >= 8 path; ragged sizes everywhere
+    ([5, 3], "relu", 7),                   # no hidden layer: head straight from the gathered rows
+    ([300, 64, 64, 1], "sigmoid", 100),    # wide input: several 128-column rounds of the gather
+])
+def test_gradient_against_autograd_on_the_uncommon_paths(dims, act, B):
+    """One gradient-only step against torch autograd of the oracle's energy (the restatement pinned by the reference fixture)."""
+    g = torch.Generator().manual_seed(5)
+    net = [((torch.rand(o, i, generator=g) - 0.5) * (6.0 / (i + o)) ** 0.5, (torch.rand(o, generator=g) - 0.5) * 0.2)
+           for i, o in zip(dims[:-1], dims[1:])]
+    lp = 0.2 * torch.randn(dims[-1], generator=g)
+    arch, chain = make_chain(dims, act, B, net, lp)
+    N = 3 * B + 5
+    X, y = torch.randn(N, dims[0], generator=g), torch.randn(N, dims[-1], generator=g)
+    chain.bind(X.cuda(), y.cuda())
+    perm = torch.randperm(N, generator=g)
+    for off, rows in ((B, B), (3 * B, 5)):                           # a full batch and the short last one
+        gd, loss = chain.grad(perm.cuda(), perm_off=off)
+        torch.cuda.synchronize()
+        chain.check()
+        idx = perm[off: off + rows]
+        ps = [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in net]
+        lpr = lp.clone().requires_grad_(True)
+        U = O.sgdmc_neg_log_post(ps, lpr, X[idx], y[idx], act, N, 1e-2, 1e-1)
+        gs = torch.autograd.grad(U, [q for pr in ps for q in pr] + [lpr])
+        assert abs(float(loss) - float(U.detach())) <= 2e-5 * abs(float(U.detach()))
+        pairs, glp = unpack_grad(arch, gd)
+        for l, (gW, gb) in enumerate(pairs):
+            for got, ref in ((gW, gs[2 * l]), (gb, gs[2 * l + 1])):
+                assert float((got - ref).abs().max()) <= 3e-5 * float(ref.abs().max()), (l, tuple(ref.shape))
+        assert float((glp - gs[-1]).abs().max()) <= 3e-5 * float(gs[-1].abs().max())
+    # and a few real steps stay finite and keep the layout padding at zero
+    chain.run(perm.cuda(), 0, 3)
+    torch.cuda.synchronize()
+    chain.check()
+    st = chain.state
+    assert bool(torch.isfinite(st).all())
+    assert not bool(st[: arch.stride][~arch.valid_mask().cuda()].any())
+
+
 @pytest.mark.parametrize("dims,act,B", [([90, 512, 512, 512, 1], "tanh", 128), ([13, 50, 1], "relu", 32), ([7, 20, 3], "sigmoid", 10)])
 def test_update_epilogue_equals_standalone_kernel(dims, act, B):
     """One fused step == gradient-only step + bnn_psgld_step with the same (seed, t) noise; thetaT stays the transpose."""
