@@ -3,9 +3,10 @@
 sample(): all S x P reparameterised draws w = mu + sqrt(softplus(max(rho,-35))) * eps in ONE launch
 of the fused reparam kernel with in-kernel Philox (replaces GaussianLinear.rsample/sample_linear and
 S x L fresh nn.Linear constructions, BNN_BBB.py:24-27,44-51,65-69,139-141); sample_predict /
-predict_mv / validate: the fused forward.  train() keeps the reference's recipe (local
-reparameterisation, analytic KL, Adam; BNN_BBB.py:29-37,101-137) in plain torch on the device --
-training is outside the hot path.
+predict_mv / validate: the fused forward.  train(): the reference's recipe (local reparameterisation,
+analytic KL, Adam; BNN_BBB.py:29-37,101-137) runs in the fused single-SM training kernel (bnn_bbb_train_run,
+SURVEY.md 8 row f2) when the network fits one SM's shared memory -- the reference's 1-50-50-1 does --,
+else in plain torch on the device.
 """
 import torch
 import torch.nn as nn
@@ -65,6 +66,8 @@ class BNN_BBB(BNN):
         self.weight_std = conf.get('weight_std', 0.1)
         self.kl_factor = conf.get('kl_factor', 1e-3)
         self.seed = int(conf.get('seed', 0))
+        self.fused_train = bool(conf.get('fused_train', True))   # the single-SM fused training kernel when the network fits it
+        self.trained_with = None
         self.precision = conf.get('precision', 'auto')   # tensor cores (3xTF32, FP32-grade) when the shape allows, else FP32 SIMT
         self.device = torch.device(conf['device']) if 'device' in conf else None
         self.arch = Arch([dim] + list(num_hiddens) + [1], act)
@@ -97,12 +100,49 @@ class BNN_BBB(BNN):
                 torch.distributions.Normal(0., self.weight_std)).sum()
         return mse, kld
 
+    def _train_fused(self, X, y):
+        """BNN_BBB.train (BNN_BBB.py:112-137) through the fused single-SM training kernel (bnn_bbb_train_run): one launch per
+        epoch, variational parameters and Adam moments device-resident, statistics read back only when an epoch is printed."""
+        dev = self._dev()
+        num_x = X.shape[0]
+        gls = self.nn.gaussian_layers()
+        tr = ops.BbbTrainer(self.arch, self.batch_size, dev, lr=self.lr, kl_factor=self.kl_factor, weight_std=self.weight_std,
+                            seed=self.seed)
+        tr.set_state(self.arch.pack_bias_last([l.mu.detach() for l in gls]), self.arch.pack_bias_last([l.rho.detach() for l in gls]))
+        tr.bind(X, y.reshape(num_x, 1))
+        gen = torch.Generator(device="cpu").manual_seed(self.seed)
+        n_steps = (num_x + self.batch_size - 1) // self.batch_size
+        for epoch in range(self.num_epochs):
+            perm = torch.randperm(num_x, generator=gen).to(dev)           # DataLoader(shuffle=True), BNN_BBB.py:119
+            show = (epoch + 1) % self.print_every == 0
+            stats = tr.run(perm, 0, n_steps, want_stats=show)
+            if show:
+                mse, kl = stats
+                rows = torch.full((n_steps,), float(self.batch_size), device=dev)
+                rows[-1] = num_x - (n_steps - 1) * self.batch_size
+                epoch_mse = float((mse * rows).sum() / num_x)
+                epoch_kl = self.kl_factor * float(kl[-1])
+                print("[Epoch %5d, loss = %8.2f (KL = %8.2f, mse = %8.2f), kl_factor = %g]" %
+                      (epoch + 1, epoch_mse + epoch_kl, epoch_kl, epoch_mse, self.kl_factor))
+        with torch.no_grad():
+            for l, layer in enumerate(gls):
+                layer.mu.copy_(self.arch.layer_view(tr.mu, l)[:, : self.arch.ins[l] + 1])
+                layer.rho.copy_(self.arch.layer_view(tr.rho, l)[:, : self.arch.ins[l] + 1])
+        self.trained_with = "fused"
+
     def train(self, X, y):
         dev = self._dev()
         num_x = X.shape[0]
         X = self._to_dev(X).reshape(num_x, self.dim)
         y = self._to_dev(y).reshape(num_x)
-        self.nn.to(dev).train()
+        self.nn.to(dev)
+        if self.fused_train and dev.type == "cuda" and ops.bbb_train_supported(self.arch, self.batch_size):
+            self.nn.train()
+            self._train_fused(X.contiguous(), y.contiguous())
+            self.nn.eval()
+            return
+        self.trained_with = "torch"
+        self.nn.train()
         opt = torch.optim.Adam(self.nn.parameters(), self.lr)
         gen = torch.Generator(device="cpu").manual_seed(self.seed)
         for epoch in range(self.num_epochs):

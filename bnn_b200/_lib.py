@@ -44,6 +44,13 @@ class SgldChain(C.Structure):
                 ("gain", C.c_float), ("precond_mode", C.c_int32), ("seed", C.c_uint64)]
 
 
+class BbbTrain(C.Structure):
+    _fields_ = [("desc", MlpDesc), ("batch", C.c_int32), ("mu", C.c_void_p), ("rho", C.c_void_p), ("adam", C.c_void_p),
+                ("X", C.c_void_p), ("y", C.c_void_p), ("perm", C.c_void_p), ("num_train", C.c_int64), ("lr", C.c_float),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("kl_factor", C.c_float),
+                ("weight_std", C.c_float), ("seed", C.c_uint64)]
+
+
 # name -> (restype, argtypes); mirrors include/bnn_b200.h one to one
 PROTOTYPES = {
     "bnn_abi_version": (C.c_int32, []),
@@ -90,6 +97,10 @@ PROTOTYPES = {
     "bnn_sgld_perm": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "bnn_sgld_trace": (C.c_int32, [C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "bnn_sgld_status": (C.c_int32, [C.POINTER(SgldChain), C.POINTER(C.c_int32), C.c_void_p]),
+    "bnn_bbb_train_supported": (C.c_int32, [C.POINTER(MlpDesc), C.c_int32]),
+    "bnn_bbb_train_eps_per_step": (C.c_int64, [C.POINTER(MlpDesc), C.c_int32]),
+    "bnn_bbb_train_run": (C.c_int32, [C.POINTER(BbbTrain), C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
     "bnn_philox_words": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]),
     "bnn_philox_normals": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]),
     "bnn_measure_fp32_tflops": (C.c_double, []),

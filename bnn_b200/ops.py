@@ -479,3 +479,68 @@ def philox_normals(seed, subsequence, tag, n, device):
     out = torch.empty(n, dtype=torch.float32, device=device)
     _lib.check(_lib.lib().bnn_philox_normals(seed, subsequence, tag, n, _ptr(out), _stream(out)), "bnn_philox_normals")
     return out
+
+
+# ---- fused Bayes-by-Backprop training step -------------------------------------------------------------------
+def bbb_train_supported(arch: Arch, batch):
+    """True if the single-SM fused training kernel takes this network at this batch size (bnn_bbb_train_supported)."""
+    d = arch.desc()
+    return bool(_lib.lib().bnn_bbb_train_supported(C.byref(d), int(batch)))
+
+
+class BbbTrainer:
+    """Device-resident variational parameters (packed bias-last mu, rho), their Adam moments and the fused training kernel
+    (bnn_bbb_train_run, csrc/bbb_train.cu): what BNN_BBB.train keeps in nn.Parameters + torch.optim.Adam (BNN_BBB.py:112-126)."""
+
+    def __init__(self, arch: Arch, batch, device, lr=1e-2, kl_factor=1e-3, weight_std=0.1, betas=(0.9, 0.999), eps=1e-8, seed=0):
+        if not bbb_train_supported(arch, batch):
+            _lib.check(-1, "bnn_bbb_train_supported")
+        self.arch, self.batch, self.device = arch, int(batch), torch.device(device)
+        self.mu = torch.zeros(arch.stride, device=self.device)
+        self.rho = torch.zeros(arch.stride, device=self.device)
+        self.adam = torch.zeros(4, arch.stride, device=self.device)
+        self.t = 0
+        d = arch.desc()
+        self.eps_per_step = int(_lib.lib().bnn_bbb_train_eps_per_step(C.byref(d), self.batch))
+        c = _lib.BbbTrain()
+        c.desc, c.batch = d, self.batch
+        c.mu, c.rho, c.adam = self.mu.data_ptr(), self.rho.data_ptr(), self.adam.data_ptr()
+        c.lr, c.beta1, c.beta2, c.eps = float(lr), float(betas[0]), float(betas[1]), float(eps)
+        c.kl_factor, c.weight_std, c.seed = float(kl_factor), float(weight_std), int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._c = c
+        self._keep = None
+
+    def set_state(self, mu_packed, rho_packed):
+        """Start at these variational parameters with a fresh optimizer (zero moments, step 0)."""
+        self.mu.copy_(mu_packed.to(self.device, torch.float32))
+        self.rho.copy_(rho_packed.to(self.device, torch.float32))
+        self.adam.zero_()
+        self.t = 0
+
+    def bind(self, X, y):
+        X, y = _dev(X, "X"), _dev(y, "y")
+        if X.dim() != 2 or X.shape[1] != self.arch.dims[0] or y.numel() != X.shape[0] * self.arch.nout:
+            raise ValueError("X must be [N, dim] and y [N, nout]")
+        self._keep = (X, y)
+        self._c.X, self._c.y, self._c.num_train = X.data_ptr(), y.data_ptr(), X.shape[0]
+
+    def run(self, perm, perm_off, n_steps, want_stats=False, eps=None):
+        """n_steps fused training steps on the batches perm[perm_off + i * batch ...].  Returns (mse[n_steps], kl[n_steps]) device
+        tensors when want_stats, else None.  eps (tests): injected noise [n_steps, eps_per_step]."""
+        if perm.dtype != torch.int64 or not perm.is_cuda or not perm.is_contiguous():
+            raise TypeError("perm must be a contiguous int64 CUDA tensor")
+        self._c.perm = perm.data_ptr()
+        mse = kl = None
+        if want_stats:
+            mse = torch.empty(n_steps, device=self.device)
+            kl = torch.empty(n_steps, device=self.device)
+        if eps is not None:
+            eps = _dev(eps, "eps").to(torch.float32).contiguous()
+            if eps.numel() != n_steps * self.eps_per_step:
+                raise ValueError(f"eps must hold {n_steps} x {self.eps_per_step} values")
+        _lib.check(_lib.lib().bnn_bbb_train_run(C.byref(self._c), int(self.t), int(perm_off), int(n_steps),
+                                                 mse.data_ptr() if want_stats else None, kl.data_ptr() if want_stats else None,
+                                                 eps.data_ptr() if eps is not None else None, _stream(self.mu)), "bnn_bbb_train_run")
+        self.t += int(n_steps)
+        self._last = (perm, eps)      # stream-ordered use: keep alive until the next call
+        return (mse, kl) if want_stats else None

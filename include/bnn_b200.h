@@ -261,6 +261,37 @@ int32_t bnn_sgld_trace(int32_t enable, long long* host_out, int32_t* grid_out, i
 /* synchronises; *status_host = 0 ok, 1 = a dependency wait of the last launch timed out (chain state undefined) */
 int32_t bnn_sgld_status(const BnnSgldChain* c, int32_t* status_host, void* stream);
 
+/* ---- (f2) fused Bayes-by-Backprop training step ----------------------------------- */
+/* replaces: the minibatch loop body of BNN_BBB.train (BNN_BBB.py:121-126) -- GaussianLinear.forward with local
+ * reparameterisation (:29-37), MSELoss (:104-106), the KL term (:107-110), loss.backward() and Adam.step() -- for n_steps
+ * consecutive steps in ONE single-CTA persistent kernel (csrc/bbb_train.cu), for networks whose variational parameters, Adam
+ * moments and activations fit one SM's shared memory (bnn_bbb_train_supported; the reference's 1-50-50-1 at batch 32 does).
+ * mu / rho: packed bias-last vectors [stride] (the layout of bnn_reparam_kl), updated in place; adam: [4][stride] = first / second
+ * moments of mu, then of rho (zero before the first step); t0 = Adam steps taken so far (bias correction).
+ * Batches: rows perm[perm_off + i * batch ..] of X / y, the last one of an epoch may be short.
+ * mse_out / kl_out ([n_steps] device floats or NULL): the step's MSE and KL(q || N(0, weight_std)) before its update.
+ * eps_in (tests): the local-reparameterisation noise, [n_steps][bnn_bbb_train_eps_per_step] = per layer [batch][out]; NULL =
+ * in-kernel Philox (seed, t0 + i).                                                                                        */
+typedef struct BnnBbbTrain {
+  BnnMlpDesc desc;
+  int32_t batch;
+  float* mu;
+  float* rho;
+  float* adam;
+  const float* X;            /* [num_train, dims[0]] */
+  const float* y;            /* [num_train, nout]    */
+  const int64_t* perm;       /* epoch permutation [num_train] */
+  int64_t num_train;
+  float lr, beta1, beta2, eps;   /* torch.optim.Adam: 1e-2 (BNN_BBB.py:93), 0.9, 0.999, 1e-8 */
+  float kl_factor;           /* BNN_BBB.py:95 */
+  float weight_std;          /* prior std, BNN_BBB.py:94 */
+  uint64_t seed;
+} BnnBbbTrain;
+int32_t bnn_bbb_train_supported(const BnnMlpDesc* d, int32_t batch);
+int64_t bnn_bbb_train_eps_per_step(const BnnMlpDesc* d, int32_t batch);
+int32_t bnn_bbb_train_run(const BnnBbbTrain* c, int64_t t0, int64_t perm_off, int32_t n_steps, float* mse_out, float* kl_out,
+                          const float* eps_in, void* stream);
+
 /* raw Philox stream dump for tests: out[n] 32-bit words / normals */
 int32_t bnn_philox_words(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, uint32_t* out, void* stream);
 int32_t bnn_philox_normals(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, float* out, void* stream);

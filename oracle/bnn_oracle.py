@@ -250,3 +250,41 @@ def merge_moments(parts):
         m2 = m2 + m2b + d * d * (n * nb / nn)
         n = nn
     return n, mean, m2
+
+
+# ---- Bayes-by-Backprop training step -------------------------------------------------------------------------
+def bbb_local_forward(mus, rhos, x, act, eps):
+    """BayesianNN.forward over GaussianLinear layers with local reparameterisation (BNN_BBB.py:29-37, :70-72) and INJECTED noise:
+    out = x mu_w^T + mu_b + eps * sqrt(x^2 s2_w^T + s2_b), s2 = stable_noise_var(rho) (util.py:52-53).  mus / rhos: per layer
+    [out, in + 1] (bias last, BNN_BBB.py:19-20); eps: per layer [B, out]."""
+    f = act_fn(act)
+    h = x
+    for l, (mu, rho) in enumerate(zip(mus, rhos)):
+        w_s2, b_s2 = stable_noise_var(rho[:, :-1]), stable_noise_var(rho[:, -1])
+        out_mu = torch.nn.functional.linear(h, mu[:, :-1], mu[:, -1])
+        out_std = torch.nn.functional.linear(h ** 2, w_s2, b_s2).sqrt()
+        h = out_mu + eps[l] * out_std
+        if l + 1 < len(mus):
+            h = f(h)
+    return h
+
+
+def bbb_train_steps(mus, rhos, X, y, batches, act, eps, lr=1e-2, kl_factor=1e-3, weight_std=0.1):
+    """The minibatch loop body of BNN_BBB.train (BNN_BBB.py:121-126): loss = MSELoss(mean) + kl_factor * KL (:104-110),
+    loss.backward(), torch.optim.Adam(lr).step() (:114).  batches: list of index tensors; eps[i][l]: the step's noise.
+    Returns (mus, rhos, [mse_i], [kl_i])."""
+    mus = [m.clone().requires_grad_(True) for m in mus]
+    rhos = [r.clone().requires_grad_(True) for r in rhos]
+    # parameter order of the reference's nn.Module: (mu, rho) per layer
+    opt = torch.optim.Adam([q for pair in zip(mus, rhos) for q in pair], lr)
+    mses, kls = [], []
+    for i, idx in enumerate(batches):
+        opt.zero_grad()
+        pred = bbb_local_forward(mus, rhos, X[idx].reshape(len(idx), -1), act, eps[i])
+        mse = torch.nn.MSELoss(reduction="mean")(pred, y[idx].reshape(len(idx), -1))
+        kl = bbb_kl(mus, rhos, weight_std)
+        (mse + kl_factor * kl).backward()
+        opt.step()
+        mses.append(float(mse))
+        kls.append(float(kl))
+    return [m.detach() for m in mus], [r.detach() for r in rhos], mses, kls

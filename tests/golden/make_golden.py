@@ -336,6 +336,60 @@ def gen_sgdmc_energy():
     save("sgdmc_energy.npz", **out)
 
 
+
+def gen_bbb_train():
+    """f2: three minibatch steps of the REFERENCE's BNN_BBB training recipe -- model.loss (GaussianLinear.forward with local
+    reparameterisation, MSELoss, KL; BNN_BBB.py:29-37,101-110), loss.backward(), torch.optim.Adam(lr).step() (:114,121-126) --
+    on fixed batches, with the torch.randn draws of the forward captured.  Pins oracle.bbb_train_steps and, on the GPU, the fused
+    training kernel."""
+    torch.manual_seed(21)
+    conf = {"weight_std": 0.1, "lr": 1e-2, "kl_factor": 1e-3}
+    model = ref_bbb.BNN_BBB(3, nn.Tanh(), [20, 12], conf=conf)
+    gls = [l for l in model.nn.nn if isinstance(l, ref_bbb.GaussianLinear)]
+    for l in gls:
+        l.mu.data += 0.2 * torch.randn_like(l.mu)
+        l.rho.data += 0.5 * torch.randn_like(l.rho)
+    gls[0].rho.data[0, 0] = -50.                    # clamp(min=-35): no gradient through it
+    N, B = 37, 16
+    X = torch.randn(N, 3)
+    y = torch.sin(X.sum(dim=1))
+    perm = torch.randperm(N)
+    batches = [perm[0:16], perm[16:32], perm[32:37]]            # the last batch of the epoch is short
+    mu0 = [l.mu.detach().clone() for l in gls]
+    rho0 = [l.rho.detach().clone() for l in gls]
+    opt = torch.optim.Adam(model.nn.parameters(), model.lr)    # BNN_BBB.py:114
+    rec = []
+    orig = torch.randn
+    torch.randn = lambda *a, **k: (rec.append(orig(*a, **k)) or rec[-1])
+    mses, kls = [], []
+    try:
+        for idx in batches:                                      # BNN_BBB.py:121-126
+            opt.zero_grad()
+            mse, kl_term = model.loss(X[idx], y[idx])
+            loss = mse + model.kl_factor * kl_term
+            loss.backward()
+            opt.step()
+            mses.append(float(mse)); kls.append(float(kl_term))
+    finally:
+        torch.randn = orig
+    assert len(rec) == len(batches) * len(gls)
+    eps = [[rec[i * len(gls) + l] for l in range(len(gls))] for i in range(len(batches))]
+    # pin the oracle restatement
+    o_mu, o_rho, o_mse, o_kl = O.bbb_train_steps(mu0, rho0, X, y, batches, "tanh", eps, lr=1e-2, kl_factor=1e-3, weight_std=0.1)
+    for l, g in enumerate(gls):
+        assert torch.allclose(o_mu[l], g.mu.detach(), rtol=1e-6, atol=1e-7), l
+        assert torch.allclose(o_rho[l], g.rho.detach(), rtol=1e-6, atol=1e-7), l
+    assert np.allclose(o_mse, mses, rtol=1e-6) and np.allclose(o_kl, kls, rtol=1e-6)
+    kw = {}
+    for l, g in enumerate(gls):
+        kw[f"mu0_{l}"], kw[f"rho0_{l}"] = mu0[l], rho0[l]
+        kw[f"mu1_{l}"], kw[f"rho1_{l}"] = g.mu.detach(), g.rho.detach()
+        for i in range(len(batches)):
+            kw[f"eps{i}_{l}"] = eps[i][l]
+    save("bbb_train.npz", dims=[3, 20, 12, 1], act="tanh", weight_std=0.1, lr=1e-2, kl_factor=1e-3, batch=B, X=X, y=y,
+         perm=perm.numpy().astype(np.int64), mse=np.array(mses, dtype=np.float32), kl=np.array(kls, dtype=np.float32), **kw)
+
+
 if __name__ == "__main__":
     gen_sgdmc_boston()
     gen_sgdmc_multiout()
@@ -343,3 +397,4 @@ if __name__ == "__main__":
     gen_dropout_protein()
     gen_cdropout_protein()
     gen_sgdmc_energy()
+    gen_bbb_train()

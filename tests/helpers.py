@@ -109,3 +109,21 @@ def check_energy_grads(case, grads, grad_log_precs, rtol=2e-5):
     glp = torch.as_tensor(grad_log_precs).detach().cpu().double().reshape(-1)
     ref = torch.from_numpy(case["grad_log_precs"]).double().reshape(-1)
     assert float((glp - ref).abs().max()) <= rtol * float(ref.abs().max() + 1e-30), (case["name"], "log_precs")
+
+
+def bbb_train_case():
+    """The reference-generated fixture of three BNN_BBB training steps (tests/golden/bbb_train.npz; make_golden.gen_bbb_train)."""
+    g = golden("bbb_train.npz")
+    dims = [int(v) for v in g["dims"]]
+    nl = len(dims) - 1
+    t = lambda a: torch.as_tensor(a)
+    case = {"dims": dims, "act": str(g["act"]), "weight_std": float(g["weight_std"]), "lr": float(g["lr"]),
+            "kl_factor": float(g["kl_factor"]), "batch": int(g["batch"]), "X": t(g["X"]), "y": t(g["y"]),
+            "perm": t(g["perm"]).long(), "mse": g["mse"], "kl": g["kl"],
+            "mu0": [t(g[f"mu0_{l}"]) for l in range(nl)], "rho0": [t(g[f"rho0_{l}"]) for l in range(nl)],
+            "mu1": [t(g[f"mu1_{l}"]) for l in range(nl)], "rho1": [t(g[f"rho1_{l}"]) for l in range(nl)]}
+    n_steps = len(case["mse"])
+    case["eps"] = [[t(g[f"eps{i}_{l}"]) for l in range(nl)] for i in range(n_steps)]
+    B, N = case["batch"], case["X"].shape[0]
+    case["batches"] = [case["perm"][i * B: min(N, (i + 1) * B)] for i in range(n_steps)]
+    return case

@@ -132,3 +132,15 @@ def test_sgdmc_energy_golden():
         assert abs(float(U) - float(c["loss"])) <= 2e-6 * abs(float(c["loss"])), c["name"]
         gs = torch.autograd.grad(U, [q for pr in ps for q in pr] + [lp])
         check_energy_grads(c, [(gs[2 * i], gs[2 * i + 1]) for i in range(len(ps))], gs[-1])
+
+
+def test_bbb_train_steps_golden():
+    """f2: the oracle's restatement of the BNN_BBB training step against the reference's own three steps."""
+    from helpers import bbb_train_case
+    c = bbb_train_case()
+    mu, rho, mse, kl = O.bbb_train_steps(c["mu0"], c["rho0"], c["X"], c["y"], c["batches"], c["act"], c["eps"], lr=c["lr"],
+                                         kl_factor=c["kl_factor"], weight_std=c["weight_std"])
+    for l in range(len(mu)):
+        assert torch.allclose(mu[l], c["mu1"][l], rtol=1e-6, atol=1e-7)
+        assert torch.allclose(rho[l], c["rho1"][l], rtol=1e-6, atol=1e-7)
+    assert np.allclose(mse, c["mse"], rtol=1e-6) and np.allclose(kl, c["kl"], rtol=1e-6)
