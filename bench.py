@@ -297,6 +297,7 @@ def run_ours(args):
 
     configs = None
     precisions = None
+    bbb_train = None
     if world == 1 and not args.no_configs:
         try:
             configs = config_blocks(dev)
@@ -308,6 +309,10 @@ def run_ours(args):
             precisions = precision_blocks(dev)
         except Exception as e:
             precisions = {"error": repr(e)[:300]}
+        try:
+            bbb_train = bbb_train_block(dev)
+        except Exception as e:
+            bbb_train = {"error": repr(e)[:300]}
 
     evals_per_step = float(S_TOTAL) * N_POINTS
     value = evals_per_step * args.steps / (ms * 1e-3)
@@ -375,7 +380,7 @@ def run_ours(args):
             "cpu_baseline": cpu_base if cpu_base is not None else {"value": None, "unit": UNIT, "cores": cores, "kind": "port",
                                                                    "sample": "not timed at N > 1 (rank 0 at N = 1 only)"},
             "clocks": clk, "outputs_finite": finite, "spot_check": spot, "sgld": sgld, "configs": configs,
-            "precision_modes": precisions,
+            "precision_modes": precisions, "bbb_train": bbb_train,
         }
         _emit(line)
     if world > 1:
@@ -457,6 +462,50 @@ def precision_blocks(dev):
                      "var_max_norm_err": float((v - v_ref.double().reshape(-1)).abs().max() / v_ref.abs().max()),
                      "kernel": "fwd_simt_kernel" if prec == "fp32" else "fwd_tc_kernel"}
     return out
+
+
+def bbb_train_block(dev):
+    """f2: the fused Bayes-by-Backprop training kernel at the cfg 2 shape (1-50-50-1 tanh, batch 32, 1000 rows): steps/s of one
+    launch per epoch, next to the reference's recipe on the host cores (oracle port, torch CPU autograd + Adam)."""
+    import torch
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    from oracle import bnn_oracle as O
+    dims, B, N = [1, 50, 50, 1], 32, 1000
+    arch = Arch(dims, "tanh")
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(N, 1, generator=g) * 6 - 3
+    y = torch.sin(X)
+    mus = [torch.empty(o, i + 1).uniform_(-0.3, 0.3, generator=g) for i, o in zip(dims[:-1], dims[1:])]
+    rhos = [torch.full((o, i + 1), -5.0) for i, o in zip(dims[:-1], dims[1:])]
+    tr = ops.BbbTrainer(arch, B, dev, seed=1)
+    tr.set_state(arch.pack_bias_last(mus), arch.pack_bias_last(rhos))
+    tr.bind(X.to(dev), y.to(dev))
+    steps = (N + B - 1) // B
+    perms = [torch.randperm(N, generator=g).to(dev) for _ in range(8)]
+    for q in perms[:2]:
+        tr.run(q, 0, steps)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 100
+    e0.record()
+    for r in range(reps):
+        tr.run(perms[r % 8], 0, steps)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * steps)
+    torch.set_num_threads(os.cpu_count() or 1)
+    n_cpu = 100
+    batches = [torch.randperm(N, generator=g)[:B] for _ in range(n_cpu)]
+    eps = [[torch.randn(B, o) for o in dims[1:]] for _ in range(n_cpu)]
+    t0 = time.perf_counter()
+    O.bbb_train_steps(mus, rhos, X, y, batches, "tanh", eps)
+    cpu = n_cpu / (time.perf_counter() - t0)
+    return {"workload": "cfg2 shape: BNN_BBB 1-50-50-1 tanh, batch 32, 1000 rows, launches of one epoch (32 steps)",
+            "kernel": "bbb_train_kernel (single-CTA persistent kernel: gather, local-reparameterisation forward, MSE, backward, "
+                      "closed-form KL gradient, Adam; state in shared memory)",
+            "steps_per_s": 1e6 / us, "us_per_step": us, "state_finite": bool(torch.isfinite(tr.mu).all()),
+            "cpu": {"steps_per_s": cpu, "cores": os.cpu_count(), "kind": "port", "sample": f"{n_cpu} steps, torch CPU autograd + Adam"}}
 
 
 def config_blocks(dev):
