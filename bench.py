@@ -494,18 +494,24 @@ def bbb_train_block(dev):
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (reps * steps)
-    torch.set_num_threads(os.cpu_count() or 1)
     n_cpu = 100
     batches = [torch.randperm(N, generator=g)[:B] for _ in range(n_cpu)]
     eps = [[torch.randn(B, o) for o in dims[1:]] for _ in range(n_cpu)]
-    t0 = time.perf_counter()
-    O.bbb_train_steps(mus, rhos, X, y, batches, "tanh", eps)
-    cpu = n_cpu / (time.perf_counter() - t0)
+    cpu, cpu_threads = 0.0, 1
+    for nt in (1, os.cpu_count() or 1):      # ops this small are often faster on one thread: report the better of the two
+        torch.set_num_threads(nt)
+        O.bbb_train_steps(mus, rhos, X, y, batches[:5], "tanh", eps[:5])
+        t0 = time.perf_counter()
+        O.bbb_train_steps(mus, rhos, X, y, batches, "tanh", eps)
+        r = n_cpu / (time.perf_counter() - t0)
+        if r > cpu:
+            cpu, cpu_threads = r, nt
     return {"workload": "cfg2 shape: BNN_BBB 1-50-50-1 tanh, batch 32, 1000 rows, launches of one epoch (32 steps)",
             "kernel": "bbb_train_kernel (single-CTA persistent kernel: gather, local-reparameterisation forward, MSE, backward, "
                       "closed-form KL gradient, Adam; state in shared memory)",
             "steps_per_s": 1e6 / us, "us_per_step": us, "state_finite": bool(torch.isfinite(tr.mu).all()),
-            "cpu": {"steps_per_s": cpu, "cores": os.cpu_count(), "kind": "port", "sample": f"{n_cpu} steps, torch CPU autograd + Adam"}}
+            "cpu": {"steps_per_s": cpu, "cores": cpu_threads, "kind": "port",
+                    "sample": f"{n_cpu} steps, torch CPU autograd + Adam, best of 1 / all threads"}}
 
 
 def config_blocks(dev):
