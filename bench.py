@@ -298,6 +298,7 @@ def run_ours(args):
     configs = None
     precisions = None
     bbb_train = None
+    dropout_train = None
     if world == 1 and not args.no_configs:
         try:
             configs = config_blocks(dev)
@@ -313,6 +314,10 @@ def run_ours(args):
             bbb_train = bbb_train_block(dev)
         except Exception as e:
             bbb_train = {"error": repr(e)[:300]}
+        try:
+            dropout_train = dropout_train_block(dev)
+        except Exception as e:
+            dropout_train = {"error": repr(e)[:300]}
 
     evals_per_step = float(S_TOTAL) * N_POINTS
     value = evals_per_step * args.steps / (ms * 1e-3)
@@ -380,7 +385,7 @@ def run_ours(args):
             "cpu_baseline": cpu_base if cpu_base is not None else {"value": None, "unit": UNIT, "cores": cores, "kind": "port",
                                                                    "sample": "not timed at N > 1 (rank 0 at N = 1 only)"},
             "clocks": clk, "outputs_finite": finite, "spot_check": spot, "sgld": sgld, "configs": configs,
-            "precision_modes": precisions, "bbb_train": bbb_train,
+            "precision_modes": precisions, "bbb_train": bbb_train, "dropout_train": dropout_train,
         }
         _emit(line)
     if world > 1:
@@ -510,6 +515,57 @@ def bbb_train_block(dev):
             "kernel": "bbb_train_kernel (single-CTA persistent kernel: gather, local-reparameterisation forward, MSE, backward, "
                       "closed-form KL gradient, Adam; state in shared memory)",
             "steps_per_s": 1e6 / us, "us_per_step": us, "state_finite": bool(torch.isfinite(tr.mu).all()),
+            "cpu": {"steps_per_s": cpu, "cores": cpu_threads, "kind": "port",
+                    "sample": f"{n_cpu} steps, torch CPU autograd + Adam, best of 1 / all threads"}}
+
+
+def dropout_train_block(dev):
+    """f2: the fused MC-dropout training kernel at the cfg 3 shape (9-100-100-1 ReLU, batch 32, 4096 rows): steps/s of one launch
+    per epoch, next to the reference's recipe on the host cores (oracle port, torch CPU autograd + Adam)."""
+    import torch
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    from oracle import bnn_oracle as O
+    dims, B, N, p = [9, 100, 100, 1], 32, 4096, 0.05
+    arch = Arch(dims, "relu")
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(N, 9, generator=g)
+    y = torch.sin(X[:, 0]) + 0.5 * X[:, 1]
+    net = [(torch.empty(o, i).uniform_(-1, 1, generator=g) / i ** 0.5, torch.zeros(o)) for i, o in zip(dims[:-1], dims[1:])]
+    tr = ops.DropoutTrainer(arch, B, dev, p_drop=p, seed=1)
+    tr.set_state(arch.pack([net])[0])
+    tr.bind(X.to(dev), y.reshape(-1, 1).to(dev))
+    steps = N // B
+    perms = [torch.randperm(N, generator=g).to(dev) for _ in range(8)]
+    first = float(tr.run(perms[0], 0, steps, want_loss=True).sum())
+    tr.run(perms[1], 0, steps)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 24
+    e0.record()
+    for r in range(reps):
+        tr.run(perms[r % 8], 0, steps)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * steps)
+    last = float(tr.run(perms[0], 0, steps, want_loss=True).sum())
+    n_cpu = 100
+    batches = [torch.randperm(N, generator=g)[:B] for _ in range(n_cpu)]
+    keeps = [[(torch.rand(B, i) < 1 - p).float() for i in dims[:-1]] for _ in range(n_cpu)]
+    cpu, cpu_threads = 0.0, 1
+    for nt in (1, os.cpu_count() or 1):
+        torch.set_num_threads(nt)
+        O.dropout_train_steps(net, X, y, batches[:5], "relu", keeps[:5])
+        t0 = time.perf_counter()
+        O.dropout_train_steps(net, X, y, batches, "relu", keeps)
+        r = n_cpu / (time.perf_counter() - t0)
+        if r > cpu:
+            cpu, cpu_threads = r, nt
+    return {"workload": "cfg3 shape: BNN_Dropout 9-100-100-1 ReLU, batch 32, 4096 rows, launches of one epoch (128 steps)",
+            "kernel": "dropout_train_kernel (single-CTA persistent kernel: gather, Philox keep masks, forward, sum-of-squares loss, "
+                      "backward, Adam with weight decay; network + moments in shared memory)",
+            "steps_per_s": 1e6 / us, "us_per_step": us, "state_finite": bool(torch.isfinite(tr.W).all()),
+            "epoch_loss_first": first, "epoch_loss_after": last,
             "cpu": {"steps_per_s": cpu, "cores": cpu_threads, "kind": "port",
                     "sample": f"{n_cpu} steps, torch CPU autograd + Adam, best of 1 / all threads"}}
 

@@ -51,6 +51,36 @@ class BNN_Dropout(BNN):
         self.nn = NN_Dropout(dim, self.act, self.num_hiddens, self.dropout_rate)
         self.noise_level = 1.
         self._draws = 0
+        self.fused_train = bool(conf.get('fused_train', True))   # the single-SM fused training kernel when the network fits it
+        self.trained_with = None
+
+    def _train_fused(self, X, y):
+        """BNN_Dropout.train (BNN_Dropout.py:39-65) through the fused single-SM training kernel (bnn_dropout_train_run): one
+        launch per epoch, the network and its Adam moments device-resident, one read-back per epoch for noise_level (:63)."""
+        dev = self._dev()
+        num_train = X.shape[0]
+        tr = ops.DropoutTrainer(self.arch, self.batch_size, dev, lr=self.lr, l2_reg=self.l2_reg, p_drop=self.dropout_rate,
+                                seed=self.seed)
+        tr.set_state(self.arch.pack([self.nn.nn])[0])
+        tr.bind(X, y.reshape(num_train, 1))
+        gen = torch.Generator(device="cpu").manual_seed(self.seed)
+        n_steps = (num_train + self.batch_size - 1) // self.batch_size
+        losses = []
+        for epoch in range(self.num_epochs):
+            perm = torch.randperm(num_train, generator=gen).to(dev)       # DataLoader(shuffle=True), BNN_Dropout.py:53
+            losses.append(tr.run(perm, 0, n_steps, want_loss=True).sum())
+            if (epoch + 1) % self.print_every == 0:
+                epoch_loss = float(losses[-1])
+                print("[Epoch %5d, loss = %g, noise_level = %g]" %
+                      (epoch + 1, epoch_loss / num_train, max(self.min_noise, np.sqrt(epoch_loss / num_train))))
+        if losses:
+            self.noise_level = max(self.min_noise, float(np.sqrt(float(losses[-1]) / num_train)))
+        with torch.no_grad():
+            lins = [m for m in self.nn.nn if isinstance(m, nn.Linear)]
+            for lin, (W, b) in zip(lins, self.arch.unpack(tr.W)):
+                lin.weight.copy_(W)
+                lin.bias.copy_(b)
+        self.trained_with = "fused"
 
     def train(self, X, y):
         assert (X.dim() == 2)
@@ -58,6 +88,12 @@ class BNN_Dropout(BNN):
         dev = self._dev()
         X, y = self._to_dev(X), self._to_dev(y)
         num_train = X.shape[0]
+        if self.fused_train and dev.type == "cuda" and ops.dropout_train_supported(self.arch, self.batch_size):
+            self.nn.to(dev)
+            self._train_fused(X.contiguous().float(), y.contiguous().float())
+            self.nn.eval()
+            return
+        self.trained_with = "torch"
         self.nn.to(dev).train()
         decay = [p for n, p in self.nn.named_parameters() if "bias" not in n]
         no_decay = [p for n, p in self.nn.named_parameters() if "bias" in n]

@@ -51,6 +51,12 @@ class BbbTrain(C.Structure):
                 ("weight_std", C.c_float), ("seed", C.c_uint64)]
 
 
+class DropoutTrain(C.Structure):
+    _fields_ = [("desc", MlpDesc), ("batch", C.c_int32), ("W", C.c_void_p), ("adam", C.c_void_p), ("X", C.c_void_p),
+                ("y", C.c_void_p), ("perm", C.c_void_p), ("num_train", C.c_int64), ("lr", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("eps", C.c_float), ("l2_reg", C.c_float), ("p_drop", C.c_float), ("seed", C.c_uint64)]
+
+
 # name -> (restype, argtypes); mirrors include/bnn_b200.h one to one
 PROTOTYPES = {
     "bnn_abi_version": (C.c_int32, []),
@@ -97,6 +103,10 @@ PROTOTYPES = {
     "bnn_sgld_perm": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "bnn_sgld_trace": (C.c_int32, [C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "bnn_sgld_status": (C.c_int32, [C.POINTER(SgldChain), C.POINTER(C.c_int32), C.c_void_p]),
+    "bnn_dropout_train_supported": (C.c_int32, [C.POINTER(MlpDesc), C.c_int32]),
+    "bnn_dropout_train_mask_per_step": (C.c_int64, [C.POINTER(MlpDesc), C.c_int32]),
+    "bnn_dropout_train_run": (C.c_int32, [C.POINTER(DropoutTrain), C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
     "bnn_bbb_train_supported": (C.c_int32, [C.POINTER(MlpDesc), C.c_int32]),
     "bnn_bbb_train_eps_per_step": (C.c_int64, [C.POINTER(MlpDesc), C.c_int32]),
     "bnn_bbb_train_run": (C.c_int32, [C.POINTER(BbbTrain), C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

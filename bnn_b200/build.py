@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbnn_b200.so")
-SOURCES = ["abi.cu", "bbb_train.cu", "forward_simt.cu", "forward_tc.cu", "forward_tcl.cu", "moments.cu", "sampling.cu", "sgld_step.cu"]
+SOURCES = ["abi.cu", "bbb_train.cu", "dropout_train.cu", "forward_simt.cu", "forward_tc.cu", "forward_tcl.cu", "moments.cu", "sampling.cu", "sgld_step.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -544,3 +544,64 @@ class BbbTrainer:
         self.t += int(n_steps)
         self._last = (perm, eps)      # stream-ordered use: keep alive until the next call
         return (mse, kl) if want_stats else None
+
+
+# ---- fused MC-dropout training step --------------------------------------------------------------------------
+def dropout_train_supported(arch: Arch, batch):
+    """True if the single-SM fused training kernel takes this network at this batch size (bnn_dropout_train_supported)."""
+    d = arch.desc()
+    return bool(_lib.lib().bnn_dropout_train_supported(C.byref(d), int(batch)))
+
+
+class DropoutTrainer:
+    """The device-resident packed network, its Adam moments and the fused training kernel (bnn_dropout_train_run,
+    csrc/dropout_train.cu): what BNN_Dropout.train keeps in nn.Parameters + torch.optim.Adam (BNN_Dropout.py:39-65)."""
+
+    def __init__(self, arch: Arch, batch, device, lr=1e-2, l2_reg=1e-6, p_drop=0.05, betas=(0.9, 0.999), eps=1e-8, seed=0):
+        if not dropout_train_supported(arch, batch):
+            _lib.check(-1, "bnn_dropout_train_supported")
+        self.arch, self.batch, self.device = arch, int(batch), torch.device(device)
+        self.W = torch.zeros(arch.stride, device=self.device)
+        self.adam = torch.zeros(2, arch.stride, device=self.device)
+        self.t = 0
+        d = arch.desc()
+        self.mask_per_step = int(_lib.lib().bnn_dropout_train_mask_per_step(C.byref(d), self.batch))
+        c = _lib.DropoutTrain()
+        c.desc, c.batch = d, self.batch
+        c.W, c.adam = self.W.data_ptr(), self.adam.data_ptr()
+        c.lr, c.beta1, c.beta2, c.eps = float(lr), float(betas[0]), float(betas[1]), float(eps)
+        c.l2_reg, c.p_drop, c.seed = float(l2_reg), float(p_drop), int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._c = c
+        self._keep = None
+
+    def set_state(self, packed):
+        """Start at this packed network with a fresh optimizer (zero moments, step 0)."""
+        self.W.copy_(packed.reshape(-1).to(self.device, torch.float32))
+        self.adam.zero_()
+        self.t = 0
+
+    def bind(self, X, y):
+        X, y = _dev(X, "X"), _dev(y, "y")
+        if X.dim() != 2 or X.shape[1] != self.arch.dims[0] or y.numel() != X.shape[0] * self.arch.nout:
+            raise ValueError("X must be [N, dim] and y [N, nout]")
+        self._keep = (X, y)
+        self._c.X, self._c.y, self._c.num_train = X.data_ptr(), y.data_ptr(), X.shape[0]
+
+    def run(self, perm, perm_off, n_steps, want_loss=False, masks=None):
+        """n_steps fused training steps on the batches perm[perm_off + i * batch ...].  Returns the per-step sums of squared
+        errors (device tensor [n_steps]) when want_loss.  masks (tests): injected keep factors [n_steps, mask_per_step]."""
+        if perm.dtype != torch.int64 or not perm.is_cuda or not perm.is_contiguous():
+            raise TypeError("perm must be a contiguous int64 CUDA tensor")
+        self._c.perm = perm.data_ptr()
+        loss = torch.empty(n_steps, device=self.device) if want_loss else None
+        if masks is not None:
+            masks = _dev(masks, "masks").to(torch.float32).contiguous()
+            if masks.numel() != n_steps * self.mask_per_step:
+                raise ValueError(f"masks must hold {n_steps} x {self.mask_per_step} values")
+        _lib.check(_lib.lib().bnn_dropout_train_run(C.byref(self._c), int(self.t), int(perm_off), int(n_steps),
+                                                     loss.data_ptr() if want_loss else None,
+                                                     masks.data_ptr() if masks is not None else None, _stream(self.W)),
+                   "bnn_dropout_train_run")
+        self.t += int(n_steps)
+        self._last = (perm, masks)    # stream-ordered use: keep alive until the next call
+        return loss

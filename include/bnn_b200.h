@@ -292,6 +292,34 @@ int64_t bnn_bbb_train_eps_per_step(const BnnMlpDesc* d, int32_t batch);
 int32_t bnn_bbb_train_run(const BnnBbbTrain* c, int64_t t0, int64_t perm_off, int32_t n_steps, float* mse_out, float* kl_out,
                           const float* eps_in, void* stream);
 
+/* replaces: the minibatch loop body of BNN_Dropout.train (BNN_Dropout.py:57-62) -- NN_Dropout.forward with fresh Bernoulli keep
+ * masks on the inputs of every Linear wider than one unit (:15-21), MSELoss(reduction='sum') (:55,59), loss.backward() and
+ * Adam.step() with weight decay l2_reg on the weights only (:43-52) -- for n_steps consecutive steps in ONE single-CTA persistent
+ * kernel (csrc/dropout_train.cu), for networks that fit one SM's shared memory (bnn_dropout_train_supported; the reference's
+ * 9-100-100-1 at batch 32 does).  W: the packed network [stride] (the layout of the forward path), updated in place;
+ * adam: [2][stride] first / second moments (zero before the first step); t0 = Adam steps taken so far.
+ * loss_out ([n_steps] device floats or NULL): the step's sum of squared errors before its update (epoch sum -> noise_level, :63).
+ * mask_in (tests): keep factors [n_steps][bnn_dropout_train_mask_per_step] = per masked layer [batch][in] (each block padded to a
+ * multiple of 4 floats); NULL = in-kernel Philox (seed, t0 + i).                                                             */
+typedef struct BnnDropoutTrain {
+  BnnMlpDesc desc;
+  int32_t batch;
+  float* W;
+  float* adam;
+  const float* X;            /* [num_train, dims[0]] */
+  const float* y;            /* [num_train, nout]    */
+  const int64_t* perm;       /* epoch permutation [num_train] */
+  int64_t num_train;
+  float lr, beta1, beta2, eps;   /* torch.optim.Adam: 1e-2 (BNN_Dropout.py:35), 0.9, 0.999, 1e-8 */
+  float l2_reg;              /* BNN_Dropout.py:34 */
+  float p_drop;              /* BNN_Dropout.py:32 */
+  uint64_t seed;
+} BnnDropoutTrain;
+int32_t bnn_dropout_train_supported(const BnnMlpDesc* d, int32_t batch);
+int64_t bnn_dropout_train_mask_per_step(const BnnMlpDesc* d, int32_t batch);
+int32_t bnn_dropout_train_run(const BnnDropoutTrain* c, int64_t t0, int64_t perm_off, int32_t n_steps, float* loss_out,
+                              const float* mask_in, void* stream);
+
 /* raw Philox stream dump for tests: out[n] 32-bit words / normals */
 int32_t bnn_philox_words(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, uint32_t* out, void* stream);
 int32_t bnn_philox_normals(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, float* out, void* stream);

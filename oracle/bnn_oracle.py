@@ -288,3 +288,38 @@ def bbb_train_steps(mus, rhos, X, y, batches, act, eps, lr=1e-2, kl_factor=1e-3,
         mses.append(float(mse))
         kls.append(float(kl))
     return [m.detach() for m in mus], [r.detach() for r in rhos], mses, kls
+
+
+# ---- MC-dropout training step --------------------------------------------------------------------------------
+def dropout_train_forward(net, x, act, keeps):
+    """NN_Dropout.forward in training mode (BNN_Dropout.py:15-21) with INJECTED keep factors: before every Linear whose input is
+    wider than one unit, x <- F.dropout(x, p) * (1 - p) = x * keep, keep in {0, ~1}.  net: [(W, b), ...]; keeps: one [B, in] tensor
+    per masked layer, in layer order."""
+    f = act_fn(act)
+    ki = 0
+    for l, (W, b) in enumerate(net):
+        if x.shape[1] > 1:
+            x = x * keeps[ki]
+            ki += 1
+        x = torch.nn.functional.linear(x, W, b)
+        if l + 1 < len(net):
+            x = f(x)
+    return x
+
+
+def dropout_train_steps(net, X, y, batches, act, keeps, lr=1e-2, l2_reg=1e-6):
+    """The minibatch loop body of BNN_Dropout.train (BNN_Dropout.py:57-62): MSELoss(reduction='sum') of the dropout forward,
+    loss.backward(), Adam with weight decay l2_reg on the weights and none on the biases (:43-52).  Returns (net, [loss_i])."""
+    Ws = [W.clone().requires_grad_(True) for W, _ in net]
+    bs = [b.clone().requires_grad_(True) for _, b in net]
+    opt = torch.optim.Adam([{"params": Ws, "weight_decay": l2_reg}, {"params": bs, "weight_decay": 0.}], lr=lr)
+    losses = []
+    for i, idx in enumerate(batches):
+        opt.zero_grad()
+        pred = dropout_train_forward(list(zip(Ws, bs)), X[idx], act, keeps[i]).squeeze(-1)
+        loss = torch.nn.MSELoss(reduction="sum")(pred, y[idx])
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    return [(W.detach(), b.detach()) for W, b in zip(Ws, bs)], losses
+

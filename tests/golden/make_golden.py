@@ -369,7 +369,7 @@ def gen_bbb_train():
             loss = mse + model.kl_factor * kl_term
             loss.backward()
             opt.step()
-            mses.append(float(mse)); kls.append(float(kl_term))
+            mses.append(float(mse.detach())); kls.append(float(kl_term.detach()))
     finally:
         torch.randn = orig
     assert len(rec) == len(batches) * len(gls)
@@ -390,6 +390,84 @@ def gen_bbb_train():
          perm=perm.numpy().astype(np.int64), mse=np.array(mses, dtype=np.float32), kl=np.array(kls, dtype=np.float32), **kw)
 
 
+def gen_dropout_train():
+    """f2: three minibatch steps of the REFERENCE's BNN_Dropout training recipe -- NN_Dropout.forward in training mode, MSELoss(sum),
+    loss.backward(), Adam with the two weight-decay groups (BNN_Dropout.py:15-21,43-62) -- on fixed batches, with the keep factors
+    of every F.dropout call captured (F.dropout(ones) * (1 - p): the same generator state as the reference's own call).  Pins
+    oracle.dropout_train_steps and, on the GPU, the fused training kernel."""
+    torch.manual_seed(22)
+    p = 0.2
+    model = ref_do.BNN_Dropout(5, nn.Tanh(), [24, 16], conf={"dropout_rate": p, "l2_reg": 1e-3, "lr": 1e-2})
+    N, B = 41, 16
+    X = torch.randn(N, 5)
+    y = torch.sin(X.sum(dim=1))
+    perm = torch.randperm(N)
+    batches = [perm[0:16], perm[16:32], perm[32:41]]             # the last batch of the epoch is short
+    net0 = seq_to_net(model.nn.nn)
+    dict_decay = {'params': [], 'weight_decay': model.l2_reg}      # BNN_Dropout.py:43-52
+    dict_no_decay = {'params': [], 'weight_decay': 0.}
+    for name, param in model.nn.named_parameters():
+        (dict_no_decay if "bias" in name else dict_decay)['params'].append(param)
+    opt = torch.optim.Adam([dict_decay, dict_no_decay], lr=model.lr)
+    crit = nn.MSELoss(reduction='sum')
+    rec = []
+    orig = F.dropout
+
+    def wrapped(x, p=0.5, training=True, inplace=False):
+        m = orig(torch.ones_like(x), p=p, training=training)      # consumes the generator exactly like orig(x, ...)
+        rec.append(m * (1 - p))
+        return x * m
+    # (1) the UNMODIFIED reference from this generator state: the fixture's targets
+    import copy
+    rng = torch.get_rng_state()
+    ref_model = copy.deepcopy(model)
+    ref_decay = {'params': [q for n, q in ref_model.nn.named_parameters() if "bias" not in n], 'weight_decay': model.l2_reg}
+    ref_no = {'params': [q for n, q in ref_model.nn.named_parameters() if "bias" in n], 'weight_decay': 0.}
+    ref_opt = torch.optim.Adam([ref_decay, ref_no], lr=model.lr)
+    ref_model.nn.train()
+    ref_losses = []
+    for idx in batches:                                            # BNN_Dropout.py:57-62, verbatim
+        ref_opt.zero_grad()
+        loss = crit(ref_model.nn(X[idx]).squeeze(), y[idx])
+        loss.backward()
+        ref_opt.step()
+        ref_losses.append(float(loss.detach()))
+    # (2) the same run again from the same generator state with F.dropout wrapped to RECORD its draws
+    torch.set_rng_state(rng)
+    model.nn.train()
+    losses = []
+    F.dropout = wrapped
+    try:
+        for idx in batches:
+            opt.zero_grad()
+            pred_y = model.nn(X[idx]).squeeze()
+            loss = crit(pred_y, y[idx])
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+    finally:
+        F.dropout = orig
+    for (W, b), (W1, b1) in zip(seq_to_net(model.nn.nn), seq_to_net(ref_model.nn.nn)):     # recording did not change the run
+        assert torch.allclose(W, W1, rtol=1e-6, atol=1e-8) and torch.allclose(b, b1, rtol=1e-6, atol=1e-8)
+    assert np.allclose(losses, ref_losses, rtol=1e-6)
+    model = ref_model
+    losses = ref_losses
+    n_masked = 3                                                   # every Linear of 5-24-16-1 has an input wider than one unit
+    assert len(rec) == len(batches) * n_masked
+    keeps = [[rec[i * n_masked + l] for l in range(n_masked)] for i in range(len(batches))]
+    o_net, o_loss = O.dropout_train_steps(net0, X, y, batches, "tanh", keeps, lr=1e-2, l2_reg=1e-3)
+    for (W, b), (W1, b1) in zip(o_net, seq_to_net(model.nn.nn)):
+        assert torch.allclose(W, W1, rtol=1e-5, atol=1e-7) and torch.allclose(b, b1, rtol=1e-5, atol=1e-7)
+    assert np.allclose(o_loss, losses, rtol=1e-6)
+    kw = {}
+    for l, ((W0, b0), (W1, b1)) in enumerate(zip(net0, seq_to_net(model.nn.nn))):
+        kw[f"W0_{l}"], kw[f"b0_{l}"], kw[f"W1_{l}"], kw[f"b1_{l}"] = W0, b0, W1, b1
+        for i in range(len(batches)):
+            kw[f"keep{i}_{l}"] = keeps[i][l]
+    save("dropout_train.npz", dims=[5, 24, 16, 1], act="tanh", p_drop=p, l2_reg=1e-3, lr=1e-2, batch=B, X=X, y=y,
+         perm=perm.numpy().astype(np.int64), loss=np.array(losses, dtype=np.float32), **kw)
+
+
 if __name__ == "__main__":
     gen_sgdmc_boston()
     gen_sgdmc_multiout()
@@ -398,3 +476,4 @@ if __name__ == "__main__":
     gen_cdropout_protein()
     gen_sgdmc_energy()
     gen_bbb_train()
+    gen_dropout_train()

@@ -127,3 +127,21 @@ def bbb_train_case():
     B, N = case["batch"], case["X"].shape[0]
     case["batches"] = [case["perm"][i * B: min(N, (i + 1) * B)] for i in range(n_steps)]
     return case
+
+
+def dropout_train_case():
+    """The reference-generated fixture of three BNN_Dropout training steps (tests/golden/dropout_train.npz;
+    make_golden.gen_dropout_train)."""
+    g = golden("dropout_train.npz")
+    dims = [int(v) for v in g["dims"]]
+    nl = len(dims) - 1
+    t = lambda a: torch.as_tensor(a)
+    case = {"dims": dims, "act": str(g["act"]), "p_drop": float(g["p_drop"]), "l2_reg": float(g["l2_reg"]), "lr": float(g["lr"]),
+            "batch": int(g["batch"]), "X": t(g["X"]), "y": t(g["y"]), "perm": t(g["perm"]).long(), "loss": g["loss"],
+            "net0": [(t(g[f"W0_{l}"]), t(g[f"b0_{l}"])) for l in range(nl)],
+            "net1": [(t(g[f"W1_{l}"]), t(g[f"b1_{l}"])) for l in range(nl)]}
+    n_steps = len(case["loss"])
+    case["keeps"] = [[t(g[f"keep{i}_{l}"]) for l in range(nl)] for i in range(n_steps)]
+    B, N = case["batch"], case["X"].shape[0]
+    case["batches"] = [case["perm"][i * B: min(N, (i + 1) * B)] for i in range(n_steps)]
+    return case

@@ -144,3 +144,17 @@ def test_bbb_train_steps_golden():
         assert torch.allclose(mu[l], c["mu1"][l], rtol=1e-6, atol=1e-7)
         assert torch.allclose(rho[l], c["rho1"][l], rtol=1e-6, atol=1e-7)
     assert np.allclose(mse, c["mse"], rtol=1e-6) and np.allclose(kl, c["kl"], rtol=1e-6)
+
+
+def test_dropout_train_steps_golden():
+    """f2: the oracle's restatement of the BNN_Dropout training step against the reference's own three steps."""
+    from helpers import dropout_train_case
+    c = dropout_train_case()
+    net, loss = O.dropout_train_steps(c["net0"], c["X"], c["y"], c["batches"], c["act"], c["keeps"], lr=c["lr"], l2_reg=c["l2_reg"])
+    for (W, b), (W1, b1) in zip(net, c["net1"]):
+        assert torch.allclose(W, W1, rtol=1e-6, atol=1e-7) and torch.allclose(b, b1, rtol=1e-6, atol=1e-7)
+    assert np.allclose(loss, c["loss"], rtol=1e-6)
+    for i, ks in enumerate(c["keeps"]):                      # F.dropout(x, p) * (1 - p): keep factors are 0 or (an ulp from) 1
+        for k in ks:
+            assert k.shape[0] == c["batches"][i].shape[0]
+            assert bool(((k == 0) | ((k - 1).abs() < 1e-6)).all())
