@@ -85,6 +85,38 @@ class BNN_CDropout(BNN):
         self.nn = NN_CDropout(dim, self.act, self.num_hiddens)
         self.noise_level = 1.
         self._draws = 0
+        self.fused_train = bool(conf.get('fused_train', True))   # the single-SM fused training kernel when the network fits it
+        self.trained_with = None
+
+    def _train_fused(self, X, y):
+        """BNN_CDropout.train (BNN_CDropout.py:114-139) through the fused single-SM training kernel (bnn_cdropout_train_run): one
+        launch per epoch; the network, the p_logits, the Adam moments AND noise_level stay on the device (the launch that ends an
+        epoch updates noise_level itself), statistics are read back only when an epoch is printed."""
+        dev = self._dev()
+        num_train = X.shape[0]
+        cls = self.nn.cd_layers()
+        tr = ops.CDropoutTrainer(self.arch, self.batch_size, dev, lr=self.lr, lscale=self.lscale, dr=self.dr,
+                                 min_noise=self.min_noise, noise_level=self.noise_level, seed=self.seed)
+        tr.set_state(self.arch.pack([[(l.layer[1].weight.detach(), l.layer[1].bias.detach()) for l in cls]])[0],
+                     torch.stack([l.layer[0].p_logit.detach().reshape(()) for l in cls]))
+        tr.bind(X, y.reshape(num_train, 1))
+        gen = torch.Generator(device="cpu").manual_seed(self.seed)
+        n_steps = (num_train + self.batch_size - 1) // self.batch_size
+        for epoch in range(self.num_epochs):
+            perm = torch.randperm(num_train, generator=gen).to(dev)       # DataLoader(shuffle=True), BNN_CDropout.py:118
+            show = (epoch + 1) % self.print_every == 0
+            stats = tr.run(perm, 0, n_steps, epoch_end=True, want_stats=show)
+            if show:
+                mse, wreg, ent = [float(v) for v in stats.sum(dim=0)]
+                print("Epoch %4d, mse = %g, noise = %g, wreg = %g, -entropy = %g" %
+                      (epoch + 1, mse / num_train, float(tr.noise_level), wreg / num_train, -1 * ent / num_train))
+        self.noise_level = float(tr.noise_level)
+        with torch.no_grad():
+            for l, (W, b), pl in zip(cls, self.arch.unpack(tr.W), tr.p_logit):
+                l.layer[1].weight.copy_(W)
+                l.layer[1].bias.copy_(b)
+                l.layer[0].p_logit.copy_(pl)
+        self.trained_with = "fused"
 
     def reg(self):                                                     # BNN_CDropout.py:141-151
         entropy, weight_reg = 0., 0.
@@ -100,6 +132,12 @@ class BNN_CDropout(BNN):
         dev = self._dev()
         X, y = self._to_dev(X), self._to_dev(y)
         num_train = X.shape[0]
+        if self.fused_train and dev.type == "cuda" and ops.cdropout_train_supported(self.arch, self.batch_size):
+            self.nn.to(dev)
+            self._train_fused(X.contiguous().float(), y.contiguous().float())
+            self.nn.eval()
+            return
+        self.trained_with = "torch"
         self.nn.to(dev).train()
         opt = torch.optim.Adam(self.nn.parameters(), lr=self.lr)
         crit = nn.MSELoss(reduction='sum')
@@ -122,7 +160,7 @@ class BNN_CDropout(BNN):
         self.nn.eval()
 
     def drop_probs(self):
-        return [float(l.dropout_rate()) for l in self.nn.cd_layers()]
+        return [float(l.dropout_rate().detach()) for l in self.nn.cd_layers()]
 
     def sample(self, num_samples=1, uniforms=None):
         """uniforms (optional, [S, mask_len]) injects the reference's torch.rand draws for exact parity."""

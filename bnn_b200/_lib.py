@@ -57,6 +57,13 @@ class DropoutTrain(C.Structure):
                 ("beta2", C.c_float), ("eps", C.c_float), ("l2_reg", C.c_float), ("p_drop", C.c_float), ("seed", C.c_uint64)]
 
 
+class CDropoutTrain(C.Structure):
+    _fields_ = [("desc", MlpDesc), ("batch", C.c_int32), ("W", C.c_void_p), ("adam", C.c_void_p), ("p_logit", C.c_void_p),
+                ("p_adam", C.c_void_p), ("noise_level", C.c_void_p), ("X", C.c_void_p), ("y", C.c_void_p), ("perm", C.c_void_p),
+                ("num_train", C.c_int64), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("lscale", C.c_float), ("dr", C.c_float), ("min_noise", C.c_float), ("seed", C.c_uint64)]
+
+
 # name -> (restype, argtypes); mirrors include/bnn_b200.h one to one
 PROTOTYPES = {
     "bnn_abi_version": (C.c_int32, []),
@@ -107,6 +114,10 @@ PROTOTYPES = {
     "bnn_dropout_train_mask_per_step": (C.c_int64, [C.POINTER(MlpDesc), C.c_int32]),
     "bnn_dropout_train_run": (C.c_int32, [C.POINTER(DropoutTrain), C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                           C.c_void_p]),
+    "bnn_cdropout_train_supported": (C.c_int32, [C.POINTER(MlpDesc), C.c_int32]),
+    "bnn_cdropout_train_u_per_step": (C.c_int64, [C.POINTER(MlpDesc), C.c_int32]),
+    "bnn_cdropout_train_run": (C.c_int32, [C.POINTER(CDropoutTrain), C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]),
     "bnn_bbb_train_supported": (C.c_int32, [C.POINTER(MlpDesc), C.c_int32]),
     "bnn_bbb_train_eps_per_step": (C.c_int64, [C.POINTER(MlpDesc), C.c_int32]),
     "bnn_bbb_train_run": (C.c_int32, [C.POINTER(BbbTrain), C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

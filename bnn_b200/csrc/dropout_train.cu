@@ -8,6 +8,18 @@
 // stored: forward and backward evaluate the same counter-based draw (Philox stream 6, subsequence = step) or read the injected
 // mask (tests: the reference's own F.dropout draws).  The parameter gradient is consumed by Adam in the thread that forms it.
 // The reference's cfg 3 network (9-100-100-1, batch 32: 11,704 packed parameters) needs 197 KB.
+//
+// The same kernel, instantiated with CONCRETE = true, is the concrete-dropout training step of BNN_CDropout.train
+// (BNN_CDropout.py:114-139): CDropout.forward (:21-34) scales the input of EVERY Linear by the relaxed keep factor
+//   keep = 1 - sigmoid((log(p + e) - log(1 - p + e) + log(u + e) - log(1 - u + e)) / 0.1),  e = 1e-7, u ~ U[0, 1),
+//   p = clamp_probs(sigmoid(p_logit)) (:18-19), one learnable p_logit per layer;
+// loss = MSELoss(sum) + (wreg - ent) * rows / num_train with (BNN_CDropout.reg, :141-151; CDropoutLinear.reg, :53-57)
+//   wreg = sum_l lscale^2 (1 - p_l) noise_level^2 sum(W_l^2),  ent = sum_l 2 dr noise_level^2 in_l H(p_l);
+// Adam without weight decay on W, b and p_logit (:116).  noise_level is a device scalar: the launch that ends an epoch sets it to
+// max(min_noise, sqrt(sum of the launch's squared errors / num_train)) (:134) -- no host round trip per epoch.
+// Gradients in closed form: d keep / d z = -(1 - keep) keep / T, so d L / d p_logit_l = sum_{b,k} -g[b,k] xm[b,k] (1 - keep) / T
+// (xm = the stored masked input, g = the gradient with respect to it) times dz/dp dp/dlogit, plus the regulariser's
+// -(rows / N) noise_level^2 (lscale^2 sum(W^2) + 2 dr in log((1 - p) / p)) dp/dlogit.
 #include <math.h>
 
 #include "common.cuh"
@@ -36,16 +48,37 @@ struct DtParams {
   float lr, beta1, beta2, eps, l2_reg, p_drop;
   unsigned long long seed;
   float* loss_out;                          // [n_steps] or null: sum of squared errors of the step's batch, before its update
-  const float* mask_in;                     // tests: injected keep factors [n_steps][mask_per_step]; null = Philox
-  int sm_act, sm_g0, sm_g1, sm_y, sm_red, max_w;
+  const float* mask_in;                     // tests: injected keep factors (concrete: uniforms) [n_steps][mask_per_step]; null = Philox
+  int sm_act, sm_g0, sm_g1, sm_y, sm_red, sm_cd, max_w;
+  // concrete dropout only
+  float* plogit; float* padam;              // global: [L], [2][L]
+  float* noise_level;                       // device scalar, in / out
+  float* stats_out;                         // [n_steps][3] or null: squared errors, wreg * rows / N, ent * rows / N
+  float lscale2, dr, min_noise;
+  int epoch_end;
 };
 
-// keep factor of input unit k of row b of layer l at launch step `it`
-__device__ __forceinline__ float dt_keep(const DtParams& p, const DtLayer& Y, int it, int b, int k) {
+constexpr float kCdEps = 1e-7f, kCdInvTemp = 10.0f;                  // BNN_CDropout.py:23-24
+constexpr float kProbEps = 1.1920928955078125e-07f;                   // torch clamp_probs: finfo(float32).eps
+
+// per-layer concrete-dropout state in shared memory (floats): [0] p_logit [1] m [2] v [3] p [4] log(p+e) - log(1-p+e) [5] grad
+constexpr int kCdStride = 8;
+
+// keep factor of input unit k of row b of layer l at launch step `it` (lpr: the layer's log(p + e) - log(1 - p + e), concrete only)
+template <bool CONCRETE>
+__device__ __forceinline__ float dt_keep(const DtParams& p, const DtLayer& Y, int it, int b, int k, float lpr) {
   const long long u = Y.m_off + (long long)b * Y.in + k;
-  if (p.mask_in) return p.mask_in[(long long)it * p.mask_per_step + u];
-  const u32x4 w = philox_block(p.seed, (uint32_t)(p.t0 + it), STREAM_DROPOUT_TRAIN, (uint64_t)(u >> 2));
-  return bernoulli_keep(u24(pick_word(w, (int)(u & 3))), p.p_drop);
+  float r;
+  if (p.mask_in) {
+    r = p.mask_in[(long long)it * p.mask_per_step + u];
+    if (!CONCRETE) return r;
+  } else {
+    const u32x4 w = philox_block(p.seed, (uint32_t)(p.t0 + it), STREAM_DROPOUT_TRAIN, (uint64_t)(u >> 2));
+    r = u24(pick_word(w, (int)(u & 3)));
+    if (!CONCRETE) return bernoulli_keep(r, p.p_drop);
+  }
+  const float z = (lpr + logf(r + kCdEps) - logf(1.0f - r + kCdEps)) * kCdInvTemp;
+  return 1.0f - 1.0f / (1.0f + expf(-z));
 }
 __device__ __forceinline__ float dt_act_bwd(float a, int act) {   // derivative through the activation's OUTPUT
   switch (act) {
@@ -56,9 +89,11 @@ __device__ __forceinline__ float dt_act_bwd(float a, int act) {   // derivative 
   }
 }
 
+template <bool CONCRETE>
 __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __grid_constant__ DtParams p) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
+  constexpr int kWarps = kDtThreads / 32;
   const long long P = p.stride;
   float* s_w = sm;
   float* s_m = s_w + P;
@@ -68,28 +103,69 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
   float* s_gb = sm + p.sm_g1;   // ... and of the layer below (ping-pong)
   float* s_y = sm + p.sm_y;
   double* s_red = reinterpret_cast<double*>(sm + p.sm_red);   // [warps]: loss partial sums
+  double* s_redp = s_red + kWarps;                            // [warps]: p_logit gradient partial sums (concrete)
+  double* s_redw = s_redp + kWarps;                           // [L][warps]: sum(W^2) partial sums (concrete)
+  double* s_w2 = s_redw + BNN_MAX_LINEAR * kWarps;            // [L] sum(W_l^2) at the start of the step; [L] = the launch's loss sum
+  float* s_cd = sm + p.sm_cd;                                 // [L][kCdStride]
 
   for (long long i = tid; i < P; i += kDtThreads) { s_w[i] = p.W[i]; s_m[i] = p.adam[i]; s_v[i] = p.adam[P + i]; }
+  const int L = p.L, B = p.B;
+  float nv = 1.0f;
+  if (CONCRETE) {
+    if (tid < L) { s_cd[tid * kCdStride] = p.plogit[tid]; s_cd[tid * kCdStride + 1] = p.padam[tid]; s_cd[tid * kCdStride + 2] = p.padam[L + tid]; }
+    if (tid == 0) s_w2[L] = 0.0;
+    const float nl = *p.noise_level;
+    nv = nl * nl;
+  }
   __syncthreads();
   double b1t = pow((double)p.beta1, (double)p.t0), b2t = pow((double)p.beta2, (double)p.t0);
-  const int L = p.L, B = p.B;
 
 #pragma unroll 1
   for (int it = 0; it < p.n_steps; ++it) {
     const long long boff = p.perm_off + (long long)it * B;
     const long long left = p.num_train - boff;
     const int rows = left < B ? (int)left : B;                     // the last batch of an epoch may be short
+    const float frac = (float)((double)rows / (double)p.num_train);
+    if (CONCRETE) {
+      // the step's dropout probabilities (BNN_CDropout.py:18-19) and sum(W_l^2) of the weights before the update
+      if (tid < L) {
+        float* c = s_cd + tid * kCdStride;
+        const float sg = 1.0f / (1.0f + expf(-c[0]));
+        const float pr = fminf(fmaxf(sg, kProbEps), 1.0f - kProbEps);
+        c[3] = pr;
+        c[4] = logf(pr + kCdEps) - logf(1.0f - pr + kCdEps);
+      }
+      for (int l = 0; l < L; ++l) {
+        const DtLayer& Y = p.ly[l];
+        double part = 0.0;
+        for (int i = tid; i < Y.out * Y.ld; i += kDtThreads) {
+          const int k = i % Y.ld;
+          const float w = s_w[Y.off + i];
+          if (k < Y.in) part += (double)(w * w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if ((tid & 31) == 0) s_redw[l * kWarps + (tid >> 5)] = part;
+      }
+      __syncthreads();
+      if (tid < L) {
+        double s = 0.0;
+        for (int w = 0; w < kWarps; ++w) s += s_redw[tid * kWarps + w];
+        s_w2[tid] = s;
+      }
+    }
     // ---- gather: masked, augmented rows (x * keep | 1 | 0) of the batch, and the targets
     {
       const DtLayer& Y0 = p.ly[0];
       float* a0 = s_act + Y0.a_off;
+      const float lpr = CONCRETE ? s_cd[4] : 0.0f;
       for (int i = tid; i < B * Y0.ld; i += kDtThreads) {
         const int b = i / Y0.ld, k = i - b * Y0.ld;
         float v = 0.0f;
         if (b < rows) {
           if (k < p.D) {
             v = __ldg(p.X + __ldg(p.perm + boff + b) * p.D + k);
-            if (Y0.masked) v *= dt_keep(p, Y0, it, b, k);
+            if (Y0.masked) v *= dt_keep<CONCRETE>(p, Y0, it, b, k, lpr);
           } else if (k == p.D) v = 1.0f;
         }
         a0[i] = v;
@@ -108,6 +184,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
       const bool last = l + 1 == L;
       float* nxt = last ? s_gb : s_act + p.ly[l + 1].a_off;        // the last layer's output goes to s_gb as "pred"
       const int ldn = last ? p.nout : p.ly[l + 1].ld;
+      const float lpr = (CONCRETE && !last) ? s_cd[(l + 1) * kCdStride + 4] : 0.0f;
       for (int i = tid; i < B * Y.out; i += kDtThreads) {
         const int b = i / Y.out, j = i - b * Y.out;
         const float* ar = a + b * Y.ld;
@@ -122,7 +199,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
         if (!last) {
           o = apply_act(o, p.act);
           const DtLayer& N = p.ly[l + 1];
-          if (N.masked && b < rows) o *= dt_keep(p, N, it, b, j);
+          if (N.masked && b < rows) o *= dt_keep<CONCRETE>(p, N, it, b, j, lpr);
         }
         nxt[b * ldn + j] = o;
       }
@@ -150,10 +227,22 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
       if ((tid & 31) == 0) s_red[tid >> 5] = part;
     }
     __syncthreads();
-    if (tid == 0 && p.loss_out) {
+    if (tid == 0) {
       double s = 0.0;
-      for (int w = 0; w < kDtThreads / 32; ++w) s += s_red[w];
-      p.loss_out[it] = (float)s;
+      for (int w = 0; w < kWarps; ++w) s += s_red[w];
+      if (p.loss_out) p.loss_out[it] = (float)s;
+      if (CONCRETE) {
+        s_w2[L] += (double)(float)s;
+        if (p.stats_out) {                                           // BNN_CDropout.py:127-129,141-151
+          float wreg = 0.0f, ent = 0.0f;
+          for (int l = 0; l < L; ++l) {
+            const float pr = s_cd[l * kCdStride + 3];
+            wreg += p.lscale2 * (1.0f - pr) * nv * (float)s_w2[l];
+            ent += p.dr * 2.0f * nv * ((float)p.ly[l].in * -(pr * logf(pr) + (1.0f - pr) * logf(1.0f - pr)));
+          }
+          p.stats_out[3 * it] = (float)s; p.stats_out[3 * it + 1] = wreg * frac; p.stats_out[3 * it + 2] = ent * frac;
+        }
+      }
     }
     // ---- backward + Adam, layer by layer from the top
     b1t *= (double)p.beta1; b2t *= (double)p.beta2;
@@ -167,9 +256,11 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
       const DtLayer& Y = p.ly[l];
       const float* a = s_act + Y.a_off;
       // gradient of the layer's (unmasked, pre-dropout) input, through the keep mask and the activation below: needs the
-      // weights BEFORE their update
-      if (l > 0) {
+      // weights BEFORE their update.  Concrete dropout also needs it at layer 0: the masked input's gradient drives p_logit.
+      if (l > 0 || CONCRETE) {
         const int q4 = (Y.in + 3) >> 2;
+        const float lpr = CONCRETE ? s_cd[l * kCdStride + 4] : 0.0f;
+        float gp = 0.0f;
         for (int i = tid; i < B * q4; i += kDtThreads) {
           const int b = i / q4, k = (i - b * q4) * 4;
           float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -184,17 +275,37 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
           for (int c = 0; c < 4; ++c) {
             if (k + c < Y.in) {
               float keep = 1.0f;
-              if (Y.masked) keep = b < rows ? dt_keep(p, Y, it, b, k + c) : 0.0f;
-              // keep is 0 or (within an ulp of) 1: where it is not 0, the stored value is the activation's output itself
-              g1[b * p.max_w + k + c] = keep != 0.0f ? gs[c] * keep * dt_act_bwd(xs[c] / keep, p.act) : 0.0f;
+              if (Y.masked) keep = b < rows ? dt_keep<CONCRETE>(p, Y, it, b, k + c, lpr) : 0.0f;
+              if (CONCRETE) gp -= gs[c] * xs[c] * (1.0f - keep);      // d keep / d z = -(1 - keep) keep / T; xs = act * keep
+              // where keep is not 0 the unmasked activation is xs / keep (Bernoulli: keep is 0 or within an ulp of 1;
+              // concrete: keep = 1 - sigmoid is 0 or at least 2^-24)
+              if (l > 0) g1[b * p.max_w + k + c] = keep != 0.0f ? gs[c] * keep * dt_act_bwd(xs[c] / keep, p.act) : 0.0f;
             }
           }
         }
+        if (CONCRETE) {
+          double part = (double)gp;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          if ((tid & 31) == 0) s_redp[tid >> 5] = part;
+        }
       }
       __syncthreads();
+      if (CONCRETE && tid == 0) {
+        float* c = s_cd + l * kCdStride;
+        double s = 0.0;
+        for (int w = 0; w < kWarps; ++w) s += s_redp[w];
+        const float pr = c[3];
+        const float sg = 1.0f / (1.0f + expf(-c[0]));
+        const float dpdl = (sg >= kProbEps && sg <= 1.0f - kProbEps) ? sg * (1.0f - sg) : 0.0f;   // clamp_probs passes no gradient outside
+        const float dzdp = 1.0f / (pr + kCdEps) + 1.0f / (1.0f - pr + kCdEps);
+        const float greg = frac * nv * (-p.lscale2 * (float)s_w2[l] - 2.0f * p.dr * (float)Y.in * (logf(1.0f - pr) - logf(pr)));
+        c[5] = ((float)s * kCdInvTemp * dzdp + greg) * dpdl;
+      }
       // parameters: thread = four consecutive (j, k..k+3) entries: gradient over the batch, weight decay, Adam, in place
       {
         const int q4 = Y.ld >> 2;
+        const float decay = CONCRETE ? 2.0f * frac * p.lscale2 * (1.0f - s_cd[l * kCdStride + 3]) * nv : p.l2_reg;
         for (int i = tid; i < Y.out * q4; i += kDtThreads) {
           const int j = i / q4, k = (i - j * q4) * 4;
           float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -210,7 +321,8 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
             if (k + c <= Y.in) {
               const long long w = w0 + c;
               const float wv = s_w[w];
-              const float gr = k + c < Y.in ? fmaf(p.l2_reg, wv, gs[c]) : gs[c];   // Adam's weight_decay: weights only (:43-51)
+              // Adam's weight_decay (BNN_Dropout.py:43-51) / the gradient of wreg (BNN_CDropout.py:148): weights only
+              const float gr = k + c < Y.in ? fmaf(decay, wv, gs[c]) : gs[c];
               const float m = p.beta1 * s_m[w] + om1 * gr, v = p.beta2 * s_v[w] + om2 * gr * gr;
               s_m[w] = m; s_v[w] = v;
               s_w[w] = wv - step_size * (m / (sqrtf(v) / bc2_sqrt + p.eps));
@@ -221,8 +333,20 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
       __syncthreads();
       float* t = g0; g0 = g1; g1 = t;
     }
+    if (CONCRETE && tid < L) {                                        // Adam on the p_logits; read again by this thread next step
+      float* c = s_cd + tid * kCdStride;
+      const float gr = c[5];
+      const float m = p.beta1 * c[1] + om1 * gr, v = p.beta2 * c[2] + om2 * gr * gr;
+      c[1] = m; c[2] = v;
+      c[0] -= step_size * (m / (sqrtf(v) / bc2_sqrt + p.eps));
+    }
   }
   for (long long i = tid; i < P; i += kDtThreads) { p.W[i] = s_w[i]; p.adam[i] = s_m[i]; p.adam[P + i] = s_v[i]; }
+  if (CONCRETE) {
+    if (tid < L) { p.plogit[tid] = s_cd[tid * kCdStride]; p.padam[tid] = s_cd[tid * kCdStride + 1]; p.padam[L + tid] = s_cd[tid * kCdStride + 2]; }
+    if (tid == 0 && p.epoch_end)                                      // BNN_CDropout.py:134
+      *p.noise_level = fmaxf(p.min_noise, (float)sqrt(s_w2[L] / (double)p.num_train));
+  }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------------
@@ -232,7 +356,7 @@ struct DtPlan {
 };
 
 // 0 = ok, 1 = does not fit one SM (message set), < 0 = bad arguments
-static int dt_plan(const BnnMlpDesc* d, int batch, DtPlan* plan) {
+static int dt_plan(const BnnMlpDesc* d, int batch, bool concrete, DtPlan* plan) {
   Layout Lo;
   if (make_layout(d, &Lo)) return -1;
   if (batch < 1 || batch > 1024) { set_error("bnn_dropout_train: batch must be in [1, 1024] (got %d)", batch); return -1; }
@@ -245,7 +369,7 @@ static int dt_plan(const BnnMlpDesc* d, int batch, DtPlan* plan) {
   for (int l = 0; l < p.L; ++l) {
     DtLayer& Y = p.ly[l];
     Y.in = Lo.in[l]; Y.out = Lo.out[l]; Y.ld = Lo.ld[l]; Y.off = Lo.off[l];
-    Y.masked = Y.in > 1 ? 1 : 0;                                   // BNN_Dropout.py:18: "x.shape[1] > 1"
+    Y.masked = (concrete || Y.in > 1) ? 1 : 0;                     // BNN_Dropout.py:18: "x.shape[1] > 1"; CDropout: every layer
     Y.a_off = (int)act; act += (long long)batch * Y.ld;
     Y.m_off = Y.masked ? m : -1;
     if (Y.masked) m += ((long long)batch * Y.in + 3) & ~3LL;
@@ -259,10 +383,11 @@ static int dt_plan(const BnnMlpDesc* d, int batch, DtPlan* plan) {
   p.sm_g0 = (int)f; f += ((long long)batch * max_w + 3) & ~3LL;
   p.sm_g1 = (int)f; f += ((long long)batch * max_w + 3) & ~3LL;
   p.sm_y = (int)f; f += ((long long)batch * p.nout + 3) & ~3LL;
-  p.sm_red = (int)f; f += 2 * (kDtThreads / 32);
+  p.sm_red = (int)f; f += 2 * ((2 + BNN_MAX_LINEAR) * (kDtThreads / 32) + BNN_MAX_LINEAR + 1);
+  p.sm_cd = (int)f; f += BNN_MAX_LINEAR * kCdStride;
   plan->smem = (size_t)f * 4;
   if (plan->smem > (size_t)227 * 1024) {
-    set_error("bnn_dropout_train: %lld packed parameters at batch %d need %zu bytes of shared memory (one SM has 227 KB)",
+    set_error("bnn_(c)dropout_train: %lld packed parameters at batch %d need %zu bytes of shared memory (one SM has 227 KB)",
               (long long)p.stride, batch, plan->smem);
     return 1;
   }
@@ -276,13 +401,13 @@ using namespace bnn;
 extern "C" int32_t bnn_dropout_train_supported(const BnnMlpDesc* d, int32_t batch) {
   if (!d) return 0;
   DtPlan plan;
-  return dt_plan(d, batch, &plan) == 0;
+  return dt_plan(d, batch, false, &plan) == 0;
 }
 
 extern "C" int64_t bnn_dropout_train_mask_per_step(const BnnMlpDesc* d, int32_t batch) {
   if (!d) { set_error("null desc"); return -1; }
   DtPlan plan;
-  if (dt_plan(d, batch, &plan) < 0) return -1;
+  if (dt_plan(d, batch, false, &plan) < 0) return -1;
   return plan.p.mask_per_step;
 }
 
@@ -296,7 +421,7 @@ extern "C" int32_t bnn_dropout_train_run(const BnnDropoutTrain* c, int64_t t0, i
     BNN_FAIL("bnn_dropout_train_run: %d steps of batch %d from offset %lld run past the epoch (%lld rows)", n_steps, c->batch,
              (long long)perm_off, (long long)c->num_train);
   DtPlan plan;
-  if (dt_plan(&c->desc, c->batch, &plan)) return -1;
+  if (dt_plan(&c->desc, c->batch, false, &plan)) return -1;
   DtParams& p = plan.p;
   p.W = c->W; p.adam = c->adam;
   p.X = c->X; p.y = c->y; p.perm = (const long long*)c->perm; p.num_train = c->num_train; p.perm_off = perm_off;
@@ -304,8 +429,46 @@ extern "C" int32_t bnn_dropout_train_run(const BnnDropoutTrain* c, int64_t t0, i
   p.lr = c->lr; p.beta1 = c->beta1; p.beta2 = c->beta2; p.eps = c->eps; p.l2_reg = c->l2_reg; p.p_drop = c->p_drop;
   p.seed = c->seed;
   p.loss_out = loss_out; p.mask_in = mask_in;
-  BNN_CUDA(cudaFuncSetAttribute(dropout_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-  dropout_train_kernel<<<1, kDtThreads, plan.smem, (cudaStream_t)stream>>>(p);
+  BNN_CUDA(cudaFuncSetAttribute(dropout_train_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+  dropout_train_kernel<false><<<1, kDtThreads, plan.smem, (cudaStream_t)stream>>>(p);
+  BNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t bnn_cdropout_train_supported(const BnnMlpDesc* d, int32_t batch) {
+  if (!d) return 0;
+  DtPlan plan;
+  return dt_plan(d, batch, true, &plan) == 0;
+}
+
+extern "C" int64_t bnn_cdropout_train_u_per_step(const BnnMlpDesc* d, int32_t batch) {
+  if (!d) { set_error("null desc"); return -1; }
+  DtPlan plan;
+  if (dt_plan(d, batch, true, &plan) < 0) return -1;
+  return plan.p.mask_per_step;
+}
+
+extern "C" int32_t bnn_cdropout_train_run(const BnnCDropoutTrain* c, int64_t t0, int64_t perm_off, int32_t n_steps, int32_t epoch_end,
+                                          float* stats_out, const float* u_in, void* stream) {
+  if (!c || n_steps < 1 || t0 < 0 || perm_off < 0) BNN_FAIL("bnn_cdropout_train_run: bad arguments");
+  if (!c->W || !c->adam || !c->p_logit || !c->p_adam || !c->noise_level || !c->X || !c->y || !c->perm || c->num_train < 1)
+    BNN_FAIL("bnn_cdropout_train_run: W, adam, p_logit, p_adam, noise_level, X, y, perm and num_train are required");
+  if (!(c->lr > 0.f)) BNN_FAIL("bnn_cdropout_train_run: lr must be positive");
+  if (perm_off + (int64_t)(n_steps - 1) * c->batch >= c->num_train)
+    BNN_FAIL("bnn_cdropout_train_run: %d steps of batch %d from offset %lld run past the epoch (%lld rows)", n_steps, c->batch,
+             (long long)perm_off, (long long)c->num_train);
+  DtPlan plan;
+  if (dt_plan(&c->desc, c->batch, true, &plan)) return -1;
+  DtParams& p = plan.p;
+  p.W = c->W; p.adam = c->adam; p.plogit = c->p_logit; p.padam = c->p_adam; p.noise_level = c->noise_level;
+  p.X = c->X; p.y = c->y; p.perm = (const long long*)c->perm; p.num_train = c->num_train; p.perm_off = perm_off;
+  p.t0 = t0; p.n_steps = n_steps; p.epoch_end = epoch_end;
+  p.lr = c->lr; p.beta1 = c->beta1; p.beta2 = c->beta2; p.eps = c->eps;
+  p.lscale2 = c->lscale * c->lscale; p.dr = c->dr; p.min_noise = c->min_noise;
+  p.seed = c->seed;
+  p.stats_out = stats_out; p.mask_in = u_in;
+  BNN_CUDA(cudaFuncSetAttribute(dropout_train_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+  dropout_train_kernel<true><<<1, kDtThreads, plan.smem, (cudaStream_t)stream>>>(p);
   BNN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -605,3 +605,74 @@ class DropoutTrainer:
         self.t += int(n_steps)
         self._last = (perm, masks)    # stream-ordered use: keep alive until the next call
         return loss
+
+
+# ---- fused concrete-dropout training step --------------------------------------------------------------------
+def cdropout_train_supported(arch: Arch, batch):
+    """True if the single-SM fused training kernel takes this network at this batch size (bnn_cdropout_train_supported)."""
+    d = arch.desc()
+    return bool(_lib.lib().bnn_cdropout_train_supported(C.byref(d), int(batch)))
+
+
+class CDropoutTrainer:
+    """The device-resident packed network, the per-layer p_logits, their Adam moments, the noise level and the fused training
+    kernel (bnn_cdropout_train_run, csrc/dropout_train.cu): the state of BNN_CDropout.train (BNN_CDropout.py:114-139)."""
+
+    def __init__(self, arch: Arch, batch, device, lr=1e-2, lscale=1e-1, dr=2., min_noise=0., noise_level=1., betas=(0.9, 0.999),
+                 eps=1e-8, seed=0):
+        if not cdropout_train_supported(arch, batch):
+            _lib.check(-1, "bnn_cdropout_train_supported")
+        self.arch, self.batch, self.device = arch, int(batch), torch.device(device)
+        self.W = torch.zeros(arch.stride, device=self.device)
+        self.adam = torch.zeros(2, arch.stride, device=self.device)
+        self.p_logit = torch.zeros(arch.n_linear, device=self.device)
+        self.p_adam = torch.zeros(2, arch.n_linear, device=self.device)
+        self.noise_level = torch.full((1,), float(noise_level), device=self.device)
+        self.t = 0
+        d = arch.desc()
+        self.u_per_step = int(_lib.lib().bnn_cdropout_train_u_per_step(C.byref(d), self.batch))
+        c = _lib.CDropoutTrain()
+        c.desc, c.batch = d, self.batch
+        c.W, c.adam, c.p_logit, c.p_adam = self.W.data_ptr(), self.adam.data_ptr(), self.p_logit.data_ptr(), self.p_adam.data_ptr()
+        c.noise_level = self.noise_level.data_ptr()
+        c.lr, c.beta1, c.beta2, c.eps = float(lr), float(betas[0]), float(betas[1]), float(eps)
+        c.lscale, c.dr, c.min_noise, c.seed = float(lscale), float(dr), float(min_noise), int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._c = c
+        self._keep = None
+
+    def set_state(self, packed, p_logits, noise_level=None):
+        """Start at this packed network / these p_logits with a fresh optimizer (zero moments, step 0)."""
+        self.W.copy_(packed.reshape(-1).to(self.device, torch.float32))
+        self.p_logit.copy_(torch.as_tensor(p_logits, dtype=torch.float32).reshape(-1))
+        self.adam.zero_()
+        self.p_adam.zero_()
+        if noise_level is not None:
+            self.noise_level.fill_(float(noise_level))
+        self.t = 0
+
+    def bind(self, X, y):
+        X, y = _dev(X, "X"), _dev(y, "y")
+        if X.dim() != 2 or X.shape[1] != self.arch.dims[0] or y.numel() != X.shape[0] * self.arch.nout:
+            raise ValueError("X must be [N, dim] and y [N, nout]")
+        self._keep = (X, y)
+        self._c.X, self._c.y, self._c.num_train = X.data_ptr(), y.data_ptr(), X.shape[0]
+
+    def run(self, perm, perm_off, n_steps, epoch_end=False, want_stats=False, uniforms=None):
+        """n_steps fused training steps on the batches perm[perm_off + i * batch ...]; epoch_end: the launch updates noise_level
+        from its squared errors (BNN_CDropout.py:134).  Returns per-step (squared errors, wreg, ent) [n_steps, 3] when want_stats.
+        uniforms (tests): injected torch.rand_like draws [n_steps, u_per_step]."""
+        if perm.dtype != torch.int64 or not perm.is_cuda or not perm.is_contiguous():
+            raise TypeError("perm must be a contiguous int64 CUDA tensor")
+        self._c.perm = perm.data_ptr()
+        stats = torch.empty(n_steps, 3, device=self.device) if want_stats else None
+        if uniforms is not None:
+            uniforms = _dev(uniforms, "uniforms").to(torch.float32).contiguous()
+            if uniforms.numel() != n_steps * self.u_per_step:
+                raise ValueError(f"uniforms must hold {n_steps} x {self.u_per_step} values")
+        _lib.check(_lib.lib().bnn_cdropout_train_run(C.byref(self._c), int(self.t), int(perm_off), int(n_steps), int(bool(epoch_end)),
+                                                      stats.data_ptr() if want_stats else None,
+                                                      uniforms.data_ptr() if uniforms is not None else None, _stream(self.W)),
+                   "bnn_cdropout_train_run")
+        self.t += int(n_steps)
+        self._last = (perm, uniforms)  # stream-ordered use: keep alive until the next call
+        return stats

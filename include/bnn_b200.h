@@ -320,6 +320,38 @@ int64_t bnn_dropout_train_mask_per_step(const BnnMlpDesc* d, int32_t batch);
 int32_t bnn_dropout_train_run(const BnnDropoutTrain* c, int64_t t0, int64_t perm_off, int32_t n_steps, float* loss_out,
                               const float* mask_in, void* stream);
 
+/* replaces: the minibatch loop body of BNN_CDropout.train (BNN_CDropout.py:121-133) -- CDropout.forward's relaxed keep factors on
+ * the input of EVERY Linear (:21-34; temperature 0.1, one learnable p_logit per layer, :13-19), MSELoss(reduction='sum'), the
+ * regulariser (wreg - ent) * rows / num_train of BNN_CDropout.reg (:141-151) + CDropoutLinear.reg (:53-57), loss.backward() and
+ * Adam.step() on W, b and p_logit (:116) -- in the same single-CTA persistent kernel as bnn_dropout_train_run
+ * (csrc/dropout_train.cu, CONCRETE = true).  p_logit: [n_linear] device floats, p_adam: [2][n_linear] (zero before the first step).
+ * noise_level: ONE device float, read at launch (the regulariser's noise_level^2, :144); with epoch_end != 0 the launch ends by
+ * storing max(min_noise, sqrt(sum of its squared errors / num_train)) (:134), so an epoch needs no host round trip.
+ * stats_out ([n_steps][3] device floats or NULL): squared errors, wreg * rows / N, ent * rows / N of each step (:127-132).
+ * u_in (tests): the uniforms of torch.rand_like [n_steps][bnn_cdropout_train_u_per_step] = per layer [batch][in] (each block
+ * padded to a multiple of 4 floats); NULL = in-kernel Philox (seed, t0 + i).                                                    */
+typedef struct BnnCDropoutTrain {
+  BnnMlpDesc desc;
+  int32_t batch;
+  float* W;
+  float* adam;
+  float* p_logit;
+  float* p_adam;
+  float* noise_level;
+  const float* X;            /* [num_train, dims[0]] */
+  const float* y;            /* [num_train, nout]    */
+  const int64_t* perm;       /* epoch permutation [num_train] */
+  int64_t num_train;
+  float lr, beta1, beta2, eps;   /* torch.optim.Adam: 1e-2 (BNN_CDropout.py:107), 0.9, 0.999, 1e-8 */
+  float lscale, dr;          /* BNN_CDropout.py:108-109 */
+  float min_noise;           /* BNN_CDropout.py:105 */
+  uint64_t seed;
+} BnnCDropoutTrain;
+int32_t bnn_cdropout_train_supported(const BnnMlpDesc* d, int32_t batch);
+int64_t bnn_cdropout_train_u_per_step(const BnnMlpDesc* d, int32_t batch);
+int32_t bnn_cdropout_train_run(const BnnCDropoutTrain* c, int64_t t0, int64_t perm_off, int32_t n_steps, int32_t epoch_end,
+                               float* stats_out, const float* u_in, void* stream);
+
 /* raw Philox stream dump for tests: out[n] 32-bit words / normals */
 int32_t bnn_philox_words(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, uint32_t* out, void* stream);
 int32_t bnn_philox_normals(uint64_t seed, uint32_t subsequence, uint32_t tag, int64_t n, float* out, void* stream);

@@ -320,6 +320,61 @@ def dropout_train_steps(net, X, y, batches, act, keeps, lr=1e-2, l2_reg=1e-6):
         loss = torch.nn.MSELoss(reduction="sum")(pred, y[idx])
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     return [(W.detach(), b.detach()) for W, b in zip(Ws, bs)], losses
 
+
+# ---- concrete-dropout training step --------------------------------------------------------------------------
+def cdropout_rate(p_logit):
+    """CDropout.dropout_rate (BNN_CDropout.py:18-19)."""
+    return torch.distributions.utils.clamp_probs(torch.sigmoid(p_logit))
+
+
+def cdropout_train_forward(net, p_logits, x, act, us):
+    """NN_CDropout.forward in training mode (BNN_CDropout.py:21-34,45-46,92-93) with INJECTED uniforms: the input of EVERY Linear is
+    scaled by 1 - sigmoid((log(p + e) - log(1 - p + e) + log(u + e) - log(1 - u + e)) / 0.1), e = 1e-7.  us: one [B, in] per layer."""
+    f = act_fn(act)
+    eps, temp = 1e-7, 0.1
+    for l, (W, b) in enumerate(net):
+        p = cdropout_rate(p_logits[l])
+        u = us[l]
+        drop = torch.log(p + eps) - torch.log(1 - p + eps) + torch.log(u + eps) - torch.log(1 - u + eps)
+        x = x * (1 - torch.sigmoid(drop / temp))
+        x = torch.nn.functional.linear(x, W, b)
+        if l + 1 < len(net):
+            x = f(x)
+    return x
+
+
+def cdropout_reg(net, p_logits, noise_level, lscale=1e-1, dr=2.):
+    """BNN_CDropout.reg (BNN_CDropout.py:141-151) over CDropoutLinear.reg (:53-57): (weight_reg, entropy)."""
+    noise_var = noise_level ** 2
+    wreg, ent = 0., 0.
+    for (W, _), pl in zip(net, p_logits):
+        p = cdropout_rate(pl)
+        entropy = -1 * (p * p.log() + (1 - p) * (1 - p).log())
+        wreg = wreg + lscale ** 2 * (1 - p) * noise_var * torch.sum(W ** 2)
+        ent = ent + dr * 2 * noise_var * (1. * W.shape[1]) * entropy
+    return wreg, ent
+
+
+def cdropout_train_steps(net, p_logits, X, y, batches, act, us, num_train, noise_level=1., lr=1e-2, lscale=1e-1, dr=2.):
+    """The minibatch loop body of BNN_CDropout.train (BNN_CDropout.py:121-133): MSELoss(sum) + (wreg - ent) * rows / num_train,
+    backward, Adam on W, b and p_logit (:116).  Returns (net, p_logits, [(mse, wreg, ent)_i])."""
+    Ws = [W.clone().requires_grad_(True) for W, _ in net]
+    bs = [b.clone().requires_grad_(True) for _, b in net]
+    pls = [torch.as_tensor(q, dtype=torch.float32).clone().requires_grad_(True) for q in p_logits]
+    opt = torch.optim.Adam(Ws + bs + pls, lr=lr)
+    stats = []
+    for i, idx in enumerate(batches):
+        opt.zero_grad()
+        cur = list(zip(Ws, bs))
+        pred = cdropout_train_forward(cur, pls, X[idx], act, us[i]).squeeze(-1)
+        mse = torch.nn.MSELoss(reduction="sum")(pred, y[idx])
+        wreg, ent = cdropout_reg(cur, pls, noise_level, lscale, dr)
+        wreg = wreg * (idx.shape[0] / num_train)
+        ent = ent * (idx.shape[0] / num_train)
+        (mse + (wreg - ent)).backward()
+        opt.step()
+        stats.append((float(mse.detach()), float(wreg.detach()), float(ent.detach())))
+    return [(W.detach(), b.detach()) for W, b in zip(Ws, bs)], [q.detach() for q in pls], stats

@@ -468,6 +468,86 @@ def gen_dropout_train():
          perm=perm.numpy().astype(np.int64), loss=np.array(losses, dtype=np.float32), **kw)
 
 
+def gen_cdropout_train():
+    """f2: three minibatch steps of the REFERENCE's BNN_CDropout training recipe -- NN_CDropout.forward in training mode, MSELoss(sum),
+    model.reg(), loss.backward(), Adam on every parameter (BNN_CDropout.py:114-133) -- on fixed batches, with the uniforms of every
+    torch.rand_like call captured.  Distinct p_logits per layer and noise_level = 0.7 so that every term of the regulariser shows.
+    Pins oracle.cdropout_train_steps and, on the GPU, the fused training kernel."""
+    import copy
+    torch.manual_seed(23)
+    model = ref_cdo.BNN_CDropout(5, nn.Tanh(), [24, 16], conf={"lr": 1e-2, "lscale": 0.3, "dr": 1.5})
+    model.noise_level = 0.7
+    cls = [l for l in model.nn.nn if isinstance(l, ref_cdo.CDropoutLinear)]
+    with torch.no_grad():
+        for l, pl in zip(cls, (-2.0, -0.5, 0.4)):
+            l.layer[0].p_logit.fill_(pl)
+    N, B = 41, 16
+    X = torch.randn(N, 5)
+    y = torch.sin(X.sum(dim=1))
+    perm = torch.randperm(N)
+    batches = [perm[0:16], perm[16:32], perm[32:41]]
+    net0 = [(l.layer[1].weight.detach().clone(), l.layer[1].bias.detach().clone()) for l in cls]
+    pl0 = [l.layer[0].p_logit.detach().clone() for l in cls]
+    num_train = N
+    rng = torch.get_rng_state()
+
+    def run(m, record):
+        opt = torch.optim.Adam(m.nn.parameters(), lr=m.lr)              # BNN_CDropout.py:116
+        crit = nn.MSELoss(reduction='sum')
+        stats = []
+        for idx in batches:                                            # BNN_CDropout.py:123-133, verbatim
+            bx, by = X[idx], y[idx]
+            opt.zero_grad()
+            py = m.nn(bx).squeeze()
+            mse_loss = crit(py, by)
+            wreg, ent = m.reg()
+            wreg *= bx.shape[0] / num_train
+            ent *= bx.shape[0] / num_train
+            loss = mse_loss + (wreg - ent)
+            loss.backward()
+            opt.step()
+            stats.append((float(mse_loss.detach()), float(wreg.detach()), float(ent.detach())))
+        return stats
+    ref_model = copy.deepcopy(model)
+    ref_stats = run(ref_model, False)                                  # (1) the unmodified reference: the fixture's targets
+    torch.set_rng_state(rng)                                           # (2) the same run with torch.rand_like wrapped to record
+    rec = []
+    orig = torch.rand_like
+
+    def wrapped(t, *a, **k):
+        u = orig(t, *a, **k)
+        rec.append(u.clone())
+        return u
+    torch.rand_like = wrapped
+    try:
+        stats = run(model, True)
+    finally:
+        torch.rand_like = orig
+    assert stats == ref_stats
+    rcls = [l for l in ref_model.nn.nn if isinstance(l, ref_cdo.CDropoutLinear)]
+    net1 = [(l.layer[1].weight.detach().clone(), l.layer[1].bias.detach().clone()) for l in rcls]
+    pl1 = [l.layer[0].p_logit.detach().clone() for l in rcls]
+    for (W, b), l in zip(net1, cls):
+        assert torch.equal(W, l.layer[1].weight) and torch.equal(b, l.layer[1].bias)
+    nl = len(cls)
+    assert len(rec) == len(batches) * nl
+    us = [[rec[i * nl + l] for l in range(nl)] for i in range(len(batches))]
+    o_net, o_pl, o_stats = O.cdropout_train_steps(net0, pl0, X, y, batches, "tanh", us, num_train, noise_level=0.7, lr=1e-2,
+                                                  lscale=0.3, dr=1.5)
+    for (W, b), (W1, b1) in zip(o_net, net1):
+        assert torch.allclose(W, W1, rtol=1e-5, atol=1e-7) and torch.allclose(b, b1, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(torch.stack(o_pl), torch.stack(pl1), rtol=1e-5, atol=1e-7)
+    assert np.allclose(np.array(o_stats), np.array(ref_stats), rtol=1e-6)
+    kw = {}
+    for l in range(nl):
+        kw[f"W0_{l}"], kw[f"b0_{l}"], kw[f"W1_{l}"], kw[f"b1_{l}"] = net0[l][0], net0[l][1], net1[l][0], net1[l][1]
+        for i in range(len(batches)):
+            kw[f"u{i}_{l}"] = us[i][l]
+    save("cdropout_train.npz", dims=[5, 24, 16, 1], act="tanh", lr=1e-2, lscale=0.3, dr=1.5, noise_level=0.7, batch=B, X=X, y=y,
+         perm=perm.numpy().astype(np.int64), stats=np.array(ref_stats, dtype=np.float32),
+         p_logit0=torch.stack(pl0), p_logit1=torch.stack(pl1), **kw)
+
+
 if __name__ == "__main__":
     gen_sgdmc_boston()
     gen_sgdmc_multiout()
@@ -477,3 +557,4 @@ if __name__ == "__main__":
     gen_sgdmc_energy()
     gen_bbb_train()
     gen_dropout_train()
+    gen_cdropout_train()

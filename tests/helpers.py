@@ -145,3 +145,22 @@ def dropout_train_case():
     B, N = case["batch"], case["X"].shape[0]
     case["batches"] = [case["perm"][i * B: min(N, (i + 1) * B)] for i in range(n_steps)]
     return case
+
+
+def cdropout_train_case():
+    """The reference-generated fixture of three BNN_CDropout training steps (tests/golden/cdropout_train.npz;
+    make_golden.gen_cdropout_train)."""
+    g = golden("cdropout_train.npz")
+    dims = [int(v) for v in g["dims"]]
+    nl = len(dims) - 1
+    t = lambda a: torch.as_tensor(a)
+    case = {"dims": dims, "act": str(g["act"]), "lr": float(g["lr"]), "lscale": float(g["lscale"]), "dr": float(g["dr"]),
+            "noise_level": float(g["noise_level"]), "batch": int(g["batch"]), "X": t(g["X"]), "y": t(g["y"]),
+            "perm": t(g["perm"]).long(), "stats": g["stats"], "p_logit0": t(g["p_logit0"]), "p_logit1": t(g["p_logit1"]),
+            "net0": [(t(g[f"W0_{l}"]), t(g[f"b0_{l}"])) for l in range(nl)],
+            "net1": [(t(g[f"W1_{l}"]), t(g[f"b1_{l}"])) for l in range(nl)]}
+    n_steps = case["stats"].shape[0]
+    case["us"] = [[t(g[f"u{i}_{l}"]) for l in range(nl)] for i in range(n_steps)]
+    B, N = case["batch"], case["X"].shape[0]
+    case["batches"] = [case["perm"][i * B: min(N, (i + 1) * B)] for i in range(n_steps)]
+    return case

@@ -158,3 +158,15 @@ def test_dropout_train_steps_golden():
         for k in ks:
             assert k.shape[0] == c["batches"][i].shape[0]
             assert bool(((k == 0) | ((k - 1).abs() < 1e-6)).all())
+
+
+def test_cdropout_train_steps_golden():
+    """f2: the oracle's restatement of the BNN_CDropout training step against the reference's own three steps."""
+    from helpers import cdropout_train_case
+    c = cdropout_train_case()
+    net, pl, stats = O.cdropout_train_steps(c["net0"], list(c["p_logit0"]), c["X"], c["y"], c["batches"], c["act"], c["us"],
+                                            c["X"].shape[0], noise_level=c["noise_level"], lr=c["lr"], lscale=c["lscale"], dr=c["dr"])
+    for (W, b), (W1, b1) in zip(net, c["net1"]):
+        assert torch.allclose(W, W1, rtol=1e-6, atol=1e-7) and torch.allclose(b, b1, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(torch.stack(pl), c["p_logit1"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(np.array(stats), c["stats"], rtol=1e-6)
