@@ -29,10 +29,11 @@ def build(force=False, verbose=False, trace=False):
     """trace=True builds libbnn_b200_trace.so: the same library with the in-kernel timeline probes of the tensor-core
     forward compiled in (-DBNN_TC_TRACE_BUILD; debugging only, see tools/tc_trace.py)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objdir = os.path.join(HERE, "build_trace" if trace else "build")
-    lib = LIB.replace(".so", "_trace.so") if trace else LIB
+    tag = "trace" if trace else os.environ.get("BNN_BUILD_TAG", "")     # BNN_BUILD_TAG=x: experiment build libbnn_b200_x.so
+    objdir = os.path.join(HERE, "build_" + tag if tag else "build")
+    lib = LIB.replace(".so", "_" + tag + ".so") if tag else LIB
     flags = NVCC_FLAGS + (["-DBNN_TC_TRACE_BUILD"] if trace else [])
-    for knob in ("BNN_SG_MI",):                 # experiment knobs (compile-time)
+    for knob in ("BNN_SG_MI", "BNN_TC_SETS", "BNN_TC_REG_E1", "BNN_TC_REG_E2", "BNN_TC_REG_MMA", "BNN_TC_REG_SLACK"):   # experiment knobs (compile-time)
         if os.environ.get(knob):
             flags = flags + [f"-D{knob}=" + os.environ[knob]]
     os.makedirs(objdir, exist_ok=True)

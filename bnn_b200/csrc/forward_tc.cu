@@ -30,8 +30,36 @@
 
 namespace bnn {
 
-constexpr int kTcThreads = 544;       // WG-A (8 warps) + WG-B (8 warps) + 1 MMA/loader warp
-constexpr int kTcMmaWarp = 16;
+// Warp roles.  BNN_TC_SETS = number of epilogue-1 warp sets (4 warps each, one per TMEM lane quarter; a set takes every
+// BNN_TC_SETS-th 16-column stage of a tile).  2: 8 + 8 + 1 = 17 warps (allocated like 20: 96 registers per thread).
+// 3: 12 + 8 + 1 (+ 3 idle warps completing the last warpgroup) = 24 warps launched at 80 registers per thread and rebalanced
+// with setmaxnreg: the MMA / loader warpgroup gives registers back, the epilogue-2 warpgroups (which keep a 32-column TMEM
+// batch, the running sums and the FP64 Welford state in registers) take them.
+#ifndef BNN_TC_SETS
+#define BNN_TC_SETS 2
+#endif
+constexpr int kTcSets = BNN_TC_SETS;
+static_assert(kTcSets == 2 || kTcSets == 3, "BNN_TC_SETS must be 2 or 3");
+constexpr int kTcE1Warps = 4 * kTcSets;
+constexpr int kTcE1Threads = 32 * kTcE1Warps;
+constexpr int kTcMmaWarp = kTcE1Warps + 8;
+constexpr int kTcThreads = kTcSets == 2 ? 544 : 768;
+#ifndef BNN_TC_REG_E2
+#define BNN_TC_REG_E2 88
+#endif
+#ifndef BNN_TC_REG_MMA
+#define BNN_TC_REG_MMA 40
+#endif
+#ifndef BNN_TC_REG_E1
+#define BNN_TC_REG_E1 88
+#endif
+#ifndef BNN_TC_REG_SLACK
+#define BNN_TC_REG_SLACK 0      /* registers of the SM the launch left unallocated (65536 - 768 x 80 = 4096), if the pool has them */
+#endif
+// registers released by the MMA warpgroup must cover what the epilogue warpgroups request (setmaxnreg.inc blocks otherwise)
+static_assert(kTcSets == 2 || 128 * (80 - BNN_TC_REG_MMA) >= 384 * (BNN_TC_REG_E1 - 80) + 256 * (BNN_TC_REG_E2 - 80) - BNN_TC_REG_SLACK, "register budget");
+template <int kRegs> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 constexpr int kTcRing = 6;            // max A2 ring stages
 constexpr int kTcStageCols = 32;       // one A2 stage = 16 K-columns (two K = 8 MMA steps) in tensor memory: hi[16] then lo[16]
 
@@ -382,6 +410,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + (uint32_t)p.N1, tmem_a2 = tmem_d2 + (uint32_t)p.N2;
 
+  if (warp >= kTcMmaWarp) {
+    if constexpr (kTcSets == 3) setmaxnreg_dec<BNN_TC_REG_MMA>();   // whole warpgroup (warps 20-23); 21-23 have no other work
+  }
   if (warp == kTcMmaWarp) {
     // ===================== weight loader + MMA issuer =========================================================
     // The whole warp runs this loop CONVERGED with warp-uniform variables; only the tcgen05 / bulk-copy issue is
@@ -544,8 +575,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         trace_ev(tr, 0, tn, 21, tile_cnt);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < kTcE1Warps) {
     // ===================== WG-A: A1 + epilogue 1; thread = one point (TMEM lane) ===============================
+    if constexpr (kTcSets == 3 && BNN_TC_REG_E1 < 80) setmaxnreg_dec<BNN_TC_REG_E1>();
+    if constexpr (kTcSets == 3 && BNN_TC_REG_E1 > 80) setmaxnreg_inc<BNN_TC_REG_E1>();
     const int quarter = warp & 3, set = warp >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
@@ -600,8 +633,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
       float* m0 = mk_base + ((sm - s0) & 1) * mk_sz;
       float* m1 = m0 + p.Dp;
       const int t256 = warp * 32 + lane;
-      if (has_m0) for (int j = t256; j < p.D; j += 256) m0[j] = tc_mask_value(p, p.sample_offset + sm, sm, 0, p.m_off[0] + j);
-      if (has_m1) for (int j = t256; j < p.N1; j += 256) m1[j] = j < p.H1 ? tc_mask_value(p, p.sample_offset + sm, sm, 1, p.m_off[1] + j) : 0.0f;
+      if (has_m0) for (int j = t256; j < p.D; j += kTcE1Threads) m0[j] = tc_mask_value(p, p.sample_offset + sm, sm, 0, p.m_off[0] + j);
+      if (has_m1) for (int j = t256; j < p.N1; j += kTcE1Threads) m1[j] = j < p.H1 ? tc_mask_value(p, p.sample_offset + sm, sm, 1, p.m_off[1] + j) : 0.0f;
     };
     for (int s = s0; s < s1; ++s) {
       const bool reload = !p.shared_w || s == s0;
@@ -611,10 +644,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
       if (has_m0 || has_m1) {
         // masks are drawn ONE SAMPLE AHEAD (the next sample's first A1 needs them during this sample's last tile): every
         // WG-A warp has left sample s - 1, whose buffer is the one overwritten now (named barrier 5)
-        named_bar_sync(5, 256);
+        named_bar_sync(5, kTcE1Threads);
         if (s == s0) draw_masks(s0);
         if (s + 1 < s1) draw_masks(s + 1);
-        named_bar_sync(5, 256);
+        named_bar_sync(5, kTcE1Threads);
       }
       mk0 = mk_base + ((s - s0) & 1) * mk_sz;
       mk1 = mk0 + p.Dp;
@@ -679,7 +712,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
           constexpr bool kMasked = decltype(masked_tag)::value;
           uint32_t d[16];
           if (set < n_b2) tc::tmem_ld16_issue(tmem_d1 + lane_sel + (uint32_t)(set * 16), d);
-          for (int b = set; b < n_b2; b += 2) {
+          for (int b = set; b < n_b2; b += kTcSets) {
             const int c0 = b * 16;
             const uint32_t gb = tile_cnt * (uint32_t)n_b2 + (uint32_t)b;   // global stage-use index
             // ring slot / use parity of stage gb, advanced incrementally (gb % ring and gb / ring cost ~25 instructions)
@@ -719,7 +752,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
                 for (int e = 0; e < 4; ++e) lo[q4 * 4 + e] = __float_as_uint(l[e]);
               }
             }
-            if (b + 2 < n_b2) tc::tmem_ld16_issue(tmem_d1 + lane_sel + (uint32_t)(c0 + 32), d);   // next stage of this warp
+            if (b + kTcSets < n_b2) tc::tmem_ld16_issue(tmem_d1 + lane_sel + (uint32_t)(c0 + 16 * kTcSets), d);   // next stage of this warp
             const uint32_t st = ring_st;
             trace_ev(tr, who, tn, 12, gb);
             mbar_wait(&bars[BAR_A2_EMPTY + st], ring_use ^ 1u);   // the MMAs that read this stage's previous contents are done
@@ -737,14 +770,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         else epilogue1(std::false_type{});
       }
     }
-  } else {
+  } else if (warp < kTcMmaWarp) {
     // ===================== WG-B: epilogue 2 + predictive reduction; thread = one point ===============================
-    const int quarter = warp & 3, half = (warp - 8) >> 2;
+    if constexpr (kTcSets == 3 && BNN_TC_REG_E2 > 80) setmaxnreg_inc<BNN_TC_REG_E2>();
+    const int quarter = warp & 3, half = (warp - kTcE1Warps) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     uint32_t tile_cnt = 0, tn = 0;
     unsigned long long* tr = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && quarter == 0 && (p.trace_mask & 4)) ? p.trace : nullptr;
-    const int who = 3 + half;
+    const int who = 1 + kTcSets + half;
     const long long M = p.N * p.O;
     double* st_mean = p.part ? p.part + (long long)g * 2 * M : nullptr;
     double* st_m2 = p.part ? st_mean + M : nullptr;
@@ -763,7 +797,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
       if (!p.shared_w || s == s0) mbar_wait(&bars[BAR_W_FULL], (uint32_t)(s - s0) & 1u);
       if (has_m2) {
         named_bar_sync(6, 256);
-        const int t256 = (warp - 8) * 32 + lane;
+        const int t256 = (warp - kTcE1Warps) * 32 + lane;
         for (int j = t256; j < p.N2; j += 256) {
           const float m = j < p.H2 ? tc_mask_value(p, p.sample_offset + s, s, 2, p.m_off[2] + j) : 0.0f;
           for (int o = 0; o < p.O; ++o) w3m[o * p.N2 + j] = w3s[o * p.N2 + j] * m;
@@ -1305,7 +1339,7 @@ int forward_tc(const BnnForwardArgs* a, cudaStream_t st) {
 #ifdef BNN_TC_TRACE_BUILD
   if (getenv("BNN_TC_TRACE")) {   // debug only: leaks one small buffer per call
     unsigned long long* tb = nullptr;
-    if (cudaMalloc(&tb, 5 * 4096 * 16) == cudaSuccess) { cudaMemsetAsync(tb, 0, 5 * 4096 * 16, st); p.trace = tb; g_tc_trace = tb; p.trace_mask = atoi(getenv("BNN_TC_TRACE")); }
+    if (cudaMalloc(&tb, 6 * 4096 * 16) == cudaSuccess) { cudaMemsetAsync(tb, 0, 6 * 4096 * 16, st); p.trace = tb; g_tc_trace = tb; p.trace_mask = atoi(getenv("BNN_TC_TRACE")); }
   }
 #endif
   {
