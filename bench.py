@@ -299,6 +299,7 @@ def run_ours(args):
     precisions = None
     bbb_train = None
     dropout_train = None
+    sgld_cfg1 = None
     if world == 1 and not args.no_configs:
         try:
             configs = config_blocks(dev)
@@ -314,6 +315,10 @@ def run_ours(args):
             bbb_train = bbb_train_block(dev)
         except Exception as e:
             bbb_train = {"error": repr(e)[:300]}
+        try:
+            sgld_cfg1 = sgld_cfg1_block(dev)
+        except Exception as e:
+            sgld_cfg1 = {"error": repr(e)[:300]}
         try:
             dropout_train = dropout_train_block(dev)
         except Exception as e:
@@ -385,7 +390,7 @@ def run_ours(args):
             "cpu_baseline": cpu_base if cpu_base is not None else {"value": None, "unit": UNIT, "cores": cores, "kind": "port",
                                                                    "sample": "not timed at N > 1 (rank 0 at N = 1 only)"},
             "clocks": clk, "outputs_finite": finite, "spot_check": spot, "sgld": sgld, "configs": configs,
-            "precision_modes": precisions, "bbb_train": bbb_train, "dropout_train": dropout_train,
+            "precision_modes": precisions, "bbb_train": bbb_train, "dropout_train": dropout_train, "sgld_cfg1": sgld_cfg1,
         }
         _emit(line)
     if world > 1:
@@ -517,6 +522,40 @@ def bbb_train_block(dev):
             "steps_per_s": 1e6 / us, "us_per_step": us, "state_finite": bool(torch.isfinite(tr.mu).all()),
             "cpu": {"steps_per_s": cpu, "cores": cpu_threads, "kind": "port",
                     "sample": f"{n_cpu} steps, torch CPU autograd + Adam, best of 1 / all threads"}}
+
+
+def sgld_cfg1_block(dev):
+    """cfg 1's training job as the reference runs it (experiments/SGDMC.py: 13-50-1 ReLU, batch 32, 455 training rows, 2500 burn-in
+    + 2500 sampling steps, keep_every 50): BNN_SGDMC.train end to end, wall clock, on the single-SM step kernel the library picks
+    for a chain this small and -- for comparison -- on the multi-CTA dataflow kernel (BNN_SGLD_SMALL=0)."""
+    import torch
+    import torch.nn as nn
+    from bnn_b200.BNN_SGDMC import BNN_SGDMC
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn(455, 13, generator=g)
+    y = torch.sin(X[:, 0]) + 0.3 * X[:, 1] + 0.1 * torch.randn(455, generator=g)
+    out = {"workload": "cfg1 training: BNN_SGDMC.train, 13-50-1 ReLU, batch 32, 455 rows, 2500 + 2500 steps, keep_every 50 "
+                       "(launches end at epoch boundaries: <= 15 steps each)"}
+    for name, env in (("single_sm", "1"), ("dataflow", "0")):
+        os.environ["BNN_SGLD_SMALL"] = env
+        try:
+            best = None
+            for rep in range(3):
+                m = BNN_SGDMC(13, nn.ReLU(), [50], nout=1, conf={"device": str(dev), "seed": 5})
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                m.train(X, y)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            rmse, nll = m.validate(X, y, num_samples=50)
+            out[name] = {"train_s": best, "steps_per_s": 5000 / best, "us_per_step": best / 5000 * 1e6,
+                         "train_rmse": float(rmse), "train_nll": float(nll)}
+        finally:
+            os.environ.pop("BNN_SGLD_SMALL", None)
+    out["kernel"] = ("sgld_small_kernel (one CTA, chain state in shared memory for the whole launch: gather, forward, Gaussian head, "
+                     "backward, prior gradient, pSGLD update with in-kernel Philox; CTA barriers only)")
+    return out
 
 
 def dropout_train_block(dev):

@@ -33,7 +33,7 @@ def build(force=False, verbose=False, trace=False):
     objdir = os.path.join(HERE, "build_" + tag if tag else "build")
     lib = LIB.replace(".so", "_" + tag + ".so") if tag else LIB
     flags = NVCC_FLAGS + (["-DBNN_TC_TRACE_BUILD"] if trace else [])
-    for knob in ("BNN_SG_MI", "BNN_TC_SETS", "BNN_TC_REG_E1", "BNN_TC_REG_E2", "BNN_TC_REG_MMA", "BNN_TC_REG_SLACK"):   # experiment knobs (compile-time)
+    for knob in ("BNN_SG_MI", "BNN_TC_SETS", "BNN_TC_REG_E1", "BNN_TC_REG_E2", "BNN_TC_REG_MMA", "BNN_TC_REG_SLACK", "BNN_DT_THREADS"):   # experiment knobs (compile-time)
         if os.environ.get(knob):
             flags = flags + [f"-D{knob}=" + os.environ[knob]]
     os.makedirs(objdir, exist_ok=True)

@@ -27,18 +27,28 @@
 
 namespace bnn {
 
-constexpr int kDtThreads = 1024;
+#ifndef BNN_DT_THREADS
+#define BNN_DT_THREADS 1024
+#endif
+constexpr int kDtThreads = BNN_DT_THREADS;
 constexpr uint32_t STREAM_DROPOUT_TRAIN = 6;
 
 struct DtLayer {
   int in, out, ld, masked;
-  long long off;      // float offset of the layer in the packed vector
-  int a_off;          // shared-memory float offset of this layer's (masked, augmented) input [B][ld]
+  int lp;             // shared-memory row pitch of the layer's weight rows AND of its input rows: ld rounded up so that lp / 4 is
+                      // odd -- eight threads reading float4s of eight different rows then hit eight different bank groups
+  int half;           // ceil(out / 2): a thread of the forward / parameter phases owns output units j and j + half
+  int k4p;            // float4 columns of the input, rounded up to a multiple of 8 (lane mapping of the input-gradient phase)
+  long long off;      // float offset of the layer in the packed vector (global memory, row pitch ld)
+  int soff;           // float offset of the layer in the shared-memory copies of W / m / v (row pitch lp)
+  int a_off;          // shared-memory float offset of this layer's (masked, augmented) input [Bp][lp]
   long long m_off;    // offset of this layer's keep mask in the per-step mask block ([B][in]); -1 = not masked
 };
 
 struct DtParams {
   int L, act, B, nout, D;
+  int Bp, gp;                               // batch rounded up to 4; pitch of the transposed gradient panels (Bp + 4: gp / 4 odd)
+  int sP;                                   // floats of one shared-memory parameter vector (pitch lp)
   DtLayer ly[BNN_MAX_LINEAR];
   long long stride, mask_per_step;
   float* W; float* adam;                    // global: [stride], [2][stride] = m, v
@@ -89,27 +99,47 @@ __device__ __forceinline__ float dt_act_bwd(float a, int act) {   // derivative 
   }
 }
 
+// ---- the kernel ------------------------------------------------------------------------------------------------------------
+// Thread tiles (the shared-memory pipe, not the FMA pipe, bounds a one-SM step: every phase is arranged so that a thread issues
+// at most ~6 LDS.128 per 32 FMAs, and so that the float4s a quarter-warp reads are either one address or eight bank groups):
+//   forward    out[b][j]:  4 rows b x 2 units (j, j + half); consecutive threads = consecutive j  (x: broadcast, W: 8 rows)
+//   input grad dh[b][k]:   4 rows b x 4 columns k, the sum over j split over 4 lanes (lane bits 3-4) and folded by shuffles;
+//                          lane bits 0-2 = consecutive float4 columns (W: contiguous, gT: broadcast)
+//   parameters dW[j][k]:   2 units (j, j + half) x 4 columns k over the batch in steps of 4 rows, then Adam on those 8 entries
+// The gradient panels are kept TRANSPOSED (gT[unit][row], pitch gp) so that both backward phases read them as float4s.
 template <bool CONCRETE>
 __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __grid_constant__ DtParams p) {
   extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   constexpr int kWarps = kDtThreads / 32;
-  const long long P = p.stride;
+  const int sP = p.sP;
   float* s_w = sm;
-  float* s_m = s_w + P;
-  float* s_v = s_m + P;
+  float* s_m = s_w + sP;
+  float* s_v = s_m + sP;
   float* s_act = sm + p.sm_act;
-  float* s_ga = sm + p.sm_g0;   // dL/d(out) of the current layer [B][max_w] ...
+  float* s_ga = sm + p.sm_g0;   // dL/d(out) of the current layer, transposed [max_w][gp] ...
   float* s_gb = sm + p.sm_g1;   // ... and of the layer below (ping-pong)
-  float* s_y = sm + p.sm_y;
+  float* s_y = sm + p.sm_y;     // [B][nout] targets, then [B][nout] predictions
   double* s_red = reinterpret_cast<double*>(sm + p.sm_red);   // [warps]: loss partial sums
   double* s_redp = s_red + kWarps;                            // [warps]: p_logit gradient partial sums (concrete)
   double* s_redw = s_redp + kWarps;                           // [L][warps]: sum(W^2) partial sums (concrete)
   double* s_w2 = s_redw + BNN_MAX_LINEAR * kWarps;            // [L] sum(W_l^2) at the start of the step; [L] = the launch's loss sum
   float* s_cd = sm + p.sm_cd;                                 // [L][kCdStride]
+  const int L = p.L, B = p.B, Bp = p.Bp, gp = p.gp;
+  float* s_pred = s_y + B * p.nout;
 
-  for (long long i = tid; i < P; i += kDtThreads) { s_w[i] = p.W[i]; s_m[i] = p.adam[i]; s_v[i] = p.adam[P + i]; }
-  const int L = p.L, B = p.B;
+  // parameters and moments: global rows of pitch ld -> shared rows of pitch lp (pad columns zero)
+  for (int i = tid; i < 3 * sP; i += kDtThreads) sm[i] = 0.0f;
+  __syncthreads();
+  for (int l = 0; l < L; ++l) {
+    const DtLayer& Y = p.ly[l];
+    for (int i = tid; i < Y.out * Y.ld; i += kDtThreads) {
+      const int j = i / Y.ld, k = i - j * Y.ld;
+      const long long g = Y.off + i;
+      const int d = Y.soff + j * Y.lp + k;
+      s_w[d] = p.W[g]; s_m[d] = p.adam[g]; s_v[d] = p.adam[p.stride + g];
+    }
+  }
   float nv = 1.0f;
   if (CONCRETE) {
     if (tid < L) { s_cd[tid * kCdStride] = p.plogit[tid]; s_cd[tid * kCdStride + 1] = p.padam[tid]; s_cd[tid * kCdStride + 2] = p.padam[L + tid]; }
@@ -138,14 +168,14 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
       for (int l = 0; l < L; ++l) {
         const DtLayer& Y = p.ly[l];
         double part = 0.0;
-        for (int i = tid; i < Y.out * Y.ld; i += kDtThreads) {
-          const int k = i % Y.ld;
-          const float w = s_w[Y.off + i];
+        for (int i = tid; i < Y.out * Y.lp; i += kDtThreads) {
+          const int k = i % Y.lp;
+          const float w = s_w[Y.soff + i];
           if (k < Y.in) part += (double)(w * w);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if ((tid & 31) == 0) s_redw[l * kWarps + (tid >> 5)] = part;
+        if (lane == 0) s_redw[l * kWarps + (tid >> 5)] = part;
       }
       __syncthreads();
       if (tid < L) {
@@ -159,8 +189,8 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
       const DtLayer& Y0 = p.ly[0];
       float* a0 = s_act + Y0.a_off;
       const float lpr = CONCRETE ? s_cd[4] : 0.0f;
-      for (int i = tid; i < B * Y0.ld; i += kDtThreads) {
-        const int b = i / Y0.ld, k = i - b * Y0.ld;
+      for (int i = tid; i < Bp * Y0.lp; i += kDtThreads) {
+        const int b = i / Y0.lp, k = i - b * Y0.lp;
         float v = 0.0f;
         if (b < rows) {
           if (k < p.D) {
@@ -176,55 +206,77 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
       }
     }
     __syncthreads();
-    // ---- forward (thread = one output unit of one row; float4 along k over 16-byte aligned, zero-padded rows)
+    // ---- forward
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
       const DtLayer& Y = p.ly[l];
       const float* a = s_act + Y.a_off;
       const bool last = l + 1 == L;
-      float* nxt = last ? s_gb : s_act + p.ly[l + 1].a_off;        // the last layer's output goes to s_gb as "pred"
-      const int ldn = last ? p.nout : p.ly[l + 1].ld;
       const float lpr = (CONCRETE && !last) ? s_cd[(l + 1) * kCdStride + 4] : 0.0f;
-      for (int i = tid; i < B * Y.out; i += kDtThreads) {
-        const int b = i / Y.out, j = i - b * Y.out;
-        const float* ar = a + b * Y.ld;
-        const float* wr = s_w + Y.off + (long long)j * Y.ld;
-        float o = 0.0f;
-        for (int k = 0; k < Y.ld; k += 4) {
-          const float4 x = *reinterpret_cast<const float4*>(ar + k);
-          const float4 w = *reinterpret_cast<const float4*>(wr + k);
-          o = fmaf(x.x, w.x, o); o = fmaf(x.y, w.y, o); o = fmaf(x.z, w.z, o); o = fmaf(x.w, w.w, o);
+      const int n_item = (Bp >> 2) * Y.half;
+      for (int i = tid; i < n_item; i += kDtThreads) {
+        const int bq = i / Y.half, j0 = i - bq * Y.half, j1 = j0 + Y.half;
+        const bool two = j1 < Y.out;
+        const float* ar = a + (bq * 4) * Y.lp;
+        const float* w0 = s_w + Y.soff + j0 * Y.lp;
+        const float* w1 = two ? w0 + Y.half * Y.lp : w0;
+        float o[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { o[r][0] = 0.0f; o[r][1] = 0.0f; }
+        for (int k = 0; k < Y.lp; k += 4) {
+          const float4 wa = *reinterpret_cast<const float4*>(w0 + k);
+          const float4 wb = *reinterpret_cast<const float4*>(w1 + k);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(ar + r * Y.lp + k);
+            o[r][0] = fmaf(x.x, wa.x, o[r][0]); o[r][0] = fmaf(x.y, wa.y, o[r][0]);
+            o[r][0] = fmaf(x.z, wa.z, o[r][0]); o[r][0] = fmaf(x.w, wa.w, o[r][0]);
+            o[r][1] = fmaf(x.x, wb.x, o[r][1]); o[r][1] = fmaf(x.y, wb.y, o[r][1]);
+            o[r][1] = fmaf(x.z, wb.z, o[r][1]); o[r][1] = fmaf(x.w, wb.w, o[r][1]);
+          }
         }
-        if (b >= rows) o = 0.0f;
-        if (!last) {
-          o = apply_act(o, p.act);
-          const DtLayer& N = p.ly[l + 1];
-          if (N.masked && b < rows) o *= dt_keep<CONCRETE>(p, N, it, b, j, lpr);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int b = bq * 4 + r;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int j = c ? j1 : j0;
+            if (c && !two) continue;
+            float v = o[r][c];
+            if (last) {
+              if (b < B) s_pred[b * p.nout + j] = b < rows ? v : 0.0f;
+            } else {
+              const DtLayer& N = p.ly[l + 1];
+              v = b < rows ? apply_act(v, p.act) : 0.0f;
+              if (N.masked && b < rows) v *= dt_keep<CONCRETE>(p, N, it, b, j, lpr);
+              s_act[N.a_off + b * N.lp + j] = v;
+            }
+          }
         }
-        nxt[b * ldn + j] = o;
       }
       if (!last) {          // ones column and zero pad of the next layer's augmented input
         const DtLayer& N = p.ly[l + 1];
         float* an = s_act + N.a_off;
-        for (int i = tid; i < B * (N.ld - N.in); i += kDtThreads) {
-          const int b = i / (N.ld - N.in), k = N.in + (i - b * (N.ld - N.in));
-          an[b * N.ld + k] = (k == N.in && b < rows) ? 1.0f : 0.0f;
+        const int padw = N.lp - N.in;
+        for (int i = tid; i < Bp * padw; i += kDtThreads) {
+          const int b = i / padw, k = N.in + (i - b * padw);
+          an[b * N.lp + k] = (k == N.in && b < rows) ? 1.0f : 0.0f;
         }
       }
       __syncthreads();
     }
-    // ---- loss = sum (pred - y)^2 (MSELoss(reduction='sum'), BNN_Dropout.py:55); dL/d(pred) -> s_ga
+    // ---- loss = sum (pred - y)^2 (MSELoss(reduction='sum'), BNN_Dropout.py:55); dL/d(pred) -> s_ga (transposed)
     {
       double part = 0.0;
-      for (int i = tid; i < B * p.nout; i += kDtThreads) {
-        const int b = i / p.nout;
-        const float r = b < rows ? s_gb[i] - s_y[i] : 0.0f;
+      for (int i = tid; i < Bp * p.nout; i += kDtThreads) {
+        const int b = i / p.nout, o = i - b * p.nout;
+        const float r = b < rows ? s_pred[i] - s_y[i] : 0.0f;
         part += (double)r * (double)r;
-        s_ga[b * p.max_w + (i - b * p.nout)] = 2.0f * r;
+        s_ga[o * gp + b] = 2.0f * r;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if ((tid & 31) == 0) s_red[tid >> 5] = part;
+      if (lane == 0) s_red[tid >> 5] = part;
     }
     __syncthreads();
     if (tid == 0) {
@@ -258,36 +310,67 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
       // gradient of the layer's (unmasked, pre-dropout) input, through the keep mask and the activation below: needs the
       // weights BEFORE their update.  Concrete dropout also needs it at layer 0: the masked input's gradient drives p_logit.
       if (l > 0 || CONCRETE) {
-        const int q4 = (Y.in + 3) >> 2;
         const float lpr = CONCRETE ? s_cd[l * kCdStride + 4] : 0.0f;
-        float gp = 0.0f;
-        for (int i = tid; i < B * q4; i += kDtThreads) {
-          const int b = i / q4, k = (i - b * q4) * 4;
-          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int j = 0; j < Y.out; ++j) {
-            const float4 w = *reinterpret_cast<const float4*>(s_w + Y.off + (long long)j * Y.ld + k);
-            const float gj = g0[b * p.max_w + j];
-            g.x = fmaf(gj, w.x, g.x); g.y = fmaf(gj, w.y, g.y); g.z = fmaf(gj, w.z, g.z); g.w = fmaf(gj, w.w, g.w);
+        const int k4n = (Y.in + 3) >> 2, k8 = Y.k4p >> 3;
+        const int n_item = 32 * k8 * (Bp >> 2);                      // lane = k4 & 7 | part << 3; above: k4 >> 3, then the row quad
+        float gpart = 0.0f;
+        for (int i = tid; i < n_item; i += kDtThreads) {
+          const int part = (i >> 3) & 3, r = i >> 5;
+          const int k4 = (i & 7) + 8 * (r % k8), bq = r / k8;
+          const bool live = k4 < k4n;
+          float g[4][4];
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) g[rr][c] = 0.0f;
+          if (live) {
+            const float* wp = s_w + Y.soff + k4 * 4;
+            const float* gq = g0 + bq * 4;
+            for (int j = part; j < Y.out; j += 4) {
+              const float4 w = *reinterpret_cast<const float4*>(wp + j * Y.lp);
+              const float4 gj = *reinterpret_cast<const float4*>(gq + j * gp);
+              const float gs[4] = {gj.x, gj.y, gj.z, gj.w};
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr) {
+                g[rr][0] = fmaf(gs[rr], w.x, g[rr][0]); g[rr][1] = fmaf(gs[rr], w.y, g[rr][1]);
+                g[rr][2] = fmaf(gs[rr], w.z, g[rr][2]); g[rr][3] = fmaf(gs[rr], w.w, g[rr][3]);
+              }
+            }
           }
-          const float4 x = *reinterpret_cast<const float4*>(a + b * Y.ld + k);   // act(z) * keep
-          const float xs[4] = {x.x, x.y, x.z, x.w}, gs[4] = {g.x, g.y, g.z, g.w};
+          // fold the four partial sums (lanes differing in bits 3 and 4); afterwards lane `part` finishes column k4 * 4 + part
+          float mine[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            if (k + c < Y.in) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              float v = g[rr][c];
+              v += __shfl_xor_sync(0xffffffffu, v, 8);
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              if (c == part) mine[rr] = v;
+            }
+          }
+          const int k = k4 * 4 + part;
+          if (live && k < Y.in) {
+            float out4[4];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const int b = bq * 4 + rr;
+              const float xs = a[b * Y.lp + k];                                     // act(z) * keep
               float keep = 1.0f;
-              if (Y.masked) keep = b < rows ? dt_keep<CONCRETE>(p, Y, it, b, k + c, lpr) : 0.0f;
-              if (CONCRETE) gp -= gs[c] * xs[c] * (1.0f - keep);      // d keep / d z = -(1 - keep) keep / T; xs = act * keep
+              if (Y.masked) keep = b < rows ? dt_keep<CONCRETE>(p, Y, it, b, k, lpr) : 0.0f;
+              if (CONCRETE) gpart -= mine[rr] * xs * (1.0f - keep);                 // d keep / d z = -(1 - keep) keep / T; xs = act * keep
               // where keep is not 0 the unmasked activation is xs / keep (Bernoulli: keep is 0 or within an ulp of 1;
               // concrete: keep = 1 - sigmoid is 0 or at least 2^-24)
-              if (l > 0) g1[b * p.max_w + k + c] = keep != 0.0f ? gs[c] * keep * dt_act_bwd(xs[c] / keep, p.act) : 0.0f;
+              out4[rr] = keep != 0.0f ? mine[rr] * keep * dt_act_bwd(xs / keep, p.act) : 0.0f;
             }
+            if (l > 0) *reinterpret_cast<float4*>(g1 + k * gp + bq * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
           }
         }
         if (CONCRETE) {
-          double part = (double)gp;
+          double part = (double)gpart;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-          if ((tid & 31) == 0) s_redp[tid >> 5] = part;
+          if (lane == 0) s_redp[tid >> 5] = part;
         }
       }
       __syncthreads();
@@ -302,30 +385,47 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
         const float greg = frac * nv * (-p.lscale2 * (float)s_w2[l] - 2.0f * p.dr * (float)Y.in * (logf(1.0f - pr) - logf(pr)));
         c[5] = ((float)s * kCdInvTemp * dzdp + greg) * dpdl;
       }
-      // parameters: thread = four consecutive (j, k..k+3) entries: gradient over the batch, weight decay, Adam, in place
+      // parameters: thread = units (j, j + half) x four columns: gradient over the batch, weight decay, Adam, in place
       {
-        const int q4 = Y.ld >> 2;
+        const int q4 = Y.lp >> 2;
         const float decay = CONCRETE ? 2.0f * frac * p.lscale2 * (1.0f - s_cd[l * kCdStride + 3]) * nv : p.l2_reg;
-        for (int i = tid; i < Y.out * q4; i += kDtThreads) {
-          const int j = i / q4, k = (i - j * q4) * 4;
-          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int b = 0; b < B; ++b) {
-            const float4 x = *reinterpret_cast<const float4*>(a + b * Y.ld + k);
-            const float gj = g0[b * p.max_w + j];
-            g.x = fmaf(gj, x.x, g.x); g.y = fmaf(gj, x.y, g.y); g.z = fmaf(gj, x.z, g.z); g.w = fmaf(gj, x.w, g.w);
-          }
-          const float gs[4] = {g.x, g.y, g.z, g.w};
-          const long long w0 = Y.off + (long long)j * Y.ld + k;
+        const int n_item = Y.half * q4;
+        for (int i = tid; i < n_item; i += kDtThreads) {
+          const int j0 = i / q4, k = (i - j0 * q4) * 4, j1 = j0 + Y.half;
+          const bool two = j1 < Y.out;
+          const float* ga = g0 + j0 * gp;
+          const float* gb = two ? g0 + j1 * gp : ga;
+          float d[2][4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (k + c <= Y.in) {
-              const long long w = w0 + c;
-              const float wv = s_w[w];
-              // Adam's weight_decay (BNN_Dropout.py:43-51) / the gradient of wreg (BNN_CDropout.py:148): weights only
-              const float gr = k + c < Y.in ? fmaf(decay, wv, gs[c]) : gs[c];
-              const float m = p.beta1 * s_m[w] + om1 * gr, v = p.beta2 * s_v[w] + om2 * gr * gr;
-              s_m[w] = m; s_v[w] = v;
-              s_w[w] = wv - step_size * (m / (sqrtf(v) / bc2_sqrt + p.eps));
+          for (int c = 0; c < 4; ++c) { d[0][c] = 0.0f; d[1][c] = 0.0f; }
+          for (int b = 0; b < Bp; b += 4) {
+            const float4 u = *reinterpret_cast<const float4*>(ga + b);
+            const float4 v = *reinterpret_cast<const float4*>(gb + b);
+            const float us[4] = {u.x, u.y, u.z, u.w}, vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const float4 x = *reinterpret_cast<const float4*>(a + (b + rr) * Y.lp + k);
+              d[0][0] = fmaf(us[rr], x.x, d[0][0]); d[0][1] = fmaf(us[rr], x.y, d[0][1]);
+              d[0][2] = fmaf(us[rr], x.z, d[0][2]); d[0][3] = fmaf(us[rr], x.w, d[0][3]);
+              d[1][0] = fmaf(vs[rr], x.x, d[1][0]); d[1][1] = fmaf(vs[rr], x.y, d[1][1]);
+              d[1][2] = fmaf(vs[rr], x.z, d[1][2]); d[1][3] = fmaf(vs[rr], x.w, d[1][3]);
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h && !two) continue;
+            const int w0 = Y.soff + (h ? j1 : j0) * Y.lp + k;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (k + c <= Y.in) {
+                const int w = w0 + c;
+                const float wv = s_w[w];
+                // Adam's weight_decay (BNN_Dropout.py:43-51) / the gradient of wreg (BNN_CDropout.py:148): weights only
+                const float gr = k + c < Y.in ? fmaf(decay, wv, d[h][c]) : d[h][c];
+                const float m = p.beta1 * s_m[w] + om1 * gr, v = p.beta2 * s_v[w] + om2 * gr * gr;
+                s_m[w] = m; s_v[w] = v;
+                s_w[w] = wv - step_size * (m / (sqrtf(v) / bc2_sqrt + p.eps));
+              }
             }
           }
         }
@@ -341,7 +441,15 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
       c[0] -= step_size * (m / (sqrtf(v) / bc2_sqrt + p.eps));
     }
   }
-  for (long long i = tid; i < P; i += kDtThreads) { p.W[i] = s_w[i]; p.adam[i] = s_m[i]; p.adam[P + i] = s_v[i]; }
+  for (int l = 0; l < L; ++l) {
+    const DtLayer& Y = p.ly[l];
+    for (int i = tid; i < Y.out * Y.ld; i += kDtThreads) {
+      const int j = i / Y.ld, k = i - j * Y.ld;
+      const long long g = Y.off + i;
+      const int d = Y.soff + j * Y.lp + k;
+      p.W[g] = s_w[d]; p.adam[g] = s_m[d]; p.adam[p.stride + g] = s_v[d];
+    }
+  }
   if (CONCRETE) {
     if (tid < L) { p.plogit[tid] = s_cd[tid * kCdStride]; p.padam[tid] = s_cd[tid * kCdStride + 1]; p.padam[L + tid] = s_cd[tid * kCdStride + 2]; }
     if (tid == 0 && p.epoch_end)                                      // BNN_CDropout.py:134
@@ -364,25 +472,33 @@ static int dt_plan(const BnnMlpDesc* d, int batch, bool concrete, DtPlan* plan) 
   memset(&p, 0, sizeof(p));
   p.L = Lo.n_lin; p.act = Lo.act; p.B = batch; p.nout = Lo.out[Lo.n_lin - 1]; p.D = Lo.in[0];
   p.stride = (Lo.off[Lo.n_lin] + 3) & ~3LL;
-  long long act = 0, m = 0;
+  p.Bp = (batch + 3) & ~3;
+  p.gp = p.Bp + 4 - (p.Bp & 4);                                    // gp / 4 odd
+  if (((p.gp >> 2) & 1) == 0) p.gp += 4;
+  long long act = 0, m = 0, sP = 0;
   int max_w = p.nout;
   for (int l = 0; l < p.L; ++l) {
     DtLayer& Y = p.ly[l];
     Y.in = Lo.in[l]; Y.out = Lo.out[l]; Y.ld = Lo.ld[l]; Y.off = Lo.off[l];
+    Y.lp = ((Y.ld >> 2) & 1) ? Y.ld : Y.ld + 4;
+    Y.half = (Y.out + 1) >> 1;
+    Y.k4p = (((Y.in + 3) >> 2) + 7) & ~7;
+    Y.soff = (int)sP; sP += (long long)Y.out * Y.lp;
     Y.masked = (concrete || Y.in > 1) ? 1 : 0;                     // BNN_Dropout.py:18: "x.shape[1] > 1"; CDropout: every layer
-    Y.a_off = (int)act; act += (long long)batch * Y.ld;
+    Y.a_off = (int)act; act += (long long)p.Bp * Y.lp;
     Y.m_off = Y.masked ? m : -1;
     if (Y.masked) m += ((long long)batch * Y.in + 3) & ~3LL;
     if (Y.out > max_w) max_w = Y.out;
     if (Y.in + 1 > max_w) max_w = Y.in + 1;
   }
+  p.sP = (int)sP;
   p.mask_per_step = m;
   p.max_w = max_w;
-  long long f = 3 * p.stride;
+  long long f = 3 * sP;
   p.sm_act = (int)f; f += (act + 3) & ~3LL;
-  p.sm_g0 = (int)f; f += ((long long)batch * max_w + 3) & ~3LL;
-  p.sm_g1 = (int)f; f += ((long long)batch * max_w + 3) & ~3LL;
-  p.sm_y = (int)f; f += ((long long)batch * p.nout + 3) & ~3LL;
+  p.sm_g0 = (int)f; f += (long long)max_w * p.gp;
+  p.sm_g1 = (int)f; f += (long long)max_w * p.gp;
+  p.sm_y = (int)f; f += (2LL * p.Bp * p.nout + 3) & ~3LL;
   p.sm_red = (int)f; f += 2 * ((2 + BNN_MAX_LINEAR) * (kDtThreads / 32) + BNN_MAX_LINEAR + 1);
   p.sm_cd = (int)f; f += BNN_MAX_LINEAR * kCdStride;
   plan->smem = (size_t)f * 4;

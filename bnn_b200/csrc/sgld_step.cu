@@ -1103,6 +1103,384 @@ extern "C" int32_t bnn_sgld_init(const BnnSgldChain* c, int32_t cur, void* strea
   return 0;
 }
 
+// ---- the same step for networks that fit ONE SM ----------------------------------------------------------------------------
+// The reference's own SGLD use (experiments/SGDMC.py, BO.py: one hidden layer of 50 units, batch 32) is a 751-parameter chain:
+// a step is ~150 kFLOP, and on the dataflow kernel above it costs seven inter-SM hand-overs (~15 us).  When theta, V, the
+// batch's activations and two gradient panels fit one SM's shared memory, `sgld_small_kernel` runs the launch's n steps as ONE
+// CTA with the chain state resident in shared memory: gather -> forward -> Gaussian head -> per layer (input gradient, then
+// dW + prior gradient + pSGLD update of the thread's own entries) -> log-precision group, CTA barriers only.  Same arithmetic,
+// same Philox stream (seed, t, block = packed offset / 4) and same LambdaLR factors as the dataflow kernel, so the two are
+// interchangeable between launches (BNN_SGLD_SMALL=0 forces the dataflow kernel; tests compare them step for step).
+// Thread tiles as in csrc/dropout_train.cu: weight / activation rows at a pitch lp with lp / 4 odd, gradient panels transposed.
+constexpr int kSsThreads = 512;
+constexpr long long kSsMaxWork = 96 * 1024;
+struct SsLayer { int lp, half, k4p, soff, a_off; };
+struct SsParams {
+  SsLayer sy[BNN_MAX_LINEAR];
+  int sP, gp, max_w, hd;                 // hd = n_theta - n_head (log-precisions + pad)
+  int sm_v, sm_act, sm_g0, sm_g1, sm_y, sm_red, want_quad;
+  float* th_out; float* thT_out;         // buffer cur ^ (n_steps & 1)
+};
+
+__global__ void __launch_bounds__(kSsThreads, 1) sgld_small_kernel(const __grid_constant__ SgParams p, const __grid_constant__ SsParams q) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kSsThreads / 32;
+  float* s_th = sm;                        // [sP] network (pitch lp) | [hd] log-precisions
+  float* s_v = sm + q.sm_v;                // same shape
+  float* s_act = sm + q.sm_act;
+  float* s_ga = sm + q.sm_g0;
+  float* s_gb = sm + q.sm_g1;
+  float* s_y = sm + q.sm_y;                // [Bp][nout] targets, [Bp][nout] predictions
+  double* s_red = reinterpret_cast<double*>(sm + q.sm_red);   // [nout + 1][warps] partial sums: r^2 per output | prior quad
+  double* s_acc = s_red + (p.nout + 1) * kWarps;              // [nout + 1]
+  float* s_f = reinterpret_cast<float*>(s_acc + p.nout + 1);  // LambdaLR factor of the step
+  const int L = p.L, B = p.B, Bp = p.Bp, gp = q.gp, nout = p.nout;
+  float* s_pred = s_y + Bp * nout;
+  const float* th_in = p.theta[p.cur];
+  const bool debug = p.grad_out != nullptr;
+
+  for (int i = tid; i < q.sm_act; i += kSsThreads) sm[i] = 0.0f;
+  __syncthreads();
+  for (int l = 0; l < L; ++l) {
+    const SgLayer& Y = p.ly[l];
+    for (int i = tid; i < Y.out * Y.ld; i += kSsThreads) {
+      const int j = i / Y.ld, k = i - j * Y.ld;
+      const int d = q.sy[l].soff + j * q.sy[l].lp + k;
+      s_th[d] = th_in[Y.off + i];
+      s_v[d] = p.V[Y.off + i];
+    }
+  }
+  for (int i = tid; i < q.hd; i += kSsThreads) { s_th[q.sP + i] = th_in[p.n_head + i]; s_v[q.sP + i] = p.V[p.n_head + i]; }
+  __syncthreads();
+
+#pragma unroll 1
+  for (int it = 0; it < p.n_steps; ++it) {
+    const long long t = p.t0 + it;
+    const long long boff = p.perm_off + (long long)it * B;
+    const long long left = p.num_train - boff;
+    const int rows = left < B ? (int)left : B;
+    const float scale = (float)((double)p.num_train / (double)rows);   // N / |b|  (:83)
+    const bool want_quad = q.want_quad && it + 1 == p.n_steps;
+    if (tid == 0) *s_f = it == 0 ? p.f0 : (float)pow((double)(1 + t), -0.33);   // LambdaLR (:101)
+    // ---- gather (DataLoader batch, :80,110): augmented rows (x | 1 | 0), targets
+    {
+      const int lp0 = q.sy[0].lp;
+      float* a0 = s_act + q.sy[0].a_off;
+      for (int i = tid; i < Bp * lp0; i += kSsThreads) {
+        const int b = i / lp0, k = i - b * lp0;
+        float v = 0.0f;
+        if (b < rows) {
+          if (k < p.D) v = __ldg(p.X + __ldg(p.perm + boff + b) * p.D + k);
+          else if (k == p.D) v = 1.0f;
+        }
+        a0[i] = v;
+      }
+      for (int i = tid; i < Bp * nout; i += kSsThreads) {
+        const int b = i / nout;
+        s_y[i] = b < rows ? __ldg(p.y + __ldg(p.perm + boff + b) * nout + (i - b * nout)) : 0.0f;
+      }
+    }
+    __syncthreads();
+    // ---- forward: thread = 4 rows x units (j, j + half)
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+      const SgLayer& Y = p.ly[l];
+      const SsLayer& S = q.sy[l];
+      const float* a = s_act + S.a_off;
+      const bool last = l + 1 == L;
+      const int n_item = (Bp >> 2) * S.half;
+      for (int i = tid; i < n_item; i += kSsThreads) {
+        const int bq = i / S.half, j0 = i - bq * S.half, j1 = j0 + S.half;
+        const bool two = j1 < Y.out;
+        const float* ar = a + (bq * 4) * S.lp;
+        const float* w0 = s_th + S.soff + j0 * S.lp;
+        const float* w1 = two ? w0 + S.half * S.lp : w0;
+        float o[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { o[r][0] = 0.0f; o[r][1] = 0.0f; }
+        for (int k = 0; k < S.lp; k += 4) {
+          const float4 wa = *reinterpret_cast<const float4*>(w0 + k);
+          const float4 wb = *reinterpret_cast<const float4*>(w1 + k);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(ar + r * S.lp + k);
+            o[r][0] = fmaf(x.x, wa.x, o[r][0]); o[r][0] = fmaf(x.y, wa.y, o[r][0]);
+            o[r][0] = fmaf(x.z, wa.z, o[r][0]); o[r][0] = fmaf(x.w, wa.w, o[r][0]);
+            o[r][1] = fmaf(x.x, wb.x, o[r][1]); o[r][1] = fmaf(x.y, wb.y, o[r][1]);
+            o[r][1] = fmaf(x.z, wb.z, o[r][1]); o[r][1] = fmaf(x.w, wb.w, o[r][1]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int b = bq * 4 + r;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (c && !two) continue;
+            const int j = c ? j1 : j0;
+            const float v = b < rows ? o[r][c] : 0.0f;
+            if (last) s_pred[b * nout + j] = v;
+            else s_act[q.sy[l + 1].a_off + b * q.sy[l + 1].lp + j] = b < rows ? act_fwd(v, p.act) : 0.0f;
+          }
+        }
+      }
+      if (!last) {          // ones column and zero pad of the next layer's augmented input
+        const int nin = p.ly[l + 1].in, nlp = q.sy[l + 1].lp, padw = nlp - nin;
+        float* an = s_act + q.sy[l + 1].a_off;
+        for (int i = tid; i < Bp * padw; i += kSsThreads) {
+          const int b = i / padw, k = nin + (i - b * padw);
+          an[b * nlp + k] = (k == nin && b < rows) ? 1.0f : 0.0f;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- Gaussian head (:69-74,83): r = f - y, dU/d(out) = (N / |b|) prec r, sum r^2 per output
+    for (int o = 0; o < nout; ++o) {
+      const float prec = expf(s_th[q.sP + o]);
+      double part = 0.0;
+      for (int b = tid; b < Bp; b += kSsThreads) {
+        float dzv = 0.0f;
+        if (b < rows) {
+          const float r = s_pred[b * nout + o] - s_y[b * nout + o];
+          dzv = scale * prec * r;
+          part += (double)r * (double)r;
+        }
+        s_ga[o * gp + b] = dzv;
+      }
+#pragma unroll
+      for (int w = 16; w > 0; w >>= 1) part += __shfl_xor_sync(0xffffffffu, part, w);
+      if (lane == 0) s_red[o * kWarps + warp] = part;
+    }
+    __syncthreads();
+    if (tid < nout) {
+      double s = 0.0;
+      for (int w = 0; w < kWarps; ++w) s += s_red[tid * kWarps + w];
+      s_acc[tid] = s;
+    }
+    if (tid == 32) s_acc[nout] = 0.0;
+    // ---- backward, layer by layer from the top
+    const float lr_w = p.lr_w * *s_f;
+    float* g0 = s_ga;
+    float* g1 = s_gb;
+#pragma unroll 1
+    for (int l = L - 1; l >= 0; --l) {
+      const SgLayer& Y = p.ly[l];
+      const SsLayer& S = q.sy[l];
+      const float* a = s_act + S.a_off;
+      // dz_{l-1} = (dz_l theta_l) * act'(h_l): 4 rows x 4 columns per thread, the sum over j split over 4 lanes (bits 3-4)
+      if (l > 0) {
+        const int k4n = (Y.in + 3) >> 2, k8 = S.k4p >> 3;
+        const int n_item = 32 * k8 * (Bp >> 2);
+        for (int i = tid; i < n_item; i += kSsThreads) {
+          const int part = (i >> 3) & 3, r = i >> 5;
+          const int k4 = (i & 7) + 8 * (r % k8), bq = r / k8;
+          const bool live = k4 < k4n;
+          float g[4][4];
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) g[rr][c] = 0.0f;
+          if (live) {
+            const float* wp = s_th + S.soff + k4 * 4;
+            const float* gq = g0 + bq * 4;
+            for (int j = part; j < Y.out; j += 4) {
+              const float4 w = *reinterpret_cast<const float4*>(wp + j * S.lp);
+              const float4 gj = *reinterpret_cast<const float4*>(gq + j * gp);
+              const float gs[4] = {gj.x, gj.y, gj.z, gj.w};
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr) {
+                g[rr][0] = fmaf(gs[rr], w.x, g[rr][0]); g[rr][1] = fmaf(gs[rr], w.y, g[rr][1]);
+                g[rr][2] = fmaf(gs[rr], w.z, g[rr][2]); g[rr][3] = fmaf(gs[rr], w.w, g[rr][3]);
+              }
+            }
+          }
+          float mine[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              float v = g[rr][c];
+              v += __shfl_xor_sync(0xffffffffu, v, 8);
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              if (c == part) mine[rr] = v;
+            }
+          }
+          const int k = k4 * 4 + part;
+          if (live && k < Y.in) {
+            float out4[4];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) out4[rr] = mine[rr] * act_bwd(a[(bq * 4 + rr) * S.lp + k], p.act);
+            *reinterpret_cast<float4*>(g1 + k * gp + bq * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+          }
+        }
+      }
+      __syncthreads();
+      // dW tile (units (j, j + half) x 4 columns) + prior gradient W / std^2 (:65-66) + pSGLD update of those entries
+      {
+        const int q4 = S.lp >> 2;
+        const int n_item = S.half * q4;
+        double quad = 0.0;
+        for (int i = tid; i < n_item; i += kSsThreads) {
+          const int j0 = i / q4, k = (i - j0 * q4) * 4, j1 = j0 + S.half;
+          if (k >= Y.ld) continue;
+          const bool two = j1 < Y.out;
+          const float* ga = g0 + j0 * gp;
+          const float* gb = two ? g0 + j1 * gp : ga;
+          float d[2][4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { d[0][c] = 0.0f; d[1][c] = 0.0f; }
+          for (int b = 0; b < Bp; b += 4) {
+            const float4 u = *reinterpret_cast<const float4*>(ga + b);
+            const float4 v = *reinterpret_cast<const float4*>(gb + b);
+            const float us[4] = {u.x, u.y, u.z, u.w}, vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const float4 x = *reinterpret_cast<const float4*>(a + (b + rr) * S.lp + k);
+              d[0][0] = fmaf(us[rr], x.x, d[0][0]); d[0][1] = fmaf(us[rr], x.y, d[0][1]);
+              d[0][2] = fmaf(us[rr], x.z, d[0][2]); d[0][3] = fmaf(us[rr], x.w, d[0][3]);
+              d[1][0] = fmaf(vs[rr], x.x, d[1][0]); d[1][1] = fmaf(vs[rr], x.y, d[1][1]);
+              d[1][2] = fmaf(vs[rr], x.z, d[1][2]); d[1][3] = fmaf(vs[rr], x.w, d[1][3]);
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h && !two) continue;
+            const int j = h ? j1 : j0;
+            const int w0 = S.soff + j * S.lp + k;
+            const long long e = Y.off + (long long)j * Y.ld + k;          // multiple of 4: one Philox block per quad
+            float tt[4], g[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              tt[c] = s_th[w0 + c];
+              g[c] = d[h][c];
+              if (k + c < Y.in) {
+                g[c] = fmaf(Y.inv_var, tt[c], g[c]);
+                if (want_quad) quad += (double)(Y.inv_var * tt[c]) * (double)tt[c];
+              } else if (k + c > Y.in) g[c] = 0.0f;                          // layout padding: no gradient, no noise, stays zero
+            }
+            if (debug) {
+              *reinterpret_cast<float4*>(p.grad_out + e) = make_float4(g[0], g[1], g[2], g[3]);
+              continue;
+            }
+            float z[4];
+            philox_normal4(p.seed, (uint32_t)t, STREAM_SGLD, (uint64_t)(e >> 2), z);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (k + c <= Y.in) {
+                float vv = s_v[w0 + c];
+                psgld_update1(tt[c], vv, g[c], z[c], lr_w, p.alpha, p.lam, p.precond_mode);
+                s_th[w0 + c] = tt[c];
+                s_v[w0 + c] = vv;
+              }
+            }
+          }
+        }
+        if (want_quad) {
+#pragma unroll
+          for (int w = 16; w > 0; w >>= 1) quad += __shfl_xor_sync(0xffffffffu, quad, w);
+          if (lane == 0) s_red[nout * kWarps + warp] = quad;
+        }
+      }
+      __syncthreads();
+      if (want_quad && tid == 0) {
+        double s = s_acc[nout];
+        for (int w = 0; w < kWarps; ++w) s += s_red[nout * kWarps + w];
+        s_acc[nout] = s;
+      }
+      float* tsw = g0; g0 = g1; g1 = tsw;
+    }
+    // ---- U of the launch's last step (evaluated before the update of the log-precisions)
+    if (want_quad && tid == 0) {
+      float total_ll = 0.0f, total_lp = 0.0f;
+      for (int o = 0; o < nout; ++o) {
+        const float lp = s_th[q.sP + o], prec = expf(lp);
+        const float s2 = (float)s_acc[o];
+        total_ll += -0.5f * prec * s2 + (float)rows * (0.5f * lp - 0.91893853320467274178f);
+        total_lp += p.al * p.log_be + (p.al - 1.0f) * lp - p.be * prec - p.lgamma_al + lp;
+      }
+      const float logp = -0.5f * (float)s_acc[nout] - p.log_const + total_lp;
+      p.loss_out[0] = -(total_ll * scale + logp);
+    }
+    __syncthreads();
+    // ---- log-precision group (:62, :96-98): closed-form gradient, same update rule, lr_noise
+    if (tid < (q.hd >> 2)) {
+      const float lr_n = p.lr_n * *s_f;
+      const long long e = p.n_head + (long long)tid * 4;
+      float tt[4], vv[4], g[4], z[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tt[c] = s_th[q.sP + tid * 4 + c];
+        vv[c] = s_v[q.sP + tid * 4 + c];
+        g[c] = 0.0f;
+        const int o = tid * 4 + c;
+        if (o < nout) {
+          const float prec = expf(tt[c]);
+          const float s2 = (float)s_acc[o];
+          g[c] = -scale * (-0.5f * prec * s2 + 0.5f * (float)rows) - (p.al - p.be * prec);
+        }
+      }
+      if (debug) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) p.grad_out[e + c] = g[c];
+      } else {
+        philox_normal4(p.seed, (uint32_t)t, STREAM_SGLD, (uint64_t)(e >> 2), z);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (tid * 4 + c < nout) psgld_update1(tt[c], vv[c], g[c], z[c], lr_n, p.alpha, p.lam, p.precond_mode);
+          else tt[c] = 0.0f;
+          s_th[q.sP + tid * 4 + c] = tt[c];
+          s_v[q.sP + tid * 4 + c] = vv[c];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (debug) return;
+  // ---- the chain state goes back to global memory: theta / thetaT of buffer cur ^ (n_steps & 1), V
+  for (int l = 0; l < L; ++l) {
+    const SgLayer& Y = p.ly[l];
+    for (int i = tid; i < Y.out * Y.ld; i += kSsThreads) {
+      const int j = i / Y.ld, k = i - j * Y.ld;
+      const int d = q.sy[l].soff + j * q.sy[l].lp + k;
+      const float w = s_th[d];
+      q.th_out[Y.off + i] = w;
+      p.V[Y.off + i] = s_v[d];
+      if (l > 0 && k < Y.in) q.thT_out[Y.offT + (long long)k * Y.ldT + j] = w;
+    }
+  }
+  for (int i = tid; i < q.hd; i += kSsThreads) { q.th_out[p.n_head + i] = s_th[q.sP + i]; p.V[p.n_head + i] = s_v[q.sP + i]; }
+}
+
+// 0 = the single-SM kernel takes this chain; 1 = it does not fit
+static int ss_plan(const SgParams& p, SsParams* q, size_t* smem) {
+  memset(q, 0, sizeof(*q));
+  q->gp = p.Bp + 4 - (p.Bp & 4);                                   // gp / 4 odd
+  q->hd = (int)(p.n_theta - p.n_head);
+  long long sP = 0, act = 0;
+  int max_w = p.nout;
+  for (int l = 0; l < p.L; ++l) {
+    const SgLayer& Y = p.ly[l];
+    SsLayer& S = q->sy[l];
+    S.lp = ((Y.ld >> 2) & 1) ? Y.ld : Y.ld + 4;
+    S.half = (Y.out + 1) >> 1;
+    S.k4p = (((Y.in + 3) >> 2) + 7) & ~7;
+    S.soff = (int)sP; sP += (long long)Y.out * S.lp;
+    S.a_off = (int)act; act += (long long)p.Bp * S.lp;
+    if (Y.out > max_w) max_w = Y.out;
+    if (Y.in + 1 > max_w) max_w = Y.in + 1;
+  }
+  q->sP = (int)sP; q->max_w = max_w;
+  long long f = sP + q->hd;
+  q->sm_v = (int)f; f += sP + q->hd;
+  q->sm_act = (int)f; f += act;
+  q->sm_g0 = (int)f; f += (long long)max_w * q->gp;
+  q->sm_g1 = (int)f; f += (long long)max_w * q->gp;
+  q->sm_y = (int)f; f += (2LL * p.Bp * p.nout + 3) & ~3LL;
+  q->sm_red = (int)f; f += 2 * ((long long)(p.nout + 1) * (kSsThreads / 32) + p.nout + 1) + 4;
+  *smem = (size_t)f * 4;
+  return *smem <= (size_t)227 * 1024 ? 0 : 1;
+}
+
 static long long* g_sg_trace = nullptr;   // debug: set by bnn_sgld_trace
 static int g_sg_trace_grid = 0;
 
@@ -1123,6 +1501,26 @@ extern "C" int32_t bnn_sgld_run(const BnnSgldChain* c, int32_t cur, int64_t t0, 
   p.t0 = t0; p.n_steps = n_steps; p.cur = cur;
   p.loss_out = loss_out; p.grad_out = grad_out;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // networks that fit one SM: the single-CTA kernel (chain state in shared memory for the whole launch)
+    SsParams q;
+    size_t ssmem = 0;
+    // ... and whose step is small enough that one SM beats the hand-overs of the dataflow kernel (measured: 13-50-1 at batch 32
+    // 11.4 vs 15.4 us / step, 9-100-100-1 at batch 32 36.6 vs 26.4): packed parameters x batch rows <= kSsMaxWork.
+    // BNN_SGLD_SMALL = 0 never, 1 default rule, 2 whenever it fits (tests, probes).
+    const char* e = getenv("BNN_SGLD_SMALL");
+    const int mode = e ? atoi(e) : 1;
+    const bool small_enough = mode == 2 || p.n_head * (long long)p.Bp <= kSsMaxWork;
+    if (mode != 0 && small_enough && ss_plan(p, &q, &ssmem) == 0) {
+      const int nb = cur ^ (n_steps & 1);
+      q.th_out = p.theta[nb]; q.thT_out = p.thetaT[nb];
+      q.want_quad = loss_out != nullptr;
+      BNN_CUDA(cudaFuncSetAttribute(sgld_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+      sgld_small_kernel<<<1, kSsThreads, ssmem, st>>>(p, q);
+      BNN_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   // accumulators, job / completion counters and error flag start at zero for every launch
   BNN_CUDA(cudaMemsetAsync(p.acc, 0, (size_t)plan.tail_bytes, st));
   BNN_CUDA(cudaFuncSetAttribute(sgld_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));

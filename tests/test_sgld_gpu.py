@@ -291,3 +291,41 @@ def test_warm_start_restarts_optimizer_and_continues_from_the_module():
         pass
     assert not torch.equal(model.arch.pack([model.nn.nn])[0], before)
     assert w_edit.shape == before.shape
+
+
+@pytest.mark.parametrize("dims,act,B,N", [([13, 50, 1], "relu", 32, 455), ([9, 64, 64, 2], "tanh", 24, 200), ([5, 3], "relu", 8, 50)])
+def test_single_sm_kernel_equals_dataflow_kernel(dims, act, B, N, monkeypatch):
+    """Networks that fit one SM run in sgld_small_kernel (chain state in shared memory, one CTA); BNN_SGLD_SMALL=0 forces the
+    multi-CTA dataflow kernel.  Same arithmetic, same Philox stream, same LambdaLR factors: gradients, nine steps (short last
+    batch included), the loss, and a hand-over from one kernel to the other in the middle of a chain must agree."""
+    g = torch.Generator().manual_seed(11)
+    net = [((torch.rand(o, i, generator=g) - 0.5) * 0.6, (torch.rand(o, generator=g) - 0.5) * 0.1) for i, o in zip(dims[:-1], dims[1:])]
+    lp = torch.linspace(-0.2, 0.3, dims[-1])
+    X, y = torch.randn(N, dims[0], generator=g).cuda(), torch.randn(N, dims[-1], generator=g).cuda()
+    perm = torch.randperm(N, generator=g).cuda()
+    last = ((N + B - 1) // B - 1) * B                        # offset of the epoch's (possibly short) last batch
+    res = {}
+    for mode in ("small", "dataflow", "mixed"):
+        arch, chain = make_chain(dims, act, B, net, lp, seed=9)
+        chain.bind(X, y)
+        monkeypatch.setenv("BNN_SGLD_SMALL", "0" if mode == "dataflow" else "2")
+        grad, gloss = chain.grad(perm, 0)
+        chain.run(perm, 0, 4)
+        if mode == "mixed":
+            monkeypatch.setenv("BNN_SGLD_SMALL", "0")
+        chain.run(perm, 4 * B, 3)
+        if mode == "mixed":
+            monkeypatch.setenv("BNN_SGLD_SMALL", "2")
+        loss = chain.run(perm, last, 1)
+        chain.run(perm, 0, 1)
+        torch.cuda.synchronize()
+        chain.check()
+        res[mode] = (grad, chain.state.clone(), chain.V.clone(), float(loss), float(gloss))
+    ref = res["dataflow"]
+    for mode in ("small", "mixed"):
+        got = res[mode]
+        assert float((got[0] - ref[0]).abs().max()) <= 2e-6 * float(ref[0].abs().max()), mode
+        assert float((got[1] - ref[1]).abs().max()) <= 5e-6 * float(ref[1].abs().max()), mode
+        assert float((got[2] - ref[2]).abs().max()) <= 5e-6 * float(ref[2].abs().max()), mode
+        assert abs(got[3] - ref[3]) <= 1e-5 * abs(ref[3]), mode
+        assert abs(got[4] - ref[4]) <= 1e-5 * abs(ref[4]), mode
