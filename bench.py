@@ -290,6 +290,10 @@ def run_ours(args):
             else:
                 sgld["steps_per_s_all_chains"] = sgld["steps_per_s_per_chain"]
             sgld["chains"] = world
+            try:
+                sgld["chains_per_gpu"] = sgld_multi_chain_block(dev, rank)
+            except Exception as e:
+                sgld["chains_per_gpu"] = {"error": repr(e)[:300]}
             if sgld_cpu is not None:
                 sgld["cpu"] = sgld_cpu
         except Exception as e:      # the secondary metric must never take the headline down
@@ -522,6 +526,68 @@ def bbb_train_block(dev):
             "steps_per_s": 1e6 / us, "us_per_step": us, "state_finite": bool(torch.isfinite(tr.mu).all()),
             "cpu": {"steps_per_s": cpu, "cores": cpu_threads, "kind": "port",
                     "sample": f"{n_cpu} steps, torch CPU autograd + Adam, best of 1 / all threads"}}
+
+
+def sgld_multi_chain_block(dev, rank):
+    """cfg 5 with SEVERAL independent chains on one GPU: each chain's launches on its own stream, CTAs per launch capped
+    (bnn_sgld_set_grid_cap) so the chains' dependency stalls interleave.  Same step kernel, same launches of 50 steps; the data
+    set is a 1M-row slice (the gather touches 6,400 random rows per launch either way)."""
+    import torch
+    from bnn_b200 import ops
+    from bnn_b200.layout import Arch
+    arch = Arch(SGLD_DIMS, "tanh")
+    rows, n = 1_000_000, SGLD_KEEP
+    g = torch.Generator(device=dev).manual_seed(17)
+    X = torch.randn(rows, SGLD_DIMS[0], generator=g, device=dev)
+    y = torch.randn(rows, 1, generator=g, device=dev)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    out = {}
+    try:
+        for chains in (2, 4):
+            ops.sgld_set_grid_cap(sms // chains)
+            streams = [torch.cuda.Stream(dev) for _ in range(chains)]
+            cs = []
+            for c in range(chains):
+                chain = ops.SgldChain(arch, SGLD_BATCH, dev, 2e-2, 1e-1, 1e-2, 1e-1, seed=100 + 8 * rank + c)
+                net = [(torch.randn(o, i) * (2.0 / (i + o)) ** 0.5, torch.zeros(o)) for i, o in zip(SGLD_DIMS[:-1], SGLD_DIMS[1:])]
+                chain.set_state(arch.pack([net])[0], torch.zeros(1))
+                chain.bind(X, y)
+                cs.append(chain)
+            snaps = [torch.empty(arch.stride, device=dev) for _ in range(chains)]
+
+            def sweep(reps, epoch0):
+                for r in range(reps):
+                    for c in range(chains):
+                        with torch.cuda.stream(streams[c]):
+                            perm = ops.sgld_perm(100 + c, epoch0 + r, rows, n * SGLD_BATCH, dev)
+                            cs[c].run(perm, 0, n)
+                            snaps[c].copy_(cs[c].state[: arch.stride])               # thinning snapshot
+            torch.cuda.synchronize()
+            sweep(2, 0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            e0.record()
+            for st in streams:
+                st.wait_event(e0)
+            sweep(reps, 2)
+            for st in streams:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                torch.cuda.current_stream().wait_event(ev)
+            e1.record()
+            torch.cuda.synchronize()
+            for c in cs:
+                c.check()
+            agg = chains * reps * n / (e0.elapsed_time(e1) * 1e-3)
+            out[f"{chains}_chains_x_{sms // chains}_ctas"] = {"steps_per_s_total": agg, "steps_per_s_per_chain": agg / chains,
+                                                              "state_finite": all(bool(torch.isfinite(c.state).all()) for c in cs)}
+            del cs
+    finally:
+        ops.sgld_set_grid_cap(0)
+    del X, y
+    torch.cuda.empty_cache()
+    return out
 
 
 def sgld_cfg1_block(dev):

@@ -107,6 +107,7 @@ PROTOTYPES = {
     "bnn_sgld_init": (C.c_int32, [C.POINTER(SgldChain), C.c_int32, C.c_void_p]),
     "bnn_sgld_run": (C.c_int32, [C.POINTER(SgldChain), C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    "bnn_sgld_set_grid_cap": (C.c_int32, [C.c_int32]),
     "bnn_sgld_perm": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "bnn_sgld_trace": (C.c_int32, [C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "bnn_sgld_status": (C.c_int32, [C.POINTER(SgldChain), C.POINTER(C.c_int32), C.c_void_p]),

@@ -1482,7 +1482,14 @@ static int ss_plan(const SgParams& p, SsParams* q, size_t* smem) {
 }
 
 static long long* g_sg_trace = nullptr;   // debug: set by bnn_sgld_trace
+static int g_sg_grid_cap = 0;              // bnn_sgld_set_grid_cap
 static int g_sg_trace_grid = 0;
+
+extern "C" int32_t bnn_sgld_set_grid_cap(int32_t ctas) {
+  if (ctas < 0) BNN_FAIL("bnn_sgld_set_grid_cap: ctas must be >= 0 (0 = no cap)");
+  g_sg_grid_cap = ctas;
+  return 0;
+}
 
 extern "C" int32_t bnn_sgld_run(const BnnSgldChain* c, int32_t cur, int64_t t0, int64_t perm_off, int32_t n_steps, float* loss_out,
                                 float* grad_out, void* stream) {
@@ -1529,6 +1536,10 @@ extern "C" int32_t bnn_sgld_run(const BnnSgldChain* c, int32_t cur, int64_t t0, 
   if (per_sm < 1) BNN_FAIL("bnn_sgld_run: the step kernel does not fit on an SM");
   int grid = plan.grid;
   if (grid > per_sm * sm_count()) grid = per_sm * sm_count();
+  // bnn_sgld_set_grid_cap / BNN_SGLD_GRID cap the CTAs of one chain: several chains launched on different streams then share the GPU (each launch is
+  // cooperative, so a chain only starts when all of its CTAs fit next to the others')
+  if (g_sg_grid_cap >= 1 && g_sg_grid_cap < grid) grid = g_sg_grid_cap;
+  if (const char* e = getenv("BNN_SGLD_GRID")) { const int v = atoi(e); if (v >= 1 && v < grid) grid = v; }
   p.trace = g_sg_trace;
   if (const char* e = getenv("BNN_SGLD_DBG")) p.dbg = atoi(e);
   g_sg_trace_grid = grid;

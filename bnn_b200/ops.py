@@ -379,6 +379,12 @@ def sgld_perm(seed, epoch, N, count, device, offset=0):
     return out
 
 
+def sgld_set_grid_cap(ctas):
+    """Cap the CTAs of every following fused-step launch of this process (0 = no cap): chains that run on different streams then
+    share the GPU (bnn_sgld_set_grid_cap).  One chain alone leaves about a third of the SMs idle (dependency chain of the step)."""
+    _lib.check(_lib.lib().bnn_sgld_set_grid_cap(int(ctas)), "bnn_sgld_set_grid_cap")
+
+
 class SgldChain:
     """Device-resident state of one pSGLD chain + the fused step kernel (bnn_sgld_run, csrc/sgld_step.cu).
 

@@ -252,6 +252,11 @@ int64_t bnn_sgld_workspace_bytes(const BnnMlpDesc* d, int32_t batch);
 int32_t bnn_sgld_init(const BnnSgldChain* c, int32_t cur, void* stream);
 int32_t bnn_sgld_run(const BnnSgldChain* c, int32_t cur, int64_t t0, int64_t perm_off, int32_t n_steps, float* loss_out,
                      float* grad_out, void* stream);
+/* Several chains on one GPU: a chain's step is a dependency chain of seven tile stages, so one chain leaves SMs idle about a
+ * third of the time.  Capping the CTAs of a launch (process-wide; 0 = no cap) and running each chain's launches on its own stream
+ * lets the chains interleave: cfg 5 on one B200, 1 x 148 CTAs 1.67e4 steps/s, 2 x 74 2.28e4, 4 x 37 2.42e4 in total
+ * (tools/sgld_multi_chain.py).  Launches are cooperative, so a chain starts only when all of its CTAs fit beside the others'. */
+int32_t bnn_sgld_set_grid_cap(int32_t ctas);
 /* entries [offset, offset + count) of the pseudo-random permutation of [0, N) keyed by (seed, epoch): the shuffled order of
  * DataLoader(shuffle=True) (BNN_SGDMC.py:110) without materialising all N entries -- a chain only consumes a prefix */
 int32_t bnn_sgld_perm(uint64_t seed, uint32_t epoch, int64_t N, int64_t offset, int64_t count, int64_t* out, void* stream);

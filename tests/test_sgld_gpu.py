@@ -329,3 +329,40 @@ def test_single_sm_kernel_equals_dataflow_kernel(dims, act, B, N, monkeypatch):
         assert float((got[2] - ref[2]).abs().max()) <= 5e-6 * float(ref[2].abs().max()), mode
         assert abs(got[3] - ref[3]) <= 1e-5 * abs(ref[3]), mode
         assert abs(got[4] - ref[4]) <= 1e-5 * abs(ref[4]), mode
+
+
+def test_capped_grid_and_two_streams_give_the_same_chains():
+    """bnn_sgld_set_grid_cap: two chains with half the CTAs each, launched on two streams so that they run side by side, end in
+    exactly the state each reaches alone on the whole GPU (the job list is the same, only the number of workers changes)."""
+    from bnn_b200 import ops
+    dims, act, B, N = [20, 256, 256, 1], "tanh", 64, 2000
+    g = torch.Generator().manual_seed(4)
+    X, y = torch.randn(N, 20, generator=g).cuda(), torch.randn(N, 1, generator=g).cuda()
+    perm = torch.randperm(N, generator=g).cuda()
+    nets = [[((torch.rand(o, i, generator=g) - 0.5) * 0.3, torch.zeros(o)) for i, o in zip(dims[:-1], dims[1:])] for _ in range(2)]
+
+    def run(capped):
+        chains = []
+        for c in range(2):
+            _, ch = make_chain(dims, act, B, nets[c], torch.zeros(1), seed=30 + c)
+            ch.bind(X, y)
+            chains.append(ch)
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream() for _ in range(2)] if capped else [torch.cuda.current_stream()] * 2
+        ops.sgld_set_grid_cap(torch.cuda.get_device_properties(0).multi_processor_count // 2 if capped else 0)
+        try:
+            for r in range(3):
+                for c in range(2):
+                    with torch.cuda.stream(streams[c]):
+                        chains[c].run(perm, r * 5 * B, 5)
+            torch.cuda.synchronize()
+        finally:
+            ops.sgld_set_grid_cap(0)
+        for ch in chains:
+            ch.check()
+        return [(ch.state.clone(), ch.V.clone()) for ch in chains]
+
+    alone, side = run(False), run(True)
+    for (s0, v0), (s1, v1) in zip(alone, side):
+        assert torch.allclose(s0, s1, rtol=1e-6, atol=1e-7)
+        assert torch.allclose(v0, v1, rtol=1e-6, atol=1e-9)
