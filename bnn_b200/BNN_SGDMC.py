@@ -33,6 +33,8 @@ class BNN_SGDMC(nn.Module, BNN):
         self.keep_every = conf.get('keep_every', 50)
         self.batch_size = conf.get('batch_size', 32)
         self.warm_start = conf.get('warm_start', False)
+        self.num_chains = int(conf.get('num_chains', 1))      # ours: chains trained side by side on one GPU, samples pooled
+        self._epochs = [0] * max(1, self.num_chains)
         self.lr_weight = conf.get('lr_weight', 2e-2)
         self.lr_noise = conf.get('lr_noise', 1e-1)
         self.alpha_n = torch.as_tensor(1. * conf.get('alpha_n', 1e-2))
@@ -85,32 +87,45 @@ class BNN_SGDMC(nn.Module, BNN):
         return (-0.5 * precs * (y - out) ** 2 + 0.5 * self.log_precs - 0.5 * math.log(2. * math.pi)).sum()   # :72-74
 
     # ---- the chain ----------------------------------------------------------------------------
-    def _new_chain(self, dev):
+    def _new_chain(self, dev, seed=None):
         """What the reference's train() builds at BNN_SGDMC.py:96-101: a FRESH optimizer (V = 1) and scheduler (t = 0) over
         the CURRENT self.nn / self.log_precs -- also on a warm start, which only skips init_nn() (:114-115)."""
         a = self.arch
         chain = ops.SgldChain(a, self.batch_size, dev, self.lr_weight, self.lr_noise, float(self.alpha_n), float(self.beta_n),
-                              seed=self.seed, precond_decay=self.psgld_alpha, diagonal_bias=self.psgld_lambda, gain=self.gain,
+                              seed=self.seed if seed is None else seed, precond_decay=self.psgld_alpha, diagonal_bias=self.psgld_lambda, gain=self.gain,
                               precond_mode=self.psgld_mode)
         chain.set_state(a.pack([self.nn.nn])[0], self.log_precs.data)
         return chain
 
-    def sgld_steps(self, num_steps, num_train):
+    def sgld_steps(self, num_steps, num_train, chain=None, c=0):
         """BNN_SGDMC.py:76-91: iterate the shuffled loader (a NEW permutation every time the loader is re-entered, i.e. at
         every call and after every exhausted epoch; the last batch of an epoch may be short) until num_steps are done.
         Each run of consecutive steps inside one epoch is ONE launch of the fused step kernel."""
-        chain, B = self._chain, self.batch_size
+        chain = self._chain if chain is None else chain
+        B = self.batch_size
         per_epoch = (num_train + B - 1) // B
         step_cnt, loss = 0, None
         while step_cnt < num_steps:
             n = min(num_steps - step_cnt, per_epoch)
-            perm = ops.sgld_perm(self.seed, self._epoch, num_train, min(num_train, n * B), chain.device)
-            self._epoch += 1
+            perm = ops.sgld_perm(self.seed + c, self._epochs[c], num_train, min(num_train, n * B), chain.device)
+            self._epochs[c] += 1
             loss = chain.run(perm, 0, n, want_loss=(step_cnt + n >= num_steps))
             step_cnt += n
         return loss
 
+    @property
+    def _epoch(self):
+        return self._epochs[0]
+
+    @_epoch.setter
+    def _epoch(self, v):
+        self._epochs = [int(v)] * max(1, self.num_chains)
+
     def train(self, X, y):
+        """BNN_SGDMC.train (BNN_SGDMC.py:93-125).  conf['num_chains'] = C > 1 (ours) runs C independent chains (seeds seed + c, the
+        same initial network) SIDE BY SIDE on this GPU -- each chain's launches on its own stream, the CTAs of a launch capped at
+        (#SMs / C) -- and pools their thinned samples into one bank of C x (steps / keep_every) networks; one chain alone leaves
+        about a third of the SMs idle.  self.nn / self.log_precs end at chain 0's last state."""
         dev = self._dev()
         a = self.arch
         X = self._to_dev(X)
@@ -118,22 +133,50 @@ class BNN_SGDMC(nn.Module, BNN):
         num_train = X.shape[0]
         if not self.warm_start:
             self.init_nn()
-        self._chain = self._new_chain(dev)
-        self._chain.bind(X, y)
+        C = max(1, self.num_chains)
+        chains = []
+        for c in range(C):
+            ch = self._new_chain(dev, seed=self.seed + c)
+            ch.bind(X, y)
+            chains.append(ch)
+        self._chain = chains[0]
         self._epoch = 0
-        self.sgld_steps(self.steps_burnin, num_train)                     # burn-in
         n_keep = (self.steps + self.keep_every - 1) // self.keep_every
-        bank = torch.empty(n_keep, a.stride, device=dev)
-        step_cnt, k = 0, 0
-        while step_cnt < self.steps:
-            loss = self.sgld_steps(self.keep_every, num_train)
-            step_cnt += self.keep_every
-            bank[k].copy_(self._chain.state[: a.stride])                  # thinning snapshot = one bank row (:124)
-            k += 1
-            prec = self._chain.state[a.stride: a.stride + self.nout].exp().mean()
-            print('Step %4d, loss = %8.2f, precision = %g' % (step_cnt, float(loss), float(prec)), flush=True)
-        self._chain.check()
-        self.nns = SampleBank(a, bank[:k].contiguous())
+        bank = torch.empty(C, n_keep, a.stride, device=dev)
+        main = torch.cuda.current_stream(dev)
+        streams = [main] if C == 1 else [torch.cuda.Stream(dev) for _ in range(C)]
+        if C > 1:
+            ops.sgld_set_grid_cap(max(1, torch.cuda.get_device_properties(dev).multi_processor_count // C))
+            start = torch.cuda.Event()
+            start.record(main)
+            for st in streams:
+                st.wait_event(start)
+        try:
+            for c in range(C):
+                with torch.cuda.stream(streams[c]):
+                    self.sgld_steps(self.steps_burnin, num_train, chains[c], c)       # burn-in
+            step_cnt, k = 0, 0
+            while step_cnt < self.steps:
+                losses = []
+                for c in range(C):
+                    with torch.cuda.stream(streams[c]):
+                        losses.append(self.sgld_steps(self.keep_every, num_train, chains[c], c))
+                        bank[c, k].copy_(chains[c].state[: a.stride])      # thinning snapshot = one bank row (:124)
+                step_cnt += self.keep_every
+                k += 1
+                if C > 1:
+                    for st in streams:
+                        st.synchronize()
+                prec = chains[0].state[a.stride: a.stride + self.nout].exp().mean()
+                print('Step %4d, loss = %8.2f, precision = %g' % (step_cnt, float(losses[0]), float(prec)), flush=True)
+            for st in streams:
+                st.synchronize()
+        finally:
+            if C > 1:
+                ops.sgld_set_grid_cap(0)
+        for ch in chains:
+            ch.check()
+        self.nns = SampleBank(a, bank[:, :k].reshape(C * k, a.stride).contiguous())
         self.log_precs.data = self._chain.state[a.stride: a.stride + self.nout].detach().cpu()
         self.nn.nn.load_state_dict(a.to_module(self._chain.state[: a.stride]).state_dict())
         print('Number of samples: %d' % len(self.nns))

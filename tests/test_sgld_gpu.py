@@ -366,3 +366,24 @@ def test_capped_grid_and_two_streams_give_the_same_chains():
     for (s0, v0), (s1, v1) in zip(alone, side):
         assert torch.allclose(s0, s1, rtol=1e-6, atol=1e-7)
         assert torch.allclose(v0, v1, rtol=1e-6, atol=1e-9)
+
+
+def test_num_chains_pools_the_samples_of_chains_trained_side_by_side():
+    """conf['num_chains'] = 2: two chains (seeds seed, seed + 1) share the GPU (capped grids, one stream each); the pooled bank
+    holds both chains' thinned samples, chain 0's half equals what a single-chain model with the same seed produces."""
+    from bnn_b200.BNN_SGDMC import BNN_SGDMC
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(300, 6, generator=g)
+    y = torch.sin(X[:, 0]) + 0.1 * torch.randn(300, generator=g)
+    conf = {"device": "cuda", "seed": 7, "steps_burnin": 100, "steps": 200, "keep_every": 50, "batch_size": 32}
+    banks = []
+    for C in (1, 2):
+        torch.manual_seed(1)                                    # same initial network (xavier init draws from torch's global stream)
+        m = BNN_SGDMC(6, nn.Tanh(), [64, 64], nout=1, conf=dict(conf, num_chains=C))
+        m.train(X, y)
+        assert len(m.nns) == 4 * C
+        py, pv = m.predict_mv(X, m.sample(4 * C))
+        assert bool(torch.isfinite(py).all() and (pv > 0).all())
+        banks.append(m.nns.weights.clone())
+    assert torch.allclose(banks[1][:4], banks[0], rtol=1e-6, atol=1e-7)      # chain 0 of the pair == the chain alone
+    assert not torch.allclose(banks[1][4:], banks[0], rtol=1e-3, atol=1e-4)  # chain 1 is a different chain
