@@ -7,7 +7,7 @@
 // vectors, the masked activations and two gradient panels live in shared memory for the whole launch.  The keep masks are never
 // stored: forward and backward evaluate the same counter-based draw (Philox stream 6, subsequence = step) or read the injected
 // mask (tests: the reference's own F.dropout draws).  The parameter gradient is consumed by Adam in the thread that forms it.
-// The reference's cfg 3 network (9-100-100-1, batch 32: 11,704 packed parameters) needs 197 KB.
+// The reference's cfg 3 network (9-100-100-1, batch 32: 11,704 packed parameters) needs 207 KB (rows at the conflict-free pitch).
 //
 // The same kernel, instantiated with CONCRETE = true, is the concrete-dropout training step of BNN_CDropout.train
 // (BNN_CDropout.py:114-139): CDropout.forward (:21-34) scales the input of EVERY Linear by the relaxed keep factor
