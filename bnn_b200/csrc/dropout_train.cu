@@ -74,22 +74,41 @@ constexpr float kProbEps = 1.1920928955078125e-07f;                   // torch c
 // per-layer concrete-dropout state in shared memory (floats): [0] p_logit [1] m [2] v [3] p [4] log(p+e) - log(1-p+e) [5] grad
 constexpr int kCdStride = 8;
 
-// keep factor of input unit k of row b of layer l at launch step `it` (lpr: the layer's log(p + e) - log(1 - p + e), concrete only)
+// keep factors of input units k0 .. k0 + 3 (k0 a multiple of 4) of row b: ONE Philox block when the row's draws start on a block
+// boundary (in % 4 == 0: every hidden width that matters), two otherwise -- a draw per element would use one word of every block
 template <bool CONCRETE>
-__device__ __forceinline__ float dt_keep(const DtParams& p, const DtLayer& Y, int it, int b, int k, float lpr) {
-  const long long u = Y.m_off + (long long)b * Y.in + k;
-  float r;
+__device__ __forceinline__ void dt_keep4(const DtParams& p, const DtLayer& Y, int it, int b, int k0, float lpr, float keep[4]) {
+  const long long u0 = Y.m_off + (long long)b * Y.in + k0;
+  float r[4];
   if (p.mask_in) {
-    r = p.mask_in[(long long)it * p.mask_per_step + u];
-    if (!CONCRETE) return r;
+    const float* src = p.mask_in + (long long)it * p.mask_per_step + u0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) r[c] = k0 + c < Y.in ? src[c] : 0.0f;
   } else {
-    const u32x4 w = philox_block(p.seed, (uint32_t)(p.t0 + it), STREAM_DROPOUT_TRAIN, (uint64_t)(u >> 2));
-    r = u24(pick_word(w, (int)(u & 3)));
-    if (!CONCRETE) return bernoulli_keep(r, p.p_drop);
+    const uint32_t sub = (uint32_t)(p.t0 + it);
+    const u32x4 w0 = philox_block(p.seed, sub, STREAM_DROPOUT_TRAIN, (uint64_t)(u0 >> 2));
+    const int sh = (int)(u0 & 3);
+    if (sh == 0) {
+      r[0] = u24(w0.x); r[1] = u24(w0.y); r[2] = u24(w0.z); r[3] = u24(w0.w);
+    } else {
+      const u32x4 w1 = philox_block(p.seed, sub, STREAM_DROPOUT_TRAIN, (uint64_t)(u0 >> 2) + 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) r[c] = u24(sh + c < 4 ? pick_word(w0, sh + c) : pick_word(w1, sh + c - 4));
+    }
   }
-  const float z = (lpr + logf(r + kCdEps) - logf(1.0f - r + kCdEps)) * kCdInvTemp;
-  return 1.0f - 1.0f / (1.0f + expf(-z));
+  if constexpr (CONCRETE) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float z = (lpr + logf(r[c] + kCdEps) - logf(1.0f - r[c] + kCdEps)) * kCdInvTemp;
+      keep[c] = 1.0f - 1.0f / (1.0f + expf(-z));
+    }
+  } else {
+    // injected masks are the keep factors themselves; drawn ones are Bernoulli(1 - p) of the 24-bit uniforms
+#pragma unroll
+    for (int c = 0; c < 4; ++c) keep[c] = p.mask_in ? r[c] : bernoulli_keep(r[c], p.p_drop);
+  }
 }
+
 __device__ __forceinline__ float dt_act_bwd(float a, int act) {   // derivative through the activation's OUTPUT
   switch (act) {
     case BNN_ACT_RELU: return a > 0.0f ? 1.0f : 0.0f;
@@ -189,16 +208,22 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
       const DtLayer& Y0 = p.ly[0];
       float* a0 = s_act + Y0.a_off;
       const float lpr = CONCRETE ? s_cd[4] : 0.0f;
-      for (int i = tid; i < Bp * Y0.lp; i += kDtThreads) {
-        const int b = i / Y0.lp, k = i - b * Y0.lp;
-        float v = 0.0f;
+      const int q0 = Y0.lp >> 2;
+      for (int i = tid; i < Bp * q0; i += kDtThreads) {
+        const int b = i / q0, k0 = (i - b * q0) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (b < rows) {
-          if (k < p.D) {
-            v = __ldg(p.X + __ldg(p.perm + boff + b) * p.D + k);
-            if (Y0.masked) v *= dt_keep<CONCRETE>(p, Y0, it, b, k, lpr);
-          } else if (k == p.D) v = 1.0f;
+          const float* xr = p.X + __ldg(p.perm + boff + b) * p.D;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[c] = k0 + c < p.D ? __ldg(xr + k0 + c) : (k0 + c == p.D ? 1.0f : 0.0f);
+          if (Y0.masked && k0 < p.D) {
+            float keep[4];
+            dt_keep4<CONCRETE>(p, Y0, it, b, k0, lpr, keep);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (k0 + c < p.D) v[c] *= keep[c];
+          }
         }
-        a0[i] = v;
+        *reinterpret_cast<float4*>(a0 + b * Y0.lp + k0) = make_float4(v[0], v[1], v[2], v[3]);
       }
       for (int i = tid; i < B * p.nout; i += kDtThreads) {
         const int b = i / p.nout;
@@ -247,23 +272,31 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
               if (b < B) s_pred[b * p.nout + j] = b < rows ? v : 0.0f;
             } else {
               const DtLayer& N = p.ly[l + 1];
-              v = b < rows ? apply_act(v, p.act) : 0.0f;
-              if (N.masked && b < rows) v *= dt_keep<CONCRETE>(p, N, it, b, j, lpr);
-              s_act[N.a_off + b * N.lp + j] = v;
+              s_act[N.a_off + b * N.lp + j] = b < rows ? apply_act(v, p.act) : 0.0f;      // the keep factors follow below
             }
           }
         }
       }
-      if (!last) {          // ones column and zero pad of the next layer's augmented input
+      __syncthreads();
+      if (!last) {          // the next layer's input: keep factors on its units (one Philox block per four), ones column, zero pad
         const DtLayer& N = p.ly[l + 1];
         float* an = s_act + N.a_off;
-        const int padw = N.lp - N.in;
-        for (int i = tid; i < Bp * padw; i += kDtThreads) {
-          const int b = i / padw, k = N.in + (i - b * padw);
-          an[b * N.lp + k] = (k == N.in && b < rows) ? 1.0f : 0.0f;
+        const int qn = N.lp >> 2;
+        for (int i = tid; i < Bp * qn; i += kDtThreads) {
+          const int b = i / qn, k0 = (i - b * qn) * 4;
+          const float4 x = *reinterpret_cast<const float4*>(an + b * N.lp + k0);
+          float v[4] = {x.x, x.y, x.z, x.w};
+          float keep[4] = {1.f, 1.f, 1.f, 1.f};
+          if (N.masked && b < rows && k0 < N.in) dt_keep4<CONCRETE>(p, N, it, b, k0, lpr, keep);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int k = k0 + c;
+            v[c] = b < rows ? (k < N.in ? v[c] * keep[c] : (k == N.in ? 1.0f : 0.0f)) : 0.0f;
+          }
+          *reinterpret_cast<float4*>(an + b * N.lp + k0) = make_float4(v[0], v[1], v[2], v[3]);
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
     // ---- loss = sum (pred - y)^2 (MSELoss(reduction='sum'), BNN_Dropout.py:55); dL/d(pred) -> s_ga (transposed)
     {
@@ -337,33 +370,37 @@ __global__ void __launch_bounds__(kDtThreads, 1) dropout_train_kernel(const __gr
               }
             }
           }
-          // fold the four partial sums (lanes differing in bits 3 and 4); afterwards lane `part` finishes column k4 * 4 + part
+          // fold the four partial sums (lanes differing in bits 3 and 4); afterwards lane `part` finishes ROW bq * 4 + part over the
+          // tile's four columns: their keep factors are one Philox block
           float mine[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int rr = 0; rr < 4; ++rr) {
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
+            for (int c = 0; c < 4; ++c) {
               float v = g[rr][c];
               v += __shfl_xor_sync(0xffffffffu, v, 8);
               v += __shfl_xor_sync(0xffffffffu, v, 16);
-              if (c == part) mine[rr] = v;
+              if (rr == part) mine[c] = v;
             }
           }
-          const int k = k4 * 4 + part;
-          if (live && k < Y.in) {
-            float out4[4];
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-              const int b = bq * 4 + rr;
-              const float xs = a[b * Y.lp + k];                                     // act(z) * keep
-              float keep = 1.0f;
-              if (Y.masked) keep = b < rows ? dt_keep<CONCRETE>(p, Y, it, b, k, lpr) : 0.0f;
-              if (CONCRETE) gpart -= mine[rr] * xs * (1.0f - keep);                 // d keep / d z = -(1 - keep) keep / T; xs = act * keep
-              // where keep is not 0 the unmasked activation is xs / keep (Bernoulli: keep is 0 or within an ulp of 1;
-              // concrete: keep = 1 - sigmoid is 0 or at least 2^-24)
-              out4[rr] = keep != 0.0f ? mine[rr] * keep * dt_act_bwd(xs / keep, p.act) : 0.0f;
+          if (live) {
+            const int b = bq * 4 + part, k0 = k4 * 4;
+            const float4 x4 = *reinterpret_cast<const float4*>(a + b * Y.lp + k0);                // act(z) * keep
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+            float keep[4] = {1.f, 1.f, 1.f, 1.f};
+            if (Y.masked) {
+              if (b < rows) dt_keep4<CONCRETE>(p, Y, it, b, k0, lpr, keep);
+              else keep[0] = keep[1] = keep[2] = keep[3] = 0.0f;
             }
-            if (l > 0) *reinterpret_cast<float4*>(g1 + k * gp + bq * 4) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (k0 + c < Y.in) {
+                if (CONCRETE) gpart -= mine[c] * xs[c] * (1.0f - keep[c]);          // d keep / d z = -(1 - keep) keep / T; xs = act * keep
+                // where keep is not 0 the unmasked activation is xs / keep (Bernoulli: keep is 0 or within an ulp of 1;
+                // concrete: keep = 1 - sigmoid is 0 or at least 2^-24)
+                if (l > 0) g1[(k0 + c) * gp + b] = keep[c] != 0.0f ? mine[c] * keep[c] * dt_act_bwd(xs[c] / keep[c], p.act) : 0.0f;
+              }
+            }
           }
         }
         if (CONCRETE) {
