@@ -116,6 +116,25 @@ __global__ void __launch_bounds__(kBtThreads, 1) bbb_train_kernel(const __grid_c
         const int b = i / p.nout;
         s_y[i] = b < rows ? __ldg(p.y + __ldg(p.perm + boff + b) * p.nout + (i - b * p.nout)) : 0.0f;
       }
+      // the step's local-reparameterisation noise for ALL layers, four normals per Philox block over the step's flat noise index
+      // (layer-major, then [b][j]) -- drawn here, under the latency of the gather's global loads, instead of one block (and one
+      // Box-Muller pair) per unit inside the forward
+      if (!p.eps_in) {
+        const long long nq = (p.eps_per_step + 3) >> 2;
+        for (long long q = tid; q < nq; q += kBtThreads) {
+          float z[4];
+          philox_normal4(p.seed, (uint32_t)(p.t0 + it), STREAM_BBB_LOCAL, (unsigned long long)q, z);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const long long u = q * 4 + c;
+            if (u < p.eps_per_step) {
+              int l = 0;
+              while (l + 1 < L && u >= p.ly[l + 1].e_off) ++l;
+              s_act[p.ly[l].s_off + B * p.ly[l].out + (int)(u - p.ly[l].e_off)] = z[c];
+            }
+          }
+        }
+      }
     }
     __syncthreads();
     // ---- forward: local reparameterisation, layer by layer (thread = one output unit of one row)
@@ -142,15 +161,7 @@ __global__ void __launch_bounds__(kBtThreads, 1) bbb_train_kernel(const __grid_c
           mean = fmaf(x.x, m.x, mean); mean = fmaf(x.y, m.y, mean); mean = fmaf(x.z, m.z, mean); mean = fmaf(x.w, m.w, mean);
           var = fmaf(x.x * x.x, v.x, var); var = fmaf(x.y * x.y, v.y, var); var = fmaf(x.z * x.z, v.z, var); var = fmaf(x.w * x.w, v.w, var);
         }
-        float e;
-        if (p.eps_in) e = p.eps_in[(long long)it * p.eps_per_step + Y.e_off + i];
-        else {
-          // four consecutive units share one Philox block; every thread draws the block of its own unit
-          float z[4];
-          const unsigned long long u = (unsigned long long)(Y.e_off + i);
-          philox_normal4(p.seed, (uint32_t)(p.t0 + it), STREAM_BBB_LOCAL, u >> 2, z);
-          e = z[u & 3];
-        }
+        const float e = p.eps_in ? p.eps_in[(long long)it * p.eps_per_step + Y.e_off + i] : ep[i];
         const float s = sqrtf(var);
         sd[i] = s; ep[i] = e;
         const float o = b < rows ? mean + s * e : 0.0f;
@@ -257,8 +268,10 @@ __global__ void __launch_bounds__(kBtThreads, 1) bbb_train_kernel(const __grid_c
           const long long w = Y.off + (long long)j * Y.ld + k;
           const float mu = s_mu[w], rho = s_rho[w], s2 = s_s2[w];
           // KL(N(mu, s) || N(0, w0)) = 0.5 (s2 / w0^2 + mu^2 / w0^2 - 1 - log(s2 / w0^2))          (BNN_BBB.py:107-110)
-          const float vr = s2 * p.inv_w2;
-          klp += 0.5 * ((double)vr + (double)(mu * mu * p.inv_w2) - 1.0 - (double)logf(vr));
+          if (p.kl_out) {
+            const float vr = s2 * p.inv_w2;
+            klp += 0.5 * ((double)vr + (double)(mu * mu * p.inv_w2) - 1.0 - (double)logf(vr));
+          }
           const float g_mu = s_gmu[w] + p.kl_factor * mu * p.inv_w2;
           const float g_rho = (s_gs2[w] + p.kl_factor * 0.5f * (p.inv_w2 - 1.0f / s2)) * bt_ds2(rho);
           float m = s_mm[w], v = s_vm[w];
