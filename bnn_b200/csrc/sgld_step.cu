@@ -1112,13 +1112,15 @@ extern "C" int32_t bnn_sgld_init(const BnnSgldChain* c, int32_t cur, void* strea
 // same Philox stream (seed, t, block = packed offset / 4) and same LambdaLR factors as the dataflow kernel, so the two are
 // interchangeable between launches (BNN_SGLD_SMALL=0 forces the dataflow kernel; tests compare them step for step).
 // Thread tiles as in csrc/dropout_train.cu: weight / activation rows at a pitch lp with lp / 4 odd, gradient panels transposed.
-constexpr int kSsThreads = 512;
+constexpr int kSsThreads = 512;          // 14 compute warps + 2 prefetch warps
+constexpr int kSsPrefetch = 64;
+constexpr int kSsCompute = kSsThreads - kSsPrefetch;
 constexpr long long kSsMaxWork = 96 * 1024;
 struct SsLayer { int lp, half, k4p, soff, a_off; };
 struct SsParams {
   SsLayer sy[BNN_MAX_LINEAR];
   int sP, gp, max_w, hd;                 // hd = n_theta - n_head (log-precisions + pad)
-  int sm_v, sm_act, sm_g0, sm_g1, sm_y, sm_red, want_quad;
+  int sm_v, sm_z, sm_a0, sm_act, sm_g0, sm_g1, sm_y, sm_red, want_quad;   // sm_z: [2] normals, sm_a0: [2] gathered batch, sm_y: [2]
   float* th_out; float* thT_out;         // buffer cur ^ (n_steps & 1)
 };
 
@@ -1128,19 +1130,66 @@ __global__ void __launch_bounds__(kSsThreads, 1) sgld_small_kernel(const __grid_
   constexpr int kWarps = kSsThreads / 32;
   float* s_th = sm;                        // [sP] network (pitch lp) | [hd] log-precisions
   float* s_v = sm + q.sm_v;                // same shape
-  float* s_act = sm + q.sm_act;
+  float* s_zz = sm + q.sm_z;               // [2] the step's normals, same shape (by step parity)
+  float* s_a0 = sm + q.sm_a0;              // [2][Bp][lp0] gathered batch (by step parity)
+  float* s_act = sm + q.sm_act;            // inputs of Linear 1..
   float* s_ga = sm + q.sm_g0;
   float* s_gb = sm + q.sm_g1;
-  float* s_y = sm + q.sm_y;                // [Bp][nout] targets, [Bp][nout] predictions
+  float* s_yy = sm + q.sm_y;               // [2][Bp][nout] targets (by step parity), [Bp][nout] predictions
   double* s_red = reinterpret_cast<double*>(sm + q.sm_red);   // [nout + 1][warps] partial sums: r^2 per output | prior quad
   double* s_acc = s_red + (p.nout + 1) * kWarps;              // [nout + 1]
   float* s_f = reinterpret_cast<float*>(s_acc + p.nout + 1);  // LambdaLR factor of the step
   const int L = p.L, B = p.B, Bp = p.Bp, gp = q.gp, nout = p.nout;
-  float* s_pred = s_y + Bp * nout;
+  float* s_pred = s_yy + 2 * Bp * nout;
   const float* th_in = p.theta[p.cur];
   const bool debug = p.grad_out != nullptr;
+  constexpr int kCW = kSsCompute / 32;     // compute warps
+  const int zlen = q.sP + q.hd, a0len = Bp * q.sy[0].lp;
 
-  for (int i = tid; i < q.sm_act; i += kSsThreads) sm[i] = 0.0f;
+  // What a step needs that does not depend on the chain state -- the batch rows (two dependent global loads per row) and the
+  // Philox normals of every parameter -- is produced ONE STEP AHEAD by the two prefetch warps while the compute warps run the
+  // current step (the first step's by everybody in the prologue); double-buffered by step parity.
+  auto prefetch = [&](int it2, int first, int stride) {
+    const long long boff2 = p.perm_off + (long long)it2 * B;
+    const long long left2 = p.num_train - boff2;
+    const int rows2 = left2 < B ? (int)left2 : B;
+    const int lp0 = q.sy[0].lp;
+    float* a0 = s_a0 + (it2 & 1) * a0len;
+    float* yb = s_yy + (it2 & 1) * Bp * nout;
+    for (int i = first; i < Bp * lp0; i += stride) {                   // gather (DataLoader batch, :80,110): rows (x | 1 | 0)
+      const int b = i / lp0, k = i - b * lp0;
+      float v = 0.0f;
+      if (b < rows2) {
+        if (k < p.D) v = __ldg(p.X + __ldg(p.perm + boff2 + b) * p.D + k);
+        else if (k == p.D) v = 1.0f;
+      }
+      a0[i] = v;
+    }
+    for (int i = first; i < Bp * nout; i += stride) {
+      const int b = i / nout;
+      yb[i] = b < rows2 ? __ldg(p.y + __ldg(p.perm + boff2 + b) * nout + (i - b * nout)) : 0.0f;
+    }
+    if (debug) return;
+    float* zb = s_zz + (it2 & 1) * zlen;
+    const uint32_t sub = (uint32_t)(p.t0 + it2);
+    for (int l = 0; l < L; ++l) {
+      const SgLayer& Y = p.ly[l];
+      const int q4 = Y.ld >> 2;
+      for (int i = first; i < Y.out * q4; i += stride) {
+        const int j = i / q4, k4 = i - j * q4;
+        float z[4];
+        philox_normal4(p.seed, sub, STREAM_SGLD, (uint64_t)((Y.off + (long long)j * Y.ld + k4 * 4) >> 2), z);
+        *reinterpret_cast<float4*>(zb + q.sy[l].soff + j * q.sy[l].lp + k4 * 4) = make_float4(z[0], z[1], z[2], z[3]);
+      }
+    }
+    for (int i = first; i < (q.hd >> 2); i += stride) {
+      float z[4];
+      philox_normal4(p.seed, sub, STREAM_SGLD, (uint64_t)((p.n_head + (long long)i * 4) >> 2), z);
+      *reinterpret_cast<float4*>(zb + q.sP + i * 4) = make_float4(z[0], z[1], z[2], z[3]);
+    }
+  };
+
+  for (int i = tid; i < q.sm_z; i += kSsThreads) sm[i] = 0.0f;
   __syncthreads();
   for (int l = 0; l < L; ++l) {
     const SgLayer& Y = p.ly[l];
@@ -1152,6 +1201,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) sgld_small_kernel(const __grid_
     }
   }
   for (int i = tid; i < q.hd; i += kSsThreads) { s_th[q.sP + i] = th_in[p.n_head + i]; s_v[q.sP + i] = p.V[p.n_head + i]; }
+  prefetch(0, tid, kSsThreads);
   __syncthreads();
 
 #pragma unroll 1
@@ -1162,35 +1212,24 @@ __global__ void __launch_bounds__(kSsThreads, 1) sgld_small_kernel(const __grid_
     const int rows = left < B ? (int)left : B;
     const float scale = (float)((double)p.num_train / (double)rows);   // N / |b|  (:83)
     const bool want_quad = q.want_quad && it + 1 == p.n_steps;
-    if (tid == 0) *s_f = it == 0 ? p.f0 : (float)pow((double)(1 + t), -0.33);   // LambdaLR (:101)
-    // ---- gather (DataLoader batch, :80,110): augmented rows (x | 1 | 0), targets
-    {
-      const int lp0 = q.sy[0].lp;
-      float* a0 = s_act + q.sy[0].a_off;
-      for (int i = tid; i < Bp * lp0; i += kSsThreads) {
-        const int b = i / lp0, k = i - b * lp0;
-        float v = 0.0f;
-        if (b < rows) {
-          if (k < p.D) v = __ldg(p.X + __ldg(p.perm + boff + b) * p.D + k);
-          else if (k == p.D) v = 1.0f;
-        }
-        a0[i] = v;
-      }
-      for (int i = tid; i < Bp * nout; i += kSsThreads) {
-        const int b = i / nout;
-        s_y[i] = b < rows ? __ldg(p.y + __ldg(p.perm + boff + b) * nout + (i - b * nout)) : 0.0f;
-      }
+    if (tid >= kSsCompute) {
+      if (it + 1 < p.n_steps) prefetch(it + 1, tid - kSsCompute, kSsPrefetch);
+      __syncthreads();                     // end of the step (the compute warps' matching barrier is at the bottom of the loop)
+      continue;
     }
-    __syncthreads();
+    const float* s_y = s_yy + (it & 1) * Bp * nout;
+    const float* s_z = s_zz + (it & 1) * zlen;
+    if (tid == 0) *s_f = it == 0 ? p.f0 : (float)pow((double)(1 + t), -0.33);   // LambdaLR (:101)
+    // (first use of *s_f is behind the first barrier of the forward)
     // ---- forward: thread = 4 rows x units (j, j + half)
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
       const SgLayer& Y = p.ly[l];
       const SsLayer& S = q.sy[l];
-      const float* a = s_act + S.a_off;
+      const float* a = l == 0 ? s_a0 + (it & 1) * a0len : s_act + S.a_off;
       const bool last = l + 1 == L;
       const int n_item = (Bp >> 2) * S.half;
-      for (int i = tid; i < n_item; i += kSsThreads) {
+      for (int i = tid; i < n_item; i += kSsCompute) {
         const int bq = i / S.half, j0 = i - bq * S.half, j1 = j0 + S.half;
         const bool two = j1 < Y.out;
         const float* ar = a + (bq * 4) * S.lp;
@@ -1227,18 +1266,18 @@ __global__ void __launch_bounds__(kSsThreads, 1) sgld_small_kernel(const __grid_
       if (!last) {          // ones column and zero pad of the next layer's augmented input
         const int nin = p.ly[l + 1].in, nlp = q.sy[l + 1].lp, padw = nlp - nin;
         float* an = s_act + q.sy[l + 1].a_off;
-        for (int i = tid; i < Bp * padw; i += kSsThreads) {
+        for (int i = tid; i < Bp * padw; i += kSsCompute) {
           const int b = i / padw, k = nin + (i - b * padw);
           an[b * nlp + k] = (k == nin && b < rows) ? 1.0f : 0.0f;
         }
       }
-      __syncthreads();
+      named_bar_sync(1, kSsCompute);
     }
     // ---- Gaussian head (:69-74,83): r = f - y, dU/d(out) = (N / |b|) prec r, sum r^2 per output
     for (int o = 0; o < nout; ++o) {
       const float prec = expf(s_th[q.sP + o]);
       double part = 0.0;
-      for (int b = tid; b < Bp; b += kSsThreads) {
+      for (int b = tid; b < Bp; b += kSsCompute) {
         float dzv = 0.0f;
         if (b < rows) {
           const float r = s_pred[b * nout + o] - s_y[b * nout + o];
@@ -1251,10 +1290,10 @@ __global__ void __launch_bounds__(kSsThreads, 1) sgld_small_kernel(const __grid_
       for (int w = 16; w > 0; w >>= 1) part += __shfl_xor_sync(0xffffffffu, part, w);
       if (lane == 0) s_red[o * kWarps + warp] = part;
     }
-    __syncthreads();
+    named_bar_sync(1, kSsCompute);
     if (tid < nout) {
       double s = 0.0;
-      for (int w = 0; w < kWarps; ++w) s += s_red[tid * kWarps + w];
+      for (int w = 0; w < kCW; ++w) s += s_red[tid * kWarps + w];
       s_acc[tid] = s;
     }
     if (tid == 32) s_acc[nout] = 0.0;
@@ -1266,12 +1305,12 @@ __global__ void __launch_bounds__(kSsThreads, 1) sgld_small_kernel(const __grid_
     for (int l = L - 1; l >= 0; --l) {
       const SgLayer& Y = p.ly[l];
       const SsLayer& S = q.sy[l];
-      const float* a = s_act + S.a_off;
+      const float* a = l == 0 ? s_a0 + (it & 1) * a0len : s_act + S.a_off;
       // dz_{l-1} = (dz_l theta_l) * act'(h_l): 4 rows x 4 columns per thread, the sum over j split over 4 lanes (bits 3-4)
       if (l > 0) {
         const int k4n = (Y.in + 3) >> 2, k8 = S.k4p >> 3;
         const int n_item = 32 * k8 * (Bp >> 2);
-        for (int i = tid; i < n_item; i += kSsThreads) {
+        for (int i = tid; i < n_item; i += kSsCompute) {
           const int part = (i >> 3) & 3, r = i >> 5;
           const int k4 = (i & 7) + 8 * (r % k8), bq = r / k8;
           const bool live = k4 < k4n;
@@ -1314,13 +1353,13 @@ __global__ void __launch_bounds__(kSsThreads, 1) sgld_small_kernel(const __grid_
           }
         }
       }
-      __syncthreads();
+      named_bar_sync(1, kSsCompute);
       // dW tile (units (j, j + half) x 4 columns) + prior gradient W / std^2 (:65-66) + pSGLD update of those entries
       {
         const int q4 = S.lp >> 2;
         const int n_item = S.half * q4;
         double quad = 0.0;
-        for (int i = tid; i < n_item; i += kSsThreads) {
+        for (int i = tid; i < n_item; i += kSsCompute) {
           const int j0 = i / q4, k = (i - j0 * q4) * 4, j1 = j0 + S.half;
           if (k >= Y.ld) continue;
           const bool two = j1 < Y.out;
@@ -1362,8 +1401,8 @@ __global__ void __launch_bounds__(kSsThreads, 1) sgld_small_kernel(const __grid_
               *reinterpret_cast<float4*>(p.grad_out + e) = make_float4(g[0], g[1], g[2], g[3]);
               continue;
             }
-            float z[4];
-            philox_normal4(p.seed, (uint32_t)t, STREAM_SGLD, (uint64_t)(e >> 2), z);
+            const float4 z4 = *reinterpret_cast<const float4*>(s_z + w0);     // Philox (seed, t), block e / 4: drawn a step ahead
+            const float z[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               if (k + c <= Y.in) {
@@ -1381,10 +1420,10 @@ __global__ void __launch_bounds__(kSsThreads, 1) sgld_small_kernel(const __grid_
           if (lane == 0) s_red[nout * kWarps + warp] = quad;
         }
       }
-      __syncthreads();
+      named_bar_sync(1, kSsCompute);
       if (want_quad && tid == 0) {
         double s = s_acc[nout];
-        for (int w = 0; w < kWarps; ++w) s += s_red[nout * kWarps + w];
+        for (int w = 0; w < kCW; ++w) s += s_red[nout * kWarps + w];
         s_acc[nout] = s;
       }
       float* tsw = g0; g0 = g1; g1 = tsw;
@@ -1401,7 +1440,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) sgld_small_kernel(const __grid_
       const float logp = -0.5f * (float)s_acc[nout] - p.log_const + total_lp;
       p.loss_out[0] = -(total_ll * scale + logp);
     }
-    __syncthreads();
+    named_bar_sync(1, kSsCompute);
     // ---- log-precision group (:62, :96-98): closed-form gradient, same update rule, lr_noise
     if (tid < (q.hd >> 2)) {
       const float lr_n = p.lr_n * *s_f;
@@ -1423,7 +1462,8 @@ __global__ void __launch_bounds__(kSsThreads, 1) sgld_small_kernel(const __grid_
 #pragma unroll
         for (int c = 0; c < 4; ++c) p.grad_out[e + c] = g[c];
       } else {
-        philox_normal4(p.seed, (uint32_t)t, STREAM_SGLD, (uint64_t)(e >> 2), z);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) z[c] = s_z[q.sP + tid * 4 + c];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (tid * 4 + c < nout) psgld_update1(tt[c], vv[c], g[c], z[c], lr_n, p.alpha, p.lam, p.precond_mode);
@@ -1472,10 +1512,12 @@ static int ss_plan(const SgParams& p, SsParams* q, size_t* smem) {
   q->sP = (int)sP; q->max_w = max_w;
   long long f = sP + q->hd;
   q->sm_v = (int)f; f += sP + q->hd;
+  q->sm_z = (int)f; f += 2 * (sP + q->hd);
+  q->sm_a0 = (int)f; f += 2LL * p.Bp * q->sy[0].lp;
   q->sm_act = (int)f; f += act;
   q->sm_g0 = (int)f; f += (long long)max_w * q->gp;
   q->sm_g1 = (int)f; f += (long long)max_w * q->gp;
-  q->sm_y = (int)f; f += (2LL * p.Bp * p.nout + 3) & ~3LL;
+  q->sm_y = (int)f; f += (3LL * p.Bp * p.nout + 3) & ~3LL;
   q->sm_red = (int)f; f += 2 * ((long long)(p.nout + 1) * (kSsThreads / 32) + p.nout + 1) + 4;
   *smem = (size_t)f * 4;
   return *smem <= (size_t)227 * 1024 ? 0 : 1;
@@ -1513,7 +1555,8 @@ extern "C" int32_t bnn_sgld_run(const BnnSgldChain* c, int32_t cur, int64_t t0, 
     SsParams q;
     size_t ssmem = 0;
     // ... and whose step is small enough that one SM beats the hand-overs of the dataflow kernel (measured: 13-50-1 at batch 32
-    // 11.4 vs 15.4 us / step, 9-100-100-1 at batch 32 36.6 vs 26.4): packed parameters x batch rows <= kSsMaxWork.
+    // 10.0 vs 15.9 us / step, at batch 128 18.4 vs 16.8, 9-100-100-1 at batch 32 26.7 vs 26.6): packed parameters x batch rows <=
+    // kSsMaxWork.
     // BNN_SGLD_SMALL = 0 never, 1 default rule, 2 whenever it fits (tests, probes).
     const char* e = getenv("BNN_SGLD_SMALL");
     const int mode = e ? atoi(e) : 1;
