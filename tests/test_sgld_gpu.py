@@ -368,9 +368,11 @@ def test_capped_grid_and_two_streams_give_the_same_chains():
         assert torch.allclose(v0, v1, rtol=1e-6, atol=1e-9)
 
 
-def test_num_chains_pools_the_samples_of_chains_trained_side_by_side():
-    """conf['num_chains'] = 2: two chains (seeds seed, seed + 1) share the GPU (capped grids, one stream each); the pooled bank
-    holds both chains' thinned samples, chain 0's half equals what a single-chain model with the same seed produces."""
+@pytest.mark.parametrize("hidden", [[64, 64], [50]], ids=["dataflow_kernel", "single_sm_kernel"])
+def test_num_chains_pools_the_samples_of_chains_trained_side_by_side(hidden):
+    """conf['num_chains'] = 2: two chains (seeds seed, seed + 1) share the GPU (one stream each; capped grids on the dataflow
+    kernel, one SM each on the single-SM kernel); the pooled bank holds both chains' thinned samples, chain 0's half equals what
+    a single-chain model with the same seed produces."""
     from bnn_b200.BNN_SGDMC import BNN_SGDMC
     g = torch.Generator().manual_seed(0)
     X = torch.randn(300, 6, generator=g)
@@ -379,7 +381,7 @@ def test_num_chains_pools_the_samples_of_chains_trained_side_by_side():
     banks = []
     for C in (1, 2):
         torch.manual_seed(1)                                    # same initial network (xavier init draws from torch's global stream)
-        m = BNN_SGDMC(6, nn.Tanh(), [64, 64], nout=1, conf=dict(conf, num_chains=C))
+        m = BNN_SGDMC(6, nn.Tanh(), hidden, nout=1, conf=dict(conf, num_chains=C))
         m.train(X, y)
         assert len(m.nns) == 4 * C
         py, pv = m.predict_mv(X, m.sample(4 * C))
