@@ -116,3 +116,30 @@ def test_plain_c_consumer(tmp_path):
                     "-o", exe, "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.parametrize("dims,batch", [([9, 100, 100, 1], 32), ([1, 50, 50, 1], 32), ([5, 24, 16, 1], 16), ([13, 50, 1], 10), ([3, 7, 2], 1)])
+def test_training_kernel_plans_host_side(dims, batch):
+    """The single-SM training kernels' host-side plans (no GPU): per-step draw counts follow the documented layout -- per layer
+    [batch][in] (MC dropout: only layers whose input is wider than one unit; concrete dropout: every layer), each block padded to
+    a multiple of four floats; local-reparameterisation noise [batch][out] per layer -- and oversized networks are refused."""
+    from bnn_b200 import _lib
+    from bnn_b200.layout import Arch
+    a = Arch(dims, "tanh")
+    d = a.desc()
+    L = _lib.lib()
+    r4 = lambda n: (n + 3) // 4 * 4
+    assert L.bnn_dropout_train_supported(C.byref(d), batch) == 1
+    assert L.bnn_cdropout_train_supported(C.byref(d), batch) == 1
+    assert L.bnn_dropout_train_mask_per_step(C.byref(d), batch) == sum(r4(batch * i) for i in a.ins if i > 1)
+    assert L.bnn_cdropout_train_u_per_step(C.byref(d), batch) == sum(r4(batch * i) for i in a.ins)
+    # Bayes by Backprop keeps nine packed vectors in shared memory: 9-100-100-1 (11,704 parameters) does not fit one SM
+    assert L.bnn_bbb_train_supported(C.byref(d), batch) == (0 if dims == [9, 100, 100, 1] else 1)
+    assert L.bnn_bbb_train_eps_per_step(C.byref(d), batch) == sum(batch * o for o in a.outs)
+    big = Arch([90, 512, 512, 1], "tanh").desc()
+    assert L.bnn_dropout_train_supported(C.byref(big), 32) == 0
+    assert L.bnn_cdropout_train_supported(C.byref(big), 32) == 0
+    assert L.bnn_bbb_train_supported(C.byref(big), 32) == 0
+    assert L.bnn_dropout_train_supported(C.byref(d), 0) == 0          # bad batch: refused, not a crash
+    assert L.bnn_sgld_set_grid_cap(-1) == -1 and b"ctas" in L.bnn_last_error()
+    assert L.bnn_sgld_set_grid_cap(0) == 0
