@@ -378,3 +378,79 @@ def cdropout_train_steps(net, p_logits, X, y, batches, act, us, num_train, noise
         opt.step()
         stats.append((float(mse.detach()), float(wreg.detach()), float(ent.detach())))
     return [(W.detach(), b.detach()) for W, b in zip(Ws, bs)], [q.detach() for q in pls], stats
+
+
+def cdropout_train_steps_closed_form(net, p_logits, X, y, batches, act, us, num_train, noise_level=1., lr=1e-2, lscale=1e-1, dr=2.,
+                                     betas=(0.9, 0.999), adam_eps=1e-8):
+    """The SAME three steps without autograd, in float64: the closed-form gradients the fused kernel uses (csrc/dropout_train.cu) --
+    d keep / d z = -(1 - keep) keep / T, so d L / d p_logit_l = sum_{b,k} -g[b,k] xm[b,k] (1 - keep[b,k]) / T * dz/dp * dp/dlogit plus the
+    regulariser's -(rows / N) noise^2 (lscale^2 sum(W^2) + 2 dr in log((1 - p) / p)) dp/dlogit; wreg acts on W as the per-layer decay
+    2 (rows / N) lscale^2 (1 - p) noise^2 -- and torch.optim.Adam restated.  Checked against the reference-recorded fixture on the
+    CPU, this pins the kernel's derivation independently of the GPU.  tanh / relu / sigmoid activations."""
+    dt = torch.float64
+    net = [(W.to(dt).clone(), b.to(dt).clone()) for W, b in net]
+    pl = torch.stack([torch.as_tensor(q, dtype=dt).reshape(()) for q in p_logits]).clone()
+    X, y = X.to(dt), y.to(dt)
+    nl = len(net)
+    nv, eps, T = float(noise_level) ** 2, 1e-7, 0.1
+    peps = float(torch.finfo(torch.float32).eps)
+    m = [[torch.zeros_like(W), torch.zeros_like(b)] for W, b in net]
+    v = [[torch.zeros_like(W), torch.zeros_like(b)] for W, b in net]
+    pm, pv = torch.zeros(nl, dtype=dt), torch.zeros(nl, dtype=dt)
+    b1, b2 = betas
+    f = act_fn(act)
+
+    def dact(a):                                            # derivative through the activation's OUTPUT
+        return {"tanh": 1 - a * a, "relu": (a > 0).to(dt), "sigmoid": a * (1 - a)}[act]
+    stats = []
+    for it, idx in enumerate(batches):
+        rows = idx.shape[0]
+        frac = rows / num_train
+        sg = torch.sigmoid(pl)
+        p = sg.clamp(peps, 1 - peps)
+        lpr = torch.log(p + eps) - torch.log(1 - p + eps)
+        w2 = [(W ** 2).sum() for W, _ in net]
+        xs, keeps = [], []
+        x = X[idx]
+        for l, (W, b) in enumerate(net):
+            u = us[it][l].to(dt)
+            keep = 1 - torch.sigmoid((lpr[l] + torch.log(u + eps) - torch.log(1 - u + eps)) / T)
+            keeps.append(keep)
+            xm = x * keep
+            xs.append(xm)
+            x = xm @ W.T + b
+            if l + 1 < nl:
+                x = f(x)
+        r = x.squeeze(-1) - y[idx]
+        wreg = sum(lscale ** 2 * (1 - p[l]) * nv * w2[l] for l in range(nl)) * frac
+        ent = sum(dr * 2 * nv * net[l][0].shape[1] * -(p[l] * p[l].log() + (1 - p[l]) * (1 - p[l]).log()) for l in range(nl)) * frac
+        stats.append((float((r ** 2).sum()), float(wreg), float(ent)))
+        g0 = (2 * r).unsqueeze(-1)
+        step = it + 1
+        ss, bc2 = lr / (1 - b1 ** step), (1 - b2 ** step) ** 0.5
+        gp = torch.zeros(nl, dtype=dt)
+        new = [None] * nl
+        for l in range(nl - 1, -1, -1):
+            W, b = net[l]
+            gxm = g0 @ W                                     # gradient with respect to the layer's MASKED input
+            dpdl = sg[l] * (1 - sg[l]) if peps <= float(sg[l]) <= 1 - peps else 0.0
+            dzdp = 1 / (p[l] + eps) + 1 / (1 - p[l] + eps)
+            greg = frac * nv * (-lscale ** 2 * w2[l] - 2 * dr * W.shape[1] * (torch.log(1 - p[l]) - torch.log(p[l])))
+            gp[l] = (-(gxm * xs[l] * (1 - keeps[l])).sum() / T * dzdp + greg) * dpdl
+            if l > 0:
+                a = torch.where(keeps[l] != 0, xs[l] / keeps[l], torch.zeros_like(xs[l]))
+                g1 = gxm * keeps[l] * dact(a)
+            grads = (g0.T @ xs[l] + 2 * frac * lscale ** 2 * (1 - p[l]) * nv * W, g0.sum(0))
+            upd = []
+            for q, (par, gr) in enumerate(zip((W, b), grads)):
+                m[l][q] = b1 * m[l][q] + (1 - b1) * gr
+                v[l][q] = b2 * v[l][q] + (1 - b2) * gr * gr
+                upd.append(par - ss * m[l][q] / (v[l][q].sqrt() / bc2 + adam_eps))
+            new[l] = tuple(upd)
+            if l > 0:
+                g0 = g1
+        net = new
+        pm = b1 * pm + (1 - b1) * gp
+        pv = b2 * pv + (1 - b2) * gp * gp
+        pl = pl - ss * pm / (pv.sqrt() / bc2 + adam_eps)
+    return net, pl, stats

@@ -170,3 +170,18 @@ def test_cdropout_train_steps_golden():
         assert torch.allclose(W, W1, rtol=1e-6, atol=1e-7) and torch.allclose(b, b1, rtol=1e-6, atol=1e-7)
     assert torch.allclose(torch.stack(pl), c["p_logit1"], rtol=1e-6, atol=1e-7)
     assert np.allclose(np.array(stats), c["stats"], rtol=1e-6)
+
+
+def test_cdropout_closed_form_gradients_match_the_reference():
+    """The closed-form gradients of the fused concrete-dropout kernel (keep factors, regulariser, p_logit; no autograd), restated in
+    float64, reproduce the reference's three recorded steps: pins the kernel's derivation on the CPU."""
+    from helpers import cdropout_train_case
+    c = cdropout_train_case()
+    net, pl, stats = O.cdropout_train_steps_closed_form(c["net0"], list(c["p_logit0"]), c["X"], c["y"], c["batches"], c["act"], c["us"],
+                                                        c["X"].shape[0], noise_level=c["noise_level"], lr=c["lr"], lscale=c["lscale"],
+                                                        dr=c["dr"])
+    for (W, b), (W1, b1) in zip(net, c["net1"]):
+        assert float((W.float() - W1).abs().max()) <= 2e-6 * float(W1.abs().max())
+        assert float((b.float() - b1).abs().max()) <= 2e-6 * float(b1.abs().max()) + 1e-8
+    assert float((pl.float() - c["p_logit1"]).abs().max()) <= 2e-6 * float(c["p_logit1"].abs().max())
+    assert np.allclose(np.array(stats), c["stats"], rtol=2e-6)
