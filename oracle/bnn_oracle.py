@@ -454,3 +454,58 @@ def cdropout_train_steps_closed_form(net, p_logits, X, y, batches, act, us, num_
         pv = b2 * pv + (1 - b2) * gp * gp
         pl = pl - ss * pm / (pv.sqrt() / bc2 + adam_eps)
     return net, pl, stats
+
+
+def bbb_train_steps_closed_form(mus, rhos, X, y, batches, act, eps, lr=1e-2, kl_factor=1e-3, weight_std=0.1, betas=(0.9, 0.999),
+                                adam_eps=1e-8):
+    """bbb_train_steps without autograd, in float64: what the fused kernel computes (csrc/bbb_train.cu).  With a = (h | 1) the
+    augmented input, out = a mu^T + eps sqrt(a^2 s2^T): d L / d var = d L / d out * eps / (2 sqrt(var)); d mu = (dL/dout)^T a;
+    d s2 = (dL/dvar)^T a^2; d a = dL/dout mu + 2 a * (dL/dvar s2), through the activation below; KL(N(mu, s) || N(0, w0)) adds
+    kl_factor mu / w0^2 and kl_factor (1 / w0^2 - 1 / s2) / 2; s2 = softplus(max(rho, -35)) -> d s2 / d rho = sigmoid(rho) above the
+    clamp; torch.optim.Adam restated.  Pins the kernel's derivation on the CPU against the reference-recorded fixture."""
+    dt = torch.float64
+    mus = [m.to(dt).clone() for m in mus]
+    rhos = [r.to(dt).clone() for r in rhos]
+    X, y = X.to(dt), y.to(dt)
+    nl = len(mus)
+    iw2 = 1.0 / weight_std ** 2
+    st = [[torch.zeros_like(m) for _ in range(4)] for m in mus]       # Adam: m_mu, v_mu, m_rho, v_rho
+    b1, b2 = betas
+    f = act_fn(act)
+
+    def dact(a):
+        return {"tanh": 1 - a * a, "relu": (a > 0).to(dt), "sigmoid": a * (1 - a)}[act]
+    mses, kls = [], []
+    for it, idx in enumerate(batches):
+        rows = idx.shape[0]
+        s2 = [F.softplus(torch.clamp(r, min=-35.)) for r in rhos]
+        kls.append(float(sum((0.5 * (v * iw2 + m * m * iw2 - 1 - torch.log(v * iw2))).sum() for m, v in zip(mus, s2))))
+        h = X[idx].reshape(rows, -1)
+        A, SD = [], []
+        for l in range(nl):
+            a = torch.cat([h, torch.ones(rows, 1, dtype=dt)], dim=1)
+            sd = (a * a @ s2[l].T).sqrt()
+            A.append(a)
+            SD.append(sd)
+            h = a @ mus[l].T + eps[it][l].to(dt) * sd
+            if l + 1 < nl:
+                h = f(h)
+        r = h - y[idx].reshape(rows, -1)
+        mses.append(float((r * r).mean()))
+        g0 = 2 * r / r.numel()
+        step = it + 1
+        ss, bc2 = lr / (1 - b1 ** step), (1 - b2 ** step) ** 0.5
+        for l in range(nl - 1, -1, -1):
+            a, sd = A[l], SD[l]
+            gv = g0 * eps[it][l].to(dt) / (2 * sd)
+            g_mu = g0.T @ a + kl_factor * mus[l] * iw2
+            g_s2 = gv.T @ (a * a) + kl_factor * 0.5 * (iw2 - 1 / s2[l])
+            g_rho = g_s2 * torch.where(rhos[l] > -35., torch.sigmoid(rhos[l]), torch.zeros_like(rhos[l]))
+            if l > 0:
+                ga = g0 @ mus[l] + 2 * a * (gv @ s2[l])
+                g0 = ga[:, :-1] * dact(a[:, :-1])
+            for q, (par, gr) in enumerate(((mus, g_mu), (rhos, g_rho))):
+                st[l][2 * q] = b1 * st[l][2 * q] + (1 - b1) * gr
+                st[l][2 * q + 1] = b2 * st[l][2 * q + 1] + (1 - b2) * gr * gr
+                par[l] = par[l] - ss * st[l][2 * q] / (st[l][2 * q + 1].sqrt() / bc2 + adam_eps)
+    return mus, rhos, mses, kls

@@ -185,3 +185,16 @@ def test_cdropout_closed_form_gradients_match_the_reference():
         assert float((b.float() - b1).abs().max()) <= 2e-6 * float(b1.abs().max()) + 1e-8
     assert float((pl.float() - c["p_logit1"]).abs().max()) <= 2e-6 * float(c["p_logit1"].abs().max())
     assert np.allclose(np.array(stats), c["stats"], rtol=2e-6)
+
+
+def test_bbb_closed_form_gradients_match_the_reference():
+    """The closed-form gradients of the fused Bayes-by-Backprop kernel (local reparameterisation backward, KL gradient; no autograd),
+    restated in float64, reproduce the reference's three recorded steps."""
+    from helpers import bbb_train_case
+    c = bbb_train_case()
+    mu, rho, mse, kl = O.bbb_train_steps_closed_form(c["mu0"], c["rho0"], c["X"], c["y"], c["batches"], c["act"], c["eps"], lr=c["lr"],
+                                                     kl_factor=c["kl_factor"], weight_std=c["weight_std"])
+    for l in range(len(mu)):
+        assert float((mu[l].float() - c["mu1"][l]).abs().max()) <= 2e-6 * float(c["mu1"][l].abs().max())
+        assert float((rho[l].float() - c["rho1"][l]).abs().max()) <= 2e-6 * float(c["rho1"][l].abs().max())
+    assert np.allclose(mse, c["mse"], rtol=2e-6) and np.allclose(kl, c["kl"], rtol=2e-6)
